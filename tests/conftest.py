@@ -1,0 +1,68 @@
+"""Shared fixtures.
+
+`qi` parametrises a test over the two implementations of the reference-shaped API:
+  * "oracle": oracle/refapi.py (CPU restatement of the reference; runs everywhere)
+  * "gpu":    quant_iron_b200 (the product: C-ABI library + sm_100a kernels; needs a B200)
+The reference's own known-answer tests are ported once (tests/test_ref_ported_*.py) and run
+against both, so the oracle is pinned by the reference's tests and the GPU engine is held to
+exactly the same facts.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+AMP_TOL = 1e-12      # north star: max abs amplitude error
+EXP_RTOL = 1e-10     # north star: relative error on expectation values
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+
+
+def _load(name):
+    if name == "oracle":
+        from oracle import refapi
+        return refapi
+    import quant_iron_b200
+    return quant_iron_b200
+
+
+@pytest.fixture(params=["oracle", pytest.param("gpu", marks=pytest.mark.gpu)])
+def qi(request):
+    return _load(request.param)
+
+
+@pytest.fixture
+def ref():
+    from oracle import refapi
+    return refapi
+
+
+@pytest.fixture
+def gpu():
+    import quant_iron_b200
+    return quant_iron_b200
+
+
+def vec(state) -> np.ndarray:
+    return np.asarray(state.state_vector, dtype=np.complex128)
+
+
+def assert_amps(state, expected, tol=AMP_TOL, msg=""):
+    got = vec(state)
+    exp = np.asarray(expected, dtype=np.complex128)
+    assert got.shape == exp.shape, f"{msg}: shape {got.shape} != {exp.shape}"
+    err = float(np.max(np.abs(got - exp))) if got.size else 0.0
+    assert err <= tol, f"{msg}: max abs amplitude error {err:.3e} > {tol:.1e}"
+
+
+def basis(n, k):
+    v = np.zeros(1 << n, dtype=np.complex128)
+    v[k] = 1.0
+    return v
