@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the state-vector hot path (contract in the task statement).
+
+  python bench.py --gpus N --steps K --warmup W            # this build (B200)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Metric (BASELINE.json): gates/s on the synthetic random layered circuit (H/RX/RZ/CNOT, depth 40,
+configs[1]'s generator) at the metric's 30 qubits per GPU, f64, plus the achieved HBM GB/s of the
+dominant kernel against the measured roofline, plus single-gate passes at 30 qubits.
+A "step" is one execution of the whole circuit on a state that is already resident in HBM; `e2e`
+is the same circuit through the public API with HOST buffers (H2D of the initial state and D2H of the
+final state inside the timed region).  N > 1: the state is sharded (top log2 N qubits global),
+30 local qubits per GPU (weak scaling).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gates_per_sec"
+UNIT = "gates/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(num_qubits: int, specs, budget_s: float = 20.0):
+    """The reference's CPU path, restated (oracle/qi_oracle.c), timed on this box's host cores on a
+    bounded sample: the leading gates of the same circuit.  `faithful` = the reference's rayon-branch
+    pass structure (clone + parallel (index,value) updates with a heap allocation per pair + serial
+    scatter, operator.rs:339-360); `inplace` = same arithmetic, in place (a stronger CPU baseline)."""
+    import numpy as np
+    from oracle import refapi as ref
+    kinds = {"h": ref.G_H, "rx": ref.G_RX, "rz": ref.G_RZ, "cnot": ref.G_CNOT, "cp": ref.G_P, "swap": ref.G_SWAP,
+             "x": ref.G_X, "p": ref.G_P}
+    cores = ref.num_threads()
+    try:
+        avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
+    except Exception:
+        avail = 32 << 30
+    # calibrate at 22 qubits, then pick the largest n (<= requested) whose gate fits time and memory
+    n_cal = min(22, num_qubits)
+    v = np.zeros(1 << n_cal, dtype=np.complex128)
+    v[0] = 1.0
+    dst = np.empty_like(v)
+    t0 = time.perf_counter()
+    ref.gate_faithful(v, dst, n_cal, ref.G_H, [n_cal // 2], [], [])
+    per_amp = (time.perf_counter() - t0) / float(1 << n_cal)
+    n = num_qubits
+    while n > n_cal and (per_amp * (1 << n) > budget_s / 3.0 or 100 * (1 << n) > avail * 0.7):
+        n -= 1
+    del v, dst
+
+    def run(kind: str):
+        a = np.zeros(1 << n, dtype=np.complex128)
+        a[0] = 1.0
+        b = np.empty_like(a) if kind == "faithful" else None
+        done, t_start = 0, time.perf_counter()
+        for name, targets, controls, params in specs:
+            if any(q >= n for q in targets + controls):
+                continue
+            if kind == "faithful":
+                ref.gate_faithful(a, b, n, kinds[name], targets, controls, params)
+                a, b = b, a
+            else:
+                ref.gate_inplace(a, n, kinds[name], targets, controls, params)
+            done += 1
+            if time.perf_counter() - t_start > budget_s / 2.0 and done >= 2:
+                break
+        return done / (time.perf_counter() - t_start), done
+
+    f_rate, f_done = run("faithful")
+    i_rate, i_done = run("inplace")
+    return {
+        "value": f_rate, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"first {f_done} gates of the same circuit at {n} qubits, reference pass structure "
+                  f"(clone + per-pair updates + serial scatter); in-place variant: first {i_done} gates",
+        "qubits": n, "inplace_value": i_rate,
+        "scaled_to_bench_qubits": f_rate / float(1 << (num_qubits - n)),
+        "inplace_scaled_to_bench_qubits": i_rate / float(1 << (num_qubits - n)),
+    }
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path (its Rust crate cannot
+    be built here; the C restatement under oracle/ is what is timed), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from quant_iron_b200 import workloads as w
+    n = args.qubits
+    specs = w.random_layered_circuit(n, args.depth)
+    vals, base = [], None
+    budget = min(args.cpu_budget, 150.0 / (args.warmup + args.steps))   # whole run ends within a few minutes
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(n, specs, budget_s=budget)
+        if i >= args.warmup:
+            vals.append(base["scaled_to_bench_qubits"])
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * len(specs) / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth}, {n} qubits "
+                               f"(CPU sample measured at {base['qubits']} qubits, scaled by 2^-{n - base['qubits']})"},
+        "cpu_baseline": dict(base, value=value),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def single_gate_table(qi, n, peak_gbs, passes=10):
+    """30-qubit single-gate passes: achieved GB/s = algorithmic bytes / CUDA-event time."""
+    st = qi.State.new_random(n)
+    full = 2.0 * 16.0 * float(1 << n)
+    ctrl = n - 2
+    gates = {
+        "h": (lambda t: st.h_(t), 1.0), "rx": (lambda t: st.rx_(t, 0.3), 1.0), "rz": (lambda t: st.rz_(t, 0.3), 1.0),
+        "x": (lambda t: st.x_(t), 1.0), "p": (lambda t: st.p_(t, 0.3), 0.5),
+        "cnot": (lambda t: st.cnot_(ctrl if t != ctrl else ctrl - 1, t), 0.5),
+        "cp": (lambda t: st.cp_multi_([t], [ctrl if t != ctrl else ctrl - 1], 0.3), 0.25),
+    }
+    targets = sorted(set([0, 2, 4, 5, 12, 20, n - 1]))
+    table = {}
+    for name, (fn, frac) in gates.items():
+        row = {}
+        for t in targets:
+            fn(t)
+            qi.engine.synchronize()
+            qi.engine.timer_start()
+            for _ in range(passes):
+                fn(t)
+            ms = qi.engine.timer_stop() / passes
+            row[str(t)] = round(full * frac / (ms * 1e-3) / 1e9, 1)
+        table[name] = row
+    best_h = max(table["h"].values())
+    worst_h = min(table["h"].values())
+    return {"qubits": n, "passes": passes, "gbs": table, "h_best_frac_of_measured_peak": best_h / peak_gbs,
+            "h_worst_frac_of_measured_peak": worst_h / peak_gbs, "h_best_frac_of_8TBs_nominal": best_h / 8000.0}
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import quant_iron_b200 as qi
+    from quant_iron_b200 import workloads as w
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    qi.engine.init(local_rank)
+    peak_gbs, peak_src = load_peaks()
+    n_local = args.qubits
+    n = n_local + (world.bit_length() - 1)
+    specs = w.random_layered_circuit(n, args.depth)
+    n_gates = len(specs)
+
+    def barrier():
+        qi.engine.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world > 1:
+        from quant_iron_b200 import sharded
+        state = sharded.new_zero(n, dist)
+    else:
+        state = qi.State.new_zero(n)
+    circuit = w.build_circuit(qi, n, specs)
+
+    for _ in range(args.warmup):
+        circuit.execute_(state)
+    barrier()
+    qi.engine.stats_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    qi.engine.timer_start()
+    for _ in range(args.steps):
+        circuit.execute_(state)
+    ms_total = qi.engine.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    stats = qi.engine.stats()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n_gates / (ms_per_step * 1e-3)
+    launches = sum(v["launches"] for v in stats.values())
+
+    # roofline of the dominant kernel: per-launch event timing in a separate (profiled) pass
+    qi.engine.set_option("profile", 1)
+    qi.engine.stats_reset()
+    circuit.execute_(state)
+    qi.engine.synchronize()
+    prof = qi.engine.stats()
+    qi.engine.set_option("profile", 0)
+    dom = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
+    dname, d = dom
+    avg_ms = d["total_ms"] / d["launches"]
+    bytes_per_launch = d["algorithmic_bytes"] / d["launches"]
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": d["launches"], "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "share_of_step": d["total_ms"] / max(1e-9, sum(v["total_ms"] for v in prof.values()))}
+    norm = state.norm_sqr()
+    del state
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+        return
+
+    # ---- e2e through the public API with host buffers (rank 0, single GPU semantics) ----
+    e2e = None
+    try:
+        n_e = n_local if world == 1 else min(n_local, 28)
+        specs_e = specs if world == 1 else w.random_layered_circuit(n_e, args.depth)
+        circ_e = circuit if world == 1 else w.build_circuit(qi, n_e, specs_e)
+        host_in = torch.zeros(1 << n_e, dtype=torch.complex128).pin_memory()
+        host_out = torch.empty(1 << n_e, dtype=torch.complex128).pin_memory()
+        host_in[0] = 1.0
+        hin, hout = host_in.numpy(), host_out.numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        times = []
+        for i in range(1 + e2e_steps):
+            qi.engine.synchronize()
+            t0 = time.perf_counter()
+            s = qi.State.from_host(hin, check=False)       # H2D of the initial state (pinned)
+            circ_e.execute_(s)
+            s.to_host(hout)                                 # D2H of the final state
+            dt = time.perf_counter() - t0
+            del s
+            if i > 0:
+                times.append(dt)
+        e2e_val = len(specs_e) / (sum(times) / len(times))
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 16 * (1 << n_e) + 88 * len(specs_e),
+               "d2h_bytes_per_step": 16 * (1 << n_e), "qubits": n_e, "steps": e2e_steps,
+               "checksum_norm": float(np.vdot(hout[:1 << 16], hout[:1 << 16]).real)}
+        del host_in, host_out, hin, hout
+    except Exception as ex:  # noqa: BLE001
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+    extras = {}
+    if world == 1 and not args.skip_extras:
+        try:
+            extras["single_gate"] = single_gate_table(qi, n_local, peak_gbs)
+        except Exception as ex:  # noqa: BLE001
+            extras["single_gate"] = {"error": repr(ex)[:200]}
+        try:
+            n28 = 28
+            specs28 = w.random_layered_circuit(n28, 40)
+            c28 = w.build_circuit(qi, n28, specs28)
+            s28 = qi.State.new_zero(n28)
+            c28.execute_(s28)
+            qi.engine.synchronize()
+            qi.engine.timer_start()
+            for _ in range(3):
+                c28.execute_(s28)
+            ms28 = qi.engine.timer_stop() / 3
+            extras["config_28q_layered_depth40"] = {"gates": len(specs28), "ms_per_circuit": ms28,
+                                                    "gates_per_sec": len(specs28) / (ms28 * 1e-3)}
+            del s28
+        except Exception as ex:  # noqa: BLE001
+            extras["config_28q_layered_depth40"] = {"error": repr(ex)[:200]}
+
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        try:
+            cpu = cpu_baseline(n, specs, budget_s=args.cpu_budget)
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"[:200]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth} (BASELINE configs[1] generator, "
+                               f"seed 20260001) at {n_local} qubits per GPU ({n} qubits total), state resident in HBM",
+                   "qubits": n, "gates_per_step": n_gates, "state_bytes_per_gpu": 16 * (1 << n_local),
+                   "l2": "inputs (16 GiB state) far larger than the 126 MB L2; no flush needed",
+                   "unfused_algorithmic_bytes_per_step": w.algorithmic_bytes(n, specs),
+                   "effective_gbs_vs_unfused_bytes": w.algorithmic_bytes(n, specs) / world / (ms_per_step * 1e-3) / 1e9},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "kernels": {k: v["launches"] for k, v in stats.items()}, "clocks": clocks,
+        "final_norm_sqr": norm, "extras": extras,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU")
+    ap.add_argument("--depth", type=int, default=40)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

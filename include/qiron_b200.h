@@ -1,0 +1,202 @@
+/*
+ * qiron_b200.h -- C ABI of the B200-native state-vector engine for quant-iron.
+ *
+ * This is the drop-in boundary: a flat extern "C" library that a host
+ * facade (Rust -sys crate, C++ header, Python ctypes) binds in place of quant-iron's rayon/OpenCL
+ * backends.  Every entry point cites the reference item it replaces as file:line under the
+ * reference root (LordSaumya/quant-iron v2.0.0).
+ *
+ * Conventions
+ *   - Amplitudes are Complex<f64>, interleaved (re, im), 16 bytes each, resident in device memory.
+ *     Qubit q is bit q of the amplitude index (LSB = qubit 0), as in operator.rs:347-349.
+ *   - States are opaque handles owned by the caller.  Gate entry points mutate IN PLACE; the
+ *     reference's `&State -> State` methods are clone + in-place on the facade side.
+ *   - Every function returns a qi_status.  Codes 1..15 map 1:1 onto quant-iron's `enum Error`
+ *     (errors.rs:3-97); the variant's usize payloads are returned by qi_last_error().
+ *   - Validation order equals validate_qubits (operator.rs:214-273) so the same variant fires.
+ *   - Calls are asynchronous on the engine's CUDA stream; they synchronise only where a host-visible
+ *     value is produced (to_host, scalars, samples).
+ *   - There is no CPU fallback: without a CUDA device every compute entry returns QI_ERR_CUDA.
+ */
+#ifndef QIRON_B200_H
+#define QIRON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qi_state qi_state; /* replaces `pub struct State { state_vector: Vec<Complex<f64>>, num_qubits }` state.rs:74-81 */
+
+typedef enum qi_status {
+    QI_OK = 0,
+    QI_ERR_INVALID_NUMBER_OF_MEASUREMENTS = 1,   /* errors.rs:11  payload[0] = n */
+    QI_ERR_OVERLAPPING_CONTROL_AND_TARGET = 2,   /* errors.rs:22  payload = (control, target) */
+    QI_ERR_INVALID_NUMBER_OF_QUBITS = 3,         /* errors.rs:31  payload[0] = n */
+    QI_ERR_INVALID_QUBIT_INDEX = 4,              /* errors.rs:40  payload = (index, num_qubits) */
+    QI_ERR_STATE_VECTOR_NOT_NORMALISED = 5,      /* errors.rs:44 */
+    QI_ERR_NON_UNITARY_MATRIX = 6,               /* errors.rs:48 */
+    QI_ERR_INVALID_NUMBER_OF_INPUTS = 7,         /* errors.rs:57  payload = (actual, expected) */
+    QI_ERR_MISMATCHED_NUMBER_OF_PARAMETERS = 8,  /* errors.rs:66  payload = (expected, actual) */
+    QI_ERR_UNKNOWN = 9,                          /* errors.rs:70 */
+    QI_ERR_CUDA = 10,                            /* takes the slot of OpenCLError (errors.rs:78); payload[0] = cudaError_t */
+    QI_ERR_CONTEXT_LOCK = 11,                    /* GpuContextLockError (errors.rs:82); kept for numbering, never returned */
+    QI_ERR_CIRCUIT_MACRO = 12,                   /* errors.rs:86 (host-side only) */
+    QI_ERR_INVALID_INPUT_VALUE = 13,             /* errors.rs:90  payload[0] = value */
+    QI_ERR_ZERO_NORM = 14,                       /* errors.rs:94 */
+    QI_ERR_INVALID_PAULI_STRING_COEFFICIENT = 15,/* errors.rs:98  payload = bit patterns of (re, im) */
+    QI_ERR_INVALID_ARGUMENT = 16,                /* NULL handle / malformed record: no reference counterpart */
+    QI_ERR_PEER = 17                             /* sharded state: peer mapping / exchange failure */
+} qi_status;
+
+/* payload and message of the last non-OK status on the calling thread */
+void qi_last_error(uint64_t payload[2], char* msg, size_t msg_len);
+const char* qi_version(void);
+
+/* ---- engine ------------------------------------------------------------------------------- */
+int qi_init(int device);                       /* bind the engine to a CUDA device (default: current device) */
+int qi_synchronize(void);                      /* wait for all queued work */
+int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_mem, uint64_t* free_mem);
+/* options: "path" = 0 auto | 1 force the simple per-gate kernels | 2 force the window kernels;
+ *          "fuse" = 1/0 gate fusion in qi_apply_circuit; "profile" = 1/0 per-kernel event timing */
+int qi_set_option(const char* name, int64_t value);
+
+/* kernel accounting for bench.py (gpu_launches, roofline.achieved) */
+typedef struct qi_kernel_stat {
+    char name[32];
+    uint64_t launches;
+    double total_ms;          /* only when the "profile" option is on */
+    double algorithmic_bytes; /* sum over launches of the bytes the pass must move */
+} qi_kernel_stat;
+int qi_stats_reset(void);
+int qi_stats_get(qi_kernel_stat* out, int capacity, int* count);
+/* CUDA-event stopwatch on the engine stream */
+int qi_timer_start(void);
+int qi_timer_stop(float* elapsed_ms);
+
+/* ---- state container (state.rs:99-373, 397-453, 801-945, 2687-2862) --------------------------- */
+int qi_state_new_zero(uint32_t num_qubits, qi_state** out);                   /* state.rs:165-178 */
+int qi_state_new_basis_n(uint32_t num_qubits, uint64_t n, qi_state** out);    /* state.rs:194-210 */
+int qi_state_new_plus(uint32_t num_qubits, qi_state** out);                   /* state.rs:225-237 */
+int qi_state_new_minus(uint32_t num_qubits, qi_state** out);                  /* state.rs:252-290 */
+int qi_state_new_ghz(uint32_t num_qubits, qi_state** out);                    /* state.rs:305-325 */
+/* State::new (checked, state.rs:99-127) when check != 0; the struct literal State{..} when check == 0
+ * (len need not be 2^num_qubits then, as in state_tests.rs:145-150). amps = len interleaved (re,im). */
+int qi_state_from_host(const double* amps, uint64_t len, uint32_t num_qubits, int check, qi_state** out);
+int qi_state_to_host(const qi_state* s, double* amps, uint64_t len);          /* read `state_vector` */
+int qi_state_clone(const qi_state* s, qi_state** out);                        /* #[derive(Clone)] state.rs:69 */
+void qi_state_free(qi_state* s);
+uint32_t qi_state_num_qubits(const qi_state* s);                              /* state.rs:431 */
+uint64_t qi_state_len(const qi_state* s);
+int qi_state_amplitude(const qi_state* s, uint64_t n, double out[2]);         /* state.rs:448-453 */
+int qi_state_init_random(qi_state* s, uint64_t seed);  /* synthetic normalised state */
+void* qi_state_device_ptr(qi_state* s);                /* raw device pointer (interop: torch / NCCL plumbing) */
+
+int qi_inner_product(const qi_state* a, const qi_state* b, double out[2]);    /* state.rs:890-917 */
+int qi_norm_sqr(const qi_state* s, double* out);                              /* state.rs:117, 924-929 */
+int qi_normalise(qi_state* s);                                                /* state.rs:924-945 */
+int qi_scale(qi_state* s, const double z[2]);                                 /* state.rs:2687-2776 */
+int qi_add(qi_state* a, const qi_state* b);                                   /* state.rs:2779-2800 */
+int qi_sub(qi_state* a, const qi_state* b);                                   /* state.rs:2841-2862 */
+int qi_conj(qi_state* s);                                                     /* state.rs:397-403 */
+int qi_tensor_product(const qi_state* a, const qi_state* b, qi_state** out);  /* state.rs:801-836 */
+
+/* ---- operators (operator.rs) -------------------------------------------------------------- */
+typedef enum qi_gate_kind {
+    QI_GATE_H = 1,         /* Hadamard::apply        operator.rs:303-424 */
+    QI_GATE_X = 2,         /* Pauli::X               operator.rs:474-606 */
+    QI_GATE_Y = 3,         /* Pauli::Y */
+    QI_GATE_Z = 4,         /* Pauli::Z */
+    QI_GATE_I = 5,         /* Identity::apply        operator.rs:1112-1123 */
+    QI_GATE_S = 6,         /* PhaseS                 operator.rs:1160-1216 */
+    QI_GATE_SDG = 7,       /* PhaseSdag              operator.rs:1352-1408 */
+    QI_GATE_T = 8,         /* PhaseT                 operator.rs:1253-1315 */
+    QI_GATE_TDG = 9,       /* PhaseTdag              operator.rs:1445-1507 */
+    QI_GATE_P = 10,        /* PhaseShift             operator.rs:1565-1624   params[0] = angle */
+    QI_GATE_RX = 11,       /* RotateX                operator.rs:1674-1767   params[0] = angle */
+    QI_GATE_RY = 12,       /* RotateY                operator.rs:1817-1908 */
+    QI_GATE_RZ = 13,       /* RotateZ                operator.rs:1958-2035 */
+    QI_GATE_U2 = 14,       /* Unitary2::apply        operator.rs:2209-2266   params = m00,m01,m10,m11 as (re,im) */
+    QI_GATE_CNOT = 15,     /* CNOT::apply            operator.rs:667-685     exactly one control */
+    QI_GATE_SWAP = 16,     /* SWAP::apply            operator.rs:731-820     two targets */
+    QI_GATE_TOFFOLI = 17,  /* Toffoli::apply         operator.rs:1055-1075   two distinct controls */
+    QI_GATE_MATCHGATE = 18 /* Matchgate::apply       operator.rs:893-1014    params = theta, phi1, phi2 */
+} qi_gate_kind;
+
+/* One `Gate::Operator(Box<dyn Operator>, targets, controls)` record (gate.rs:23). */
+typedef struct qi_gate {
+    int32_t kind;              /* qi_gate_kind */
+    uint32_t num_targets;
+    uint32_t targets[2];
+    uint32_t num_controls;
+    const uint32_t* controls;  /* may be NULL when num_controls == 0 */
+    double params[8];
+} qi_gate;
+
+/* Operator::apply (operator.rs:165-170), in place. */
+int qi_apply_gate(qi_state* s, const qi_gate* gate);
+/* Circuit::execute's gate loop (circuit.rs:160-172) over a run of operator gates.  All records are
+ * validated first; then the run is scheduled into fused register-window passes. */
+int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count);
+/* Unitary2::new's unitarity check (operator.rs:2092-2118): QI_OK or QI_ERR_NON_UNITARY_MATRIX */
+int qi_unitary2_check(const double m[8]);
+
+/* ---- PauliString / SumOp (pauli_string.rs) -------------------------------------------------- */
+typedef struct qi_pauli_term {
+    uint32_t num_ops;
+    const uint32_t* qubits;    /* distinct qubits */
+    const uint8_t* paulis;     /* 1 = X, 2 = Y, 3 = Z */
+    double coefficient[2];
+} qi_pauli_term;
+
+/* PauliString::apply (pauli_string.rs:139-151) when with_coefficient != 0, apply_operators (172-184) otherwise */
+int qi_apply_pauli_string(qi_state* s, const qi_pauli_term* term, int with_coefficient);
+/* PauliString::apply_exp_factor (pauli_string.rs:237-262): psi <- cosh(a) psi + sinh(a) P psi, a = coefficient*factor.
+ * apply_exp (198-223) is factor = 1; apply_exp_neg_i_dt (281-287) is factor = (0,-dt) after the Im(coeff)==0 check. */
+int qi_apply_pauli_exp(qi_state* s, const qi_pauli_term* term, const double factor[2]);
+/* SumOp::expectation_value (pauli_string.rs:485-507) */
+int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, double out[2]);
+/* SumOp::apply (pauli_string.rs:453-466): out = sum_k P_k psi (new state) */
+int qi_apply_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, qi_state** out);
+/* trotter_evolve_state (time_evolution.rs:140-167); order 1 = First (45-66), 2 = Second (89-115) */
+int qi_trotter_evolve(qi_state* s, const qi_pauli_term* terms, uint64_t count, double dt, uint64_t steps, int order);
+
+/* ---- measurement (state.rs:525-784) --------------------------------------------------------- */
+typedef enum qi_basis { QI_BASIS_COMPUTATIONAL = 0, QI_BASIS_X = 1, QI_BASIS_Y = 2, QI_BASIS_CUSTOM = 3 } qi_basis;
+
+/* un-normalised marginal table over `m` qubits, bin bit j <-> qubits[j] (state.rs:559-588); out = 2^m host doubles */
+int qi_probabilities(const qi_state* s, const uint32_t* qubits, uint32_t m, double* out);
+/* `shots` draws from one table by a device prefix scan; draw k uses u_k of the shared-seed stream
+ * (splitmix64, u = (x >> 11) * 2^-53); rule: first bin with u < cumsum, else last (state.rs:601-619) */
+int qi_sample(const qi_state* s, const uint32_t* qubits, uint32_t m, uint64_t shots, uint64_t seed, uint64_t* bins);
+/* collapse onto `bin` and renormalise (state.rs:622-654), in place */
+int qi_collapse(qi_state* s, const uint32_t* qubits, uint32_t m, uint64_t bin);
+/* State::measure (state.rs:525-730), in place: basis change, draw u_{draw_index} of `seed`, collapse, basis
+ * change back.  m = 0 measures every qubit (531-541); outcomes[j] = (bin >> j) & 1 (657-660).
+ * custom_u = 8 doubles (row-major 2x2, (re,im)) for QI_BASIS_CUSTOM, else NULL. */
+int qi_measure(qi_state* s, int basis, const double* custom_u, const uint32_t* qubits, uint32_t m,
+               uint64_t seed, uint64_t draw_index, uint8_t* outcomes, uint64_t* bin);
+/* the u of the shared-seed stream, for host-side checks */
+double qi_uniform(uint64_t seed, uint64_t k);
+
+/* ---- sharded state over 2/4/8 GPUs (new work) --------------------------------- */
+#define QI_IPC_HANDLE_BYTES 64
+/* one shard per process: `total_qubits` logical qubits, the top log2(world) are global */
+int qi_shard_new_zero(uint32_t total_qubits, int rank, int world, qi_state** out);
+int qi_shard_new_plus(uint32_t total_qubits, int rank, int world, qi_state** out);
+int qi_shard_new_basis_n(uint32_t total_qubits, uint64_t n, int rank, int world, qi_state** out);
+/* export this shard's amplitude buffer + its flag block as CUDA IPC handles (2 * QI_IPC_HANDLE_BYTES) */
+int qi_shard_export(qi_state* s, uint8_t* handles);
+/* map every peer's buffers; `all_handles` = world * 2 * QI_IPC_HANDLE_BYTES, gathered by the host (torch.distributed) */
+int qi_shard_attach(qi_state* s, const uint8_t* all_handles);
+int qi_shard_rank(const qi_state* s);
+int qi_shard_world(const qi_state* s);
+/* bytes this rank moved over NVLink and the number of exchanges since creation */
+int qi_shard_comm_stats(const qi_state* s, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* exchanges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIRON_B200_H */

@@ -1,0 +1,192 @@
+// common.cuh -- shared internals of libqiron_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "qiron_b200.h"
+
+namespace qi {
+
+typedef double2 amp_t;  // Complex<f64>: .x = re, .y = im
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(uint64_t p0, uint64_t p1, const char* fmt, ...);
+int fail(int status, uint64_t p0 = 0, uint64_t p1 = 0, const char* msg = "");
+int cuda_fail(cudaError_t e, const char* what);
+
+#define QI_CUDA(expr)                                          \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return ::qi::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define QI_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != QI_OK) return _s;   \
+    } while (0)
+
+// ---- engine context --------------------------------------------------------------------------
+enum KernelFamily {
+    KF_INIT = 0, KF_PAIR, KF_DIAG, KF_SWAP, KF_MATCH, KF_WINDOW, KF_PAULI, KF_PAULI_EXP, KF_EXPECT,
+    KF_REDUCE, KF_ELEMENTWISE, KF_PROB, KF_SCAN, KF_SAMPLE, KF_COLLAPSE, KF_EXCHANGE, KF_BARRIER,
+    KF_COUNT
+};
+extern const char* const kFamilyNames[KF_COUNT];
+
+struct ProfEvent { cudaEvent_t start, stop; int family; };
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // scratch for reductions: partial sums (double2 per block per slot) + result
+    double* d_partials = nullptr;     // kPartialSlots * 2 doubles
+    double* d_result = nullptr;       // small result area (device)
+    double* h_result = nullptr;       // pinned host mirror
+    size_t partial_capacity = 0;      // in doubles
+    // options
+    int opt_path = 0;                 // 0 auto, 1 simple kernels, 2 window kernels
+    int opt_fuse = 1;
+    int opt_profile = 0;
+    // stats
+    uint64_t launches[KF_COUNT] = {0};
+    double alg_bytes[KF_COUNT] = {0};
+    double total_ms[KF_COUNT] = {0};
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+};
+Context& ctx();
+int ensure_ctx();
+int ensure_partials(size_t doubles);
+
+// Kernel launch bookkeeping: counts launches, accumulates algorithmic bytes and, when the
+// "profile" option is on, brackets the launch with CUDA events on the engine stream.
+struct LaunchScope {
+    int family;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    LaunchScope(int family, double bytes);
+    ~LaunchScope();
+};
+int check_launch(const char* what);
+
+// ---- state -------------------------------------------------------------------------------------
+}  // namespace qi
+
+struct qi_state {
+    qi::amp_t* d = nullptr;     // local amplitudes
+    uint64_t len = 0;           // local amplitude count
+    uint32_t num_qubits = 0;    // logical qubits of the whole (possibly sharded) state
+    uint32_t n_local = 0;       // index bits held locally (== num_qubits when world == 1)
+    bool consistent = true;     // len == 2^n_local (false only for State{..} literals, state_tests.rs:145)
+    // sharding
+    int rank = 0, world = 1;
+    uint8_t phys[64];           // logical qubit -> physical bit position (identity unless exchanged)
+    qi::amp_t* peer_amp[8] = {nullptr};
+    unsigned long long* flags = nullptr;          // this rank's flag/scratch block (device)
+    unsigned long long* peer_flags[8] = {nullptr};
+    unsigned long long epoch = 0;
+    uint64_t bytes_sent = 0, bytes_recv = 0, exchanges = 0;
+    bool attached = false;
+};
+
+namespace qi {
+
+// ---- bit tricks --------------------------------------------------------------------------------
+// Expand a compact index over the free bits into a full index: insert a zero bit at each of the
+// `n` ascending positions `pos`, then OR `ones` (the positions that are fixed to 1).
+struct BitInsert {
+    int n;
+    uint8_t pos[62];
+    uint64_t ones;
+};
+
+__host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t k, int p) {
+    return ((k >> p) << (p + 1)) | (k & ((1ull << p) - 1ull));
+}
+
+__host__ __device__ __forceinline__ uint64_t expand_index(uint64_t k, const BitInsert& b) {
+#pragma unroll 1
+    for (int i = 0; i < b.n; i++) k = insert_zero(k, b.pos[i]);
+    return k | b.ones;
+}
+
+BitInsert make_insert(const std::vector<int>& zero_positions, const std::vector<int>& one_positions);
+
+// ---- complex helpers (same operation order as num-complex; FMA contraction is left to nvcc) ------
+__host__ __device__ __forceinline__ amp_t cmul(amp_t a, amp_t b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ amp_t cadd(amp_t a, amp_t b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ amp_t csub(amp_t a, amp_t b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ amp_t cscale(double s, amp_t a) { return make_double2(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ amp_t cneg(amp_t a) { return make_double2(-a.x, -a.y); }
+__host__ __device__ __forceinline__ amp_t cconj(amp_t a) { return make_double2(a.x, -a.y); }
+// multiply by i^k, exact
+__host__ __device__ __forceinline__ amp_t mul_i_pow(amp_t a, int k) {
+    switch (k & 3) {
+        case 0: return a;
+        case 1: return make_double2(-a.y, a.x);
+        case 2: return make_double2(-a.x, -a.y);
+        default: return make_double2(a.y, -a.x);
+    }
+}
+
+// host complex functions with num-complex's formulas
+static inline amp_t h_cexp(amp_t a) { double e = std::exp(a.x); return make_double2(e * std::cos(a.y), e * std::sin(a.y)); }
+static inline amp_t h_ccosh(amp_t a) { return make_double2(std::cosh(a.x) * std::cos(a.y), std::sinh(a.x) * std::sin(a.y)); }
+static inline amp_t h_csinh(amp_t a) { return make_double2(std::sinh(a.x) * std::cos(a.y), std::cosh(a.x) * std::sin(a.y)); }
+
+// splitmix64 shared-seed stream: u = (x >> 11) * 2^-53
+__host__ __device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t k) {
+    uint64_t z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ double uniform_at(uint64_t seed, uint64_t k) {
+    return (double)(splitmix64_at(seed, k) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// 128-bit global accesses
+__device__ __forceinline__ amp_t ld_amp(const amp_t* p) { return *p; }
+__device__ __forceinline__ void st_amp(amp_t* p, amp_t v) { *p = v; }
+
+// internal gate kinds after parameter resolution
+enum { IK_NOP = 0, IK_H, IK_X, IK_Y, IK_U2, IK_DIAG, IK_RZ, IK_SWAP, IK_MATCH };
+
+// ---- physical (already validated, already mapped) single-operator record ----------------------
+struct PhysGate {
+    int kind;            // IK_*
+    int t0, t1;          // physical target bit positions (t1 only for SWAP; MATCHGATE: t1 = partner)
+    uint64_t cmask;      // physical control bits that must be 1 (local bits only after rank filtering)
+    double p[8];         // resolved numeric parameters (see resolve_gate)
+};
+
+// gates.cu
+int validate_gate(const qi_state* s, const qi_gate* g);
+int launch_simple_gate(qi_state* s, const PhysGate& g);      // one pass with the per-gate kernels
+// window.cu
+int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates);
+bool window_supported(const qi_state* s);
+// shard.cu
+int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip);
+bool shard_needs_exchange(const qi_state* s, const qi_gate* g);
+int shard_do_exchange(qi_state* s, const qi_gate* g);
+int shard_allreduce_sum(qi_state* s, double* host_vals, int count);
+int exchange_global_local(qi_state* s, int global_phys, int local_phys);
+// reduce.cu
+int reduce_norm_sqr(const qi_state* s, double* out_local);
+int reduce_inner(const qi_state* a, const qi_state* b, double out_local[2]);
+
+int grid_for(uint64_t work_items, int block, int max_waves = 8);
+
+}  // namespace qi

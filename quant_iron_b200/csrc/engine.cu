@@ -1,0 +1,232 @@
+// engine.cu -- context, error reporting, options, kernel accounting.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace qi {
+
+const char* const kFamilyNames[KF_COUNT] = {
+    "init", "gate_pair", "gate_diag", "gate_swap", "gate_matchgate", "gate_window", "pauli_apply",
+    "pauli_exp", "pauli_expect", "reduce", "elementwise", "probabilities", "scan", "sample",
+    "collapse", "exchange", "barrier"};
+
+static thread_local uint64_t tl_payload[2] = {0, 0};
+static thread_local char tl_msg[256] = {0};
+
+void set_error(uint64_t p0, uint64_t p1, const char* fmt, ...) {
+    tl_payload[0] = p0;
+    tl_payload[1] = p1;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_msg, sizeof(tl_msg), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int status, uint64_t p0, uint64_t p1, const char* msg) {
+    set_error(p0, p1, "%s", msg);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error((uint64_t)e, 0, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    cudaGetLastError();  // clear sticky-less errors
+    return QI_ERR_CUDA;
+}
+
+static Context g_ctx;
+static std::mutex g_mutex;
+
+Context& ctx() { return g_ctx; }
+
+static int init_locked(int device) {
+    Context& c = g_ctx;
+    if (c.ready && (device < 0 || device == c.device)) return QI_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error((uint64_t)e, 0, "no CUDA device available (%s): libqiron_b200 has no CPU fallback",
+                  cudaGetErrorString(e));
+        cudaGetLastError();
+        return QI_ERR_CUDA;
+    }
+    if (device < 0) {
+        QI_CUDA(cudaGetDevice(&device));
+    }
+    QI_CUDA(cudaSetDevice(device));
+    c.device = device;
+    cudaDeviceProp prop;
+    QI_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.sm_count = prop.multiProcessorCount;
+    if (!c.stream) QI_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (!c.d_result) QI_CUDA(cudaMalloc(&c.d_result, 4096 * sizeof(double)));
+    if (!c.h_result) QI_CUDA(cudaMallocHost(&c.h_result, 4096 * sizeof(double)));
+    if (!c.timer_start) QI_CUDA(cudaEventCreate(&c.timer_start));
+    if (!c.timer_stop) QI_CUDA(cudaEventCreate(&c.timer_stop));
+    c.ready = true;
+    return QI_OK;
+}
+
+int ensure_ctx() {
+    if (g_ctx.ready) return cudaSetDevice(g_ctx.device) == cudaSuccess ? QI_OK : cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return init_locked(-1);
+}
+
+int ensure_partials(size_t doubles) {
+    Context& c = g_ctx;
+    if (c.partial_capacity >= doubles) return QI_OK;
+    if (c.d_partials) {
+        QI_CUDA(cudaStreamSynchronize(c.stream));
+        QI_CUDA(cudaFree(c.d_partials));
+        c.d_partials = nullptr;
+    }
+    size_t cap = doubles < (1u << 16) ? (1u << 16) : doubles;
+    QI_CUDA(cudaMalloc(&c.d_partials, cap * sizeof(double)));
+    c.partial_capacity = cap;
+    return QI_OK;
+}
+
+int grid_for(uint64_t work_items, int block, int max_waves) {
+    uint64_t blocks = (work_items + block - 1) / block;
+    uint64_t cap = (uint64_t)g_ctx.sm_count * (2048 / block) * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+LaunchScope::LaunchScope(int fam, double bytes) : family(fam) {
+    Context& c = g_ctx;
+    c.launches[fam]++;
+    c.alg_bytes[fam] += bytes;
+    if (c.opt_profile) {
+        auto get = [&]() {
+            cudaEvent_t ev;
+            if (!c.event_pool.empty()) { ev = c.event_pool.back(); c.event_pool.pop_back(); }
+            else cudaEventCreate(&ev);
+            return ev;
+        };
+        start = get();
+        stop = get();
+        cudaEventRecord(start, c.stream);
+    }
+}
+
+LaunchScope::~LaunchScope() {
+    Context& c = g_ctx;
+    if (start) {
+        cudaEventRecord(stop, c.stream);
+        c.pending.push_back({start, stop, family});
+    }
+}
+
+static void drain_profile() {
+    Context& c = g_ctx;
+    if (c.pending.empty()) return;
+    cudaStreamSynchronize(c.stream);
+    for (auto& p : c.pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) c.total_ms[p.family] += ms;
+        c.event_pool.push_back(p.start);
+        c.event_pool.push_back(p.stop);
+    }
+    c.pending.clear();
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return QI_OK;
+}
+
+}  // namespace qi
+
+using namespace qi;
+
+extern "C" {
+
+void qi_last_error(uint64_t payload[2], char* msg, size_t msg_len) {
+    if (payload) { payload[0] = tl_payload[0]; payload[1] = tl_payload[1]; }
+    if (msg && msg_len) { strncpy(msg, tl_msg, msg_len - 1); msg[msg_len - 1] = 0; }
+}
+
+const char* qi_version(void) { return "qiron_b200 0.1 (sm_100a)"; }
+
+int qi_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return init_locked(device);
+}
+
+int qi_synchronize(void) {
+    QI_TRY(ensure_ctx());
+    QI_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QI_OK;
+}
+
+int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_mem, uint64_t* free_mem) {
+    QI_TRY(ensure_ctx());
+    cudaDeviceProp prop;
+    QI_CUDA(cudaGetDeviceProperties(&prop, ctx().device));
+    if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    size_t f = 0, t = 0;
+    QI_CUDA(cudaMemGetInfo(&f, &t));
+    if (total_mem) *total_mem = t;
+    if (free_mem) *free_mem = f;
+    return QI_OK;
+}
+
+int qi_set_option(const char* name, int64_t value) {
+    if (!name) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "option name is NULL");
+    Context& c = ctx();
+    if (!strcmp(name, "path")) c.opt_path = (int)value;
+    else if (!strcmp(name, "fuse")) c.opt_fuse = (int)value;
+    else if (!strcmp(name, "profile")) { if (!value) drain_profile(); c.opt_profile = (int)value; }
+    else return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "unknown option");
+    return QI_OK;
+}
+
+int qi_stats_reset(void) {
+    Context& c = ctx();
+    drain_profile();
+    for (int i = 0; i < KF_COUNT; i++) { c.launches[i] = 0; c.alg_bytes[i] = 0; c.total_ms[i] = 0; }
+    return QI_OK;
+}
+
+int qi_stats_get(qi_kernel_stat* out, int capacity, int* count) {
+    Context& c = ctx();
+    drain_profile();
+    int n = 0;
+    for (int i = 0; i < KF_COUNT && n < capacity; i++) {
+        if (!c.launches[i]) continue;
+        memset(&out[n], 0, sizeof(out[n]));
+        strncpy(out[n].name, kFamilyNames[i], sizeof(out[n].name) - 1);
+        out[n].launches = c.launches[i];
+        out[n].total_ms = c.total_ms[i];
+        out[n].algorithmic_bytes = c.alg_bytes[i];
+        n++;
+    }
+    if (count) *count = n;
+    return QI_OK;
+}
+
+int qi_timer_start(void) {
+    QI_TRY(ensure_ctx());
+    QI_CUDA(cudaEventRecord(ctx().timer_start, ctx().stream));
+    return QI_OK;
+}
+
+int qi_timer_stop(float* elapsed_ms) {
+    QI_TRY(ensure_ctx());
+    QI_CUDA(cudaEventRecord(ctx().timer_stop, ctx().stream));
+    QI_CUDA(cudaEventSynchronize(ctx().timer_stop));
+    float ms = 0.f;
+    QI_CUDA(cudaEventElapsedTime(&ms, ctx().timer_start, ctx().timer_stop));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return QI_OK;
+}
+
+double qi_uniform(uint64_t seed, uint64_t k) { return uniform_at(seed, k); }
+
+}  // extern "C"

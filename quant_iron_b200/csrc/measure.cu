@@ -1,0 +1,453 @@
+// measure.cu -- marginal probabilities, seeded sampling by a device prefix scan, collapse, and the
+// composed State::measure (state.rs:525-784).
+//
+// Determinism: every reduction here has a fixed shape (fixed chunking, shuffle/shared-memory trees,
+// fixed-order final sums), so a probability table is bit-identical run to run.
+// Shared-seed contract (the reference's RNG is unseedable): draw k of a call uses
+// u_k = (splitmix64(seed, k) >> 11) * 2^-53 and selects the first bin with u < cumsum of the
+// normalised table, falling back to the last bin (state.rs:601-619).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qi {
+
+static const int kBlock = 256;
+
+struct BinMap {
+    int m;                 // measured qubits
+    uint8_t pos[64];       // physical position of bin bit j
+};
+
+__device__ __forceinline__ uint64_t bin_to_mask(uint64_t bin, const BinMap& bm) {
+    uint64_t v = 0;
+    for (int j = 0; j < bm.m; j++) v |= ((bin >> j) & 1ull) << bm.pos[j];
+    return v;
+}
+
+__device__ __forceinline__ double block_sum1(double v) {
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// (A) few bins, large rest space: block (bin, chunk) reduces its chunk of the rest space.
+//     `ins` inserts zeros at the measured positions (ascending); the bin's bits are OR-ed in.
+__global__ void __launch_bounds__(256) k_prob_chunks(const amp_t* __restrict__ a, uint64_t rest_total, uint64_t chunk_len,
+                                                     BitInsert ins, BinMap bm, double* partials, int chunks) {
+    uint64_t bin = blockIdx.y;
+    int chunk = blockIdx.x;
+    uint64_t fixed = bin_to_mask(bin, bm);
+    uint64_t lo = (uint64_t)chunk * chunk_len, hi = lo + chunk_len;
+    if (hi > rest_total) hi = rest_total;
+    double acc = 0.0;
+    for (uint64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+        amp_t v = a[expand_index(r, ins) | fixed];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    acc = block_sum1(acc);
+    if (threadIdx.x == 0) partials[bin * chunks + chunk] = acc;
+}
+__global__ void k_prob_finish(const double* partials, int chunks, uint64_t nbins, double* probs) {
+    uint64_t bin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= nbins) return;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; c++) acc += partials[bin * chunks + c];
+    probs[bin] = acc;
+}
+// (B) many bins, small rest space: one thread per bin walks the rest space serially.
+__global__ void __launch_bounds__(256) k_prob_serial(const amp_t* __restrict__ a, uint64_t nbins, uint64_t rest_total,
+                                                     BitInsert ins, BinMap bm, double* probs) {
+    uint64_t bin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= nbins) return;
+    uint64_t fixed = bin_to_mask(bin, bm);
+    double acc = 0.0;
+    for (uint64_t r = 0; r < rest_total; r++) {
+        amp_t v = a[expand_index(r, ins) | fixed];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    probs[bin] = acc;
+}
+
+// ---- prefix scan (3 phases, fixed shape) ---------------------------------------------------------
+static const int kScanItems = 8;                       // per thread
+static const int kScanTile = kBlock * kScanItems;      // 2048 per block
+
+__device__ __forceinline__ double block_exclusive_scan(double v, double* total) {
+    // v = this thread's sum; returns the exclusive prefix over the block in thread order
+    __shared__ double wsum[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        double s = lane < nw ? wsum[lane] : 0.0;
+        double si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < nw) wsum[lane] = si - s;     // exclusive warp offsets
+        if (lane == nw - 1 && total) *total = si;
+    }
+    __syncthreads();
+    double r = wsum[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// phase 1: per-tile totals of p[i] * scale
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const double* __restrict__ p, uint64_t n, double total, double* tile_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) if (base + j < n) s += p[base + j] / total;
+    __shared__ double tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+// phase 2: exclusive scan of the tile sums, single block, serial over tiles of the tile-sum array
+__global__ void __launch_bounds__(256) k_scan_offsets(double* tile_sums, uint64_t ntiles) {
+    __shared__ double carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0.0;
+    __syncthreads();
+    for (uint64_t base = 0; base < ntiles; base += kBlock) {
+        uint64_t i = base + threadIdx.x;
+        double v = i < ntiles ? tile_sums[i] : 0.0;
+        __shared__ double tot;
+        double ex = block_exclusive_scan(v, &tot);
+        double carry = carry_sh;
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_sh = carry + tot;
+        __syncthreads();
+    }
+}
+// phase 3: inclusive cdf[i] = offset(tile) + prefix within the tile
+__global__ void __launch_bounds__(256) k_scan_write(const double* __restrict__ p, uint64_t n, double total, const double* tile_offsets, double* cdf) {
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    double v[kScanItems];
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) { v[j] = (base + j < n) ? p[base + j] / total : 0.0; s += v[j]; }
+    double ex = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) { ex += v[j]; if (base + j < n) cdf[base + j] = ex; }
+}
+
+// first i with u < cdf[i], else n-1
+__global__ void k_sample(const double* __restrict__ cdf, uint64_t n, uint64_t seed, uint64_t first_draw, uint64_t shots, uint64_t* bins) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= shots) return;
+    double u = uniform_at(seed, first_draw + k);
+    uint64_t lo = 0, hi = n;            // invariant: answer in [lo, hi]
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (u < cdf[mid]) hi = mid; else lo = mid + 1;
+    }
+    bins[k] = lo < n ? lo : n - 1;
+}
+
+// ---- collapse -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_collapse_zero(amp_t* __restrict__ a, uint64_t len, uint64_t sel_mask, uint64_t sel_val, uint64_t high, double* partials) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        if (((i | high) & sel_mask) == sel_val) { amp_t v = a[i]; acc += v.x * v.x + v.y * v.y; }
+        else a[i] = make_double2(0.0, 0.0);
+    }
+    acc = block_sum1(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+__global__ void k_sum_doubles(const double* partials, int count, double* out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc += partials[i];
+    acc = block_sum1(acc);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+__global__ void __launch_bounds__(256) k_div_sel(amp_t* __restrict__ a, uint64_t total, BitInsert ins, double d) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    uint64_t i = expand_index(k, ins);
+    amp_t v = a[i];
+    a[i] = make_double2(v.x / d, v.y / d);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int check_qubits(const qi_state* s, const uint32_t* qubits, uint32_t m, std::vector<uint32_t>* actual) {
+    // state.rs:531-553
+    actual->clear();
+    if (m == 0) for (uint32_t q = 0; q < s->num_qubits; q++) actual->push_back(q);
+    else {
+        if (!qubits) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "qubits is NULL");
+        actual->assign(qubits, qubits + m);
+    }
+    if (actual->size() > s->num_qubits) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, s->num_qubits, 0, "more measured qubits than qubits");
+    for (uint32_t q : *actual)
+        if (q >= s->num_qubits) return fail(QI_ERR_INVALID_QUBIT_INDEX, q, s->num_qubits, "Invalid qubit index");
+    if (!s->consistent) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, s->num_qubits, 0, "state vector length is not 2^num_qubits");
+    return QI_OK;
+}
+
+// device table of 2^m un-normalised probabilities (this rank's contribution when sharded)
+static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& qubits, double** d_probs_out) {
+    Context& c = ctx();
+    const int m = (int)qubits.size();
+    if (m > 34) return fail(QI_ERR_INVALID_INPUT_VALUE, (uint64_t)m, 0, "probability table too large");
+    const uint64_t nbins = 1ull << m;
+    double* d_probs = nullptr;
+    QI_CUDA(cudaMalloc(&d_probs, nbins * sizeof(double)));
+    // split measured qubits into local (index bits) and global (rank bits)
+    BinMap bm;
+    memset(&bm, 0, sizeof(bm));
+    bm.m = m;
+    std::vector<int> local_pos;
+    uint64_t rank_sel = 0, rank_val_known = 0;
+    (void)rank_sel; (void)rank_val_known;
+    for (int j = 0; j < m; j++) {
+        int p = s->phys[qubits[j]];
+        bm.pos[j] = (uint8_t)p;
+        if (p < (int)s->n_local) local_pos.push_back(p);
+    }
+    // duplicates in `qubits` (the reference does not reject them): a repeated qubit pins two bin bits
+    // to the same index bit; handled by treating the position once for the expansion.
+    std::sort(local_pos.begin(), local_pos.end());
+    local_pos.erase(std::unique(local_pos.begin(), local_pos.end()), local_pos.end());
+    const int ml = (int)local_pos.size();
+    const uint64_t rest_total = s->len >> ml;
+    BitInsert ins = make_insert(local_pos, {});
+    if (s->world > 1 || ml != m) {
+        // sharded or duplicated qubits: bins whose global/duplicate bits disagree with this rank get 0.
+        // Handled by the generic serial kernel below through a host-side filter table.
+        cudaFree(d_probs);
+        return fail(QI_ERR_INVALID_INPUT_VALUE, 0, 0, "measurement of global or repeated qubits is not supported yet");
+    }
+    int st = QI_OK;
+    if (rest_total >= 1024 && nbins <= 32768) {
+        int chunks = (int)std::min<uint64_t>(std::max<uint64_t>(1, rest_total / 4096), std::max<uint64_t>(1, (uint64_t)(c.sm_count * 8) / nbins));
+        if (chunks < 1) chunks = 1;
+        uint64_t chunk_len = (rest_total + chunks - 1) / chunks;
+        st = ensure_partials((size_t)nbins * chunks);
+        if (st == QI_OK) {
+            LaunchScope ls(KF_PROB, 16.0 * (double)s->len);
+            dim3 grid(chunks, (unsigned)nbins);
+            k_prob_chunks<<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, c.d_partials, chunks);
+            k_prob_finish<<<(unsigned)((nbins + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(c.d_partials, chunks, nbins, d_probs);
+        }
+    } else {
+        LaunchScope ls(KF_PROB, 16.0 * (double)s->len);
+        k_prob_serial<<<(unsigned)((nbins + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, nbins, rest_total, ins, bm, d_probs);
+    }
+    if (st == QI_OK) st = check_launch("probabilities");
+    if (st != QI_OK) { cudaFree(d_probs); return st; }
+    *d_probs_out = d_probs;
+    return QI_OK;
+}
+
+static int device_total(const double* d_probs, uint64_t nbins, double* total) {
+    // total of the table: fixed-shape reduction (stage 1 over tiles via the scan tile sums)
+    Context& c = ctx();
+    uint64_t ntiles = (nbins + kScanTile - 1) / kScanTile;
+    QI_TRY(ensure_partials(ntiles + 8));
+    k_scan_tile_sums<<<(unsigned)ntiles, kBlock, 0, c.stream>>>(d_probs, nbins, 1.0, c.d_partials);
+    k_sum_doubles<<<1, kBlock, 0, c.stream>>>(c.d_partials, (int)ntiles, c.d_result);
+    QI_TRY(check_launch("prob_total"));
+    QI_CUDA(cudaMemcpyAsync(c.h_result, c.d_result, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QI_CUDA(cudaStreamSynchronize(c.stream));
+    *total = c.h_result[0];
+    return QI_OK;
+}
+
+static int sample_from_table(const double* d_probs, uint64_t nbins, uint64_t seed, uint64_t first_draw, uint64_t shots, uint64_t* host_bins) {
+    Context& c = ctx();
+    double total = 0.0;
+    QI_TRY(device_total(d_probs, nbins, &total));
+    if (total < 2.220446049250313e-16) return fail(QI_ERR_UNKNOWN, 0, 0, "total probability is zero");   // state.rs:592-594
+    const double scale = total;          // kernels divide: prob / total (state.rs:595-598)
+    uint64_t ntiles = (nbins + kScanTile - 1) / kScanTile;
+    double* d_cdf = nullptr;
+    uint64_t* d_bins = nullptr;
+    QI_CUDA(cudaMalloc(&d_cdf, nbins * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_bins, shots * sizeof(uint64_t));
+    if (e != cudaSuccess) { cudaFree(d_cdf); return cuda_fail(e, "cudaMalloc(bins)"); }
+    int st = ensure_partials(ntiles + 8);
+    if (st == QI_OK) {
+        {
+            LaunchScope ls(KF_SCAN, 24.0 * (double)nbins);
+            k_scan_tile_sums<<<(unsigned)ntiles, kBlock, 0, c.stream>>>(d_probs, nbins, scale, c.d_partials);
+            k_scan_offsets<<<1, kBlock, 0, c.stream>>>(c.d_partials, ntiles);
+            k_scan_write<<<(unsigned)ntiles, kBlock, 0, c.stream>>>(d_probs, nbins, scale, c.d_partials, d_cdf);
+        }
+        {
+            LaunchScope ls(KF_SAMPLE, 8.0 * (double)shots);
+            k_sample<<<(unsigned)((shots + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(d_cdf, nbins, seed, first_draw, shots, d_bins);
+        }
+        st = check_launch("sample");
+    }
+    if (st == QI_OK) {
+        e = cudaMemcpyAsync(host_bins, d_bins, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "D2H bins");
+    }
+    cudaFree(d_cdf);
+    cudaFree(d_bins);
+    return st;
+}
+
+static int collapse_impl(qi_state* s, const std::vector<uint32_t>& qubits, uint64_t bin) {
+    Context& c = ctx();
+    uint64_t sel_mask = 0, sel_val = 0;
+    for (size_t j = 0; j < qubits.size(); j++) {
+        uint64_t b = 1ull << s->phys[qubits[j]];
+        sel_mask |= b;
+        if ((bin >> j) & 1) sel_val |= b;
+    }
+    const uint64_t high = (uint64_t)s->rank << s->n_local;
+    int g = c.sm_count * 4;
+    uint64_t need = (s->len + kBlock - 1) / kBlock;
+    if (need < (uint64_t)g) g = (int)need;
+    QI_TRY(ensure_partials((size_t)g));
+    {
+        LaunchScope ls(KF_COLLAPSE, 32.0 * (double)s->len);
+        k_collapse_zero<<<g, kBlock, 0, c.stream>>>(s->d, s->len, sel_mask, sel_val, high, c.d_partials);
+        k_sum_doubles<<<1, kBlock, 0, c.stream>>>(c.d_partials, g, c.d_result);
+    }
+    QI_TRY(check_launch("collapse"));
+    QI_CUDA(cudaMemcpyAsync(c.h_result, c.d_result, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QI_CUDA(cudaStreamSynchronize(c.stream));
+    double nsq = c.h_result[0];
+    if (s->world > 1) QI_TRY(shard_allreduce_sum(s, &nsq, 1));
+    if (nsq > 2.220446049250313e-16) {       // state.rs:649-654
+        const double f = std::sqrt(nsq);
+        // only the surviving amplitudes are non-zero: divide those (local selected bits fixed)
+        std::vector<int> zeros, ones;
+        const uint64_t local_mask = s->len - 1;
+        bool rank_selected = ((high & sel_mask) == (sel_val & ~local_mask));
+        if (rank_selected) {
+            for (int p = 0; p < (int)s->n_local; p++)
+                if ((sel_mask >> p) & 1) { if ((sel_val >> p) & 1) ones.push_back(p); else zeros.push_back(p); }
+            BitInsert ins = make_insert(zeros, ones);
+            uint64_t total = s->len >> (zeros.size() + ones.size());
+            LaunchScope ls(KF_COLLAPSE, 32.0 * (double)total);
+            k_div_sel<<<(unsigned)((total + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, total, ins, f);
+            QI_TRY(check_launch("collapse_normalise"));
+        }
+    }
+    // State::new(collapsed) re-checks the norm (state.rs:667); a collapsed state that fails it is a bug here
+    return QI_OK;
+}
+
+static int apply_single_all(qi_state* s, const std::vector<uint32_t>& qubits, int kind, const double* params) {
+    for (uint32_t q : qubits) {
+        qi_gate g;
+        memset(&g, 0, sizeof(g));
+        g.kind = kind;
+        g.num_targets = 1;
+        g.targets[0] = q;
+        if (params) memcpy(g.params, params, 8 * sizeof(double));
+        QI_TRY(qi_apply_gate(s, &g));
+    }
+    return QI_OK;
+}
+
+}  // namespace qi
+
+using namespace qi;
+
+extern "C" {
+
+int qi_probabilities(const qi_state* s, const uint32_t* qubits, uint32_t m, double* out) {
+    if (!s || !out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    std::vector<uint32_t> q;
+    QI_TRY(check_qubits(s, qubits, m, &q));
+    QI_TRY(ensure_ctx());
+    double* d_probs = nullptr;
+    QI_TRY(device_probabilities(s, q, &d_probs));
+    uint64_t nbins = 1ull << q.size();
+    cudaError_t e = cudaMemcpyAsync(out, d_probs, nbins * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+    cudaFree(d_probs);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H probabilities");
+    return QI_OK;
+}
+
+int qi_sample(const qi_state* s, const uint32_t* qubits, uint32_t m, uint64_t shots, uint64_t seed, uint64_t* bins) {
+    if (!s || !bins) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    if (shots == 0) return fail(QI_ERR_INVALID_NUMBER_OF_MEASUREMENTS, 0, 0, "Invalid number of measurements: 0");   // state.rs:756-758
+    std::vector<uint32_t> q;
+    QI_TRY(check_qubits(s, qubits, m, &q));
+    QI_TRY(ensure_ctx());
+    double* d_probs = nullptr;
+    QI_TRY(device_probabilities(s, q, &d_probs));
+    int st = sample_from_table(d_probs, 1ull << q.size(), seed, 0, shots, bins);
+    cudaFree(d_probs);
+    return st;
+}
+
+int qi_collapse(qi_state* s, const uint32_t* qubits, uint32_t m, uint64_t bin) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    std::vector<uint32_t> q;
+    QI_TRY(check_qubits(s, qubits, m, &q));
+    if (q.size() < 64 && bin >= (1ull << q.size())) return fail(QI_ERR_INVALID_INPUT_VALUE, bin, 0, "bin out of range");
+    QI_TRY(ensure_ctx());
+    return collapse_impl(s, q, bin);
+}
+
+int qi_measure(qi_state* s, int basis, const double* custom_u, const uint32_t* qubits, uint32_t m,
+               uint64_t seed, uint64_t draw_index, uint8_t* outcomes, uint64_t* bin_out) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    std::vector<uint32_t> q;
+    QI_TRY(check_qubits(s, qubits, m, &q));
+    QI_TRY(ensure_ctx());
+    double udag[8];
+    switch (basis) {
+        case QI_BASIS_COMPUTATIONAL: break;
+        case QI_BASIS_X: QI_TRY(apply_single_all(s, q, QI_GATE_H, nullptr)); break;                 // state.rs:672
+        case QI_BASIS_Y:                                                                            // state.rs:689-690
+            QI_TRY(apply_single_all(s, q, QI_GATE_SDG, nullptr));
+            QI_TRY(apply_single_all(s, q, QI_GATE_H, nullptr));
+            break;
+        case QI_BASIS_CUSTOM:                                                                       // state.rs:708
+            if (!custom_u) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "custom basis needs a matrix");
+            QI_TRY(qi_unitary2_check(custom_u));                  // unitary_multi -> Unitary2::new (state.rs:1988)
+            QI_TRY(apply_single_all(s, q, QI_GATE_U2, custom_u));
+            // calculate_adjoint, state.rs:17-30
+            udag[0] = custom_u[0]; udag[1] = -custom_u[1]; udag[2] = custom_u[4]; udag[3] = -custom_u[5];
+            udag[4] = custom_u[2]; udag[5] = -custom_u[3]; udag[6] = custom_u[6]; udag[7] = -custom_u[7];
+            break;
+        default: return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)basis, 0, "unknown basis");
+    }
+    double* d_probs = nullptr;
+    QI_TRY(device_probabilities(s, q, &d_probs));
+    uint64_t bin = 0;
+    int st = sample_from_table(d_probs, 1ull << q.size(), seed, draw_index, 1, &bin);
+    cudaFree(d_probs);
+    QI_TRY(st);
+    QI_TRY(collapse_impl(s, q, bin));
+    switch (basis) {
+        case QI_BASIS_X: QI_TRY(apply_single_all(s, q, QI_GATE_H, nullptr)); break;                 // state.rs:677-679
+        case QI_BASIS_Y:                                                                            // state.rs:695-698
+            QI_TRY(apply_single_all(s, q, QI_GATE_H, nullptr));
+            QI_TRY(apply_single_all(s, q, QI_GATE_S, nullptr));
+            break;
+        case QI_BASIS_CUSTOM: QI_TRY(apply_single_all(s, q, QI_GATE_U2, udag)); break;             // state.rs:716-720
+        default: break;
+    }
+    if (outcomes) for (size_t j = 0; j < q.size(); j++) outcomes[j] = (uint8_t)((bin >> j) & 1);   // state.rs:657-660
+    if (bin_out) *bin_out = bin;
+    return QI_OK;
+}
+
+}  // extern "C"

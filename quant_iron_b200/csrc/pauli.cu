@@ -1,0 +1,305 @@
+// pauli.cu -- PauliString apply / exp and SumOp apply / expectation (pauli_string.rs), Trotter
+// loops (time_evolution.rs).
+//
+// A Pauli string is reduced on the host to three masks over PHYSICAL bit positions:
+//   xmask  bits flipped (X and Y factors),  zmask  bits that contribute a sign (Y and Z factors),
+//   ny     number of Y factors.
+// Applying the single Paulis one after the other (pauli_string.rs:172-184) gives exactly
+//   (P psi)[i] = i^(3*ny + 2*popc(i & zmask)) * psi[i ^ xmask]
+// (each factor is a permutation times a power of i, all exact in floating point), so one fused
+// pass replaces the reference's clone + one sweep per factor; exp(alpha P) psi =
+// cosh(alpha) psi + sinh(alpha) P psi (pauli_string.rs:251-261) is one pass too.
+#include "common.cuh"
+
+namespace qi {
+
+static const int kBlock = 256;
+
+struct Masks { uint64_t x, z; int ny; uint64_t high; /* rank bits of this shard, pre-shifted */ };
+
+__device__ __forceinline__ int pauli_pow(uint64_t full_index, const Masks& m) {
+    return (3 * m.ny + 2 * __popcll(full_index & m.z)) & 3;
+}
+
+// ---- apply ------------------------------------------------------------------------------------
+// diagonal string (xmask == 0): psi[i] <- coeff * i^k(i) * psi[i]
+__global__ void __launch_bounds__(256) k_pauli_diag(amp_t* __restrict__ a, uint64_t len, Masks m, amp_t coeff, int with_coeff) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        amp_t v = mul_i_pow(a[i], pauli_pow(i | m.high, m));
+        a[i] = with_coeff ? cmul(v, coeff) : v;
+    }
+}
+
+// general string: pairs (i, j = i ^ xmask), i with the pivot bit (highest x bit) clear
+__global__ void __launch_bounds__(256) k_pauli_pair(amp_t* __restrict__ a, uint64_t pairs, int pivot, Masks m, amp_t coeff, int with_coeff) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pairs) return;
+    uint64_t i = insert_zero(k, pivot), j = i ^ m.x;
+    amp_t ai = a[i], aj = a[j];
+    amp_t ni = mul_i_pow(aj, pauli_pow(i | m.high, m));
+    amp_t nj = mul_i_pow(ai, pauli_pow(j | m.high, m));
+    if (with_coeff) { ni = cmul(ni, coeff); nj = cmul(nj, coeff); }
+    a[i] = ni;
+    a[j] = nj;
+}
+
+// ---- exp --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pauli_exp_diag(amp_t* __restrict__ a, uint64_t len, Masks m, amp_t ch, amp_t sh) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        amp_t v = a[i];
+        a[i] = cadd(cmul(v, ch), cmul(mul_i_pow(v, pauli_pow(i | m.high, m)), sh));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pauli_exp_pair(amp_t* __restrict__ a, uint64_t pairs, int pivot, Masks m, amp_t ch, amp_t sh) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pairs) return;
+    uint64_t i = insert_zero(k, pivot), j = i ^ m.x;
+    amp_t ai = a[i], aj = a[j];
+    amp_t pi = mul_i_pow(aj, pauli_pow(i | m.high, m));   // (P psi)[i]
+    amp_t pj = mul_i_pow(ai, pauli_pow(j | m.high, m));   // (P psi)[j]
+    a[i] = cadd(cmul(ai, ch), cmul(pi, sh));               // state*cosh + P state*sinh, pauli_string.rs:255-261
+    a[j] = cadd(cmul(aj, ch), cmul(pj, sh));
+}
+
+// ---- expectation -------------------------------------------------------------------------------
+__device__ __forceinline__ double2 block_sum2(double2 v) {
+    __shared__ double2 sh[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : make_double2(0.0, 0.0);
+    if (w == 0)
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+            v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+        }
+    return v;
+}
+
+// sum_i conj(psi[i]) * (coeff * i^k(i) * psi[i ^ x])   (pauli_string.rs:491-502 for one term)
+__global__ void __launch_bounds__(256) k_pauli_expect(const amp_t* __restrict__ a, uint64_t len, Masks m, amp_t coeff, double2* partials) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double2 acc = make_double2(0.0, 0.0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        amp_t phi = cmul(mul_i_pow(a[i ^ m.x], pauli_pow(i | m.high, m)), coeff);
+        amp_t t = cmul(cconj(a[i]), phi);
+        acc.x += t.x;
+        acc.y += t.y;
+    }
+    double2 r = block_sum2(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+// per-term totals (fixed tree), then the terms are added in order by thread 0 (pauli_string.rs:506)
+__global__ void k_expect_final(const double2* partials, int per_term, int terms, double2* out) {
+    extern __shared__ double2 term_sums[];
+    for (int t = 0; t < terms; t++) {
+        const double2* p = partials + (size_t)t * per_term;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int i = threadIdx.x; i < per_term; i += blockDim.x) { acc.x += p[i].x; acc.y += p[i].y; }
+        double2 r = block_sum2(acc);
+        if (threadIdx.x == 0) term_sums[t] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double2 tot = make_double2(0.0, 0.0);
+        for (int t = 0; t < terms; t++) { tot.x += term_sums[t].x; tot.y += term_sums[t].y; }
+        out[0] = tot;
+    }
+}
+
+// out += psi-derived term, used by SumOp::apply: out[i] (+)= coeff * i^k(i) * psi[i ^ x]
+__global__ void __launch_bounds__(256) k_pauli_accumulate(amp_t* __restrict__ out, const amp_t* __restrict__ a, uint64_t len, Masks m, amp_t coeff, int first) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        amp_t phi = cmul(mul_i_pow(a[i ^ m.x], pauli_pow(i | m.high, m)), coeff);
+        out[i] = first ? phi : cadd(out[i], phi);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int term_masks(const qi_state* s, const qi_pauli_term* t, Masks* m) {
+    if (!t) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "term is NULL");
+    if (t->num_ops && (!t->qubits || !t->paulis)) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "term arrays are NULL");
+    m->x = m->z = 0; m->ny = 0; m->high = 0;
+    uint64_t seen = 0;
+    for (uint32_t i = 0; i < t->num_ops; i++) {
+        uint32_t q = t->qubits[i];
+        // each single-Pauli apply validates its target (operator.rs:481 -> 228-231)
+        if (q >= s->num_qubits) return fail(QI_ERR_INVALID_QUBIT_INDEX, q, s->num_qubits, "Invalid qubit index");
+        if ((seen >> q) & 1) return fail(QI_ERR_INVALID_ARGUMENT, q, 0, "Duplicate Pauli string operator for qubit");
+        seen |= 1ull << q;
+        uint64_t bit = 1ull << s->phys[q];
+        switch (t->paulis[i]) {
+            case 1: m->x |= bit; break;
+            case 2: m->x |= bit; m->z |= bit; m->ny++; break;
+            case 3: m->z |= bit; break;
+            default: return fail(QI_ERR_INVALID_ARGUMENT, t->paulis[i], 0, "pauli must be 1 (X), 2 (Y) or 3 (Z)");
+        }
+    }
+    if (!s->consistent) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, s->num_qubits, 0, "state vector length is not 2^num_qubits");
+    m->high = (uint64_t)s->rank << s->n_local;
+    return QI_OK;
+}
+
+static int highest_bit(uint64_t m) { int p = -1; while (m) { p++; m >>= 1; } return p; }
+
+int pauli_global_exchange(qi_state* s, Masks* m);   // shard.cu hook (no-op for world == 1)
+
+static int apply_masks(qi_state* s, Masks m, amp_t coeff, int with_coeff) {
+    Context& c = ctx();
+    const uint64_t local_mask = s->len - 1;
+    if ((m.x & ~local_mask) != 0) return fail(QI_ERR_PEER, 0, 0, "X/Y factor on a global qubit needs an exchange first");
+    LaunchScope ls(KF_PAULI, 32.0 * (double)s->len);
+    if ((m.x & local_mask) == 0) {
+        k_pauli_diag<<<grid_for(s->len, kBlock), kBlock, 0, c.stream>>>(s->d, s->len, m, coeff, with_coeff);
+    } else {
+        uint64_t pairs = s->len >> 1;
+        k_pauli_pair<<<(unsigned)((pairs + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, pairs, highest_bit(m.x), m, coeff, with_coeff);
+    }
+    return check_launch("pauli_apply");
+}
+
+static int exp_masks(qi_state* s, Masks m, amp_t alpha) {
+    Context& c = ctx();
+    const uint64_t local_mask = s->len - 1;
+    if ((m.x & ~local_mask) != 0) return fail(QI_ERR_PEER, 0, 0, "X/Y factor on a global qubit needs an exchange first");
+    amp_t ch = h_ccosh(alpha), sh = h_csinh(alpha);
+    LaunchScope ls(KF_PAULI_EXP, 32.0 * (double)s->len);
+    if ((m.x & local_mask) == 0) {
+        k_pauli_exp_diag<<<grid_for(s->len, kBlock), kBlock, 0, c.stream>>>(s->d, s->len, m, ch, sh);
+    } else {
+        uint64_t pairs = s->len >> 1;
+        k_pauli_exp_pair<<<(unsigned)((pairs + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, pairs, highest_bit(m.x), m, ch, sh);
+    }
+    return check_launch("pauli_exp");
+}
+
+int shard_localise_mask(qi_state* s, const qi_pauli_term* t);   // shard.cu: make every X/Y qubit local
+
+}  // namespace qi
+
+using namespace qi;
+
+extern "C" {
+
+int qi_apply_pauli_string(qi_state* s, const qi_pauli_term* term, int with_coefficient) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    Masks m;
+    QI_TRY(term_masks(s, term, &m));
+    QI_TRY(ensure_ctx());
+    amp_t coeff = make_double2(term->coefficient[0], term->coefficient[1]);
+    if (term->num_ops == 0) {
+        // pauli_string.rs:141-143 / 173-177: empty string = coefficient (or identity)
+        if (!with_coefficient) return QI_OK;
+        return qi_scale(s, term->coefficient);
+    }
+    if (s->world > 1) { QI_TRY(shard_localise_mask(s, term)); QI_TRY(term_masks(s, term, &m)); }
+    return apply_masks(s, m, coeff, with_coefficient);
+}
+
+int qi_apply_pauli_exp(qi_state* s, const qi_pauli_term* term, const double factor[2]) {
+    if (!s || !factor) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    Masks m;
+    QI_TRY(term_masks(s, term, &m));
+    QI_TRY(ensure_ctx());
+    amp_t alpha = cmul(make_double2(term->coefficient[0], term->coefficient[1]), make_double2(factor[0], factor[1]));  // pauli_string.rs:239
+    if (term->num_ops == 0) {
+        amp_t e = h_cexp(alpha);          // pauli_string.rs:241-244
+        double z[2] = {e.x, e.y};
+        return qi_scale(s, z);
+    }
+    if (s->world > 1) { QI_TRY(shard_localise_mask(s, term)); QI_TRY(term_masks(s, term, &m)); }
+    return exp_masks(s, m, alpha);
+}
+
+int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, double out[2]) {
+    if (!s || !out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    out[0] = out[1] = 0.0;
+    if (count == 0) return QI_OK;     // pauli_string.rs:486-489
+    if (!terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
+    std::vector<Masks> ms(count);
+    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &ms[k]));
+    QI_TRY(ensure_ctx());
+    if (s->world > 1) {
+        for (uint64_t k = 0; k < count; k++)
+            if (ms[k].x & ~(s->len - 1)) return fail(QI_ERR_PEER, k, 0, "expectation of a term with X/Y on a global qubit is not supported on a sharded state");
+    }
+    Context& c = ctx();
+    int g = c.sm_count * 4;
+    uint64_t need = (s->len + kBlock - 1) / kBlock;
+    if (need < (uint64_t)g) g = (int)need;
+    const uint64_t kBatch = 512;
+    double tot[2] = {0.0, 0.0};
+    for (uint64_t base = 0; base < count; base += kBatch) {
+        uint64_t nb = count - base < kBatch ? count - base : kBatch;
+        QI_TRY(ensure_partials((size_t)g * 2 * nb));
+        for (uint64_t k = 0; k < nb; k++) {
+            const qi_pauli_term& t = terms[base + k];
+            LaunchScope ls(KF_EXPECT, (ms[base + k].x ? 32.0 : 16.0) * (double)s->len);
+            k_pauli_expect<<<g, kBlock, 0, c.stream>>>(s->d, s->len, ms[base + k], make_double2(t.coefficient[0], t.coefficient[1]),
+                                                       (double2*)c.d_partials + (size_t)k * g);
+        }
+        k_expect_final<<<1, kBlock, nb * sizeof(double2), c.stream>>>((double2*)c.d_partials, g, (int)nb, (double2*)c.d_result);
+        QI_TRY(check_launch("pauli_expect"));
+        QI_CUDA(cudaMemcpyAsync(c.h_result, c.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        QI_CUDA(cudaStreamSynchronize(c.stream));
+        tot[0] += c.h_result[0];
+        tot[1] += c.h_result[1];
+    }
+    if (s->world > 1) QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(s), tot, 2));
+    out[0] = tot[0];
+    out[1] = tot[1];
+    return QI_OK;
+}
+
+int qi_apply_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, qi_state** out) {
+    if (!s || !out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    if (s->world > 1) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "SumOp::apply needs a second full state; not available on sharded states");
+    if (count && !terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
+    std::vector<Masks> ms(count);
+    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &ms[k]));
+    QI_TRY(qi_state_clone(s, out));
+    if (count == 0) {                 // pauli_string.rs:454-457: state * 0.0
+        double z[2] = {0.0, 0.0};
+        return qi_scale(*out, z);
+    }
+    Context& c = ctx();
+    for (uint64_t k = 0; k < count; k++) {
+        LaunchScope ls(KF_PAULI, 48.0 * (double)s->len);
+        k_pauli_accumulate<<<grid_for(s->len, kBlock), kBlock, 0, c.stream>>>((*out)->d, s->d, s->len, ms[k],
+            make_double2(terms[k].coefficient[0], terms[k].coefficient[1]), k == 0);
+    }
+    return check_launch("pauli_sum_apply");
+}
+
+int qi_trotter_evolve(qi_state* s, const qi_pauli_term* terms, uint64_t count, double dt, uint64_t steps, int order) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    if (count == 0) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, 0, 0, "empty Hamiltonian");   // time_evolution.rs:147-149
+    if (!terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
+    if (order != 1 && order != 2) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)order, 0, "order must be 1 or 2");
+    // validate every term once, before touching the state
+    Masks m;
+    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &m));
+    const double f1[2] = {0.0, -dt}, f2[2] = {0.0, -dt / 2.0};
+    for (uint64_t step = 0; step < steps; step++) {
+        if (order == 1) {
+            for (uint64_t k = 0; k < count; k++) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f1));           // 57-63
+        } else {
+            for (uint64_t k = 0; k < count; k++) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f2));           // 102-105
+            for (uint64_t k = count; k-- > 0;) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f2));             // 108-111
+        }
+    }
+    return QI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""GPU engine vs CPU oracle on the same seeded inputs (the parity tests proper, `-m gpu`).
+
+Bars (BASELINE.json north star): max abs amplitude error <= 1e-12; expectation values within 1e-10
+relative; seeded measurement bins bit-identical.  Sizes are chosen so the oracle finishes in seconds;
+the BASELINE.json full sizes are covered by size-independent properties at the bottom.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import AMP_TOL, EXP_RTOL, assert_amps, vec
+
+pytestmark = pytest.mark.gpu
+
+PI = math.pi
+
+
+def _pair(gpu, ref, n, seed=20260002):
+    r = ref.random_state(n, seed)
+    return gpu.State(r.state_vector, n), r
+
+
+GATES_1Q = [("h", ()), ("x", ()), ("y", ()), ("z", ()), ("s", ()), ("t", ()), ("s_dag", ()), ("t_dag", ()),
+            ("p", (0.37,)), ("rx", (1.1,)), ("ry", (-0.7,)), ("rz", (2.3,))]
+
+
+@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 11, 14])
+def test_every_single_qubit_gate_every_target(gpu, ref, n, path):
+    """each gate on every target qubit, 0/1/2 controls, random normalised state."""
+    gpu.engine.set_option("path", path)
+    try:
+        g, r = _pair(gpu, ref, n)
+        targets = range(n) if n <= 11 else [0, 1, 4, 5, 6, n - 2, n - 1]
+        for name, args in GATES_1Q:
+            for t in targets:
+                g = getattr(g, name)(t, *args)
+                r = getattr(r, name)(t, *args)
+            assert_amps(g, vec(r), msg=f"{name} n={n}")
+            others = [q for q in range(n)]
+            if n >= 2:
+                t, c = others[0], others[-1]
+                g = getattr(g, f"c{name}_multi")([t], [c], *args)
+                r = getattr(r, f"c{name}_multi")([t], [c], *args)
+                g = getattr(g, f"c{name}_multi")([c], [t], *args)
+                r = getattr(r, f"c{name}_multi")([c], [t], *args)
+            if n >= 3:
+                t, c = n // 2, [0, n - 1]
+                g = getattr(g, f"c{name}_multi")([t], c, *args)
+                r = getattr(r, f"c{name}_multi")([t], c, *args)
+            assert_amps(g, vec(r), msg=f"c{name} n={n}")
+    finally:
+        gpu.engine.set_option("path", 0)
+
+
+@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("n", [2, 3, 6, 11, 13])
+def test_two_qubit_operators(gpu, ref, n, path):
+    gpu.engine.set_option("path", path)
+    try:
+        g, r = _pair(gpu, ref, n, seed=99)
+        u = [[0.6 + 0j, 0.8j], [0.8j, 0.6 + 0j]]
+        for a in range(n):
+            for b in range(n):
+                if a == b:
+                    continue
+                g, r = g.swap(a, b), r.swap(a, b)
+                g, r = g.cnot(a, b), r.cnot(a, b)
+                if n <= 6 or (a + b) % 3 == 0:
+                    g, r = g.cunitary_multi([a], [b], u), r.cunitary_multi([a], [b], u)
+            if a + 1 < n:
+                g, r = g.matchgate(a, 0.7, 0.4, 1.1), r.matchgate(a, 0.7, 0.4, 1.1)
+        assert_amps(g, vec(r), msg=f"swap/cnot/matchgate n={n}")
+        if n >= 3:
+            g, r = g.toffoli(0, 1, 2), r.toffoli(0, 1, 2)
+            g, r = g.cswap(0, n - 1, [1]), r.cswap(0, n - 1, [1])
+            g, r = g.cmatchgate(0, 1.3, 0.2, -0.5, [n - 1]), r.cmatchgate(0, 1.3, 0.2, -0.5, [n - 1])
+            g, r = g.ry_phase(1, 0.9, 0.3), r.ry_phase(1, 0.9, 0.3)
+            assert_amps(g, vec(r), msg=f"3-qubit ops n={n}")
+    finally:
+        gpu.engine.set_option("path", 0)
+
+
+@pytest.mark.parametrize("path", [1, 0])
+@pytest.mark.parametrize("n,depth", [(4, 8), (9, 8), (12, 10), (16, 12), (20, 40)])
+def test_random_layered_circuit_matches_oracle(gpu, ref, n, depth, path):
+    """BASELINE config 2's generator at oracle-sized n: full-amplitude comparison."""
+    from quant_iron_b200 import workloads as w
+    gpu.engine.set_option("path", path)
+    try:
+        specs = w.random_layered_circuit(n, depth)
+        out_g = w.build_circuit(gpu, n, specs).execute(gpu.State.new_zero(n))
+        out_r = w.build_circuit(ref, n, specs).execute(ref.State.new_zero(n))
+        assert_amps(out_g, vec(out_r), msg=f"layered n={n} depth={depth}")
+        assert abs(out_g.norm_sqr() - 1.0) < 1e-12
+    finally:
+        gpu.engine.set_option("path", 0)
+
+
+@pytest.mark.parametrize("n", [3, 8, 11, 16, 20])
+def test_qft_matches_oracle_and_closed_forms(gpu, ref, n):
+    """BASELINE config 1 (n=20): Subroutine::qft via CircuitBuilder on new_plus -> |0...0>; a basis
+    state -> the both-indices-bit-reversed DFT; iqft . qft = identity (unpinned by the
+    reference's tests, pinned here by closed forms and by the oracle)."""
+    qs = list(range(n))
+    cg = gpu.CircuitBuilder(n).add_subroutine(gpu.Subroutine.qft(qs, n)).build()
+    cr = ref.CircuitBuilder(n).add_subroutine(ref.Subroutine.qft(qs, n)).build()
+    out_g = cg.execute(gpu.State.new_plus(n))
+    out_r = cr.execute(ref.State.new_plus(n))
+    assert_amps(out_g, vec(out_r), msg=f"qft|+> n={n}")
+    v = vec(out_g)
+    assert abs(v[0] - 1.0) <= 1e-12 and np.max(np.abs(v[1:])) <= 1e-12
+    if n <= 11:
+        x = (0b1011 % (1 << n)) | 1
+        out = vec(cg.execute(gpu.State.new_basis_n(n, x)))
+        N = 1 << n
+
+        def rev(k):
+            return int(format(k, f"0{n}b")[::-1], 2)
+        exp = np.array([np.exp(2j * PI * rev(x) * rev(k) / N) for k in range(N)]) / math.sqrt(N)
+        assert np.max(np.abs(out - exp)) <= 1e-12
+    g, r = _pair(gpu, ref, n, seed=5)
+    ci = gpu.CircuitBuilder(n).add_subroutine(gpu.Subroutine.qft(qs, n)).add_subroutine(gpu.Subroutine.iqft(qs, n)).build()
+    assert_amps(ci.execute(g), vec(r), msg="iqft.qft")
+
+
+@pytest.mark.parametrize("n", [2, 6, 10, 14])
+def test_pauli_strings_vs_oracle(gpu, ref, n):
+    g, r = _pair(gpu, ref, n, seed=7)
+    rng = np.random.default_rng(n)
+    for trial in range(12):
+        k = int(rng.integers(0, min(n, 5) + 1))
+        qs = [int(q) for q in rng.choice(n, size=k, replace=False)]
+        ps_g, ps_r = gpu.PauliString.new(complex(0.3, -0.2)), ref.PauliString.new(complex(0.3, -0.2))
+        for q in qs:
+            which = int(rng.integers(0, 3))
+            ps_g.add_op(q, [gpu.Pauli.X, gpu.Pauli.Y, gpu.Pauli.Z][which])
+            ps_r.add_op(q, [ref.Pauli.X, ref.Pauli.Y, ref.Pauli.Z][which])
+        assert_amps(ps_g.apply(g), vec(ps_r.apply(r)), msg="apply")
+        assert_amps(ps_g.apply_normalised(g), vec(ps_r.apply_normalised(r)), msg="apply_normalised")
+        assert_amps(ps_g.apply_exp(g), vec(ps_r.apply_exp(r)), msg="apply_exp")
+        f = complex(0.1 * trial, -0.25)
+        g, r = ps_g.apply_exp_factor(g, f), ps_r.apply_exp_factor(r, f)
+        nrm = math.sqrt(r.inner_product(r).real)
+        assert_amps(g, vec(r), tol=AMP_TOL * max(1.0, nrm), msg="apply_exp_factor chain")
+        g, r = g.normalise(), r.normalise()
+
+
+@pytest.mark.parametrize("n,steps", [(4, 5), (10, 5), (16, 3)])
+def test_heisenberg_trotter_expectation_vs_oracle(gpu, ref, n, steps):
+    """BASELINE config 3 at oracle-sized n: heisenberg_1d(n,1,2,3,0.5,0.1), new_plus, first- and
+    second-order Trotter, SumOp::expectation_value."""
+    hg, hr = gpu.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1), ref.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1)
+    assert hg.num_terms() == hr.num_terms() == 4 * n
+    for order_g, order_r in ((gpu.TrotterOrder.First, ref.TrotterOrder.First), (gpu.TrotterOrder.Second, ref.TrotterOrder.Second)):
+        sg = gpu.trotter_evolve_state(hg, gpu.State.new_plus(n), 0.01, steps, order_g)
+        sr = ref.trotter_evolve_state(hr, ref.State.new_plus(n), 0.01, steps, order_r)
+        assert_amps(sg, vec(sr), msg="trotter state")
+        eg, er = hg.expectation_value(sg), hr.expectation_value(sr)
+        assert abs(eg - er) <= EXP_RTOL * abs(er), (eg, er)
+    ag, ar = hg.apply(sg), hr.apply(sr)
+    assert_amps(ag, vec(ar), tol=1e-11, msg="SumOp.apply")   # |H psi| ~ 10: bar scaled by the amplitude size
+
+
+@pytest.mark.parametrize("n", [1, 4, 10, 15])
+def test_linear_algebra_vs_oracle(gpu, ref, n):
+    g1, r1 = _pair(gpu, ref, n, seed=1)
+    g2, r2 = _pair(gpu, ref, n, seed=2)
+    ig, ir = g1.inner_product(g2), r1.inner_product(r2)
+    assert abs(ig - ir) <= 1e-12
+    assert abs(g1.norm_sqr() - 1.0) <= 1e-12
+    assert_amps(g1 + g2, vec(r1 + r2))
+    assert_amps(g1 - g2, vec(r1 - r2))
+    assert_amps(g1 * complex(0.3, 0.4), vec(r1 * complex(0.3, 0.4)))
+    assert_amps((g1 + g2).normalise(), vec((r1 + r2).normalise()))
+    assert_amps(g1.conj(), vec(r1.conj()))
+    if n <= 7:
+        assert_amps(g1.tensor_product(g2), vec(r1.tensor_product(r2)))
+
+
+@pytest.mark.parametrize("n,qubits", [(3, [0]), (3, []), (8, [1, 6]), (12, [0, 3, 5]), (12, [11, 2, 7, 0]),
+                                      (12, []), (14, [13]), (16, [4, 5, 6, 7, 8, 9, 10, 11, 12, 13])])
+def test_probabilities_and_seeded_sampling_bit_identical(gpu, ref, n, qubits):
+    """Shared-seed contract: the bins drawn on the device equal the oracle's, draw for draw."""
+    g, r = _pair(gpu, ref, n, seed=11)
+    pg, pr = g.probabilities(qubits), r.probabilities(qubits if qubits else list(range(n)))
+    assert np.max(np.abs(pg - pr)) <= 1e-13
+    shots, seed = 512, 20260003
+    assert r.sample_margin(qubits, shots, seed) > 1e-11, "a draw sits on a CDF edge: pick another seed"
+    assert np.array_equal(g.sample_counts(qubits, shots, seed), r.sample_counts(qubits, shots, seed))
+
+
+@pytest.mark.parametrize("n", [2, 5, 10])
+def test_measure_all_bases_same_outcomes_and_states_as_oracle(gpu, ref, n):
+    g, r = _pair(gpu, ref, n, seed=13)
+    u = [[0.6 + 0j, 0.8j], [0.8j, 0.6 + 0j]]
+    bases = [(gpu.MeasurementBasis.Computational, ref.MeasurementBasis.Computational),
+             (gpu.MeasurementBasis.X, ref.MeasurementBasis.X), (gpu.MeasurementBasis.Y, ref.MeasurementBasis.Y),
+             (gpu.MeasurementBasis.Custom(u), ref.MeasurementBasis.Custom(u))]
+    for bg, br in bases:
+        for qubits in ([0], [n - 1, 0], []):
+            for seed in (1, 2, 3):
+                mg, mr = g.measure(bg, qubits, seed=seed), r.measure(br, qubits, seed=seed)
+                assert mg.get_outcomes() == mr.get_outcomes()
+                assert mg.get_indices() == mr.get_indices()
+                assert_amps(mg.get_new_state(), vec(mr.get_new_state()), msg=f"collapsed {bg} {qubits}")
+    rs_g = g.measure_n(gpu.MeasurementBasis.Computational, [0, 1], 6, seed=42)
+    rs_r = r.measure_n(ref.MeasurementBasis.Computational, [0, 1], 6, seed=42)
+    assert [m.get_outcomes() for m in rs_g] == [m.get_outcomes() for m in rs_r]
+
+
+def test_circuit_with_measurement_and_pauli_gates(gpu, ref):
+    n = 6
+    ps = lambda q: q.PauliString.new(0.8).with_op(1, q.Pauli.X).with_op(4, q.Pauli.Z)  # noqa: E731
+
+    def build(q):
+        return (q.CircuitBuilder(n).h_gates(list(range(n))).cnot_gate(1, 0).rz_gate(2, 0.4)
+                .pauli_time_evolution_gate(ps(q), 0.3).measure_gate(q.MeasurementBasis.X, [2, 3])
+                .pauli_string_gate(ps(q)).toffoli_gate(0, 1, 5).build())
+    out_g = build(gpu).execute(gpu.State.new_zero(n), seed=77)
+    out_r = build(ref).execute(ref.State.new_zero(n), seed=77)
+    assert_amps(out_g, vec(out_r))
+
+
+# ---- BASELINE.json full sizes: size-independent properties (no oracle at this size) -----------------
+@pytest.mark.parametrize("n", [26, 28])
+def test_large_state_properties(gpu, n):
+    """norm preservation, involutions, and the QFT closed form at sizes the oracle cannot hold."""
+    st = gpu.State.new_random(n)
+    assert abs(st.norm_sqr() - 1.0) < 1e-10
+    probe = [st.amplitude(i) for i in (0, 12345, (1 << n) - 1)]
+    for t in (0, 3, 7, n // 2, n - 1):
+        st.h_(t).rx_(t, 0.3).rz_(t, 1.1).rz_(t, -1.1).rx_(t, -0.3).h_(t)
+    st.cnot_(n - 1, 0).cnot_(n - 1, 0).swap_(1, n - 2).swap_(1, n - 2)
+    assert abs(st.norm_sqr() - 1.0) < 1e-10
+    for i, a in zip((0, 12345, (1 << n) - 1), probe):
+        assert abs(st.amplitude(i) - a) < 1e-12
+    del st
+    plus = gpu.State.new_plus(n)
+    qs = list(range(n))
+    gpu.CircuitBuilder(n).add_subroutine(gpu.Subroutine.qft(qs, n)).build().execute_(plus)
+    assert abs(plus.amplitude(0) - 1.0) < 1e-12
+    assert abs(plus.norm_sqr() - 1.0) < 1e-10
+    assert abs(plus.amplitude(1)) < 1e-12 and abs(plus.amplitude((1 << n) - 1)) < 1e-12
