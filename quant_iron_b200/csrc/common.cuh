@@ -63,6 +63,11 @@ struct Context {
     std::vector<ProfEvent> pending;
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+    // op-program staging for the window executor
+    void* h_ops = nullptr;
+    void* d_ops = nullptr;
+    size_t ops_cap = 0;
+    cudaEvent_t ops_event = nullptr;
 };
 Context& ctx();
 int ensure_ctx();
