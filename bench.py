@@ -285,6 +285,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e through the public API with host buffers (rank 0, single GPU semantics) ----
     e2e = None
     try:
+        if args.skip_e2e:
+            raise RuntimeError("skipped (--skip-e2e)")
         n_e = n_local if world == 1 else min(n_local, 28)
         specs_e = specs if world == 1 else w.random_layered_circuit(n_e, args.depth)
         circ_e = circuit if world == 1 else w.build_circuit(qi, n_e, specs_e)
@@ -372,6 +374,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,7 +11,7 @@ import os
 from .errors import Error
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libqiron_b200.so")
+LIB_PATH = os.environ.get("QIRON_B200_LIB") or os.path.join(_PKG, "lib", "libqiron_b200.so")  # env override: kernel experiments
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

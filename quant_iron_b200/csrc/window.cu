@@ -6,10 +6,17 @@
 //   lanes      <-> physical qubits 0..4   (32 consecutive amplitudes = one coalesced 512 B access)
 //   registers  <-> R "window" qubits chosen per pass (any positions >= 5); slot s of a thread holds
 //                  the amplitude whose window bits spell s
+//   tile index <-> all remaining qubits (uniform across the warp)
 // A gate whose target is a window qubit pairs two registers of the same thread (no data movement);
 // a target on qubits 0..4 pairs two lanes (warp shuffles); controls and diagonal gates can sit on
-// ANY qubit, because every thread knows the full index of each amplitude it holds.  No shared
-// memory, no block-level synchronisation.
+// ANY qubit: a control on a tile bit is a warp-uniform skip, on a lane bit a per-thread predicate,
+// on a register bit a per-slot uniform predicate.  No shared memory, no block synchronisation.
+// The op program of a pass travels in the kernel's parameter space (constant bank, uniform loads).
+//
+// Diagonal gates that meet in a pass are merged into PHASE-TABLE ops: a group "if hub bit set,
+// multiply by prod_j f_j(bit_j)" (the QFT's H + controlled-phase ladder is exactly one such group
+// per Hadamard) is applied with one lookup per lane/slot/tile-chunk table instead of one sweep per
+// gate (subroutine.rs:93-106 emits n-1-i controlled phases after H(i)).
 //
 // The host scheduler walks the gate list greedily: a gate joins the current pass if it commutes
 // with every gate deferred so far (two gates commute when on each shared qubit both act diagonally)
@@ -20,22 +27,35 @@
 
 namespace qi {
 
-enum { WK_H = 1, WK_X, WK_Y, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ };
+enum { WK_H = 1, WK_X, WK_Y, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };
+enum { CLS_NONE = 0, CLS_LANE = 1, CLS_REG = 2, CLS_TILE = 3 };
 
-struct WOp {              // 88 bytes
-    uint32_t kind;        // WK_*
-    uint32_t tpos;        // target: 0..4 = lane bit, 5+j = register bit j (pair ops only)
-    uint64_t cmask;       // physical index bits that must all be 1 (for WK_DIAG: includes the target bit)
-    uint64_t tmask;       // WK_RZ: the target bit in the physical index
-    double m[8];          // WK_U2: m00,m01,m10,m11 (re,im); WK_RX: c,s; WK_REAL: m00,m01,m10,m11; WK_H: 1/sqrt2;
-                          // WK_DIAG: phase (re,im); WK_RZ: phase0 (re,im), phase1 (re,im)
+static const int kMaxOps = 120;      // per launch (parameter space: 120 * 104 B + header < 16 KB)
+static const int kLaneQubits = 5;
+
+struct DOp {                 // device op, 104 bytes
+    uint8_t kind;            // WK_*
+    uint8_t tpos;            // pair ops: 0..4 lane bit, 5+j register bit j
+    uint8_t hub_cls;         // WK_TABLE: class of the hub bit (CLS_*)
+    uint8_t hub_bit;         // WK_TABLE: lane bit / slot bit / compact tile bit index
+    uint8_t nchunks;         // WK_TABLE: number of 8-bit tile chunks with a table
+    uint8_t has_reg;         // WK_TABLE: register table is not all ones
+    uint8_t pad[2];
+    uint32_t c_lane, c_reg;  // control bits in lane space / slot space (all must be 1)
+    uint32_t t_lane, t_reg;  // WK_RZ: target bit in lane space / slot space (0 if elsewhere)
+    uint64_t c_tile;         // control bits in compact tile-index space
+    uint64_t t_tile;         // WK_RZ: target bit in tile space
+    double m[8];             // matrix / phases; WK_TABLE: m[0] holds the table offset (as integer bits)
 };
 
 template <int R>
-struct WParams {
+struct WProgram {
     BitInsert ins;              // zero-insert positions of the R window qubits (ascending)
     uint64_t off[1 << R];       // slot -> index offset
     uint32_t nops;
+    uint32_t pad;
+    const amp_t* tables;        // phase-table arena
+    DOp ops[kMaxOps];
 };
 
 __device__ __forceinline__ amp_t shfl_xor_amp(amp_t v, int mask) {
@@ -43,108 +63,100 @@ __device__ __forceinline__ amp_t shfl_xor_amp(amp_t v, int mask) {
 }
 
 // ---- pair gate on register bit B --------------------------------------------------------------
-template <int R, int B>
-__device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint64_t base, const uint64_t* off, uint32_t kind,
-                                            uint64_t cmask, const double* __restrict__ m) {
+template <int R, int B, int KIND>
+__device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], uint32_t c_reg, bool thread_ok, const double* __restrict__ m) {
 #pragma unroll
     for (int p = 0; p < (1 << (R - 1)); p++) {
         const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int s1 = s0 | (1 << B);
-        const bool ok = ((base | off[s0]) & cmask) == cmask;
-        const amp_t a0 = v[s0], a1 = v[s1];
-        amp_t r0, r1;
-        switch (kind) {
-            case WK_H: {
+        if (((s0 & c_reg) == c_reg) && thread_ok) {
+            const amp_t a0 = v[s0], a1 = v[s1];
+            if (KIND == WK_H) {
                 const double s = m[0];
-                r0 = cscale(s, cadd(a0, a1));
-                r1 = cscale(s, csub(a0, a1));
-                break;
-            }
-            case WK_X: r0 = a1; r1 = a0; break;
-            case WK_Y: r0 = make_double2(a1.y, -a1.x); r1 = make_double2(-a0.y, a0.x); break;
-            case WK_RX: {   // [[c, -i s], [-i s, c]]
+                v[s0] = cscale(s, cadd(a0, a1));
+                v[s1] = cscale(s, csub(a0, a1));
+            } else if (KIND == WK_X) {
+                v[s0] = a1; v[s1] = a0;
+            } else if (KIND == WK_Y) {
+                v[s0] = make_double2(a1.y, -a1.x);
+                v[s1] = make_double2(-a0.y, a0.x);
+            } else if (KIND == WK_RX) {   // [[c, -i s], [-i s, c]]
                 const double c = m[0], s = m[1];
-                r0 = make_double2(c * a0.x + s * a1.y, c * a0.y - s * a1.x);
-                r1 = make_double2(c * a1.x + s * a0.y, c * a1.y - s * a0.x);
-                break;
-            }
-            case WK_REAL: {  // real 2x2
-                r0 = make_double2(m[0] * a0.x + m[1] * a1.x, m[0] * a0.y + m[1] * a1.y);
-                r1 = make_double2(m[2] * a0.x + m[3] * a1.x, m[2] * a0.y + m[3] * a1.y);
-                break;
-            }
-            default: {       // WK_U2
+                v[s0] = make_double2(c * a0.x + s * a1.y, c * a0.y - s * a1.x);
+                v[s1] = make_double2(c * a1.x + s * a0.y, c * a1.y - s * a0.x);
+            } else if (KIND == WK_REAL) {
+                v[s0] = make_double2(m[0] * a0.x + m[1] * a1.x, m[0] * a0.y + m[1] * a1.y);
+                v[s1] = make_double2(m[2] * a0.x + m[3] * a1.x, m[2] * a0.y + m[3] * a1.y);
+            } else {
                 const amp_t m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
                 const amp_t m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
-                r0 = cadd(cmul(m00, a0), cmul(m01, a1));
-                r1 = cadd(cmul(m10, a0), cmul(m11, a1));
-                break;
+                v[s0] = cadd(cmul(m00, a0), cmul(m01, a1));
+                v[s1] = cadd(cmul(m10, a0), cmul(m11, a1));
             }
         }
-        v[s0] = ok ? r0 : a0;
-        v[s1] = ok ? r1 : a1;
+    }
+}
+
+template <int R, int B>
+__device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, bool thread_ok,
+                                            const double* __restrict__ m) {
+    switch (kind) {
+        case WK_H: reg_pair_kind<R, B, WK_H>(v, c_reg, thread_ok, m); break;
+        case WK_X: reg_pair_kind<R, B, WK_X>(v, c_reg, thread_ok, m); break;
+        case WK_Y: reg_pair_kind<R, B, WK_Y>(v, c_reg, thread_ok, m); break;
+        case WK_RX: reg_pair_kind<R, B, WK_RX>(v, c_reg, thread_ok, m); break;
+        case WK_REAL: reg_pair_kind<R, B, WK_REAL>(v, c_reg, thread_ok, m); break;
+        default: reg_pair_kind<R, B, WK_U2>(v, c_reg, thread_ok, m); break;
     }
 }
 
 // ---- pair gate on lane bit tpos (warp shuffles) --------------------------------------------------
 template <int R>
-__device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint64_t base, const uint64_t* off, uint32_t kind,
-                                             uint32_t tpos, uint64_t cmask, const double* __restrict__ m, int lane) {
+__device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
+                                             const double* __restrict__ m, int lane) {
     const int xm = 1 << tpos;
     const bool hi = (lane >> tpos) & 1;     // this lane holds the |1> member of the pair
-    // own/partner coefficients: new = cA * mine + cB * partner
-    amp_t cA, cB;
-    switch (kind) {
-        case WK_H: cA = make_double2(hi ? -m[0] : m[0], 0.0); cB = make_double2(m[0], 0.0); break;
-        case WK_X: cA = make_double2(0.0, 0.0); cB = make_double2(1.0, 0.0); break;
-        case WK_Y: cA = make_double2(0.0, 0.0); cB = make_double2(0.0, hi ? 1.0 : -1.0); break;
-        case WK_RX: cA = make_double2(m[0], 0.0); cB = make_double2(0.0, -m[1]); break;
-        case WK_REAL: cA = make_double2(hi ? m[3] : m[0], 0.0); cB = make_double2(hi ? m[2] : m[1], 0.0); break;
-        default:
-            cA = hi ? make_double2(m[6], m[7]) : make_double2(m[0], m[1]);
-            cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
-            break;
+    if (kind == WK_X) {
+#pragma unroll
+        for (int s = 0; s < (1 << R); s++) {
+            const amp_t other = shfl_xor_amp(v[s], xm);
+            if (((s & c_reg) == c_reg) && thread_ok) v[s] = other;
+        }
+        return;
     }
-    const bool real_only = (kind == WK_H || kind == WK_REAL);
+    if (kind == WK_H || kind == WK_REAL) {
+        // new = cA * mine + cB * partner, real coefficients
+        const double cA = kind == WK_H ? (hi ? -m[0] : m[0]) : (hi ? m[3] : m[0]);
+        const double cB = kind == WK_H ? m[0] : (hi ? m[2] : m[1]);
+#pragma unroll
+        for (int s = 0; s < (1 << R); s++) {
+            const amp_t mine = v[s];
+            const amp_t other = shfl_xor_amp(mine, xm);
+            if (((s & c_reg) == c_reg) && thread_ok)
+                v[s] = make_double2(cA * mine.x + cB * other.x, cA * mine.y + cB * other.y);
+        }
+        return;
+    }
+    amp_t cA, cB;
+    if (kind == WK_Y) { cA = make_double2(0.0, 0.0); cB = make_double2(0.0, hi ? 1.0 : -1.0); }
+    else if (kind == WK_RX) { cA = make_double2(m[0], 0.0); cB = make_double2(0.0, -m[1]); }
+    else {
+        cA = hi ? make_double2(m[6], m[7]) : make_double2(m[0], m[1]);
+        cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
+    }
 #pragma unroll
     for (int s = 0; s < (1 << R); s++) {
         const amp_t mine = v[s];
         const amp_t other = shfl_xor_amp(mine, xm);
-        const bool ok = ((base | off[s]) & cmask) == cmask;   // cmask never contains the target bit
-        amp_t r;
-        if (kind == WK_X) r = other;
-        else if (real_only) r = make_double2(cA.x * mine.x + cB.x * other.x, cA.x * mine.y + cB.x * other.y);
-        else r = cadd(cmul(cA, mine), cmul(cB, other));
-        v[s] = ok ? r : mine;
+        if (((s & c_reg) == c_reg) && thread_ok) v[s] = cadd(cmul(cA, mine), cmul(cB, other));
     }
 }
 
+#ifndef QI_WINDOW_MIN_BLOCKS
+#define QI_WINDOW_MIN_BLOCKS 4
+#endif
 template <int R>
-__device__ __forceinline__ void diag_op(amp_t (&v)[1 << R], uint64_t base, const uint64_t* off, uint64_t mask, amp_t ph) {
-#pragma unroll
-    for (int s = 0; s < (1 << R); s++) {
-        const bool ok = ((base | off[s]) & mask) == mask;
-        const amp_t r = cmul(v[s], ph);
-        v[s] = ok ? r : v[s];
-    }
-}
-
-template <int R>
-__device__ __forceinline__ void rz_op(amp_t (&v)[1 << R], uint64_t base, const uint64_t* off, uint64_t cmask, uint64_t tmask,
-                                      amp_t p0, amp_t p1) {
-#pragma unroll
-    for (int s = 0; s < (1 << R); s++) {
-        const uint64_t idx = base | off[s];
-        const bool ok = (idx & cmask) == cmask;
-        const amp_t ph = (idx & tmask) ? p1 : p0;
-        const amp_t r = cmul(v[s], ph);
-        v[s] = ok ? r : v[s];
-    }
-}
-
-template <int R>
-__global__ void __launch_bounds__(128) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WParams<R> P,
-                                                const WOp* __restrict__ ops) {
+__global__ void __launch_bounds__(128, QI_WINDOW_MIN_BLOCKS) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -156,23 +168,53 @@ __global__ void __launch_bounds__(128) k_window(amp_t* __restrict__ a, uint64_t 
         for (int s = 0; s < S; s++) v[s] = a[base + P.off[s]];
 #pragma unroll 1
         for (uint32_t o = 0; o < P.nops; o++) {
-            const WOp* op = ops + o;
-            const uint32_t kind = op->kind, tpos = op->tpos;
-            const uint64_t cmask = op->cmask;
+            const DOp& op = P.ops[o];
+            const uint64_t c_tile = op.c_tile;
+            if ((tile & c_tile) != c_tile) continue;                      // warp-uniform control
+            const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
+            const uint32_t kind = op.kind, c_reg = op.c_reg;
             if (kind == WK_DIAG) {
-                diag_op<R>(v, base, P.off, cmask, make_double2(op->m[0], op->m[1]));
+                const amp_t ph = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if (((s & c_reg) == c_reg) && thread_ok) v[s] = cmul(v[s], ph);
             } else if (kind == WK_RZ) {
-                rz_op<R>(v, base, P.off, cmask, op->tmask, make_double2(op->m[0], op->m[1]), make_double2(op->m[2], op->m[3]));
-            } else if (tpos < 5) {
-                lane_pair_op<R>(v, base, P.off, kind, tpos, cmask, op->m, lane);
+                const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
+                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+                const uint32_t t_reg = op.t_reg;
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    const bool one = t_thread || ((s & t_reg) != 0);
+                    if (((s & c_reg) == c_reg) && thread_ok) v[s] = cmul(v[s], one ? p1 : p0);
+                }
+            } else if (kind == WK_TABLE) {
+                const amp_t* __restrict__ tab = P.tables + (uint64_t)__double_as_longlong(op.m[0]);
+                const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
+                if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
+                bool on = thread_ok && !(hub_cls == CLS_LANE && !((lane >> hub_bit) & 1));
+                amp_t f = tab[lane];                                        // lane table (32 entries)
+                const uint32_t nch = op.nchunks;
+                for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
+                    f = cmul(f, __ldg(tab + 32 + S + 256 * k + ((tile >> (8 * k)) & 255)));
+                const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
+                if (op.has_reg) {
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        if (((s & hub_slot) == hub_slot) && on) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        if (((s & hub_slot) == hub_slot) && on) v[s] = cmul(v[s], f);
+                }
+            } else if (op.tpos < 5) {
+                lane_pair_op<R>(v, kind, op.tpos, c_reg, thread_ok, op.m, lane);
             } else {
-                switch (tpos - 5) {
-                    case 0: reg_pair_op<R, 0>(v, base, P.off, kind, cmask, op->m); break;
-                    case 1: if (R > 1) reg_pair_op<R, (R > 1 ? 1 : 0)>(v, base, P.off, kind, cmask, op->m); break;
-                    case 2: if (R > 2) reg_pair_op<R, (R > 2 ? 2 : 0)>(v, base, P.off, kind, cmask, op->m); break;
-                    case 3: if (R > 3) reg_pair_op<R, (R > 3 ? 3 : 0)>(v, base, P.off, kind, cmask, op->m); break;
-                    case 4: if (R > 4) reg_pair_op<R, (R > 4 ? 4 : 0)>(v, base, P.off, kind, cmask, op->m); break;
-                    default: break;
+                switch (op.tpos - 5) {
+                    case 0: reg_pair_op<R, 0>(v, kind, c_reg, thread_ok, op.m); break;
+                    case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
+                    case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
+                    case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
+                    default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
                 }
             }
         }
@@ -183,7 +225,6 @@ __global__ void __launch_bounds__(128) k_window(amp_t* __restrict__ a, uint64_t 
 
 // ---- host: scheduling ------------------------------------------------------------------------------
 static const int kR = 4;            // register qubits per pass
-static const int kLaneQubits = 5;
 
 struct GateUse {
     uint64_t n_use;   // qubits used non-diagonally (targets of H/X/Y/U2/SWAP)
@@ -201,7 +242,34 @@ static GateUse uses_of(const PhysGate& g) {
     return u;
 }
 
-static void classify_u2(const double* p, WOp* op) {
+// host-side op with PHYSICAL masks; lowered to a DOp once the pass's window is final
+struct HOp {
+    uint32_t kind = 0;
+    int target = -1;            // pair ops: physical target
+    uint64_t cmask = 0;         // physical bits that must be 1 (WK_DIAG: includes the target)
+    uint64_t tmask = 0;         // WK_RZ: physical target bit
+    double m[8] = {0};
+    int group = -1;             // WK_TABLE: index into Pass::groups
+};
+
+// a mergeable diagonal group: [hub set] * prod_j (bit_j ? f1_j : f0_j)
+struct DiagGroup {
+    int hub = -1;                        // physical hub qubit; -1 = unconditional
+    int hub_alt = -1;                    // second hub candidate while only one 2-qubit member is present
+    std::vector<int> bits;               // member qubits
+    std::vector<amp_t> f0, f1;           // factor when the member bit is 0 / 1
+    uint64_t blocked_since = 0;          // qubits used non-diagonally by ops appended after this group
+    size_t op_index = 0;                 // position of the group's op in Pass::ops
+    int members = 0;                     // number of merged gates
+};
+
+struct Pass {
+    std::vector<int> regs;               // window qubits (physical positions >= 5)
+    std::vector<HOp> ops;
+    std::vector<DiagGroup> groups;
+};
+
+static void classify_u2(const double* p, HOp* op) {
     const bool rx_form = p[1] == 0.0 && p[2] == 0.0 && p[4] == 0.0 && p[7] == 0.0 && p[0] == p[6] && p[3] == p[5];
     const bool real_form = p[1] == 0.0 && p[3] == 0.0 && p[5] == 0.0 && p[7] == 0.0;
     memset(op->m, 0, sizeof(op->m));
@@ -209,13 +277,6 @@ static void classify_u2(const double* p, WOp* op) {
     else if (rx_form) { op->kind = WK_RX; op->m[0] = p[0]; op->m[1] = -p[3]; }
     else { op->kind = WK_U2; memcpy(op->m, p, 8 * sizeof(double)); }
 }
-
-struct Pass {
-    std::vector<int> regs;      // window qubits (physical positions >= 5), position j <-> register bit j after sort
-    std::vector<WOp> ops;       // tpos filled after the window is final
-    std::vector<int> op_target; // physical target of each pair op (-1 for diagonal ops)
-    double unfused_bytes = 0.0;
-};
 
 bool window_supported(const qi_state* s) {
     return s->consistent && (int)s->n_local >= kLaneQubits + kR;
@@ -226,19 +287,90 @@ static bool window_takes(const PhysGate& g) {
            g.kind == IK_SWAP;
 }
 
-static void push_pair(Pass& ps, uint32_t kind, int target, uint64_t cmask, const double* m8) {
-    WOp op;
-    memset(&op, 0, sizeof(op));
-    op.kind = kind;
-    op.cmask = cmask;
-    if (m8) memcpy(op.m, m8, 8 * sizeof(double));
+static void append_op(Pass& ps, const HOp& op, uint64_t n_use) {
     ps.ops.push_back(op);
-    ps.op_target.push_back(target);
+    for (DiagGroup& g : ps.groups) g.blocked_since |= n_use;
 }
 
-static void lower_gate(Pass& ps, const PhysGate& g) {
-    WOp op;
-    memset(&op, 0, sizeof(op));
+static void push_pair(Pass& ps, uint32_t kind, int target, uint64_t cmask, const double* m8) {
+    HOp op;
+    op.kind = kind;
+    op.target = target;
+    op.cmask = cmask;
+    if (m8) memcpy(op.m, m8, 8 * sizeof(double));
+    append_op(ps, op, 1ull << target);
+}
+
+// try to merge a diagonal gate into an open group of this pass; returns false if it must be a plain op
+static bool merge_diag(Pass& ps, const PhysGate& g) {
+    // normal form: optional hub h, member bit j with factors (f0, f1)
+    int h = -1, h2 = -1, j = -1;
+    amp_t f0 = make_double2(1.0, 0.0), f1 = make_double2(1.0, 0.0);
+    const int nc = __builtin_popcountll(g.cmask);
+    if (g.t0 < 0 || nc > 1) return false;
+    if (g.kind == IK_DIAG) {
+        f1 = make_double2(g.p[0], g.p[1]);
+        j = g.t0;
+        if (nc == 1) { h = __builtin_ctzll(g.cmask); h2 = g.t0; }     // symmetric: either qubit can be the hub
+    } else {   // IK_RZ
+        f0 = make_double2(g.p[0], g.p[1]);
+        f1 = make_double2(g.p[2], g.p[3]);
+        j = g.t0;
+        if (nc == 1) h = __builtin_ctzll(g.cmask);
+    }
+    const uint64_t qmask = (1ull << j) | (h >= 0 ? (1ull << h) : 0ull);
+    for (int gi = (int)ps.groups.size() - 1; gi >= 0; gi--) {
+        DiagGroup& grp = ps.groups[gi];
+        if (grp.blocked_since & qmask) continue;
+        int member = j;
+        if (h < 0) { if (grp.hub >= 0 || grp.hub_alt >= 0) continue; }            // unconditional gate: unconditional group only
+        else {
+            if (grp.hub < 0 && grp.hub_alt < 0) continue;
+            if (grp.hub_alt >= 0) {
+                // the group holds one symmetric 2-qubit member {hub, hub_alt}: fix the hub now
+                if (h == grp.hub || (h2 >= 0 && h2 == grp.hub)) { /* keep */ }
+                else if (h == grp.hub_alt || (h2 >= 0 && h2 == grp.hub_alt)) {
+                    std::swap(grp.hub, grp.hub_alt);
+                    grp.bits[0] = grp.hub_alt;
+                } else continue;
+                grp.hub_alt = -1;
+            }
+            if (h == grp.hub) member = j;
+            else if (h2 >= 0 && h2 == grp.hub) member = h;                      // symmetric gate seen from the other side
+            else continue;
+        }
+        // merge factors if the member bit is already present
+        bool found = false;
+        for (size_t k = 0; k < grp.bits.size(); k++)
+            if (grp.bits[k] == member) { grp.f0[k] = cmul(grp.f0[k], f0); grp.f1[k] = cmul(grp.f1[k], f1); found = true; break; }
+        if (!found) { grp.bits.push_back(member); grp.f0.push_back(f0); grp.f1.push_back(f1); }
+        grp.members++;
+        return true;
+    }
+    // open a new group
+    DiagGroup grp;
+    grp.hub = h;
+    grp.hub_alt = (g.kind == IK_DIAG && nc == 1) ? h2 : -1;
+    grp.bits.push_back(j);
+    grp.f0.push_back(f0);
+    grp.f1.push_back(f1);
+    grp.members = 1;
+    grp.op_index = ps.ops.size();
+    HOp op;
+    op.kind = WK_TABLE;
+    op.group = (int)ps.groups.size();
+    // remember the original gate so a single-member group can fall back to a plain op
+    op.cmask = g.cmask | (g.kind == IK_DIAG ? (1ull << g.t0) : 0ull);
+    op.tmask = g.kind == IK_RZ ? (1ull << g.t0) : 0ull;
+    memcpy(op.m, g.p, 4 * sizeof(double));
+    op.target = g.kind == IK_RZ ? -2 : -1;      // -2 marks "plain form is WK_RZ"
+    ps.ops.push_back(op);                        // diagonal: does not block other groups
+    ps.groups.push_back(grp);
+    return true;
+}
+
+static void lower_gate(Pass& ps, const PhysGate& g, bool merge) {
+    HOp op;
     switch (g.kind) {
         case IK_H: { double m[8] = {g.p[0]}; push_pair(ps, WK_H, g.t0, g.cmask, m); break; }
         case IK_X: push_pair(ps, WK_X, g.t0, g.cmask, nullptr); break;
@@ -250,77 +382,166 @@ static void lower_gate(Pass& ps, const PhysGate& g) {
             push_pair(ps, WK_X, g.t0, g.cmask | (1ull << g.t1), nullptr);
             break;
         }
-        case IK_DIAG: {
+        case IK_DIAG:
+            if (merge && merge_diag(ps, g)) break;
             op.kind = WK_DIAG;
             op.cmask = g.cmask | (g.t0 >= 0 ? (1ull << g.t0) : 0ull);
             op.m[0] = g.p[0]; op.m[1] = g.p[1];
-            ps.ops.push_back(op);
-            ps.op_target.push_back(-1);
+            append_op(ps, op, 0);
             break;
-        }
-        case IK_RZ: {
+        case IK_RZ:
+            if (merge && merge_diag(ps, g)) break;
             op.kind = WK_RZ;
             op.cmask = g.cmask;
             op.tmask = g.t0 >= 0 ? (1ull << g.t0) : 0ull;
             memcpy(op.m, g.p, 4 * sizeof(double));
-            if (g.t0 < 0) { /* target in the rank bits: caller resolved the phase into p[0..1] */ op.m[2] = g.p[0]; op.m[3] = g.p[1]; }
-            ps.ops.push_back(op);
-            ps.op_target.push_back(-1);
+            if (g.t0 < 0) { op.m[2] = g.p[0]; op.m[3] = g.p[1]; }   // target in the rank bits: phase pre-resolved
+            append_op(ps, op, 0);
             break;
-        }
         default: break;
     }
 }
 
-static double gate_unfused_bytes(const qi_state* s, const PhysGate& g) {
-    const double full = 32.0 * (double)s->len;
-    int nc = __builtin_popcountll(g.cmask);
-    double f = 1.0;
-    if (g.kind == IK_DIAG) f = g.t0 >= 0 ? 0.5 : 1.0;
-    if (g.kind == IK_SWAP) f = 0.5;
-    return full * f / (double)(1ull << nc);
+// ---- host: lowering a pass to device form -----------------------------------------------------------
+struct Layout {
+    int R;
+    std::vector<int> regs;              // sorted window qubits
+    int cls[64];                        // CLS_* per physical bit
+    int idx[64];                        // lane bit / slot bit / compact tile bit per physical bit
+    int ntile_bits;
+};
+
+static Layout make_layout(const qi_state* s, std::vector<int> regs, int R) {
+    Layout L;
+    L.R = R;
+    const int n = (int)s->n_local;
+    std::sort(regs.begin(), regs.end());
+    // pad the window with unused qubits (lowest free positions first: better locality)
+    for (int q = kLaneQubits; q < n && (int)regs.size() < R; q++)
+        if (std::find(regs.begin(), regs.end(), q) == regs.end()) regs.push_back(q);
+    std::sort(regs.begin(), regs.end());
+    L.regs = regs;
+    int t = 0;
+    for (int q = 0; q < 64; q++) {
+        L.cls[q] = CLS_NONE; L.idx[q] = 0;
+        if (q >= n) continue;
+        auto it = std::find(regs.begin(), regs.end(), q);
+        if (q < kLaneQubits) { L.cls[q] = CLS_LANE; L.idx[q] = q; }
+        else if (it != regs.end()) { L.cls[q] = CLS_REG; L.idx[q] = (int)(it - regs.begin()); }
+        else { L.cls[q] = CLS_TILE; L.idx[q] = t++; }
+    }
+    L.ntile_bits = t;
+    return L;
 }
 
-// finalise a pass on the host: pad + sort the window, slot offsets, op target positions
+static void split_mask(const Layout& L, uint64_t phys, uint32_t* lane, uint32_t* reg, uint64_t* tile) {
+    *lane = 0; *reg = 0; *tile = 0;
+    for (int q = 0; q < 64; q++) {
+        if (!((phys >> q) & 1)) continue;
+        if (L.cls[q] == CLS_LANE) *lane |= 1u << L.idx[q];
+        else if (L.cls[q] == CLS_REG) *reg |= 1u << L.idx[q];
+        else if (L.cls[q] == CLS_TILE) *tile |= 1ull << L.idx[q];
+    }
+}
+
+// build the tables of one group: [lane(32) | slot(2^R) | chunk0(256) | chunk1(256) ...]
+static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>& arena, DOp* d) {
+    const int S = 1 << L.R;
+    const int nch_total = (L.ntile_bits + 7) / 8;
+    int used_chunks = 0;
+    bool has_reg = false;
+    for (size_t k = 0; k < g.bits.size(); k++) {
+        int q = g.bits[k];
+        if (L.cls[q] == CLS_TILE) used_chunks = std::max(used_chunks, L.idx[q] / 8 + 1);
+        if (L.cls[q] == CLS_REG) has_reg = true;
+    }
+    (void)nch_total;
+    const size_t off = arena.size();
+    arena.resize(off + 32 + S + 256 * (size_t)used_chunks, make_double2(1.0, 0.0));
+    amp_t* lane_t = arena.data() + off;
+    amp_t* slot_t = lane_t + 32;
+    amp_t* chunk_t = slot_t + S;
+    for (size_t k = 0; k < g.bits.size(); k++) {
+        const int q = g.bits[k];
+        const amp_t f0 = g.f0[k], f1 = g.f1[k];
+        if (L.cls[q] == CLS_LANE) {
+            for (int i = 0; i < 32; i++) lane_t[i] = cmul(lane_t[i], ((i >> L.idx[q]) & 1) ? f1 : f0);
+        } else if (L.cls[q] == CLS_REG) {
+            for (int i = 0; i < S; i++) slot_t[i] = cmul(slot_t[i], ((i >> L.idx[q]) & 1) ? f1 : f0);
+        } else {
+            const int ch = L.idx[q] / 8, b = L.idx[q] % 8;
+            for (int i = 0; i < 256; i++) chunk_t[256 * ch + i] = cmul(chunk_t[256 * ch + i], ((i >> b) & 1) ? f1 : f0);
+        }
+    }
+    d->kind = WK_TABLE;
+    d->nchunks = (uint8_t)used_chunks;
+    d->has_reg = has_reg ? 1 : 0;
+    d->hub_cls = CLS_NONE;
+    d->hub_bit = 0;
+    if (g.hub >= 0) { d->hub_cls = (uint8_t)L.cls[g.hub]; d->hub_bit = (uint8_t)L.idx[g.hub]; }
+    long long o = (long long)off;
+    memcpy(&d->m[0], &o, sizeof(o));
+}
+
+static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp>& dops, std::vector<amp_t>& arena, Layout* Lout) {
+    Layout L = make_layout(s, ps.regs, R);
+    *Lout = L;
+    for (const HOp& h : ps.ops) {
+        DOp d;
+        memset(&d, 0, sizeof(d));
+        HOp op = h;
+        if (op.kind == WK_TABLE) {
+            const DiagGroup& g = ps.groups[op.group];
+            if (g.members >= 2) {
+                build_tables(L, g, arena, &d);
+                dops.push_back(d);
+                continue;
+            }
+            op.kind = (op.target == -2) ? WK_RZ : WK_DIAG;      // single member: plain op is cheaper
+            if (op.kind == WK_DIAG) { op.m[0] = h.m[0]; op.m[1] = h.m[1]; }
+        }
+        d.kind = (uint8_t)op.kind;
+        split_mask(L, op.cmask, &d.c_lane, &d.c_reg, &d.c_tile);
+        if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
+        memcpy(d.m, op.m, sizeof(d.m));
+        if (op.kind != WK_DIAG && op.kind != WK_RZ) {
+            const int t = op.target;
+            d.tpos = (uint8_t)(L.cls[t] == CLS_LANE ? L.idx[t] : kLaneQubits + L.idx[t]);
+        }
+        dops.push_back(d);
+    }
+}
+
 template <int R>
-static void finalise_pass(const qi_state* s, Pass& ps, WParams<R>* P) {
-    const int n = (int)s->n_local;
-    std::sort(ps.regs.begin(), ps.regs.end());
-    // pad the window with unused qubits (lowest free positions first: better locality)
-    for (int q = kLaneQubits; q < n && (int)ps.regs.size() < R; q++)
-        if (std::find(ps.regs.begin(), ps.regs.end(), q) == ps.regs.end()) ps.regs.push_back(q);
-    std::sort(ps.regs.begin(), ps.regs.end());
-    memset(P, 0, sizeof(*P));
-    P->ins = make_insert(ps.regs, {});
+static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t nops, const amp_t* d_tables) {
+    Context& c = ctx();
+    WProgram<R> P;
+    memset(&P, 0, sizeof(P));
+    P.ins = make_insert(L.regs, {});
     for (int sidx = 0; sidx < (1 << R); sidx++) {
         uint64_t o = 0;
-        for (int j = 0; j < R; j++) if ((sidx >> j) & 1) o |= 1ull << ps.regs[j];
-        P->off[sidx] = o;
+        for (int j = 0; j < R; j++) if ((sidx >> j) & 1) o |= 1ull << L.regs[j];
+        P.off[sidx] = o;
     }
-    for (size_t i = 0; i < ps.ops.size(); i++) {
-        int t = ps.op_target[i];
-        if (t < 0) continue;
-        if (t < kLaneQubits) ps.ops[i].tpos = (uint32_t)t;
-        else ps.ops[i].tpos = (uint32_t)(kLaneQubits + (std::find(ps.regs.begin(), ps.regs.end(), t) - ps.regs.begin()));
-    }
-    P->nops = (uint32_t)ps.ops.size();
-}
-
-template <int R>
-static int launch_pass(qi_state* s, const WParams<R>& P, const WOp* d_ops_slot) {
-    Context& c = ctx();
+    P.tables = d_tables;
     const uint64_t ntiles = s->len >> (kLaneQubits + R);
     const int warps_per_block = 4;
     uint64_t blocks = (ntiles + warps_per_block - 1) / warps_per_block;
-    const uint64_t cap = (uint64_t)c.sm_count * 4 * 8;      // 8 waves of 4 resident blocks per SM
+    const uint64_t cap = (uint64_t)c.sm_count * 5 * 8;      // several waves of resident blocks per SM
     if (blocks > cap) blocks = cap;
-    LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
-    k_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P, d_ops_slot);
-    return check_launch("k_window");
+    for (size_t first = 0; first < nops; first += kMaxOps) {
+        size_t cnt = std::min<size_t>(kMaxOps, nops - first);
+        P.nops = (uint32_t)cnt;
+        memcpy(P.ops, ops + first, cnt * sizeof(DOp));
+        LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
+        k_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+        QI_TRY(check_launch("k_window"));
+    }
+    return QI_OK;
 }
 
-// staging for op programs: pinned host buffer + device buffer, reused across calls
-static int ensure_ops(size_t count) {
+// staging for phase tables: pinned host buffer + device buffer, reused across calls
+static int ensure_tables(size_t count) {
     Context& c = ctx();
     if (!c.ops_event) QI_CUDA(cudaEventCreateWithFlags(&c.ops_event, cudaEventDisableTiming));
     if (c.ops_cap >= count) return QI_OK;
@@ -328,14 +549,14 @@ static int ensure_ops(size_t count) {
     if (c.h_ops) cudaFreeHost(c.h_ops);
     if (c.d_ops) cudaFree(c.d_ops);
     c.h_ops = c.d_ops = nullptr;
-    size_t cap = count < 4096 ? 4096 : count * 2;
-    QI_CUDA(cudaMallocHost(&c.h_ops, cap * sizeof(WOp)));
-    QI_CUDA(cudaMalloc(&c.d_ops, cap * sizeof(WOp)));
+    size_t cap = count < (1u << 16) ? (1u << 16) : count * 2;
+    QI_CUDA(cudaMallocHost(&c.h_ops, cap * sizeof(amp_t)));
+    QI_CUDA(cudaMalloc(&c.d_ops, cap * sizeof(amp_t)));
     c.ops_cap = cap;
     return QI_OK;
 }
 
-struct Step { bool simple; size_t gate; Pass pass; size_t op_offset; };
+struct Step { bool simple; size_t gate; Pass pass; };
 
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     Context& c = ctx();
@@ -348,8 +569,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     while (first < G) {
         if (done[first]) { first++; continue; }
         if (!window_takes(gates[first])) {
-            Step st{true, first, Pass(), 0};
-            steps.push_back(std::move(st));
+            steps.push_back(Step{true, first, Pass()});
             done[first++] = 1;
             continue;
         }
@@ -372,8 +592,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
                         if ((need >> q) & 1) { ps.regs.push_back(q); window_mask |= 1ull << q; need &= ~(1ull << q); }
             }
             if (take) {
-                lower_gate(ps, g);
-                ps.unfused_bytes += gate_unfused_bytes(s, g);
+                lower_gate(ps, g, fuse);
                 done[i] = 1;
                 if (!fuse) break;
             } else {
@@ -382,30 +601,24 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
             }
         }
         if (ps.ops.empty()) return fail(QI_ERR_UNKNOWN, 0, 0, "scheduler made no progress");
-        Step st{false, 0, std::move(ps), 0};
-        steps.push_back(std::move(st));
+        steps.push_back(Step{false, 0, std::move(ps)});
     }
-    // one staging copy for the whole run, then back-to-back launches
-    size_t total_ops = 0;
-    std::vector<WParams<kR>> params(steps.size());
-    for (size_t i = 0; i < steps.size(); i++) {
-        if (steps[i].simple) continue;
-        finalise_pass<kR>(s, steps[i].pass, &params[i]);
-        steps[i].op_offset = total_ops;
-        total_ops += steps[i].pass.ops.size();
-    }
-    if (total_ops) {
-        QI_TRY(ensure_ops(total_ops));
-        QI_CUDA(cudaEventSynchronize(c.ops_event));      // previous run's copy has left the pinned buffer
-        WOp* h = (WOp*)c.h_ops;
-        for (const Step& st : steps)
-            if (!st.simple) memcpy(h + st.op_offset, st.pass.ops.data(), st.pass.ops.size() * sizeof(WOp));
-        QI_CUDA(cudaMemcpyAsync(c.d_ops, c.h_ops, total_ops * sizeof(WOp), cudaMemcpyHostToDevice, c.stream));
+    // lower every pass, upload all phase tables in one copy, then launch back to back
+    std::vector<std::vector<DOp>> dops(steps.size());
+    std::vector<Layout> layouts(steps.size());
+    std::vector<amp_t> arena;
+    for (size_t i = 0; i < steps.size(); i++)
+        if (!steps[i].simple) lower_pass(s, steps[i].pass, kR, dops[i], arena, &layouts[i]);
+    if (!arena.empty()) {
+        QI_TRY(ensure_tables(arena.size()));
+        QI_CUDA(cudaEventSynchronize(c.ops_event));      // the previous run's copy has left the pinned buffer
+        memcpy(c.h_ops, arena.data(), arena.size() * sizeof(amp_t));
+        QI_CUDA(cudaMemcpyAsync(c.d_ops, c.h_ops, arena.size() * sizeof(amp_t), cudaMemcpyHostToDevice, c.stream));
         QI_CUDA(cudaEventRecord(c.ops_event, c.stream));
     }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, gates[steps[i].gate]));
-        else QI_TRY(launch_pass<kR>(s, params[i], (const WOp*)c.d_ops + steps[i].op_offset));
+        else QI_TRY(launch_program<kR>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
     }
     return QI_OK;
 }
