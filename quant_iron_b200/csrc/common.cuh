@@ -56,6 +56,7 @@ struct Context {
     int opt_path = 0;                 // 0 auto, 1 simple kernels, 2 window kernels
     int opt_fuse = 1;
     int opt_profile = 0;
+    int opt_window_regs = 0;          // 0 = default
     // stats
     uint64_t launches[KF_COUNT] = {0};
     double alg_bytes[KF_COUNT] = {0};

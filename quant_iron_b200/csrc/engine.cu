@@ -182,6 +182,7 @@ int qi_set_option(const char* name, int64_t value) {
     Context& c = ctx();
     if (!strcmp(name, "path")) c.opt_path = (int)value;
     else if (!strcmp(name, "fuse")) c.opt_fuse = (int)value;
+    else if (!strcmp(name, "window_regs")) c.opt_window_regs = (int)value;
     else if (!strcmp(name, "profile")) { if (!value) drain_profile(); c.opt_profile = (int)value; }
     else return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "unknown option");
     return QI_OK;

@@ -27,7 +27,7 @@
 
 namespace qi {
 
-enum { WK_H = 1, WK_X, WK_Y, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };
+enum { WK_X = 1, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };   // pair kinds first (<= WK_U2)
 enum { CLS_NONE = 0, CLS_LANE = 1, CLS_REG = 2, CLS_TILE = 3 };
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 104 B + header < 16 KB)
@@ -63,33 +63,33 @@ __device__ __forceinline__ amp_t shfl_xor_amp(amp_t v, int mask) {
 }
 
 // ---- pair gate on register bit B --------------------------------------------------------------
-template <int R, int B, int KIND>
-__device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], uint32_t c_reg, bool thread_ok, const double* __restrict__ m) {
+// COND = false: no register-bit controls, straight-line code.  COND = true: the slot predicate
+// (s0 & c_reg) == c_reg is warp-uniform (c_reg comes from the constant bank, s0 is a literal), so a
+// controlled gate costs a uniform branch per pair, not a select per register.
+// Kinds: X (swap), RX ([[c,-is],[-is,c]]), REAL (real 2x2; H is REAL), U2 (complex 2x2; Y is U2).
+template <int R, int B, int KIND, bool COND>
+__device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t c_reg, const double* __restrict__ m) {
+    double k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, k7 = 0;
+    if (KIND == WK_RX) { k0 = m[0]; k1 = m[1]; }
+    if (KIND == WK_REAL) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; }
+    if (KIND == WK_U2) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; k4 = m[4]; k5 = m[5]; k6 = m[6]; k7 = m[7]; }
 #pragma unroll
     for (int p = 0; p < (1 << (R - 1)); p++) {
         const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int s1 = s0 | (1 << B);
-        if (((s0 & c_reg) == c_reg) && thread_ok) {
+        if (!COND || ((s0 & c_reg) == c_reg)) {
             const amp_t a0 = v[s0], a1 = v[s1];
-            if (KIND == WK_H) {
-                const double s = m[0];
-                v[s0] = cscale(s, cadd(a0, a1));
-                v[s1] = cscale(s, csub(a0, a1));
-            } else if (KIND == WK_X) {
+            if (KIND == WK_X) {
                 v[s0] = a1; v[s1] = a0;
-            } else if (KIND == WK_Y) {
-                v[s0] = make_double2(a1.y, -a1.x);
-                v[s1] = make_double2(-a0.y, a0.x);
-            } else if (KIND == WK_RX) {   // [[c, -i s], [-i s, c]]
-                const double c = m[0], s = m[1];
-                v[s0] = make_double2(c * a0.x + s * a1.y, c * a0.y - s * a1.x);
-                v[s1] = make_double2(c * a1.x + s * a0.y, c * a1.y - s * a0.x);
+            } else if (KIND == WK_RX) {
+                v[s0] = make_double2(k0 * a0.x + k1 * a1.y, k0 * a0.y - k1 * a1.x);
+                v[s1] = make_double2(k0 * a1.x + k1 * a0.y, k0 * a1.y - k1 * a0.x);
             } else if (KIND == WK_REAL) {
-                v[s0] = make_double2(m[0] * a0.x + m[1] * a1.x, m[0] * a0.y + m[1] * a1.y);
-                v[s1] = make_double2(m[2] * a0.x + m[3] * a1.x, m[2] * a0.y + m[3] * a1.y);
+                v[s0] = make_double2(k0 * a0.x + k1 * a1.x, k0 * a0.y + k1 * a1.y);
+                v[s1] = make_double2(k2 * a0.x + k3 * a1.x, k2 * a0.y + k3 * a1.y);
             } else {
-                const amp_t m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
-                const amp_t m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
+                const amp_t m00 = make_double2(k0, k1), m01 = make_double2(k2, k3);
+                const amp_t m10 = make_double2(k4, k5), m11 = make_double2(k6, k7);
                 v[s0] = cadd(cmul(m00, a0), cmul(m01, a1));
                 v[s1] = cadd(cmul(m10, a0), cmul(m11, a1));
             }
@@ -98,65 +98,74 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], uint32_t c_reg
 }
 
 template <int R, int B>
-__device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, bool thread_ok,
-                                            const double* __restrict__ m) {
+__device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
     switch (kind) {
-        case WK_H: reg_pair_kind<R, B, WK_H>(v, c_reg, thread_ok, m); break;
-        case WK_X: reg_pair_kind<R, B, WK_X>(v, c_reg, thread_ok, m); break;
-        case WK_Y: reg_pair_kind<R, B, WK_Y>(v, c_reg, thread_ok, m); break;
-        case WK_RX: reg_pair_kind<R, B, WK_RX>(v, c_reg, thread_ok, m); break;
-        case WK_REAL: reg_pair_kind<R, B, WK_REAL>(v, c_reg, thread_ok, m); break;
-        default: reg_pair_kind<R, B, WK_U2>(v, c_reg, thread_ok, m); break;
+        case WK_X: reg_pair_kind<R, B, WK_X, true>(v, c_reg, m); break;
+        case WK_RX: reg_pair_kind<R, B, WK_RX, true>(v, c_reg, m); break;
+        case WK_REAL: reg_pair_kind<R, B, WK_REAL, true>(v, c_reg, m); break;
+        default: reg_pair_kind<R, B, WK_U2, true>(v, c_reg, m); break;
     }
 }
 
-// ---- pair gate on lane bit tpos (warp shuffles) --------------------------------------------------
+// ---- pair gate on lane bit tpos (warp shuffles; every lane takes part in the exchange) -----------
+// A lane whose lane-bit controls are off keeps its value: its coefficients become (1, 0); its partner
+// differs only in the target bit, so it sees the same controls.
 template <int R>
 __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
                                              const double* __restrict__ m, int lane) {
     const int xm = 1 << tpos;
     const bool hi = (lane >> tpos) & 1;     // this lane holds the |1> member of the pair
     if (kind == WK_X) {
+        const int src = thread_ok ? (lane ^ xm) : lane;
 #pragma unroll
-        for (int s = 0; s < (1 << R); s++) {
-            const amp_t other = shfl_xor_amp(v[s], xm);
-            if (((s & c_reg) == c_reg) && thread_ok) v[s] = other;
-        }
+        for (int s = 0; s < (1 << R); s++)
+            if ((s & c_reg) == c_reg)
+                v[s] = make_double2(__shfl_sync(0xffffffffu, v[s].x, src), __shfl_sync(0xffffffffu, v[s].y, src));
         return;
     }
-    if (kind == WK_H || kind == WK_REAL) {
-        // new = cA * mine + cB * partner, real coefficients
-        const double cA = kind == WK_H ? (hi ? -m[0] : m[0]) : (hi ? m[3] : m[0]);
-        const double cB = kind == WK_H ? m[0] : (hi ? m[2] : m[1]);
+    if (kind == WK_REAL) {
+        double cA = hi ? m[3] : m[0], cB = hi ? m[2] : m[1];
+        if (!thread_ok) { cA = 1.0; cB = 0.0; }
 #pragma unroll
         for (int s = 0; s < (1 << R); s++) {
-            const amp_t mine = v[s];
-            const amp_t other = shfl_xor_amp(mine, xm);
-            if (((s & c_reg) == c_reg) && thread_ok)
+            if ((s & c_reg) == c_reg) {
+                const amp_t mine = v[s];
+                const amp_t other = shfl_xor_amp(mine, xm);
                 v[s] = make_double2(cA * mine.x + cB * other.x, cA * mine.y + cB * other.y);
+            }
         }
         return;
     }
-    amp_t cA, cB;
-    if (kind == WK_Y) { cA = make_double2(0.0, 0.0); cB = make_double2(0.0, hi ? 1.0 : -1.0); }
-    else if (kind == WK_RX) { cA = make_double2(m[0], 0.0); cB = make_double2(0.0, -m[1]); }
-    else {
-        cA = hi ? make_double2(m[6], m[7]) : make_double2(m[0], m[1]);
-        cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
+    if (kind == WK_RX) {       // mine' = c*mine - i*s*other
+        double c = m[0], sn = m[1];
+        if (!thread_ok) { c = 1.0; sn = 0.0; }
+#pragma unroll
+        for (int s = 0; s < (1 << R); s++) {
+            if ((s & c_reg) == c_reg) {
+                const amp_t mine = v[s];
+                const amp_t other = shfl_xor_amp(mine, xm);
+                v[s] = make_double2(c * mine.x + sn * other.y, c * mine.y - sn * other.x);
+            }
+        }
+        return;
     }
+    amp_t cA = hi ? make_double2(m[6], m[7]) : make_double2(m[0], m[1]);
+    amp_t cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
+    if (!thread_ok) { cA = make_double2(1.0, 0.0); cB = make_double2(0.0, 0.0); }
 #pragma unroll
     for (int s = 0; s < (1 << R); s++) {
-        const amp_t mine = v[s];
-        const amp_t other = shfl_xor_amp(mine, xm);
-        if (((s & c_reg) == c_reg) && thread_ok) v[s] = cadd(cmul(cA, mine), cmul(cB, other));
+        if ((s & c_reg) == c_reg) {
+            const amp_t mine = v[s];
+            const amp_t other = shfl_xor_amp(mine, xm);
+            v[s] = cadd(cmul(cA, mine), cmul(cB, other));
+        }
     }
 }
 
-#ifndef QI_WINDOW_MIN_BLOCKS
-#define QI_WINDOW_MIN_BLOCKS 4
-#endif
+// resident blocks per SM the register budget is tuned for: 8 amplitudes/thread -> 8 blocks,
+// 16 -> 4 blocks (128 registers), 32 -> 2 blocks
 template <int R>
-__global__ void __launch_bounds__(128, QI_WINDOW_MIN_BLOCKS) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
+__global__ void __launch_bounds__(128, (R <= 3 ? 8 : (R == 4 ? 4 : 2))) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -172,26 +181,40 @@ __global__ void __launch_bounds__(128, QI_WINDOW_MIN_BLOCKS) k_window(amp_t* __r
             const uint64_t c_tile = op.c_tile;
             if ((tile & c_tile) != c_tile) continue;                      // warp-uniform control
             const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
-            const uint32_t kind = op.kind, c_reg = op.c_reg;
+            const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
+            if (kind <= WK_U2 && tpos < 5) {                              // pair gate across lanes
+                lane_pair_op<R>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
+                continue;
+            }
+            if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
             if (kind == WK_DIAG) {
                 const amp_t ph = make_double2(op.m[0], op.m[1]);
 #pragma unroll
                 for (int s = 0; s < S; s++)
-                    if (((s & c_reg) == c_reg) && thread_ok) v[s] = cmul(v[s], ph);
+                    if ((s & c_reg) == c_reg) v[s] = cmul(v[s], ph);
             } else if (kind == WK_RZ) {
                 const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
-                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
                 const uint32_t t_reg = op.t_reg;
+                if (t_reg == 0 && c_reg == 0) {                           // target outside the registers: one phase per thread
+                    const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+                    const amp_t pt = t_thread ? p1 : p0;
 #pragma unroll
-                for (int s = 0; s < S; s++) {
-                    const bool one = t_thread || ((s & t_reg) != 0);
-                    if (((s & c_reg) == c_reg) && thread_ok) v[s] = cmul(v[s], one ? p1 : p0);
+                    for (int s = 0; s < S; s++) v[s] = cmul(v[s], pt);
+                } else {
+                    const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+                    const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        if ((s & c_reg) == c_reg) {
+                            if (s & t_reg) v[s] = cmul(v[s], p1);
+                            else v[s] = cmul(v[s], pt);
+                        }
                 }
             } else if (kind == WK_TABLE) {
                 const amp_t* __restrict__ tab = P.tables + (uint64_t)__double_as_longlong(op.m[0]);
                 const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
                 if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
-                bool on = thread_ok && !(hub_cls == CLS_LANE && !((lane >> hub_bit) & 1));
+                if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) continue;
                 amp_t f = tab[lane];                                        // lane table (32 entries)
                 const uint32_t nch = op.nchunks;
                 for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
@@ -200,21 +223,19 @@ __global__ void __launch_bounds__(128, QI_WINDOW_MIN_BLOCKS) k_window(amp_t* __r
                 if (op.has_reg) {
 #pragma unroll
                     for (int s = 0; s < S; s++)
-                        if (((s & hub_slot) == hub_slot) && on) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
+                        if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
                 } else {
 #pragma unroll
                     for (int s = 0; s < S; s++)
-                        if (((s & hub_slot) == hub_slot) && on) v[s] = cmul(v[s], f);
+                        if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], f);
                 }
-            } else if (op.tpos < 5) {
-                lane_pair_op<R>(v, kind, op.tpos, c_reg, thread_ok, op.m, lane);
             } else {
-                switch (op.tpos - 5) {
-                    case 0: reg_pair_op<R, 0>(v, kind, c_reg, thread_ok, op.m); break;
-                    case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
-                    case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
-                    case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
-                    default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, thread_ok, op.m); break;
+                switch (tpos - 5) {
+                    case 0: reg_pair_op<R, 0>(v, kind, c_reg, op.m); break;
+                    case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, op.m); break;
+                    case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, op.m); break;
+                    case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, op.m); break;
+                    default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, op.m); break;
                 }
             }
         }
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_MIN_BLOCKS) k_window(amp_t* __r
 }
 
 // ---- host: scheduling ------------------------------------------------------------------------------
-static const int kR = 4;            // register qubits per pass
+static const int kDefaultR = 4;     // register qubits per pass (option "window_regs": 3, 4 or 5)
 
 struct GateUse {
     uint64_t n_use;   // qubits used non-diagonally (targets of H/X/Y/U2/SWAP)
@@ -278,8 +299,16 @@ static void classify_u2(const double* p, HOp* op) {
     else { op->kind = WK_U2; memcpy(op->m, p, 8 * sizeof(double)); }
 }
 
+static int window_regs(const qi_state* s) {
+    int r = ctx().opt_window_regs ? ctx().opt_window_regs : kDefaultR;
+    if (r < 3) r = 3;
+    if (r > 5) r = 5;
+    while (r > 3 && (int)s->n_local < kLaneQubits + r) r--;
+    return r;
+}
+
 bool window_supported(const qi_state* s) {
-    return s->consistent && (int)s->n_local >= kLaneQubits + kR;
+    return s->consistent && (int)s->n_local >= kLaneQubits + 3;
 }
 
 static bool window_takes(const PhysGate& g) {
@@ -372,9 +401,9 @@ static bool merge_diag(Pass& ps, const PhysGate& g) {
 static void lower_gate(Pass& ps, const PhysGate& g, bool merge) {
     HOp op;
     switch (g.kind) {
-        case IK_H: { double m[8] = {g.p[0]}; push_pair(ps, WK_H, g.t0, g.cmask, m); break; }
+        case IK_H: { double m[8] = {g.p[0], g.p[0], g.p[0], -g.p[0]}; push_pair(ps, WK_REAL, g.t0, g.cmask, m); break; }   // H = s*[[1,1],[1,-1]]
         case IK_X: push_pair(ps, WK_X, g.t0, g.cmask, nullptr); break;
-        case IK_Y: push_pair(ps, WK_Y, g.t0, g.cmask, nullptr); break;
+        case IK_Y: { double m[8] = {0, 0, 0, -1, 0, 1, 0, 0}; push_pair(ps, WK_U2, g.t0, g.cmask, m); break; }   // [[0,-i],[i,0]]
         case IK_U2: classify_u2(g.p, &op); push_pair(ps, op.kind, g.t0, g.cmask, op.m); break;
         case IK_SWAP: {   // SWAP(a,b) = CX(b->a) CX(a->b) CX(b->a), each under the original controls
             push_pair(ps, WK_X, g.t0, g.cmask | (1ull << g.t1), nullptr);
@@ -561,6 +590,7 @@ struct Step { bool simple; size_t gate; Pass pass; };
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     Context& c = ctx();
     const bool fuse = c.opt_fuse != 0;
+    const int R = window_regs(s);
     const size_t G = gates.size();
     std::vector<char> done(G, 0);
     std::vector<Step> steps;
@@ -586,7 +616,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
             if (take) {
                 // non-diagonal targets above the lane qubits must be (or become) window qubits
                 uint64_t need = u.n_use & ~((1ull << kLaneQubits) - 1) & ~window_mask;
-                if ((int)ps.regs.size() + __builtin_popcountll(need) > kR) take = false;
+                if ((int)ps.regs.size() + __builtin_popcountll(need) > R) take = false;
                 else
                     for (int q = kLaneQubits; q < 64 && need; q++)
                         if ((need >> q) & 1) { ps.regs.push_back(q); window_mask |= 1ull << q; need &= ~(1ull << q); }
@@ -608,7 +638,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     std::vector<Layout> layouts(steps.size());
     std::vector<amp_t> arena;
     for (size_t i = 0; i < steps.size(); i++)
-        if (!steps[i].simple) lower_pass(s, steps[i].pass, kR, dops[i], arena, &layouts[i]);
+        if (!steps[i].simple) lower_pass(s, steps[i].pass, R, dops[i], arena, &layouts[i]);
     if (!arena.empty()) {
         QI_TRY(ensure_tables(arena.size()));
         QI_CUDA(cudaEventSynchronize(c.ops_event));      // the previous run's copy has left the pinned buffer
@@ -618,7 +648,9 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, gates[steps[i].gate]));
-        else QI_TRY(launch_program<kR>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
+        else if (R == 3) QI_TRY(launch_program<3>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
+        else if (R == 4) QI_TRY(launch_program<4>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
+        else QI_TRY(launch_program<5>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
     }
     return QI_OK;
 }
