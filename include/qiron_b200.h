@@ -195,6 +195,13 @@ int qi_shard_rank(const qi_state* s);
 int qi_shard_world(const qi_state* s);
 /* bytes this rank moved over NVLink and the number of exchanges since creation */
 int qi_shard_comm_stats(const qi_state* s, uint64_t* bytes_sent, uint64_t* bytes_received, uint64_t* exchanges);
+/* logical qubit -> physical bit position (64 entries) and the number of local index bits: uncontrolled SWAP
+ * gates and global<->local exchanges only relabel this map.  qi_state_to_host / qi_state_amplitude undo it. */
+int qi_state_layout(const qi_state* s, uint8_t* phys, uint32_t* n_local);
+/* host-only planner (no device): number of global<->local exchanges the engine performs for a gate list on
+ * `world` ranks, the number of gates touching a global qubit that need NO communication, and the final map */
+int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* exchanges,
+                  uint64_t* comm_free_global_gates, uint8_t* final_phys);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ struct Context {
     int opt_fuse = 1;
     int opt_profile = 0;
     int opt_window_regs = 0;          // 0 = default
+    int opt_lazy_swap = 1;            // uncontrolled SWAP = relabelling of the qubit map
     // stats
     uint64_t launches[KF_COUNT] = {0};
     double alg_bytes[KF_COUNT] = {0};
@@ -101,7 +102,10 @@ struct qi_state {
     unsigned long long* peer_flags[8] = {nullptr};
     unsigned long long epoch = 0;
     uint64_t bytes_sent = 0, bytes_recv = 0, exchanges = 0;
+    uint64_t reduce_count = 0;          // parity selects the allreduce scratch buffer
+    uint64_t lookahead_remaining = 0;   // gates left in the current qi_apply_circuit call (eviction heuristic)
     bool attached = false;
+    bool identity_layout() const { for (uint32_t q = 0; q < num_qubits; q++) if (phys[q] != q) return false; return true; }
 };
 
 namespace qi {
@@ -194,5 +198,11 @@ int reduce_norm_sqr(const qi_state* s, double* out_local);
 int reduce_inner(const qi_state* a, const qi_state* b, double out_local[2]);
 
 int grid_for(uint64_t work_items, int block, int max_waves = 8);
+// state.cu
+int fill_state(qi_state* s, amp_t v);
+int set_amplitude(qi_state* s, uint64_t local_index, amp_t v);
+// gates.cu: undo lazy SWAP relabelling (physical swaps until logical qubit q sits at bit q)
+int canonicalise(qi_state* s);
+int shard_localise_mask(qi_state* s, const qi_pauli_term* t);
 
 }  // namespace qi

@@ -264,6 +264,33 @@ int launch_simple_gate(qi_state* s, const PhysGate& g) {
     return fail(QI_ERR_UNKNOWN, 0, 0, "unhandled internal gate kind");
 }
 
+// Undo lazy SWAP relabelling: physically swap bit positions until logical qubit q sits at bit q.
+int canonicalise(qi_state* s) {
+    if (s->identity_layout()) return QI_OK;
+    if (s->world > 1) return fail(QI_ERR_PEER, 0, 0, "canonicalise is not available on sharded states");
+    std::vector<PhysGate> swaps;
+    uint8_t phys[64];
+    memcpy(phys, s->phys, sizeof(phys));
+    for (uint32_t p = 0; p < s->num_qubits; p++) {
+        if (phys[p] == p) continue;
+        const int pp = phys[p];                 // logical p currently lives at physical pp
+        int q = -1;                             // logical qubit currently at physical p
+        for (uint32_t k = 0; k < s->num_qubits; k++) if (phys[k] == p) q = (int)k;
+        PhysGate g;
+        memset(&g, 0, sizeof(g));
+        g.kind = IK_SWAP;
+        g.t0 = (int)p;
+        g.t1 = pp;
+        swaps.push_back(g);
+        phys[p] = (uint8_t)p;
+        if (q >= 0) phys[q] = (uint8_t)pp;
+    }
+    if (ctx().opt_path != 1 && window_supported(s)) QI_TRY(run_circuit_windowed(s, swaps));
+    else for (const PhysGate& g : swaps) QI_TRY(launch_simple_gate(s, g));
+    for (int i = 0; i < 64; i++) s->phys[i] = (uint8_t)i;
+    return QI_OK;
+}
+
 }  // namespace qi
 
 using namespace qi;
@@ -314,9 +341,16 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
     for (uint64_t i = 0; i < count; i++) {
         PhysGate pg;
         bool skip = false;
+        if (gates[i].kind == QI_GATE_SWAP && gates[i].num_controls == 0 && c.opt_lazy_swap) {
+            // an uncontrolled SWAP is a relabelling of the logical->physical qubit map: no data moves now
+            // (gates queued before it were mapped with the old labels, later ones use the new ones)
+            std::swap(s->phys[gates[i].targets[0]], s->phys[gates[i].targets[1]]);
+            continue;
+        }
         if (s->world > 1 && shard_needs_exchange(s, &gates[i])) {
             // a global<->local qubit exchange changes the qubit map: queued gates must run first
             QI_TRY(flush());
+            s->lookahead_remaining = count - i;
             QI_TRY(shard_do_exchange(s, &gates[i]));
         }
         QI_TRY(prepare_gate(s, &gates[i], &pg, &skip));

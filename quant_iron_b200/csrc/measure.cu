@@ -201,39 +201,22 @@ static int check_qubits(const qi_state* s, const uint32_t* qubits, uint32_t m, s
     return QI_OK;
 }
 
-// device table of 2^m un-normalised probabilities (this rank's contribution when sharded)
-static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& qubits, double** d_probs_out) {
+// device table of 2^k un-normalised marginals over DISTINCT LOCAL bit positions (bin bit j <-> pos[j])
+static int local_table(const qi_state* s, const std::vector<int>& pos, double** d_probs_out) {
     Context& c = ctx();
-    const int m = (int)qubits.size();
+    const int m = (int)pos.size();
     if (m > 34) return fail(QI_ERR_INVALID_INPUT_VALUE, (uint64_t)m, 0, "probability table too large");
     const uint64_t nbins = 1ull << m;
     double* d_probs = nullptr;
     QI_CUDA(cudaMalloc(&d_probs, nbins * sizeof(double)));
-    // split measured qubits into local (index bits) and global (rank bits)
     BinMap bm;
     memset(&bm, 0, sizeof(bm));
     bm.m = m;
-    std::vector<int> local_pos;
-    uint64_t rank_sel = 0, rank_val_known = 0;
-    (void)rank_sel; (void)rank_val_known;
-    for (int j = 0; j < m; j++) {
-        int p = s->phys[qubits[j]];
-        bm.pos[j] = (uint8_t)p;
-        if (p < (int)s->n_local) local_pos.push_back(p);
-    }
-    // duplicates in `qubits` (the reference does not reject them): a repeated qubit pins two bin bits
-    // to the same index bit; handled by treating the position once for the expansion.
-    std::sort(local_pos.begin(), local_pos.end());
-    local_pos.erase(std::unique(local_pos.begin(), local_pos.end()), local_pos.end());
-    const int ml = (int)local_pos.size();
-    const uint64_t rest_total = s->len >> ml;
-    BitInsert ins = make_insert(local_pos, {});
-    if (s->world > 1 || ml != m) {
-        // sharded or duplicated qubits: bins whose global/duplicate bits disagree with this rank get 0.
-        // Handled by the generic serial kernel below through a host-side filter table.
-        cudaFree(d_probs);
-        return fail(QI_ERR_INVALID_INPUT_VALUE, 0, 0, "measurement of global or repeated qubits is not supported yet");
-    }
+    for (int j = 0; j < m; j++) bm.pos[j] = (uint8_t)pos[j];
+    std::vector<int> sorted(pos);
+    std::sort(sorted.begin(), sorted.end());
+    const uint64_t rest_total = s->len >> m;
+    BitInsert ins = make_insert(sorted, {});
     int st = QI_OK;
     if (rest_total >= 1024 && nbins <= 32768) {
         int chunks = (int)std::min<uint64_t>(std::max<uint64_t>(1, rest_total / 4096), std::max<uint64_t>(1, (uint64_t)(c.sm_count * 8) / nbins));
@@ -252,6 +235,57 @@ static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& 
     }
     if (st == QI_OK) st = check_launch("probabilities");
     if (st != QI_OK) { cudaFree(d_probs); return st; }
+    *d_probs_out = d_probs;
+    return QI_OK;
+}
+
+// device table of 2^m un-normalised probabilities over `qubits` (bin bit j <-> qubits[j], state.rs:567-571);
+// on a sharded state the table is summed over ranks, so every rank holds the same full table
+static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& qubits, double** d_probs_out) {
+    Context& c = ctx();
+    const int m = (int)qubits.size();
+    const int nl = (int)s->n_local;
+    std::vector<int> pos(m), local_pos;
+    bool plain = (s->world == 1);
+    for (int j = 0; j < m; j++) {
+        pos[j] = s->phys[qubits[j]];
+        if (pos[j] < nl) {
+            if (std::find(local_pos.begin(), local_pos.end(), pos[j]) == local_pos.end()) local_pos.push_back(pos[j]);
+            else plain = false;                 // repeated qubit (the reference does not reject it)
+        } else plain = false;
+    }
+    if (plain) return local_table(s, pos, d_probs_out);
+    // general case: local table over the distinct local positions, scattered into the full table on the
+    // host (bins whose rank bits / repeated bits disagree stay 0), then summed across ranks
+    if (m > 20) return fail(QI_ERR_INVALID_INPUT_VALUE, (uint64_t)m, 0, "too many measured qubits for a sharded state");
+    double* d_local = nullptr;
+    QI_TRY(local_table(s, local_pos, &d_local));
+    const uint64_t nloc = 1ull << local_pos.size(), nbins = 1ull << m;
+    std::vector<double> hl(nloc), full(nbins, 0.0);
+    cudaError_t e = cudaMemcpyAsync(hl.data(), d_local, nloc * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(d_local);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H local table");
+    for (uint64_t b = 0; b < nbins; b++) {
+        uint64_t lb = 0, seen = 0, val = 0;
+        bool ok = true;
+        for (int j = 0; j < m && ok; j++) {
+            const uint64_t bit = (b >> j) & 1;
+            if (pos[j] >= nl) { ok = (((uint64_t)s->rank >> (pos[j] - nl)) & 1) == bit; continue; }
+            const int k = (int)(std::find(local_pos.begin(), local_pos.end(), pos[j]) - local_pos.begin());
+            if ((seen >> k) & 1) ok = ((val >> k) & 1) == bit;
+            else { seen |= 1ull << k; val |= bit << k; lb |= bit << k; }
+        }
+        if (ok) full[b] = hl[lb];
+    }
+    if (s->world > 1)
+        for (uint64_t off = 0; off < nbins; off += 512)
+            QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(s), full.data() + off, (int)std::min<uint64_t>(512, nbins - off)));
+    double* d_probs = nullptr;
+    QI_CUDA(cudaMalloc(&d_probs, nbins * sizeof(double)));
+    e = cudaMemcpyAsync(d_probs, full.data(), nbins * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { cudaFree(d_probs); return cuda_fail(e, "H2D full table"); }
     *d_probs_out = d_probs;
     return QI_OK;
 }

@@ -231,8 +231,9 @@ int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t 
     for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &ms[k]));
     QI_TRY(ensure_ctx());
     if (s->world > 1) {
-        for (uint64_t k = 0; k < count; k++)
-            if (ms[k].x & ~(s->len - 1)) return fail(QI_ERR_PEER, k, 0, "expectation of a term with X/Y on a global qubit is not supported on a sharded state");
+        // a term with X/Y on a global qubit pairs amplitudes across ranks: bring that qubit into the local
+        // bits first (an exchange changes the layout, not the logical state), then re-derive every mask
+        // (done term by term below, right before each term's kernel is queued)
     }
     Context& c = ctx();
     int g = c.sm_count * 4;
@@ -245,6 +246,10 @@ int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t 
         QI_TRY(ensure_partials((size_t)g * 2 * nb));
         for (uint64_t k = 0; k < nb; k++) {
             const qi_pauli_term& t = terms[base + k];
+            if (s->world > 1) {
+                if (ms[base + k].x & ~(s->len - 1)) QI_TRY(shard_localise_mask(const_cast<qi_state*>(s), &t));
+                QI_TRY(term_masks(s, &t, &ms[base + k]));      // the layout may have changed since the first pass
+            }
             LaunchScope ls(KF_EXPECT, (ms[base + k].x ? 32.0 : 16.0) * (double)s->len);
             k_pauli_expect<<<g, kBlock, 0, c.stream>>>(s->d, s->len, ms[base + k], make_double2(t.coefficient[0], t.coefficient[1]),
                                                        (double2*)c.d_partials + (size_t)k * g);

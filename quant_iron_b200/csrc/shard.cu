@@ -1,31 +1,419 @@
-// shard.cu -- sharded state over 2/4/8 GPUs (placeholder until the exchange kernels land).
+// shard.cu -- state sharded over 2/4/8 GPUs of one NVSwitch domain (new work,
+// the reference is single-process and its oracle is the single-device result).
+//
+// Layout: amplitude index = [rank bits (top log2 P) | local bits].  One process per GPU; every rank
+// maps every peer's amplitude buffer and flag block through CUDA IPC (handles travel over
+// torch.distributed on the host side), so kernels address peer HBM directly over NVLink.
+//
+//   * gates on local targets run the ordinary kernels; a control on a rank bit enables/disables the
+//     whole rank; a DIAGONAL gate on a rank-bit target (Z,S,T,P,RZ, every QFT controlled phase) is a
+//     rank-dependent phase -- no communication;
+//   * a non-diagonal gate on a global qubit first swaps that qubit with a local one:
+//     k_exchange swaps half of this shard with half of the partner's (rank ^ 2^g) IN PLACE through
+//     peer loads/stores -- each rank moves one quarter shard out and one quarter in per direction,
+//     no staging buffer (a 64 GiB receive buffer does not fit beside a 128 GiB shard);
+//     the logical->physical qubit map absorbs the swap, nothing is swapped back;
+//   * an uncontrolled SWAP gate is only a relabelling of the map (also on a single GPU);
+//   * cross-rank synchronisation is a device-side flag barrier on the engine stream (no host sync);
+//   * reductions: each rank publishes its partial in its flag block, all ranks read all partials
+//     and add them in rank order (deterministic, identical on every rank).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace qi {
 
-int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip) {
-    (void)s; (void)g; (void)out; (void)skip;
-    return fail(QI_ERR_PEER, 0, 0, "sharded states are not available in this build");
+static const size_t kFlagBytes = 64 * 1024;      // per-rank flag block
+static const int kScratchOff = 64;               // in 8-byte words: [0..63] barrier flags, then 2 x 512 doubles
+static const int kScratchDoubles = 512;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-bool shard_needs_exchange(const qi_state* s, const qi_gate* g) { (void)s; (void)g; return false; }
-int shard_do_exchange(qi_state* s, const qi_gate* g) { (void)s; (void)g; return QI_OK; }
-int shard_allreduce_sum(qi_state* s, double* host_vals, int count) { (void)s; (void)host_vals; (void)count; return QI_OK; }
-int shard_localise_mask(qi_state* s, const qi_pauli_term* t) { (void)s; (void)t; return QI_OK; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct PeerPtrs { unsigned long long* f[8]; };
+
+// thread j: tell peer j "rank `me` reached epoch e", then wait until peer j has told me the same
+__global__ void k_barrier(PeerPtrs peers, unsigned long long* mine, int me, int world, unsigned long long epoch,
+                          unsigned long long* timeout_flag) {
+    int j = threadIdx.x;
+    if (j >= world) return;
+    __threadfence_system();
+    st_release_sys(peers.f[j] + me, epoch);
+    long long t0 = clock64();
+    while (ld_acquire_sys(mine + j) < epoch) {
+        if (clock64() - t0 > 40000000000ll) { *timeout_flag = epoch; break; }   // ~20 s: a peer died
+    }
+    __threadfence_system();
+}
+
+// In-place swap of a rank bit with local bit l between this rank and its partner.
+// This rank handles its own indices j with bit_l(j) = !my_bit and bit_h(j) = my_bit; the partner
+// handles the complementary half, so every element pair is touched by exactly one rank.
+__global__ void __launch_bounds__(256) k_exchange(amp_t* __restrict__ mine, amp_t* __restrict__ peer, uint64_t total,
+                                                  BitInsert ins, uint64_t lbit) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += 4 * stride) {
+        uint64_t j[4];
+        amp_t a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) j[u] = (k + u * stride < total) ? expand_index(k + u * stride, ins) : ~0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { a[u] = mine[j[u]]; b[u] = peer[j[u] ^ lbit]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { mine[j[u]] = b[u]; peer[j[u] ^ lbit] = a[u]; }
+    }
+}
+
+static int log2i(int w) { int p = 0; while ((1 << p) < w) p++; return p; }
+
+static int barrier(qi_state* s) {
+    Context& c = ctx();
+    if (!s->attached) return fail(QI_ERR_PEER, 0, 0, "shard is not attached to its peers (qi_shard_attach)");
+    PeerPtrs pp;
+    for (int r = 0; r < 8; r++) pp.f[r] = s->peer_flags[r];
+    s->epoch++;
+    LaunchScope ls(KF_BARRIER, 0.0);
+    k_barrier<<<1, 32, 0, c.stream>>>(pp, s->flags, s->rank, s->world, s->epoch, s->flags + 32);
+    return check_launch("k_barrier");
+}
+
+// position of logical qubit q / logical qubit at physical position p
+static int logical_at(const qi_state* s, int p) {
+    for (uint32_t q = 0; q < s->num_qubits; q++) if (s->phys[q] == p) return (int)q;
+    return -1;
+}
+
+int exchange_global_local(qi_state* s, int global_phys, int local_phys) {
+    Context& c = ctx();
+    const int nl = (int)s->n_local;
+    if (global_phys < nl || local_phys >= nl) return fail(QI_ERR_PEER, 0, 0, "bad exchange positions");
+    const int gbit = global_phys - nl;
+    const int partner = s->rank ^ (1 << gbit);
+    const int my_bit = (s->rank >> gbit) & 1;
+    int h = nl - 1;
+    if (h == local_phys) h--;
+    if (h < 0) return fail(QI_ERR_PEER, 0, 0, "shard too small to exchange");
+    QI_TRY(barrier(s));                               // everyone's earlier kernels are complete
+    std::vector<int> zeros, ones;
+    (my_bit ? zeros : ones).push_back(local_phys);   // bit_l = !my_bit
+    (my_bit ? ones : zeros).push_back(h);            // bit_h = my_bit
+    BitInsert ins = make_insert(zeros, ones);
+    const uint64_t total = s->len >> 2;
+    {
+        LaunchScope ls(KF_EXCHANGE, 16.0 * (double)s->len);   // quarter shard out + quarter in, read and written
+        int blocks = c.sm_count * 8;
+        k_exchange<<<blocks, 256, 0, c.stream>>>(s->d, s->peer_amp[partner], total, ins, 1ull << local_phys);
+    }
+    QI_TRY(check_launch("k_exchange"));
+    QI_TRY(barrier(s));                               // partner's half has landed before anything reads it
+    // per direction: the quarter shard this rank writes to / reads from the partner (4 B x len each)
+    // plus the quarter the partner reads from / writes to this rank = half a shard each way
+    s->bytes_sent += 8ull * s->len;
+    s->bytes_recv += 8ull * s->len;
+    s->exchanges++;
+    int qg = logical_at(s, global_phys), ql = logical_at(s, local_phys);
+    if (qg >= 0) s->phys[qg] = (uint8_t)local_phys;
+    if (ql >= 0) s->phys[ql] = (uint8_t)global_phys;
+    return QI_OK;
+}
+
+// choose the local position to evict: the one whose logical qubit is needed (non-diagonally) latest
+static int pick_local_slot(const qi_state* s, uint64_t avoid_phys, const qi_gate* upcoming, uint64_t n_upcoming) {
+    const int nl = (int)s->n_local;
+    int best = -1;
+    uint64_t best_next = 0;
+    for (int p = nl - 1; p >= 0; p--) {
+        if ((avoid_phys >> p) & 1) continue;
+        int q = logical_at(s, p);
+        uint64_t next = ~0ull;
+        for (uint64_t i = 0; i < n_upcoming && i < 4096; i++) {
+            const qi_gate& g = upcoming[i];
+            bool diag = g.kind == QI_GATE_Z || g.kind == QI_GATE_S || g.kind == QI_GATE_SDG || g.kind == QI_GATE_T ||
+                        g.kind == QI_GATE_TDG || g.kind == QI_GATE_P || g.kind == QI_GATE_RZ || g.kind == QI_GATE_I;
+            bool lazy_swap = g.kind == QI_GATE_SWAP && g.num_controls == 0;
+            if (diag || lazy_swap) continue;
+            bool hit = (int)g.targets[0] == q || (g.kind == QI_GATE_SWAP && (int)g.targets[1] == q) ||
+                       (g.kind == QI_GATE_MATCHGATE && (int)g.targets[0] + 1 == q);
+            if (hit) { next = i; break; }
+        }
+        // prefer high positions on ties (p counts down), and keep the lane qubits 0..4 unless nothing else is free
+        if (best < 0 || next > best_next || (next == best_next && p >= 5 && best < 5)) { best = p; best_next = next; }
+        if (next == ~0ull && p >= 5) break;
+    }
+    return best;
+}
+
+static bool is_diag_kind(int k) {
+    return k == QI_GATE_Z || k == QI_GATE_S || k == QI_GATE_SDG || k == QI_GATE_T || k == QI_GATE_TDG || k == QI_GATE_P ||
+           k == QI_GATE_RZ || k == QI_GATE_I;
+}
+
+// physical positions (of this gate's non-diagonal targets) that sit in the rank bits
+static uint64_t global_targets(const qi_state* s, const qi_gate* g) {
+    if (is_diag_kind(g->kind)) return 0;
+    if (g->kind == QI_GATE_SWAP && g->num_controls == 0) return 0;     // relabelled
+    uint64_t m = 0;
+    const int nl = (int)s->n_local;
+    auto add = [&](uint32_t q) { int p = s->phys[q]; if (p >= nl) m |= 1ull << p; };
+    add(g->targets[0]);
+    if (g->kind == QI_GATE_SWAP) add(g->targets[1]);
+    if (g->kind == QI_GATE_MATCHGATE) add(g->targets[0] + 1);
+    return m;
+}
+
+bool shard_needs_exchange(const qi_state* s, const qi_gate* g) { return s->world > 1 && global_targets(s, g) != 0; }
+
+int shard_do_exchange(qi_state* s, const qi_gate* g) {
+    // `g` points into the caller's gate array: what follows it is the lookahead for the eviction choice
+    uint64_t gm;
+    while ((gm = global_targets(s, g)) != 0) {
+        int gp = 63 - __builtin_clzll(gm);
+        uint64_t avoid = 0;
+        avoid |= 1ull << s->phys[g->targets[0]];
+        if (g->kind == QI_GATE_SWAP) avoid |= 1ull << s->phys[g->targets[1]];
+        if (g->kind == QI_GATE_MATCHGATE) avoid |= 1ull << s->phys[g->targets[0] + 1];
+        int lp = pick_local_slot(s, avoid, g + 1, s->lookahead_remaining ? s->lookahead_remaining - 1 : 0);
+        if (lp < 0) return fail(QI_ERR_PEER, 0, 0, "no local qubit available for the exchange");
+        QI_TRY(exchange_global_local(s, gp, lp));
+    }
+    return QI_OK;
+}
+
+// logical record -> physical record on this rank
+int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* o, bool* skip) {
+    const int nl = (int)s->n_local;
+    *skip = false;
+    o->cmask = 0;
+    for (uint32_t c = 0; c < g->num_controls; c++) {
+        int p = s->phys[g->controls[c]];
+        if (p >= nl) {
+            if (!((s->rank >> (p - nl)) & 1)) { *skip = true; return QI_OK; }   // control on a rank bit that is 0 here
+        } else o->cmask |= 1ull << p;
+    }
+    int t0 = s->phys[g->targets[0]];
+    o->t1 = -1;
+    if (o->kind == IK_DIAG || o->kind == IK_RZ) {
+        if (t0 >= nl) {
+            const int bit = (s->rank >> (t0 - nl)) & 1;
+            if (o->kind == IK_DIAG) { if (!bit) { *skip = true; return QI_OK; } }
+            else { if (bit) { o->p[0] = o->p[2]; o->p[1] = o->p[3]; } o->kind = IK_DIAG; }   // RZ: this rank's phase
+            t0 = -1;
+        }
+        o->t0 = t0;
+        return QI_OK;
+    }
+    if (t0 >= nl) return fail(QI_ERR_PEER, 0, 0, "internal: non-diagonal target still global");
+    o->t0 = t0;
+    if (g->kind == QI_GATE_SWAP) o->t1 = s->phys[g->targets[1]];
+    if (g->kind == QI_GATE_MATCHGATE) o->t1 = s->phys[g->targets[0] + 1];
+    if (o->t1 >= nl) return fail(QI_ERR_PEER, 0, 0, "internal: second target still global");
+    return QI_OK;
+}
+
+// make every X/Y qubit of a Pauli term local (exchanges as needed)
+int shard_localise_mask(qi_state* s, const qi_pauli_term* t) {
+    const int nl = (int)s->n_local;
+    for (;;) {
+        uint64_t avoid = 0;
+        int gp = -1;
+        for (uint32_t i = 0; i < t->num_ops; i++) {
+            if (t->paulis[i] == 3) continue;
+            int p = s->phys[t->qubits[i]];
+            if (p >= nl) gp = p; else avoid |= 1ull << p;
+        }
+        if (gp < 0) return QI_OK;
+        int lp = pick_local_slot(s, avoid, nullptr, 0);
+        if (lp < 0) return fail(QI_ERR_PEER, 0, 0, "no local qubit available for the exchange");
+        QI_TRY(exchange_global_local(s, gp, lp));
+    }
+}
+
+// sum host values across ranks in rank order; every rank gets the identical result
+int shard_allreduce_sum(qi_state* s, double* vals, int count) {
+    if (s->world == 1) return QI_OK;
+    Context& c = ctx();
+    if (count > kScratchDoubles) return fail(QI_ERR_PEER, (uint64_t)count, 0, "allreduce payload too large");
+    const int parity = (int)(s->reduce_count++ & 1);
+    double* my_scratch = (double*)(s->flags + kScratchOff) + parity * kScratchDoubles;
+    QI_CUDA(cudaMemcpyAsync(my_scratch, vals, count * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    QI_TRY(barrier(s));
+    std::vector<double> all((size_t)s->world * count);
+    for (int r = 0; r < s->world; r++) {
+        const double* src = (const double*)(s->peer_flags[r] + kScratchOff) + parity * kScratchDoubles;
+        QI_CUDA(cudaMemcpyAsync(all.data() + (size_t)r * count, src, count * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    }
+    QI_CUDA(cudaStreamSynchronize(c.stream));
+    unsigned long long timed_out = 0;
+    QI_CUDA(cudaMemcpy(&timed_out, s->flags + 32, sizeof(timed_out), cudaMemcpyDeviceToHost));
+    if (timed_out) return fail(QI_ERR_PEER, timed_out, 0, "device barrier timed out: a peer rank is gone");
+    for (int i = 0; i < count; i++) {
+        double acc = 0.0;
+        for (int r = 0; r < s->world; r++) acc += all[(size_t)r * count + i];
+        vals[i] = acc;
+    }
+    return QI_OK;
+}
+
+static int alloc_shard(uint32_t total_qubits, int rank, int world, qi_state** out) {
+    if (!out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "out is NULL");
+    if (world != 1 && world != 2 && world != 4 && world != 8) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "world must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= world) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)rank, 0, "rank out of range");
+    const int p = log2i(world);
+    if (total_qubits == 0) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, 0, 0, "Invalid number of qubits: 0");
+    if ((int)total_qubits < p + 7) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, total_qubits, 0, "a shard needs at least 7 local qubits");
+    QI_TRY(ensure_ctx());
+    qi_state* s = new qi_state();
+    s->num_qubits = total_qubits;
+    s->n_local = total_qubits - p;
+    s->len = 1ull << s->n_local;
+    s->consistent = true;
+    s->rank = rank;
+    s->world = world;
+    for (int i = 0; i < 64; i++) s->phys[i] = (uint8_t)i;
+    cudaError_t e = cudaMalloc(&s->d, s->len * sizeof(amp_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->flags, kFlagBytes);
+    if (e == cudaSuccess) e = cudaMemset(s->flags, 0, kFlagBytes);
+    if (e != cudaSuccess) { if (s->d) cudaFree(s->d); if (s->flags) cudaFree(s->flags); delete s; return cuda_fail(e, "cudaMalloc(shard)"); }
+    s->peer_amp[rank] = s->d;
+    s->peer_flags[rank] = s->flags;
+    if (world == 1) s->attached = true;
+    *out = s;
+    return QI_OK;
+}
 
 }  // namespace qi
 
+using namespace qi;
+
 extern "C" {
-void qi_shard_release(qi_state* s) { (void)s; }
-int qi_shard_new_zero(uint32_t, int, int, qi_state**) { return qi::fail(QI_ERR_PEER, 0, 0, "not built"); }
-int qi_shard_new_plus(uint32_t, int, int, qi_state**) { return qi::fail(QI_ERR_PEER, 0, 0, "not built"); }
-int qi_shard_new_basis_n(uint32_t, uint64_t, int, int, qi_state**) { return qi::fail(QI_ERR_PEER, 0, 0, "not built"); }
-int qi_shard_export(qi_state*, uint8_t*) { return qi::fail(QI_ERR_PEER, 0, 0, "not built"); }
-int qi_shard_attach(qi_state*, const uint8_t*) { return qi::fail(QI_ERR_PEER, 0, 0, "not built"); }
-int qi_shard_rank(const qi_state* s) { return s ? s->rank : 0; }
-int qi_shard_world(const qi_state* s) { return s ? s->world : 1; }
-int qi_shard_comm_stats(const qi_state* s, uint64_t* a, uint64_t* b, uint64_t* c) {
-    if (!s) return qi::fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
-    if (a) *a = s->bytes_sent; if (b) *b = s->bytes_recv; if (c) *c = s->exchanges;
+
+void qi_shard_release(qi_state* s) {
+    if (!s || s->world <= 1) { if (s && s->flags) { cudaFree(s->flags); s->flags = nullptr; } return; }
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) continue;
+        if (s->peer_amp[r]) cudaIpcCloseMemHandle(s->peer_amp[r]);
+        if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
+    }
+    if (s->flags) cudaFree(s->flags);
+    s->flags = nullptr;
+}
+
+int qi_shard_new_zero(uint32_t n, int rank, int world, qi_state** out) {
+    QI_TRY(alloc_shard(n, rank, world, out));
+    QI_TRY(fill_state(*out, make_double2(0.0, 0.0)));
+    if (rank == 0) QI_TRY(set_amplitude(*out, 0, make_double2(1.0, 0.0)));
     return QI_OK;
 }
+
+int qi_shard_new_plus(uint32_t n, int rank, int world, qi_state** out) {
+    QI_TRY(alloc_shard(n, rank, world, out));
+    // 1/sqrt(2^n) with the reference's expression (state.rs:230); 2^n is exact in f64 up to n = 1023
+    return fill_state(*out, make_double2(1.0 / std::sqrt(std::ldexp(1.0, (int)n)), 0.0));
 }
+
+int qi_shard_new_basis_n(uint32_t n, uint64_t k, int rank, int world, qi_state** out) {
+    if (n >= 64 || k >= (1ull << n)) return fail(QI_ERR_INVALID_QUBIT_INDEX, k, n, "basis index out of range");
+    QI_TRY(alloc_shard(n, rank, world, out));
+    qi_state* s = *out;
+    QI_TRY(fill_state(s, make_double2(0.0, 0.0)));
+    if ((k >> s->n_local) == (uint64_t)rank) QI_TRY(set_amplitude(s, k & (s->len - 1), make_double2(1.0, 0.0)));
+    return QI_OK;
+}
+
+int qi_shard_export(qi_state* s, uint8_t* handles) {
+    if (!s || !handles) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == QI_IPC_HANDLE_BYTES, "IPC handle size");
+    QI_TRY(ensure_ctx());
+    cudaIpcMemHandle_t h;
+    QI_CUDA(cudaIpcGetMemHandle(&h, s->d));
+    memcpy(handles, &h, sizeof(h));
+    QI_CUDA(cudaIpcGetMemHandle(&h, s->flags));
+    memcpy(handles + QI_IPC_HANDLE_BYTES, &h, sizeof(h));
+    return QI_OK;
+}
+
+int qi_shard_attach(qi_state* s, const uint8_t* all_handles) {
+    if (!s || !all_handles) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    QI_TRY(ensure_ctx());
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) continue;
+        cudaIpcMemHandle_t h;
+        void* p = nullptr;
+        memcpy(&h, all_handles + (size_t)r * 2 * QI_IPC_HANDLE_BYTES, sizeof(h));
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { set_error((uint64_t)e, (uint64_t)r, "cudaIpcOpenMemHandle(amplitudes of rank %d): %s", r, cudaGetErrorString(e)); cudaGetLastError(); return QI_ERR_PEER; }
+        s->peer_amp[r] = (amp_t*)p;
+        memcpy(&h, all_handles + (size_t)r * 2 * QI_IPC_HANDLE_BYTES + QI_IPC_HANDLE_BYTES, sizeof(h));
+        e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { set_error((uint64_t)e, (uint64_t)r, "cudaIpcOpenMemHandle(flags of rank %d): %s", r, cudaGetErrorString(e)); cudaGetLastError(); return QI_ERR_PEER; }
+        s->peer_flags[r] = (unsigned long long*)p;
+    }
+    s->attached = true;
+    return QI_OK;
+}
+
+int qi_shard_rank(const qi_state* s) { return s ? s->rank : 0; }
+int qi_shard_world(const qi_state* s) { return s ? s->world : 1; }
+
+int qi_shard_comm_stats(const qi_state* s, uint64_t* sent, uint64_t* recv, uint64_t* exchanges) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    if (sent) *sent = s->bytes_sent;
+    if (recv) *recv = s->bytes_recv;
+    if (exchanges) *exchanges = s->exchanges;
+    return QI_OK;
+}
+
+int qi_state_layout(const qi_state* s, uint8_t* phys, uint32_t* n_local) {
+    if (!s || !phys) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    memcpy(phys, s->phys, 64);
+    if (n_local) *n_local = s->n_local;
+    return QI_OK;
+}
+
+// Host-only planner: how many global<->local exchanges a gate list needs on `world` ranks, following
+// exactly the decisions the engine takes (no device access; used by tests and DESIGN.md tables).
+int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* exchanges,
+                  uint64_t* comm_free_global_gates, uint8_t* final_phys) {
+    if (world != 1 && world != 2 && world != 4 && world != 8) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "world must be 1, 2, 4 or 8");
+    qi_state s;
+    s.num_qubits = total_qubits;
+    s.n_local = total_qubits - log2i(world);
+    s.len = 1ull << s.n_local;
+    s.world = world;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    uint64_t ex = 0, freeg = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        QI_TRY(validate_gate(&s, &gates[i]));
+        const qi_gate* g = &gates[i];
+        if (g->kind == QI_GATE_SWAP && g->num_controls == 0) { std::swap(s.phys[g->targets[0]], s.phys[g->targets[1]]); continue; }
+        uint64_t gm;
+        while ((gm = global_targets(&s, g)) != 0) {
+            int gp = 63 - __builtin_clzll(gm);
+            uint64_t avoid = 1ull << s.phys[g->targets[0]];
+            if (g->kind == QI_GATE_SWAP) avoid |= 1ull << s.phys[g->targets[1]];
+            if (g->kind == QI_GATE_MATCHGATE) avoid |= 1ull << s.phys[g->targets[0] + 1];
+            int lp = pick_local_slot(&s, avoid, g + 1, count - i - 1);
+            if (lp < 0) return fail(QI_ERR_PEER, 0, 0, "no local qubit available");
+            int qg = logical_at(&s, gp), ql = logical_at(&s, lp);
+            s.phys[qg] = (uint8_t)lp;
+            s.phys[ql] = (uint8_t)gp;
+            ex++;
+        }
+        bool touches_global = false;
+        for (uint32_t c = 0; c < g->num_controls; c++) touches_global |= s.phys[g->controls[c]] >= s.n_local;
+        touches_global |= s.phys[g->targets[0]] >= s.n_local;
+        if (touches_global) freeg++;
+    }
+    if (exchanges) *exchanges = ex;
+    if (comm_free_global_gates) *comm_free_global_gates = freeg;
+    if (final_phys) memcpy(final_phys, s.phys, 64);
+    return QI_OK;
+}
+
+}  // extern "C"

@@ -189,6 +189,11 @@ static int alloc_state(uint32_t num_qubits, uint64_t len, qi_state** out) {
     return QI_OK;
 }
 
+int set_amplitude(qi_state* s, uint64_t local_index, amp_t v) {
+    k_set_one<<<1, 1, 0, ctx().stream>>>(s->d, local_index, v);
+    return check_launch("set_amplitude");
+}
+
 int fill_state(qi_state* s, amp_t v) {
     if (!s->len) return QI_OK;
     LaunchScope ls(KF_INIT, 16.0 * (double)s->len);
@@ -297,6 +302,7 @@ int qi_state_to_host(const qi_state* s, double* amps, uint64_t len) {
     if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
     if (len != s->len) return fail(QI_ERR_INVALID_ARGUMENT, len, s->len, "length mismatch");
     QI_TRY(ensure_ctx());
+    if (s->world == 1 && !s->identity_layout()) QI_TRY(canonicalise(const_cast<qi_state*>(s)));   // lazy SWAPs become real
     if (len) {
         QI_CUDA(cudaMemcpyAsync(amps, s->d, len * sizeof(amp_t), cudaMemcpyDeviceToHost, ctx().stream));
     }
@@ -333,12 +339,21 @@ void* qi_state_device_ptr(qi_state* s) { return s ? (void*)s->d : nullptr; }
 
 int qi_state_amplitude(const qi_state* s, uint64_t n, double out[2]) {
     if (!s || !out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
-    if (n >= s->len) return fail(QI_ERR_INVALID_QUBIT_INDEX, n, s->num_qubits, "amplitude index out of range");
+    if (n >= ((uint64_t)s->len << (s->num_qubits - s->n_local)) || (s->world == 1 && n >= s->len))
+        return fail(QI_ERR_INVALID_QUBIT_INDEX, n, s->num_qubits, "amplitude index out of range");
     QI_TRY(ensure_ctx());
-    QI_CUDA(cudaMemcpyAsync(ctx().h_result, s->d + n, sizeof(amp_t), cudaMemcpyDeviceToHost, ctx().stream));
+    uint64_t pidx = n;
+    if (s->consistent) {     // logical index -> physical index (lazy SWAPs, global<->local exchanges)
+        pidx = 0;
+        for (uint32_t q = 0; q < s->num_qubits; q++) pidx |= ((n >> q) & 1ull) << s->phys[q];
+    }
+    ctx().h_result[0] = ctx().h_result[1] = 0.0;
+    if ((pidx >> s->n_local) == (uint64_t)s->rank || s->world == 1)
+        QI_CUDA(cudaMemcpyAsync(ctx().h_result, s->d + (pidx & (s->len - 1)), sizeof(amp_t), cudaMemcpyDeviceToHost, ctx().stream));
     QI_CUDA(cudaStreamSynchronize(ctx().stream));
     out[0] = ctx().h_result[0];
     out[1] = ctx().h_result[1];
+    if (s->world > 1) QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(s), out, 2));   // only the owner rank holds it
     return QI_OK;
 }
 
@@ -370,6 +385,11 @@ int qi_inner_product(const qi_state* a, const qi_state* b, double out[2]) {
     if (a->num_qubits == 0 || b->num_qubits == 0) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, 0, 0, "zero qubits");
     if (a->len != b->len) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, a->num_qubits, 0, "length mismatch");
     QI_TRY(ensure_ctx());
+    if (memcmp(a->phys, b->phys, sizeof(a->phys)) != 0) {
+        if (a->world > 1) return fail(QI_ERR_PEER, 0, 0, "inner product of sharded states with different qubit layouts");
+        QI_TRY(canonicalise(const_cast<qi_state*>(a)));
+        QI_TRY(canonicalise(const_cast<qi_state*>(b)));
+    }
     QI_TRY(reduce_inner(a, b, out));
     if (a->world > 1) QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(a), out, 2));
     return QI_OK;
@@ -403,6 +423,11 @@ static int addsub(qi_state* a, const qi_state* b, int sign) {
         return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, b->num_qubits, 0, "Cannot add/subtract states with different numbers of qubits");
     QI_TRY(ensure_ctx());
     if (!a->len) return QI_OK;
+    if (memcmp(a->phys, b->phys, sizeof(a->phys)) != 0) {
+        if (a->world > 1) return fail(QI_ERR_PEER, 0, 0, "sharded states with different qubit layouts");
+        QI_TRY(canonicalise(a));
+        QI_TRY(canonicalise(const_cast<qi_state*>(b)));
+    }
     LaunchScope ls(KF_ELEMENTWISE, 48.0 * (double)a->len);
     if (sign > 0) k_addsub<1><<<grid_for(a->len, kBlock), kBlock, 0, ctx().stream>>>(a->d, b->d, a->len);
     else k_addsub<-1><<<grid_for(a->len, kBlock), kBlock, 0, ctx().stream>>>(a->d, b->d, a->len);
@@ -427,6 +452,8 @@ int qi_tensor_product(const qi_state* a, const qi_state* b, qi_state** out) {
         return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "tensor_product needs whole, consistent states");
     uint32_t n = a->num_qubits + b->num_qubits;
     QI_TRY(check_nq(n));
+    QI_TRY(canonicalise(const_cast<qi_state*>(a)));
+    QI_TRY(canonicalise(const_cast<qi_state*>(b)));
     QI_TRY(alloc_state(n, 1ull << n, out));
     qi_state* s = *out;
     {
