@@ -247,8 +247,11 @@ int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t 
         for (uint64_t k = 0; k < nb; k++) {
             const qi_pauli_term& t = terms[base + k];
             if (s->world > 1) {
-                if (ms[base + k].x & ~(s->len - 1)) QI_TRY(shard_localise_mask(const_cast<qi_state*>(s), &t));
                 QI_TRY(term_masks(s, &t, &ms[base + k]));      // the layout may have changed since the first pass
+                if (ms[base + k].x & ~(s->len - 1)) {
+                    QI_TRY(shard_localise_mask(const_cast<qi_state*>(s), &t));
+                    QI_TRY(term_masks(s, &t, &ms[base + k]));
+                }
             }
             LaunchScope ls(KF_EXPECT, (ms[base + k].x ? 32.0 : 16.0) * (double)s->len);
             k_pauli_expect<<<g, kBlock, 0, c.stream>>>(s->d, s->len, ms[base + k], make_double2(t.coefficient[0], t.coefficient[1]),
