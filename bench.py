@@ -151,18 +151,18 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from quant_iron_b200 import workloads as w
-    n = args.qubits
+    n = args.qubits + (world.bit_length() - 1)       # same total size as the GPU arm at this N
     specs = w.random_layered_circuit(n, args.depth)
     vals, base = [], None
     budget = min(args.cpu_budget, 150.0 / (args.warmup + args.steps))   # whole run ends within a few minutes
     for i in range(args.warmup + args.steps):
         base = cpu_baseline(n, specs, budget_s=budget)
         if i >= args.warmup:
-            vals.append(base["scaled_to_bench_qubits"])
+            vals.append(base["scaled_to_bench_qubits"] * world)     # unit of work: gate x 2^n_per_gpu shard (see config)
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * len(specs) / value, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * len(specs) * world / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth}, {n} qubits "
                                f"(CPU sample measured at {base['qubits']} qubits, scaled by 2^-{n - base['qubits']})"},
@@ -254,7 +254,10 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = n_gates / (ms_per_step * 1e-3)
+    # unit of work: one gate applied to one 2^n_local-amplitude shard; a gate on the N-GPU state is N units
+    # (weak scaling: the per-GPU work of a gate is the same at every N)
+    raw_gates_per_sec = n_gates / (ms_per_step * 1e-3)
+    value = raw_gates_per_sec * world
     launches = sum(v["launches"] for v in stats.values())
 
     # roofline of the dominant kernel: per-launch event timing in a separate (profiled) pass
@@ -269,50 +272,73 @@ def run_ours(args, rank, world, local_rank):
     avg_ms = d["total_ms"] / d["launches"]
     bytes_per_launch = d["algorithmic_bytes"] / d["launches"]
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dname)
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": d["launches"], "avg_launch_ms": avg_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "share_of_step": d["total_ms"] / max(1e-9, sum(v["total_ms"] for v in prof.values()))}
+                "share_of_step": d["total_ms"] / max(1e-9, sum(v["total_ms"] for v in prof.values())),
+                "per_kernel_ms": {k: round(v["total_ms"], 3) for k, v in prof.items()}}
     norm = state.norm_sqr()
+    comm = None
+    if world > 1:
+        from quant_iron_b200 import sharded
+        cs = sharded.comm_stats(state)
+        per_step_ex = cs["exchanges"] / (args.warmup + args.steps + 1)
+        ex_ms = prof.get("exchange", {}).get("total_ms", 0.0)
+        comm = {"exchanges_per_step": per_step_ex, "bytes_sent_per_rank_per_step": cs["bytes_sent"] / (args.warmup + args.steps + 1),
+                "exchange_ms_per_step": ex_ms,
+                "nvlink_gbs_per_gpu_per_direction": (cs["bytes_sent"] / (args.warmup + args.steps + 1)) / max(1e-9, ex_ms * 1e-3) / 1e9}
+
+    # ---- e2e through the public API with HOST buffers: H2D of the initial state from pinned memory,
+    # the circuit, D2H of the final state, all inside the timed region; every rank moves its own shard ----
+    e2e = None
+    try:
+        if args.skip_e2e:
+            raise RuntimeError("skipped (--skip-e2e)")
+        host_in = torch.zeros(1 << n_local, dtype=torch.complex128).pin_memory()
+        host_out = torch.empty(1 << n_local, dtype=torch.complex128).pin_memory()
+        if rank == 0:
+            host_in[0] = 1.0
+        hin, hout = host_in.numpy(), host_out.numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        times = []
+        for i in range(1 + e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            state.upload_(hin)                             # H2D of the initial state (pinned)
+            circuit.execute_(state)
+            if world > 1:
+                state.to_host(hout)                        # D2H of this rank's shard of the final state
+            else:
+                state.to_host(hout)                        # D2H of the final state (logical order)
+            barrier()
+            dt = time.perf_counter() - t0
+            if i > 0:
+                times.append(dt)
+        tt = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_val = n_gates * world / float(tt.item())
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (16 * (1 << n_local)) + 88 * n_gates,
+               "d2h_bytes_per_step": world * 16 * (1 << n_local), "qubits": n, "steps": e2e_steps,
+               "seconds_per_step": float(tt.item()),
+               "checksum_norm_first_64k": float(np.vdot(hout[:1 << 16], hout[:1 << 16]).real)}
+        del host_in, host_out, hin, hout
+    except Exception as ex:  # noqa: BLE001
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     del state
 
     if rank != 0:
         if dist is not None:
             dist.barrier()
         return
-
-    # ---- e2e through the public API with host buffers (rank 0, single GPU semantics) ----
-    e2e = None
-    try:
-        if args.skip_e2e:
-            raise RuntimeError("skipped (--skip-e2e)")
-        n_e = n_local if world == 1 else min(n_local, 28)
-        specs_e = specs if world == 1 else w.random_layered_circuit(n_e, args.depth)
-        circ_e = circuit if world == 1 else w.build_circuit(qi, n_e, specs_e)
-        host_in = torch.zeros(1 << n_e, dtype=torch.complex128).pin_memory()
-        host_out = torch.empty(1 << n_e, dtype=torch.complex128).pin_memory()
-        host_in[0] = 1.0
-        hin, hout = host_in.numpy(), host_out.numpy()
-        e2e_steps = max(1, min(args.steps, 3))
-        times = []
-        for i in range(1 + e2e_steps):
-            qi.engine.synchronize()
-            t0 = time.perf_counter()
-            s = qi.State.from_host(hin, check=False)       # H2D of the initial state (pinned)
-            circ_e.execute_(s)
-            s.to_host(hout)                                 # D2H of the final state
-            dt = time.perf_counter() - t0
-            del s
-            if i > 0:
-                times.append(dt)
-        e2e_val = len(specs_e) / (sum(times) / len(times))
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 16 * (1 << n_e) + 88 * len(specs_e),
-               "d2h_bytes_per_step": 16 * (1 << n_e), "qubits": n_e, "steps": e2e_steps,
-               "checksum_norm": float(np.vdot(hout[:1 << 16], hout[:1 << 16]).real)}
-        del host_in, host_out, hin, hout
-    except Exception as ex:  # noqa: BLE001
-        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
     extras = {}
     if world == 1 and not args.skip_extras:
@@ -351,12 +377,15 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth} (BASELINE configs[1] generator, "
                                f"seed 20260001) at {n_local} qubits per GPU ({n} qubits total), state resident in HBM",
                    "qubits": n, "gates_per_step": n_gates, "state_bytes_per_gpu": 16 * (1 << n_local),
-                   "l2": "inputs (16 GiB state) far larger than the 126 MB L2; no flush needed",
+                   "unit_of_work": "one gate applied to one 2^30-amplitude shard; a gate on the N-GPU state counts N "
+                                   "(value = gates/s x N; raw_gates_per_sec is the literal circuit-gate rate)",
+                   "raw_gates_per_sec": raw_gates_per_sec,
+                   "l2": "inputs (16 GiB state per GPU) far larger than the 126 MB L2; no flush needed",
                    "unfused_algorithmic_bytes_per_step": w.algorithmic_bytes(n, specs),
-                   "effective_gbs_vs_unfused_bytes": w.algorithmic_bytes(n, specs) / world / (ms_per_step * 1e-3) / 1e9},
+                   "effective_gbs_per_gpu_vs_unfused_bytes": w.algorithmic_bytes(n, specs) / world / (ms_per_step * 1e-3) / 1e9},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "kernels": {k: v["launches"] for k, v in stats.items()}, "clocks": clocks,
-        "final_norm_sqr": norm, "extras": extras,
+        "final_norm_sqr": norm, "comm": comm, "extras": extras,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -86,6 +86,7 @@ int qi_state_new_ghz(uint32_t num_qubits, qi_state** out);                    /*
  * (len need not be 2^num_qubits then, as in state_tests.rs:145-150). amps = len interleaved (re,im). */
 int qi_state_from_host(const double* amps, uint64_t len, uint32_t num_qubits, int check, qi_state** out);
 int qi_state_to_host(const qi_state* s, double* amps, uint64_t len);          /* read `state_vector` */
+int qi_state_upload(qi_state* s, const double* amps, uint64_t len);           /* overwrite `state_vector` (this rank's shard) from host */
 int qi_state_clone(const qi_state* s, qi_state** out);                        /* #[derive(Clone)] state.rs:69 */
 void qi_state_free(qi_state* s);
 uint32_t qi_state_num_qubits(const qi_state* s);                              /* state.rs:431 */

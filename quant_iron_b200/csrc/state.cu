@@ -310,6 +310,16 @@ int qi_state_to_host(const qi_state* s, double* amps, uint64_t len) {
     return QI_OK;
 }
 
+int qi_state_upload(qi_state* s, const double* amps, uint64_t len) {
+    if (!s || (len && !amps)) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    if (len != s->len) return fail(QI_ERR_INVALID_ARGUMENT, len, s->len, "length mismatch");
+    QI_TRY(ensure_ctx());
+    if (len) QI_CUDA(cudaMemcpyAsync(s->d, amps, len * sizeof(amp_t), cudaMemcpyHostToDevice, ctx().stream));
+    QI_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (int i = 0; i < 64; i++) s->phys[i] = (uint8_t)i;     // host data is in logical (identity) order
+    return QI_OK;
+}
+
 int qi_state_clone(const qi_state* s, qi_state** out) {
     if (!s || !out) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
     if (s->world > 1) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "sharded states cannot be cloned (no room for a second shard)");

@@ -587,6 +587,14 @@ static int ensure_tables(size_t count) {
 
 struct Step { bool simple; size_t gate; Pass pass; };
 
+// fraction of the amplitudes a gate can change (f)
+static double touched_fraction(const PhysGate& g) {
+    double f = 1.0 / (double)(1ull << __builtin_popcountll(g.cmask));
+    if (g.kind == IK_DIAG && g.t0 >= 0) f *= 0.5;
+    if (g.kind == IK_SWAP) f *= 0.5;
+    return f;
+}
+
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     Context& c = ctx();
     const bool fuse = c.opt_fuse != 0;
@@ -605,7 +613,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
         }
         Pass ps;
         uint64_t blocked_any = 0, blocked_n = 0, window_mask = 0;
-        size_t scanned = 0;
+        size_t scanned = 0, taken = 0, last_taken = 0;
         for (size_t i = first; i < G && scanned < kLookahead; i++) {
             if (done[i]) continue;
             scanned++;
@@ -624,6 +632,8 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
             if (take) {
                 lower_gate(ps, g, fuse);
                 done[i] = 1;
+                taken++;
+                last_taken = i;
                 if (!fuse) break;
             } else {
                 blocked_any |= u.n_use | u.d_use;
@@ -631,6 +641,12 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
             }
         }
         if (ps.ops.empty()) return fail(QI_ERR_UNKNOWN, 0, 0, "scheduler made no progress");
+        if (taken == 1 && touched_fraction(gates[last_taken]) <= 0.5) {
+            // a lone gate that can change at most half of the amplitudes: the per-gate kernel visits only
+            // those (controls and the phase target are folded into its index expansion) and beats a full pass
+            steps.push_back(Step{true, last_taken, Pass()});
+            continue;
+        }
         steps.push_back(Step{false, 0, std::move(ps)});
     }
     // lower every pass, upload all phase tables in one copy, then launch back to back

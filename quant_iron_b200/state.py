@@ -69,6 +69,12 @@ class State:
         _ffi.check(_lib.qi_state_to_host(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0]))
         return out
 
+    def upload_(self, state_vector: np.ndarray) -> "State":
+        """Overwrite the amplitudes (this rank's shard for a sharded state) from a host array."""
+        v = np.ascontiguousarray(state_vector, dtype=np.complex128)
+        _ffi.check(_lib.qi_state_upload(self._h, v.ctypes.data_as(C.c_void_p), v.shape[0]))
+        return self
+
     def clone(self) -> "State":
         return State(_handle=_new_handle(_lib.qi_state_clone, self._h))
 
