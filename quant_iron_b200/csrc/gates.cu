@@ -15,45 +15,86 @@ static const int kBlock = 256;
 // ---- kernels ------------------------------------------------------------------------------------
 struct U2 { amp_t m00, m01, m10, m11; };
 
+// Each thread handles kUnroll independent items (loads first, then arithmetic, then stores) so that
+// 2 * kUnroll 16-byte requests are in flight per thread.
+static const int kUnroll = 4;
+
 template <int IK>
 __global__ void __launch_bounds__(256) k_pair(amp_t* __restrict__ a, uint64_t total, BitInsert ins, uint64_t tbit, U2 u) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total) return;
-    uint64_t i0 = expand_index(k, ins);
-    uint64_t i1 = i0 | tbit;
-    amp_t a0 = ld_amp(a + i0), a1 = ld_amp(a + i1);
-    amp_t r0, r1;
-    if (IK == IK_H) {            // operator.rs:401-402: s*(a0+a1), s*(a0-a1)
-        const double s = u.m00.x;
-        r0 = cscale(s, cadd(a0, a1));
-        r1 = cscale(s, csub(a0, a1));
-    } else if (IK == IK_X) {     // operator.rs:579-580
-        r0 = a1; r1 = a0;
-    } else if (IK == IK_Y) {     // operator.rs:588-589: -i*a1, i*a0
-        r0 = make_double2(a1.y, -a1.x);
-        r1 = make_double2(-a0.y, a0.x);
-    } else {                     // operator.rs:2246-2247
-        r0 = cadd(cmul(u.m00, a0), cmul(u.m01, a1));
-        r1 = cadd(cmul(u.m10, a0), cmul(u.m11, a1));
+    const uint64_t quarter = (total + kUnroll - 1) / kUnroll;
+    const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= quarter) return;
+    uint64_t i0[kUnroll];
+    amp_t a0[kUnroll], a1[kUnroll];
+    bool on[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint64_t k = k0 + (uint64_t)j * quarter;
+        on[j] = k < total;
+        i0[j] = expand_index(on[j] ? k : 0, ins);
     }
-    st_amp(a + i0, r0);
-    st_amp(a + i1, r1);
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) if (on[j]) { a0[j] = ld_amp(a + i0[j]); a1[j] = ld_amp(a + (i0[j] | tbit)); }
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        if (!on[j]) continue;
+        amp_t r0, r1;
+        if (IK == IK_H) {            // operator.rs:401-402: s*(a0+a1), s*(a0-a1)
+            const double s = u.m00.x;
+            r0 = cscale(s, cadd(a0[j], a1[j]));
+            r1 = cscale(s, csub(a0[j], a1[j]));
+        } else if (IK == IK_X) {     // operator.rs:579-580
+            r0 = a1[j]; r1 = a0[j];
+        } else if (IK == IK_Y) {     // operator.rs:588-589: -i*a1, i*a0
+            r0 = make_double2(a1[j].y, -a1[j].x);
+            r1 = make_double2(-a0[j].y, a0[j].x);
+        } else {                     // operator.rs:2246-2247
+            r0 = cadd(cmul(u.m00, a0[j]), cmul(u.m01, a1[j]));
+            r1 = cadd(cmul(u.m10, a0[j]), cmul(u.m11, a1[j]));
+        }
+        st_amp(a + i0[j], r0);
+        st_amp(a + (i0[j] | tbit), r1);
+    }
 }
 
 // amp *= phase on every index the expansion produces (target bit and controls forced to 1)
 __global__ void __launch_bounds__(256) k_diag(amp_t* __restrict__ a, uint64_t total, BitInsert ins, amp_t phase) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total) return;
-    uint64_t i = expand_index(k, ins);
-    st_amp(a + i, cmul(ld_amp(a + i), phase));
+    const uint64_t quarter = (total + kUnroll - 1) / kUnroll;
+    const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= quarter) return;
+    uint64_t idx[kUnroll];
+    amp_t v[kUnroll];
+    bool on[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint64_t k = k0 + (uint64_t)j * quarter;
+        on[j] = k < total;
+        idx[j] = expand_index(on[j] ? k : 0, ins);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) if (on[j]) v[j] = ld_amp(a + idx[j]);
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) if (on[j]) st_amp(a + idx[j], cmul(v[j], phase));
 }
 
 // RZ (operator.rs:2013-2029): every index with the controls set; phase by the target bit
 __global__ void __launch_bounds__(256) k_rz(amp_t* __restrict__ a, uint64_t total, BitInsert ins, uint64_t tbit, amp_t p0, amp_t p1) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total) return;
-    uint64_t i = expand_index(k, ins);
-    st_amp(a + i, cmul(ld_amp(a + i), (i & tbit) ? p1 : p0));
+    const uint64_t quarter = (total + kUnroll - 1) / kUnroll;
+    const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= quarter) return;
+    uint64_t idx[kUnroll];
+    amp_t v[kUnroll];
+    bool on[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint64_t k = k0 + (uint64_t)j * quarter;
+        on[j] = k < total;
+        idx[j] = expand_index(on[j] ? k : 0, ins);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) if (on[j]) v[j] = ld_amp(a + idx[j]);
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) if (on[j]) st_amp(a + idx[j], cmul(v[j], (idx[j] & tbit) ? p1 : p0));
 }
 
 // SWAP (operator.rs:800-813): expansion fixes t_a = 1, t_b = 0; partner flips both
@@ -202,6 +243,7 @@ int launch_simple_gate(qi_state* s, const PhysGate& g) {
     const int nc = (int)ctrl.size();
     const double state_bytes = 16.0 * (double)s->len;
     auto blocks = [](uint64_t total) { return (unsigned)((total + kBlock - 1) / kBlock); };
+    auto blocks4 = [](uint64_t total) { uint64_t q = (total + kUnroll - 1) / kUnroll; return (unsigned)((q + kBlock - 1) / kBlock); };
     switch (g.kind) {
         case IK_NOP: return QI_OK;
         case IK_H: case IK_X: case IK_Y: case IK_U2: {
@@ -213,10 +255,10 @@ int launch_simple_gate(qi_state* s, const PhysGate& g) {
             u.m10 = make_double2(g.p[4], g.p[5]); u.m11 = make_double2(g.p[6], g.p[7]);
             LaunchScope ls(KF_PAIR, 2.0 * state_bytes / (double)(1ull << nc));
             uint64_t tb = 1ull << g.t0;
-            if (g.kind == IK_H) k_pair<IK_H><<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
-            else if (g.kind == IK_X) k_pair<IK_X><<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
-            else if (g.kind == IK_Y) k_pair<IK_Y><<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
-            else k_pair<IK_U2><<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
+            if (g.kind == IK_H) k_pair<IK_H><<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
+            else if (g.kind == IK_X) k_pair<IK_X><<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
+            else if (g.kind == IK_Y) k_pair<IK_Y><<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
+            else k_pair<IK_U2><<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, u);
             return check_launch("k_pair");
         }
         case IK_DIAG: {
@@ -229,7 +271,7 @@ int launch_simple_gate(qi_state* s, const PhysGate& g) {
             uint64_t total = 1ull << (n - nf);
             BitInsert ins = make_insert({}, ones);
             LaunchScope ls(KF_DIAG, 2.0 * state_bytes / (double)(1ull << nf));
-            k_diag<<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, make_double2(g.p[0], g.p[1]));
+            k_diag<<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, make_double2(g.p[0], g.p[1]));
             return check_launch("k_diag");
         }
         case IK_RZ: {
@@ -237,7 +279,7 @@ int launch_simple_gate(qi_state* s, const PhysGate& g) {
             BitInsert ins = make_insert({}, ctrl);
             LaunchScope ls(KF_DIAG, 2.0 * state_bytes / (double)(1ull << nc));
             uint64_t tb = g.t0 >= 0 ? (1ull << g.t0) : 0ull;
-            k_rz<<<blocks(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, make_double2(g.p[0], g.p[1]),
+            k_rz<<<blocks4(total), kBlock, 0, c.stream>>>(s->d, total, ins, tb, make_double2(g.p[0], g.p[1]),
                                                          make_double2(g.p[2], g.p[3]));
             return check_launch("k_rz");
         }
