@@ -1,0 +1,416 @@
+// quant_iron_b200.hpp -- header-only C++ host facade over the C ABI (include/qiron_b200.h).
+//
+// The reference is compiled Rust and its toolchain is absent from this image, so the compiled-language
+// host side is C++: the same names, argument order and error behaviour as the crate's public surface
+// for the state-vector path (State gate methods, Operator, Gate/Circuit/CircuitBuilder, Subroutine::qft,
+// PauliString/SumOp, measure, Trotter, heisenberg_1d).  Citations are file:line under the reference root.
+// `&self -> State` methods are device clone + in-place kernel; methods with a trailing underscore act in place.
+#pragma once
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "qiron_b200.h"
+
+namespace quant_iron {
+
+using cplx = std::complex<double>;
+
+// errors.rs:3-97
+struct Error : std::runtime_error {
+    int code;
+    uint64_t payload[2];
+    std::string variant;
+    Error(int c, std::string v, uint64_t p0, uint64_t p1, const std::string& msg)
+        : std::runtime_error(v + ": " + msg), code(c), variant(std::move(v)) { payload[0] = p0; payload[1] = p1; }
+};
+
+inline void check(int status) {
+    if (status == QI_OK) return;
+    static const char* names[] = {"Ok", "InvalidNumberOfMeasurements", "OverlappingControlAndTargetQubits",
+        "InvalidNumberOfQubits", "InvalidQubitIndex", "StateVectorNotNormalised", "NonUnitaryMatrix", "InvalidNumberOfInputs",
+        "MismatchedNumberOfParameters", "UnknownError", "CudaError", "GpuContextLockError", "CircuitMacroError",
+        "InvalidInputValue", "ZeroNorm", "InvalidPauliStringCoefficient", "InvalidArgument", "PeerError"};
+    uint64_t p[2] = {0, 0};
+    char msg[256] = {0};
+    qi_last_error(p, msg, sizeof(msg));
+    throw Error(status, status >= 0 && status <= 17 ? names[status] : "UnknownError", p[0], p[1], msg);
+}
+
+class State;
+
+// operator.rs:151-190
+struct Operator {
+    virtual ~Operator() = default;
+    virtual int kind() const = 0;
+    virtual std::vector<double> params() const { return {}; }
+    virtual size_t base_qubits() const { return 1; }
+    State apply(const State& state, const std::vector<size_t>& targets, const std::vector<size_t>& controls = {}) const;
+};
+#define QI_SIMPLE_OP(NAME, KIND, BASE) \
+    struct NAME : Operator { int kind() const override { return KIND; } size_t base_qubits() const override { return BASE; } }
+QI_SIMPLE_OP(Hadamard, QI_GATE_H, 1);
+QI_SIMPLE_OP(PauliX, QI_GATE_X, 1);
+QI_SIMPLE_OP(PauliY, QI_GATE_Y, 1);
+QI_SIMPLE_OP(PauliZ, QI_GATE_Z, 1);
+QI_SIMPLE_OP(Identity, QI_GATE_I, 1);
+QI_SIMPLE_OP(PhaseS, QI_GATE_S, 1);
+QI_SIMPLE_OP(PhaseT, QI_GATE_T, 1);
+QI_SIMPLE_OP(PhaseSdag, QI_GATE_SDG, 1);
+QI_SIMPLE_OP(PhaseTdag, QI_GATE_TDG, 1);
+QI_SIMPLE_OP(CNOT, QI_GATE_CNOT, 2);
+QI_SIMPLE_OP(SWAP, QI_GATE_SWAP, 2);
+QI_SIMPLE_OP(Toffoli, QI_GATE_TOFFOLI, 3);
+#undef QI_SIMPLE_OP
+struct AngleOp : Operator {
+    double angle;
+    int k;
+    AngleOp(int kind_, double a) : angle(a), k(kind_) {}
+    int kind() const override { return k; }
+    std::vector<double> params() const override { return {angle}; }
+};
+struct PhaseShift : AngleOp { explicit PhaseShift(double a) : AngleOp(QI_GATE_P, a) {} };
+struct RotateX : AngleOp { explicit RotateX(double a) : AngleOp(QI_GATE_RX, a) {} };
+struct RotateY : AngleOp { explicit RotateY(double a) : AngleOp(QI_GATE_RY, a) {} };
+struct RotateZ : AngleOp { explicit RotateZ(double a) : AngleOp(QI_GATE_RZ, a) {} };
+struct Unitary2 : Operator {   // operator.rs:2058-2275
+    cplx m[2][2];
+    int kind() const override { return QI_GATE_U2; }
+    std::vector<double> params() const override {
+        return {m[0][0].real(), m[0][0].imag(), m[0][1].real(), m[0][1].imag(), m[1][0].real(), m[1][0].imag(), m[1][1].real(), m[1][1].imag()};
+    }
+    static Unitary2 make(const cplx (&u)[2][2]) {   // Unitary2::new: unitarity check, operator.rs:2092-2118
+        Unitary2 r;
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) r.m[i][j] = u[i][j];
+        auto p = r.params();
+        check(qi_unitary2_check(p.data()));
+        return r;
+    }
+    static Unitary2 from_ry_phase(double theta, double phi) {   // operator.rs:2140-2156
+        Unitary2 r;
+        double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+        cplx e(std::cos(phi), std::sin(phi));
+        r.m[0][0] = cplx(c, 0.0); r.m[0][1] = cplx(-e.real() * s, -e.imag() * s);
+        r.m[1][0] = cplx(s, 0.0); r.m[1][1] = cplx(e.real() * c, e.imag() * c);
+        return r;
+    }
+};
+struct Matchgate : Operator {   // operator.rs:852-1019
+    double theta, phi1, phi2;
+    Matchgate(double t, double p1, double p2) : theta(t), phi1(p1), phi2(p2) {}
+    int kind() const override { return QI_GATE_MATCHGATE; }
+    size_t base_qubits() const override { return 2; }
+    std::vector<double> params() const override { return {theta, phi1, phi2}; }
+};
+
+enum class MeasurementBasis { Computational = 0, X = 1, Y = 2 };   // measurement.rs:76-86 (Custom: State::measure_custom_)
+
+struct GateRecord {   // owns the control list a qi_gate points into
+    qi_gate g;
+    std::vector<uint32_t> controls;
+};
+inline GateRecord make_record(const Operator& op, const std::vector<size_t>& targets, const std::vector<size_t>& controls) {
+    GateRecord r;
+    r.g = qi_gate{};
+    r.g.kind = op.kind();
+    r.g.num_targets = (uint32_t)targets.size();
+    for (size_t i = 0; i < targets.size() && i < 2; i++) r.g.targets[i] = (uint32_t)targets[i];
+    for (size_t c : controls) r.controls.push_back((uint32_t)c);
+    r.g.num_controls = (uint32_t)r.controls.size();
+    auto p = op.params();
+    for (size_t i = 0; i < p.size() && i < 8; i++) r.g.params[i] = p[i];
+    return r;
+}
+
+// state.rs:74-81
+class State {
+    qi_state* h_ = nullptr;
+    explicit State(qi_state* h) : h_(h) {}
+    friend struct Operator;
+    friend class Circuit;
+    friend class PauliString;
+    friend class SumOp;
+
+public:
+    State(const State& o) { check(qi_state_clone(o.h_, &h_)); }
+    State(State&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    State& operator=(State o) { std::swap(h_, o.h_); return *this; }
+    ~State() { if (h_) qi_state_free(h_); }
+    qi_state* handle() const { return h_; }
+
+    static State from_vector(const std::vector<cplx>& v) {   // State::new, state.rs:99-127
+        qi_state* h = nullptr;
+        check(qi_state_from_host(reinterpret_cast<const double*>(v.data()), v.size(), 0, 1, &h));
+        return State(h);
+    }
+    static State new_zero(size_t n) { qi_state* h = nullptr; check(qi_state_new_zero((uint32_t)n, &h)); return State(h); }
+    static State new_basis_n(size_t n, uint64_t k) { qi_state* h = nullptr; check(qi_state_new_basis_n((uint32_t)n, k, &h)); return State(h); }
+    static State new_plus(size_t n) { qi_state* h = nullptr; check(qi_state_new_plus((uint32_t)n, &h)); return State(h); }
+    static State new_minus(size_t n) { qi_state* h = nullptr; check(qi_state_new_minus((uint32_t)n, &h)); return State(h); }
+    static State new_ghz(size_t n) { qi_state* h = nullptr; check(qi_state_new_ghz((uint32_t)n, &h)); return State(h); }
+
+    size_t num_qubits() const { return qi_state_num_qubits(h_); }
+    std::vector<cplx> state_vector() const {
+        std::vector<cplx> v(qi_state_len(h_));
+        check(qi_state_to_host(h_, reinterpret_cast<double*>(v.data()), v.size()));
+        return v;
+    }
+    cplx amplitude(uint64_t i) const { double o[2]; check(qi_state_amplitude(h_, i, o)); return cplx(o[0], o[1]); }
+    double probability(uint64_t i) const { return std::norm(amplitude(i)); }
+    double norm_sqr() const { double o; check(qi_norm_sqr(h_, &o)); return o; }
+    cplx inner_product(const State& o) const { double r[2]; check(qi_inner_product(h_, o.h_, r)); return cplx(r[0], r[1]); }
+    State normalise() const { State s(*this); check(qi_normalise(s.h_)); return s; }
+    State operator*(cplx z) const { State s(*this); double w[2] = {z.real(), z.imag()}; check(qi_scale(s.h_, w)); return s; }
+    State operator+(const State& o) const { State s(*this); check(qi_add(s.h_, o.h_)); return s; }
+    State operator-(const State& o) const { State s(*this); check(qi_sub(s.h_, o.h_)); return s; }
+    State tensor_product(const State& o) const { qi_state* h = nullptr; check(qi_tensor_product(h_, o.h_, &h)); return State(h); }
+    bool approx_eq(const State& o, double tol = 1.1920928955078125e-07) const {   // PartialEq, state.rs:2348-2372
+        if (num_qubits() != o.num_qubits()) return false;
+        auto a = state_vector(), b = o.state_vector();
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); i++)
+            if (std::fabs(a[i].real() - b[i].real()) > tol || std::fabs(a[i].imag() - b[i].imag()) > tol) return false;
+        return true;
+    }
+
+    // Operator::apply in place
+    State& apply_(const Operator& op, const std::vector<size_t>& targets, const std::vector<size_t>& controls = {}) {
+        GateRecord r = make_record(op, targets, controls);
+        r.g.controls = r.controls.data();
+        check(qi_apply_gate(h_, &r.g));
+        return *this;
+    }
+    // state.rs:970-1002
+    State operate(const Operator& op, const std::vector<size_t>& targets, const std::vector<size_t>& controls = {}) const {
+        if (op.base_qubits() != targets.size() + controls.size())
+            throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", op.base_qubits(), 0, "operate");
+        return op.apply(*this, targets, controls);
+    }
+    // gate methods, state.rs:1019-2345 (same names and argument order)
+    State h(size_t q) const { return Hadamard().apply(*this, {q}); }
+    State x(size_t q) const { return PauliX().apply(*this, {q}); }
+    State y(size_t q) const { return PauliY().apply(*this, {q}); }
+    State z(size_t q) const { return PauliZ().apply(*this, {q}); }
+    State i(size_t q) const { return Identity().apply(*this, {q}); }
+    State s(size_t q) const { return PhaseS().apply(*this, {q}); }
+    State t(size_t q) const { return PhaseT().apply(*this, {q}); }
+    State s_dag(size_t q) const { return PhaseSdag().apply(*this, {q}); }
+    State t_dag(size_t q) const { return PhaseTdag().apply(*this, {q}); }
+    State p(size_t q, double a) const { return PhaseShift(a).apply(*this, {q}); }
+    State rx(size_t q, double a) const { return RotateX(a).apply(*this, {q}); }
+    State ry(size_t q, double a) const { return RotateY(a).apply(*this, {q}); }
+    State rz(size_t q, double a) const { return RotateZ(a).apply(*this, {q}); }
+    State cnot(size_t control, size_t target) const { return CNOT().apply(*this, {target}, {control}); }          // state.rs:2230
+    State swap(size_t a, size_t b) const { return SWAP().apply(*this, {a, b}); }
+    State toffoli(size_t c1, size_t c2, size_t target) const { return Toffoli().apply(*this, {target}, {c1, c2}); } // state.rs:2343
+    State matchgate(size_t q, double th, double p1, double p2) const { return Matchgate(th, p1, p2).apply(*this, {q}); }
+    State ry_phase(size_t q, double th, double ph) const { return Unitary2::from_ry_phase(th, ph).apply(*this, {q}); }
+    State multi(const Operator& op, const std::vector<size_t>& targets, const std::vector<size_t>& controls = {}) const {
+        State s(*this);
+        for (size_t q : targets) s.apply_(op, {q}, controls);
+        return s;
+    }
+    State h_multi(const std::vector<size_t>& qs) const { return multi(Hadamard(), qs); }
+    State x_multi(const std::vector<size_t>& qs) const { return multi(PauliX(), qs); }
+    State cx_multi(const std::vector<size_t>& t, const std::vector<size_t>& c) const { return multi(PauliX(), t, c); }
+    State cp_multi(const std::vector<size_t>& t, const std::vector<size_t>& c, double a) const { return multi(PhaseShift(a), t, c); }
+
+    // State::measure (state.rs:525-730), in place; returns outcomes[j] = bit j of the sampled bin
+    std::vector<uint8_t> measure_(MeasurementBasis basis, const std::vector<size_t>& qubits, uint64_t seed, uint64_t draw = 0) {
+        std::vector<uint32_t> q(qubits.begin(), qubits.end());
+        std::vector<uint8_t> out(qubits.empty() ? num_qubits() : qubits.size());
+        uint64_t bin = 0;
+        check(qi_measure(h_, (int)basis, nullptr, q.data(), (uint32_t)q.size(), seed, draw, out.data(), &bin));
+        return out;
+    }
+    std::vector<uint64_t> sample_counts(const std::vector<size_t>& qubits, uint64_t shots, uint64_t seed) const {
+        std::vector<uint32_t> q(qubits.begin(), qubits.end());
+        std::vector<uint64_t> bins(shots);
+        check(qi_sample(h_, q.data(), (uint32_t)q.size(), shots, seed, bins.data()));
+        return bins;
+    }
+};
+
+inline State Operator::apply(const State& state, const std::vector<size_t>& targets, const std::vector<size_t>& controls) const {
+    State out(state);
+    out.apply_(*this, targets, controls);
+    return out;
+}
+
+// pauli_string.rs:13-287
+enum class Pauli : uint8_t { X = 1, Y = 2, Z = 3 };
+class PauliString {
+    std::map<size_t, Pauli> ops_;
+    cplx coefficient_;
+
+public:
+    explicit PauliString(cplx c) : coefficient_(c) {}
+    PauliString& add_op(size_t q, Pauli p) {
+        if (ops_.count(q)) throw std::logic_error("Duplicate Pauli string operator for qubit");   // panic, pauli_string.rs:66-70
+        ops_[q] = p;
+        return *this;
+    }
+    PauliString with_op(size_t q, Pauli p) const { PauliString r(*this); r.add_op(q, p); return r; }
+    cplx coefficient() const { return coefficient_; }
+    size_t len() const { return ops_.size(); }
+    struct Term { qi_pauli_term t; std::vector<uint32_t> q; std::vector<uint8_t> p; };
+    std::unique_ptr<Term> term() const {
+        auto r = std::make_unique<Term>();
+        for (auto& kv : ops_) { r->q.push_back((uint32_t)kv.first); r->p.push_back((uint8_t)kv.second); }
+        r->t.num_ops = (uint32_t)r->q.size();
+        r->t.qubits = r->q.data();
+        r->t.paulis = r->p.data();
+        r->t.coefficient[0] = coefficient_.real();
+        r->t.coefficient[1] = coefficient_.imag();
+        return r;
+    }
+    State apply(const State& s) const { State o(s); auto t = term(); check(qi_apply_pauli_string(o.handle(), &t->t, 1)); return o; }                 // 139-151
+    State apply_normalised(const State& s) const { State o(s); auto t = term(); check(qi_apply_pauli_string(o.handle(), &t->t, 0)); check(qi_normalise(o.handle())); return o; }
+    State apply_exp_factor(const State& s, cplx f) const {                                                                                            // 237-262
+        State o(s); auto t = term(); double w[2] = {f.real(), f.imag()};
+        check(qi_apply_pauli_exp(o.handle(), &t->t, w));
+        return o;
+    }
+    State apply_exp(const State& s) const { return apply_exp_factor(s, cplx(1.0, 0.0)); }
+    State apply_exp_neg_i_dt(const State& s, double dt) const {                                                                                       // 281-287
+        if (coefficient_.imag() != 0.0) throw Error(QI_ERR_INVALID_PAULI_STRING_COEFFICIENT, "InvalidPauliStringCoefficient", 0, 0, "imaginary coefficient");
+        return apply_exp_factor(s, cplx(0.0, -dt));
+    }
+};
+
+class SumOp {   // pauli_string.rs:398-507
+public:
+    std::vector<PauliString> terms;
+    explicit SumOp(std::vector<PauliString> t = {}) : terms(std::move(t)) {}
+    size_t num_terms() const { return terms.size(); }
+    cplx expectation_value(const State& s) const {
+        std::vector<std::unique_ptr<PauliString::Term>> keep;
+        std::vector<qi_pauli_term> arr;
+        for (auto& t : terms) { keep.push_back(t.term()); arr.push_back(keep.back()->t); }
+        double o[2];
+        check(qi_expect_pauli_sum(s.handle(), arr.data(), arr.size(), o));
+        return cplx(o[0], o[1]);
+    }
+    State trotter_evolve(const State& s, double dt, uint64_t steps, int order) const {   // time_evolution.rs:140-167
+        std::vector<std::unique_ptr<PauliString::Term>> keep;
+        std::vector<qi_pauli_term> arr;
+        for (auto& t : terms) { keep.push_back(t.term()); arr.push_back(keep.back()->t); }
+        State o(s);
+        check(qi_trotter_evolve(o.handle(), arr.data(), arr.size(), dt, steps, order));
+        return o;
+    }
+};
+
+inline SumOp heisenberg_1d(size_t n, double jx, double jy, double jz, double h, double mu) {   // models/heisenberg.rs:28-102
+    if (n < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n, 2, "heisenberg_1d");
+    std::vector<PauliString> terms;
+    if (jx == 0.0 && jy == 0.0 && jz == 0.0 && h == 0.0) return SumOp(terms);
+    for (size_t i = 0; i < n; i++) {
+        size_t j = (i + 1) % n;
+        if (jx != 0.0) terms.push_back(PauliString(cplx(-0.5 * jx, 0.0)).with_op(i, Pauli::X).with_op(j, Pauli::X));
+        if (jy != 0.0) terms.push_back(PauliString(cplx(-0.5 * jy, 0.0)).with_op(i, Pauli::Y).with_op(j, Pauli::Y));
+        if (jz != 0.0) terms.push_back(PauliString(cplx(-0.5 * jz, 0.0)).with_op(i, Pauli::Z).with_op(j, Pauli::Z));
+        if (h != 0.0) terms.push_back(PauliString(cplx(-mu * (-0.5 * h), 0.0)).with_op(i, Pauli::Z));   // code is ground truth, heisenberg.rs:49
+    }
+    return SumOp(terms);
+}
+
+// gate.rs:13-52 (operator gates), circuit.rs:27-202, circuit.rs:288-1742, subroutine.rs:90-160
+struct Gate {
+    std::shared_ptr<Operator> op;
+    std::vector<size_t> targets, controls;
+};
+struct Subroutine {
+    std::vector<Gate> gates;
+    size_t num_qubits;
+    static Subroutine qft(const std::vector<size_t>& qubits, size_t num_qubits);
+    static Subroutine iqft(const std::vector<size_t>& qubits, size_t num_qubits);
+};
+class Circuit {
+public:
+    std::vector<Gate> gates;
+    size_t num_qubits;
+    explicit Circuit(size_t n) : num_qubits(n) {}
+    void execute_(State& s) const {   // Circuit::execute's loop -> one fused run
+        if (s.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", s.num_qubits(), 0, "execute");
+        std::vector<GateRecord> recs;
+        recs.reserve(gates.size());
+        for (auto& g : gates) recs.push_back(make_record(*g.op, g.targets, g.controls));
+        std::vector<qi_gate> arr;
+        for (auto& r : recs) { r.g.controls = r.controls.data(); arr.push_back(r.g); }
+        check(qi_apply_circuit(s.handle(), arr.data(), arr.size()));
+    }
+    State execute(const State& initial) const { State s(initial); execute_(s); return s; }   // circuit.rs:160-172
+};
+class CircuitBuilder {
+    std::vector<Gate> gates_;
+    size_t n_;
+    template <class Op> CircuitBuilder& each(Op op, const std::vector<size_t>& ts, const std::vector<size_t>& cs = {}) {
+        auto sp = std::make_shared<Op>(op);
+        for (size_t q : ts) gates_.push_back(Gate{sp, {q}, cs});
+        return *this;
+    }
+
+public:
+    explicit CircuitBuilder(size_t n) : n_(n) {}
+    CircuitBuilder& h_gate(size_t q) { return each(Hadamard(), {q}); }
+    CircuitBuilder& h_gates(const std::vector<size_t>& qs) { return each(Hadamard(), qs); }
+    CircuitBuilder& x_gate(size_t q) { return each(PauliX(), {q}); }
+    CircuitBuilder& rx_gate(size_t q, double a) { return each(RotateX(a), {q}); }
+    CircuitBuilder& ry_gate(size_t q, double a) { return each(RotateY(a), {q}); }
+    CircuitBuilder& rz_gate(size_t q, double a) { return each(RotateZ(a), {q}); }
+    CircuitBuilder& p_gate(size_t q, double a) { return each(PhaseShift(a), {q}); }
+    CircuitBuilder& cp_gates(const std::vector<size_t>& ts, const std::vector<size_t>& cs, double a) { return each(PhaseShift(a), ts, cs); }
+    CircuitBuilder& cx_gates(const std::vector<size_t>& ts, const std::vector<size_t>& cs) { return each(PauliX(), ts, cs); }
+    CircuitBuilder& cnot_gate(size_t target, size_t control) { gates_.push_back(Gate{std::make_shared<CNOT>(), {target}, {control}}); return *this; }   // circuit.rs:1071
+    CircuitBuilder& swap_gate(size_t a, size_t b) { gates_.push_back(Gate{std::make_shared<SWAP>(), {a, b}, {}}); return *this; }
+    CircuitBuilder& toffoli_gate(size_t c1, size_t c2, size_t t) { gates_.push_back(Gate{std::make_shared<Toffoli>(), {t}, {c1, c2}}); return *this; }   // circuit.rs:1118
+    CircuitBuilder& add_subroutine(const Subroutine& s) { gates_.insert(gates_.end(), s.gates.begin(), s.gates.end()); return *this; }
+    Subroutine build_subroutine() { Subroutine s{gates_, n_}; gates_.clear(); return s; }
+    Circuit build() const {   // Circuit::with_gates validation, circuit.rs:35-52
+        Circuit c(n_);
+        for (auto& g : gates_) {
+            for (size_t q : g.targets) if (q >= n_) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n_, "build");
+            for (size_t q : g.controls) if (q >= n_) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n_, "build");
+        }
+        c.gates = gates_;
+        return c;
+    }
+};
+inline Subroutine Subroutine::qft(const std::vector<size_t>& q, size_t num_qubits) {   // subroutine.rs:90-112
+    CircuitBuilder b(num_qubits);
+    const size_t n = q.size();
+    for (size_t i = 0; i < n; i++) {
+        b.h_gate(q[i]);
+        double den = 2.0;
+        for (size_t k = 1; k < n - i; k++) { b.cp_gates({q[i]}, {q[i + k]}, M_PI / den); den *= 2.0; }
+    }
+    for (size_t i = 0; i < n / 2; i++) b.swap_gate(q[i], q[n - 1 - i]);
+    return b.build_subroutine();
+}
+inline Subroutine Subroutine::iqft(const std::vector<size_t>& q, size_t num_qubits) {   // subroutine.rs:125-160
+    CircuitBuilder b(num_qubits);
+    const size_t n = q.size();
+    for (size_t i = 0; i < n / 2; i++) b.swap_gate(q[i], q[n - 1 - i]);
+    for (size_t ii = n; ii-- > 0;) {
+        if (n > ii + 1) {
+            size_t k_initial = (n - 1) - ii;
+            double den = std::pow(2.0, (double)k_initial);
+            for (size_t it = 0; it < k_initial; it++) {
+                size_t k = k_initial - it;
+                b.cp_gates({q[ii]}, {q[ii + k]}, -M_PI / den);
+                if (k > 1) den /= 2.0;
+            }
+        }
+        b.h_gate(q[ii]);
+    }
+    return b.build_subroutine();
+}
+
+}  // namespace quant_iron

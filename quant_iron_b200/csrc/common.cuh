@@ -101,7 +101,7 @@ struct qi_state {
     unsigned long long* flags = nullptr;          // this rank's flag/scratch block (device)
     unsigned long long* peer_flags[8] = {nullptr};
     unsigned long long epoch = 0;
-    uint64_t bytes_sent = 0, bytes_recv = 0, exchanges = 0;
+    uint64_t bytes_sent = 0, bytes_recv = 0, exchanges = 0, exchanged_qubits = 0;
     uint64_t reduce_count = 0;          // parity selects the allreduce scratch buffer
     uint64_t lookahead_remaining = 0;   // gates left in the current qi_apply_circuit call (eviction heuristic)
     bool attached = false;

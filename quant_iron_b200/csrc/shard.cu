@@ -52,11 +52,15 @@ __global__ void k_barrier(PeerPtrs peers, unsigned long long* mine, int me, int 
     __threadfence_system();
 }
 
-// In-place swap of a rank bit with local bit l between this rank and its partner.
-// This rank handles its own indices j with bit_l(j) = !my_bit and bit_h(j) = my_bit; the partner
-// handles the complementary half, so every element pair is touched by exactly one rank.
+// In-place swap of k rank bits G with k local bits L (k = 1: a pairwise half-shard swap; k > 1: an
+// all-to-all that moves (1 - 2^-k) of every shard).  Element (rank bits rho, local bits lambda) trades
+// places with element (rank bits lambda, local bits rho); elements with lambda == rho stay.  For the
+// block this rank trades with the rank whose G bits spell lambda, one launch of this kernel swaps
+//   mine[expand(k) | or_mine]  <->  peer[expand(k) | or_peer]
+// over the half of the block selected by a further local bit h (folded into or_mine / or_peer); the peer
+// handles the other half, so every element pair is touched by exactly one rank and the work is balanced.
 __global__ void __launch_bounds__(256) k_exchange(amp_t* __restrict__ mine, amp_t* __restrict__ peer, uint64_t total,
-                                                  BitInsert ins, uint64_t lbit) {
+                                                  BitInsert ins, uint64_t or_mine, uint64_t or_peer) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += 4 * stride) {
         uint64_t j[4];
@@ -64,9 +68,9 @@ __global__ void __launch_bounds__(256) k_exchange(amp_t* __restrict__ mine, amp_
 #pragma unroll
         for (int u = 0; u < 4; u++) j[u] = (k + u * stride < total) ? expand_index(k + u * stride, ins) : ~0ull;
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { a[u] = mine[j[u]]; b[u] = peer[j[u] ^ lbit]; }
+        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { a[u] = mine[j[u] | or_mine]; b[u] = peer[j[u] | or_peer]; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { mine[j[u]] = b[u]; peer[j[u] ^ lbit] = a[u]; }
+        for (int u = 0; u < 4; u++) if (j[u] != ~0ull) { mine[j[u] | or_mine] = b[u]; peer[j[u] | or_peer] = a[u]; }
     }
 }
 
@@ -89,63 +93,81 @@ static int logical_at(const qi_state* s, int p) {
     return -1;
 }
 
-int exchange_global_local(qi_state* s, int global_phys, int local_phys) {
+// swap global positions G[i] with local positions L[i] (all i at once)
+int exchange_multi(qi_state* s, const std::vector<int>& G, const std::vector<int>& L) {
     Context& c = ctx();
-    const int nl = (int)s->n_local;
-    if (global_phys < nl || local_phys >= nl) return fail(QI_ERR_PEER, 0, 0, "bad exchange positions");
-    const int gbit = global_phys - nl;
-    const int partner = s->rank ^ (1 << gbit);
-    const int my_bit = (s->rank >> gbit) & 1;
+    const int nl = (int)s->n_local, k = (int)G.size();
+    if (k == 0) return QI_OK;
+    for (int i = 0; i < k; i++)
+        if (G[i] < nl || L[i] >= nl || L[i] < 0) return fail(QI_ERR_PEER, 0, 0, "bad exchange positions");
     int h = nl - 1;
-    if (h == local_phys) h--;
+    while (h >= 0 && std::find(L.begin(), L.end(), h) != L.end()) h--;
     if (h < 0) return fail(QI_ERR_PEER, 0, 0, "shard too small to exchange");
-    QI_TRY(barrier(s));                               // everyone's earlier kernels are complete
-    std::vector<int> zeros, ones;
-    (my_bit ? zeros : ones).push_back(local_phys);   // bit_l = !my_bit
-    (my_bit ? ones : zeros).push_back(h);            // bit_h = my_bit
-    BitInsert ins = make_insert(zeros, ones);
-    const uint64_t total = s->len >> 2;
-    {
-        LaunchScope ls(KF_EXCHANGE, 16.0 * (double)s->len);   // quarter shard out + quarter in, read and written
-        int blocks = c.sm_count * 8;
-        k_exchange<<<blocks, 256, 0, c.stream>>>(s->d, s->peer_amp[partner], total, ins, 1ull << local_phys);
+    uint64_t rho = 0;                                   // this rank's value on the G bits
+    for (int i = 0; i < k; i++) rho |= (uint64_t)((s->rank >> (G[i] - nl)) & 1) << i;
+    auto deposit = [&](uint64_t v) { uint64_t m = 0; for (int i = 0; i < k; i++) m |= ((v >> i) & 1ull) << L[i]; return m; };
+    std::vector<int> zeros(L);
+    zeros.push_back(h);
+    BitInsert ins = make_insert(zeros, {});
+    const uint64_t total = s->len >> (k + 1);
+    QI_TRY(barrier(s));                                 // everyone's earlier kernels are complete
+    for (uint64_t lambda = 0; lambda < (1ull << k); lambda++) {
+        if (lambda == rho) continue;
+        int partner = s->rank;
+        for (int i = 0; i < k; i++) partner = (partner & ~(1 << (G[i] - nl))) | ((int)((lambda >> i) & 1) << (G[i] - nl));
+        const uint64_t hsel = (rho < lambda) ? 0ull : (1ull << h);     // the lower rank value takes the h = 0 half
+        LaunchScope ls(KF_EXCHANGE, 16.0 * (double)s->len / (double)(1ull << k));
+        k_exchange<<<c.sm_count * 8, 256, 0, c.stream>>>(s->d, s->peer_amp[partner], total, ins, deposit(lambda) | hsel, deposit(rho) | hsel);
+        QI_TRY(check_launch("k_exchange"));
     }
-    QI_TRY(check_launch("k_exchange"));
-    QI_TRY(barrier(s));                               // partner's half has landed before anything reads it
-    // per direction: the quarter shard this rank writes to / reads from the partner (4 B x len each)
-    // plus the quarter the partner reads from / writes to this rank = half a shard each way
-    s->bytes_sent += 8ull * s->len;
-    s->bytes_recv += 8ull * s->len;
+    QI_TRY(barrier(s));                                 // every partner's half has landed before anything reads it
+    // per direction and GPU: (1 - 2^-k) of a shard (half of it written/read by this rank, half by its partners)
+    const uint64_t moved = (uint64_t)((double)(16ull * s->len) * (1.0 - 1.0 / (double)(1ull << k)));
+    s->bytes_sent += moved;
+    s->bytes_recv += moved;
     s->exchanges++;
-    int qg = logical_at(s, global_phys), ql = logical_at(s, local_phys);
-    if (qg >= 0) s->phys[qg] = (uint8_t)local_phys;
-    if (ql >= 0) s->phys[ql] = (uint8_t)global_phys;
+    s->exchanged_qubits += (uint64_t)k;
+    for (int i = 0; i < k; i++) {
+        int qg = logical_at(s, G[i]), ql = logical_at(s, L[i]);
+        if (qg >= 0) s->phys[qg] = (uint8_t)L[i];
+        if (ql >= 0) s->phys[ql] = (uint8_t)G[i];
+    }
     return QI_OK;
 }
 
+int exchange_global_local(qi_state* s, int global_phys, int local_phys) {
+    return exchange_multi(s, std::vector<int>{global_phys}, std::vector<int>{local_phys});
+}
+
 // choose the local position to evict: the one whose logical qubit is needed (non-diagonally) latest
-static int pick_local_slot(const qi_state* s, uint64_t avoid_phys, const qi_gate* upcoming, uint64_t n_upcoming) {
+// index (relative to `upcoming`) of the next gate that uses logical qubit q non-diagonally; ~0 if none
+static uint64_t next_nuse(int q, const qi_gate* upcoming, uint64_t n_upcoming) {
+    for (uint64_t i = 0; i < n_upcoming && i < 4096; i++) {
+        const qi_gate& g = upcoming[i];
+        bool diag = g.kind == QI_GATE_Z || g.kind == QI_GATE_S || g.kind == QI_GATE_SDG || g.kind == QI_GATE_T ||
+                    g.kind == QI_GATE_TDG || g.kind == QI_GATE_P || g.kind == QI_GATE_RZ || g.kind == QI_GATE_I;
+        bool lazy_swap = g.kind == QI_GATE_SWAP && g.num_controls == 0;
+        if (diag || lazy_swap) continue;
+        bool hit = (int)g.targets[0] == q || (g.kind == QI_GATE_SWAP && (int)g.targets[1] == q) ||
+                   (g.kind == QI_GATE_MATCHGATE && (int)g.targets[0] + 1 == q);
+        if (hit) return i;
+    }
+    return ~0ull;
+}
+
+static int pick_local_slot(const qi_state* s, uint64_t avoid_phys, const qi_gate* upcoming, uint64_t n_upcoming,
+                           uint64_t* evicted_next = nullptr) {
     const int nl = (int)s->n_local;
     int best = -1;
     uint64_t best_next = 0;
     for (int p = nl - 1; p >= 0; p--) {
         if ((avoid_phys >> p) & 1) continue;
-        int q = logical_at(s, p);
-        uint64_t next = ~0ull;
-        for (uint64_t i = 0; i < n_upcoming && i < 4096; i++) {
-            const qi_gate& g = upcoming[i];
-            bool diag = g.kind == QI_GATE_Z || g.kind == QI_GATE_S || g.kind == QI_GATE_SDG || g.kind == QI_GATE_T ||
-                        g.kind == QI_GATE_TDG || g.kind == QI_GATE_P || g.kind == QI_GATE_RZ || g.kind == QI_GATE_I;
-            bool lazy_swap = g.kind == QI_GATE_SWAP && g.num_controls == 0;
-            if (diag || lazy_swap) continue;
-            bool hit = (int)g.targets[0] == q || (g.kind == QI_GATE_SWAP && (int)g.targets[1] == q) ||
-                       (g.kind == QI_GATE_MATCHGATE && (int)g.targets[0] + 1 == q);
-            if (hit) { next = i; break; }
-        }
+        uint64_t next = next_nuse(logical_at(s, p), upcoming, n_upcoming);
         // prefer high positions on ties (p counts down), and keep the lane qubits 0..4 unless nothing else is free
         if (best < 0 || next > best_next || (next == best_next && p >= 5 && best < 5)) { best = p; best_next = next; }
         if (next == ~0ull && p >= 5) break;
     }
+    if (evicted_next) *evicted_next = best_next;
     return best;
 }
 
@@ -169,20 +191,62 @@ static uint64_t global_targets(const qi_state* s, const qi_gate* g) {
 
 bool shard_needs_exchange(const qi_state* s, const qi_gate* g) { return s->world > 1 && global_targets(s, g) != 0; }
 
-int shard_do_exchange(qi_state* s, const qi_gate* g) {
-    // `g` points into the caller's gate array: what follows it is the lookahead for the eviction choice
-    uint64_t gm;
-    while ((gm = global_targets(s, g)) != 0) {
+static uint64_t target_positions(const qi_state* s, const qi_gate* g) {
+    uint64_t m = 1ull << s->phys[g->targets[0]];
+    if (g->kind == QI_GATE_SWAP) m |= 1ull << s->phys[g->targets[1]];
+    if (g->kind == QI_GATE_MATCHGATE) m |= 1ull << s->phys[g->targets[0] + 1];
+    return m;
+}
+
+// Decide which (global, local) position pairs to swap before gate `g` can run: the gate's own global
+// targets, plus (the fused queue is being flushed anyway) the other global qubits that upcoming gates use
+// non-diagonally, each only if the qubit it evicts is needed later than the qubit it brings in.
+// Works on a scratch copy of the qubit map so that the engine and the host-only planner share it.
+static int plan_exchange(const qi_state* s, const qi_gate* g, uint64_t rem, std::vector<int>* G, std::vector<int>* L) {
+    qi_state t;
+    t.num_qubits = s->num_qubits; t.n_local = s->n_local; t.len = s->len; t.world = s->world; t.rank = s->rank;
+    memcpy(t.phys, s->phys, sizeof(t.phys));
+    auto relabel = [&](int gp, int lp) {
+        int qg = logical_at(&t, gp), ql = logical_at(&t, lp);
+        if (qg >= 0) t.phys[qg] = (uint8_t)lp;
+        if (ql >= 0) t.phys[ql] = (uint8_t)gp;
+        G->push_back(gp);
+        L->push_back(lp);
+    };
+    uint64_t used_local = 0, used_global = 0, gm;
+    while ((gm = global_targets(&t, g) & ~used_global) != 0) {
         int gp = 63 - __builtin_clzll(gm);
-        uint64_t avoid = 0;
-        avoid |= 1ull << s->phys[g->targets[0]];
-        if (g->kind == QI_GATE_SWAP) avoid |= 1ull << s->phys[g->targets[1]];
-        if (g->kind == QI_GATE_MATCHGATE) avoid |= 1ull << s->phys[g->targets[0] + 1];
-        int lp = pick_local_slot(s, avoid, g + 1, s->lookahead_remaining ? s->lookahead_remaining - 1 : 0);
+        int lp = pick_local_slot(&t, target_positions(&t, g) | used_local, g + 1, rem);
         if (lp < 0) return fail(QI_ERR_PEER, 0, 0, "no local qubit available for the exchange");
-        QI_TRY(exchange_global_local(s, gp, lp));
+        relabel(gp, lp);
+        used_local |= 1ull << lp;
+        used_global |= 1ull << gp;
+    }
+    uint64_t protect = target_positions(&t, g) | used_local;
+    for (uint64_t j = 0; j < rem && j < 512; j++) {
+        const qi_gate* gj = g + 1 + j;
+        if (gj->kind < QI_GATE_H || gj->kind > QI_GATE_MATCHGATE) break;
+        uint64_t gmj = global_targets(&t, gj) & ~used_global;
+        while (gmj) {
+            int gp = 63 - __builtin_clzll(gmj);
+            gmj &= ~(1ull << gp);
+            uint64_t ev_next = 0;
+            int lp = pick_local_slot(&t, protect | target_positions(&t, gj), g + 1, rem, &ev_next);
+            if (lp < 0 || ev_next <= j) continue;
+            relabel(gp, lp);
+            protect |= 1ull << lp;
+            used_global |= 1ull << gp;
+        }
     }
     return QI_OK;
+}
+
+int shard_do_exchange(qi_state* s, const qi_gate* g) {
+    // `g` points into the caller's gate array: what follows it is the lookahead for the eviction choice
+    const uint64_t rem = s->lookahead_remaining ? s->lookahead_remaining - 1 : 0;
+    std::vector<int> G, L;
+    QI_TRY(plan_exchange(s, g, rem, &G, &L));
+    return exchange_multi(s, G, L);
 }
 
 // logical record -> physical record on this rank
@@ -387,23 +451,21 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
     s.len = 1ull << s.n_local;
     s.world = world;
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
-    uint64_t ex = 0, freeg = 0;
+    uint64_t ex = 0, exq = 0, freeg = 0;
     for (uint64_t i = 0; i < count; i++) {
         QI_TRY(validate_gate(&s, &gates[i]));
         const qi_gate* g = &gates[i];
         if (g->kind == QI_GATE_SWAP && g->num_controls == 0) { std::swap(s.phys[g->targets[0]], s.phys[g->targets[1]]); continue; }
-        uint64_t gm;
-        while ((gm = global_targets(&s, g)) != 0) {
-            int gp = 63 - __builtin_clzll(gm);
-            uint64_t avoid = 1ull << s.phys[g->targets[0]];
-            if (g->kind == QI_GATE_SWAP) avoid |= 1ull << s.phys[g->targets[1]];
-            if (g->kind == QI_GATE_MATCHGATE) avoid |= 1ull << s.phys[g->targets[0] + 1];
-            int lp = pick_local_slot(&s, avoid, g + 1, count - i - 1);
-            if (lp < 0) return fail(QI_ERR_PEER, 0, 0, "no local qubit available");
-            int qg = logical_at(&s, gp), ql = logical_at(&s, lp);
-            s.phys[qg] = (uint8_t)lp;
-            s.phys[ql] = (uint8_t)gp;
+        if (global_targets(&s, g) != 0) {
+            std::vector<int> G, L;
+            QI_TRY(plan_exchange(&s, g, count - i - 1, &G, &L));
+            for (size_t k = 0; k < G.size(); k++) {
+                int qg = logical_at(&s, G[k]), ql = logical_at(&s, L[k]);
+                s.phys[qg] = (uint8_t)L[k];
+                s.phys[ql] = (uint8_t)G[k];
+            }
             ex++;
+            exq += G.size();
         }
         bool touches_global = false;
         for (uint32_t c = 0; c < g->num_controls; c++) touches_global |= s.phys[g->controls[c]] >= s.n_local;
@@ -411,6 +473,7 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
         if (touches_global) freeg++;
     }
     if (exchanges) *exchanges = ex;
+    (void)exq;
     if (comm_free_global_gates) *comm_free_global_gates = freeg;
     if (final_phys) memcpy(final_phys, s.phys, 64);
     return QI_OK;

@@ -1,0 +1,76 @@
+// C++ facade test: a handful of the reference's known-answer tests (src/tests/*.rs, cited) plus the QFT
+// closed form, run through include/quant_iron_b200.hpp -> C ABI -> sm_100a kernels.  Needs a GPU.
+#include <cstdio>
+#include <cstdlib>
+
+#include "quant_iron_b200.hpp"
+
+using namespace quant_iron;
+static int failures = 0;
+#define EXPECT(cond)                                                                 \
+    do {                                                                             \
+        if (!(cond)) { std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); failures++; } \
+    } while (0)
+
+template <class F>
+static bool throws(const char* variant, uint64_t p0, uint64_t p1, F f) {
+    try { f(); } catch (const Error& e) { return e.variant == variant && e.payload[0] == p0 && e.payload[1] == p1; }
+    return false;
+}
+
+int main() {
+    const double S2 = 1.0 / std::sqrt(2.0);
+    // operator_tests.rs:22-39
+    EXPECT(State::new_zero(1).h(0).approx_eq(State::new_plus(1)));
+    EXPECT(State::new_basis_n(1, 1).h(0).approx_eq(State::new_minus(1)));
+    EXPECT(State::new_zero(2).h_multi({0, 1}).approx_eq(State::new_plus(2)));
+    // operator_tests.rs:1989-2018: cnot(control, target)
+    EXPECT(State::new_basis_n(2, 1).cnot(0, 1).approx_eq(State::new_basis_n(2, 3)));
+    EXPECT(State::new_basis_n(2, 3).cnot(0, 1).approx_eq(State::new_basis_n(2, 1)));
+    // operator_tests.rs:2391-2430 toffoli(c1, c2, target)
+    EXPECT(State::new_basis_n(3, 3).toffoli(0, 1, 2).approx_eq(State::new_basis_n(3, 7)));
+    // operator_tests.rs:2073-2099 swap
+    EXPECT(State::new_basis_n(2, 2).swap(0, 1).approx_eq(State::new_basis_n(2, 1)));
+    // operator_tests.rs:2545-2566 error variants
+    EXPECT(throws("InvalidQubitIndex", 2, 2, [] { State::new_zero(2).h(2); }));
+    EXPECT(throws("OverlappingControlAndTargetQubits", 0, 0, [] { Matchgate(M_PI, 0, 0).apply(State::new_zero(3), {0}, {0}); }));
+    EXPECT(throws("InvalidNumberOfQubits", 0, 0, [] { State::new_zero(0); }));
+    // operate (operator_tests.rs:2493-2507)
+    EXPECT(State::new_basis_n(2, 1).operate(CNOT(), {1}, {0}).approx_eq(State::new_basis_n(2, 3)));
+    // pauli_string_tests.rs:408-438 golden [1/sqrt2, 0, -i/sqrt2, 0]
+    PauliString ps = PauliString(cplx(0.5 * M_PI, 0.0)).with_op(0, Pauli::Z).with_op(1, Pauli::X);
+    auto v = ps.apply_exp_neg_i_dt(State::new_zero(2), 0.5).state_vector();
+    EXPECT(std::abs(v[0] - cplx(S2, 0)) < 1e-12 && std::abs(v[2] - cplx(0, -S2)) < 1e-12 && std::abs(v[1]) < 1e-12 && std::abs(v[3]) < 1e-12);
+    // pauli_string_tests.rs:348-364: <11| 2X0 + 3Y1 + 4Z1 |11> = -4
+    SumOp so({PauliString(2.0).with_op(0, Pauli::X), PauliString(3.0).with_op(1, Pauli::Y), PauliString(4.0).with_op(1, Pauli::Z)});
+    EXPECT(std::abs(so.expectation_value(State::new_basis_n(2, 3)) - cplx(-4.0, 0.0)) < 1e-12);
+    // circuit_tests.rs:84-95
+    Circuit c = CircuitBuilder(2).h_gates({0, 1}).build();
+    EXPECT(c.execute(State::new_zero(2)).approx_eq(State::new_plus(2)));
+    EXPECT(throws("InvalidNumberOfQubits", 1, 0, [&] { c.execute(State::new_zero(1)); }));
+    // builder argument order (circuit.rs:1071, 1118-1123)
+    EXPECT(CircuitBuilder(3).x_gate(0).cnot_gate(1, 0).build().execute(State::new_zero(3)).approx_eq(State::new_basis_n(3, 3)));
+    // Subroutine::qft closed forms (unpinned by the reference): QFT|+..+> = |0..0>, iqft.qft = 1
+    const size_t n = 16;
+    std::vector<size_t> qs(n);
+    for (size_t i = 0; i < n; i++) qs[i] = i;
+    State out = CircuitBuilder(n).add_subroutine(Subroutine::qft(qs, n)).build().execute(State::new_plus(n));
+    EXPECT(std::abs(out.amplitude(0) - cplx(1.0, 0.0)) < 1e-12 && std::abs(out.amplitude(12345)) < 1e-12);
+    State ghz = State::new_ghz(n);
+    State back = CircuitBuilder(n).add_subroutine(Subroutine::qft(qs, n)).add_subroutine(Subroutine::iqft(qs, n)).build().execute(ghz);
+    EXPECT(std::abs(back.inner_product(ghz) - cplx(1.0, 0.0)) < 1e-12);
+    // measurement_tests.rs:4-30: outcome-conditional collapse of (|00>+|11>)/sqrt2
+    for (uint64_t seed = 0; seed < 8; seed++) {
+        State bell = State::from_vector({cplx(S2, 0), 0, 0, cplx(S2, 0)});
+        auto o = bell.measure_(MeasurementBasis::Computational, {0}, seed);
+        EXPECT(bell.approx_eq(State::new_basis_n(2, o[0] ? 3 : 0)));
+    }
+    // heisenberg + trotter run and keep the norm (time_evolution.rs:140-167)
+    SumOp hs = heisenberg_1d(10, 1.0, 2.0, 3.0, 0.5, 0.1);
+    EXPECT(hs.num_terms() == 40);
+    State ev = hs.trotter_evolve(State::new_plus(10), 0.01, 5, 1);
+    EXPECT(std::fabs(ev.norm_sqr() - 1.0) < 1e-12);
+    EXPECT(std::fabs(hs.expectation_value(ev).imag()) < 1e-12);
+    std::printf(failures ? "C++ facade: %d FAILURES\n" : "C++ facade: ALL PASS\n", failures);
+    return failures ? 1 : 0;
+}

@@ -1,0 +1,25 @@
+"""The compiled-language host side: include/quant_iron_b200.hpp (C++ facade over the C ABI) passes a
+selection of the reference's known-answer tests on the GPU."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "test_facade")
+
+
+def test_facade_compiles_on_cpu_box():
+    import __graft_entry__ as g
+    g.build()
+    assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+def test_facade_known_answers_on_gpu():
+    if not os.path.exists(BIN):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASS" in r.stdout
