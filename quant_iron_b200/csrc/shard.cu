@@ -111,8 +111,10 @@ int exchange_multi(qi_state* s, const std::vector<int>& G, const std::vector<int
     BitInsert ins = make_insert(zeros, {});
     const uint64_t total = s->len >> (k + 1);
     QI_TRY(barrier(s));                                 // everyone's earlier kernels are complete
-    for (uint64_t lambda = 0; lambda < (1ull << k); lambda++) {
-        if (lambda == rho) continue;
+    // XOR schedule: in step d every rank trades with rank value rho ^ d, a perfect matching, so no
+    // GPU's NVLink port is ever the target of more than one peer at a time
+    for (uint64_t d = 1; d < (1ull << k); d++) {
+        const uint64_t lambda = rho ^ d;
         int partner = s->rank;
         for (int i = 0; i < k; i++) partner = (partner & ~(1 << (G[i] - nl))) | ((int)((lambda >> i) & 1) << (G[i] - nl));
         const uint64_t hsel = (rho < lambda) ? 0ull : (1ull << h);     // the lower rank value takes the h = 0 half
