@@ -219,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's "NCCL version ..." banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     qi.engine.init(local_rank)
     peak_gbs, peak_src = load_peaks()

@@ -204,6 +204,11 @@ int qi_state_layout(const qi_state* s, uint8_t* phys, uint32_t* n_local);
 int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* exchanges,
                   uint64_t* comm_free_global_gates, uint8_t* final_phys);
 
+/* host-only: how the fused executor splits a gate list into passes on one device; rows[6*i..] =
+ * {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops} */
+int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int window_regs, int32_t* rows,
+                      uint64_t max_rows, uint64_t* n_rows);
+
 #ifdef __cplusplus
 }
 #endif

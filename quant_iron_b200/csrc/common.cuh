@@ -189,6 +189,7 @@ int launch_simple_gate(qi_state* s, const PhysGate& g);      // one pass with th
 // window.cu
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates);
 bool window_supported(const qi_state* s);
+int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<std::vector<int>>* summary);
 // shard.cu
 int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip);
 bool shard_needs_exchange(const qi_state* s, const qi_gate* g);

@@ -402,4 +402,34 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
     return flush();
 }
 
+// Host-only: how the fused executor would split a gate list into passes on a single device (no device access).
+// rows[6*i..] = {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops}
+int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int window_regs, int32_t* rows,
+                      uint64_t max_rows, uint64_t* n_rows) {
+    qi_state s;
+    s.num_qubits = num_qubits;
+    s.n_local = num_qubits;
+    s.len = 1ull << num_qubits;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    std::vector<PhysGate> run;
+    for (uint64_t i = 0; i < count; i++) {
+        QI_TRY(validate_gate(&s, &gates[i]));
+        if (gates[i].kind == QI_GATE_SWAP && gates[i].num_controls == 0) { std::swap(s.phys[gates[i].targets[0]], s.phys[gates[i].targets[1]]); continue; }
+        PhysGate pg;
+        bool skip = false;
+        QI_TRY(prepare_gate(&s, &gates[i], &pg, &skip));
+        if (!skip && pg.kind != IK_NOP) run.push_back(pg);
+    }
+    std::vector<std::vector<int>> summary;
+    QI_TRY(debug_schedule(&s, run, window_regs ? window_regs : 4, &summary));
+    uint64_t n = 0;
+    for (auto& r : summary) {
+        if (n >= max_rows) break;
+        for (int k = 0; k < 6; k++) rows[6 * n + k] = r[k];
+        n++;
+    }
+    if (n_rows) *n_rows = summary.size();
+    return QI_OK;
+}
+
 }  // extern "C"

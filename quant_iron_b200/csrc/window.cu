@@ -108,6 +108,11 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
 
 template <int R, int B>
 __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
+#ifdef QI_UNCOND_FAST
+    // uncontrolled H / RX / RY (the bulk of layered circuits): straight-line variant without slot predicates
+    if (c_reg == 0 && kind == WK_REAL) { reg_pair_kind<R, B, WK_REAL, false>(v, 0, m); return; }
+    if (c_reg == 0 && kind == WK_RX) { reg_pair_kind<R, B, WK_RX, false>(v, 0, m); return; }
+#endif
     switch (kind) {
         case WK_X: reg_pair_kind<R, B, WK_X, true>(v, c_reg, m); break;
         case WK_RX: reg_pair_kind<R, B, WK_RX, true>(v, c_reg, m); break;
@@ -610,13 +615,10 @@ static double touched_fraction(const PhysGate& g) {
     return f;
 }
 
-int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
-    Context& c = ctx();
-    const bool fuse = c.opt_fuse != 0;
-    const int R = window_regs(s);
+// greedy pass construction (host only, no device access)
+static int schedule_passes(const qi_state* s, const std::vector<PhysGate>& gates, bool fuse, int R, std::vector<Step>& steps) {
     const size_t G = gates.size();
     std::vector<char> done(G, 0);
-    std::vector<Step> steps;
     size_t first = 0;           // first gate not yet scheduled
     const size_t kLookahead = 4096;
     while (first < G) {
@@ -664,6 +666,14 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
         }
         steps.push_back(Step{false, 0, std::move(ps), R});   // (measured: the 8-amplitude kernel streams ~6% slower than R = 4)
     }
+    return QI_OK;
+}
+
+int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
+    Context& c = ctx();
+    const int R = window_regs(s);
+    std::vector<Step> steps;
+    QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
     // lower every pass, upload all phase tables in one copy, then launch back to back
     std::vector<std::vector<DOp>> dops(steps.size());
     std::vector<Layout> layouts(steps.size());
@@ -682,6 +692,23 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
         else if (steps[i].R == 3) QI_TRY(launch_program<3>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else if (steps[i].R == 4) QI_TRY(launch_program<4>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else QI_TRY(launch_program<5>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
+    }
+    return QI_OK;
+}
+
+// host-only: schedule a run of physical gates and report the passes (tuning / tests; no device access)
+int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<std::vector<int>>* summary) {
+    std::vector<Step> steps;
+    QI_TRY(schedule_passes(s, gates, true, R, steps));
+    for (const Step& st : steps) {
+        int lane_ops = 0, reg_ops = 0, diag_ops = 0, table_ops = 0;
+        for (const HOp& h : st.pass.ops) {
+            if (h.kind == WK_TABLE) table_ops++;
+            else if (h.kind == WK_DIAG || h.kind == WK_RZ) diag_ops++;
+            else if (h.target < kLaneQubits) lane_ops++;
+            else reg_ops++;
+        }
+        summary->push_back({st.simple ? 1 : 0, (int)st.pass.regs.size(), lane_ops, reg_ops, diag_ops, table_ops});
     }
     return QI_OK;
 }
