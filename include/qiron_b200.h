@@ -161,8 +161,17 @@ int qi_apply_pauli_exp(qi_state* s, const qi_pauli_term* term, const double fact
 int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, double out[2]);
 /* SumOp::apply (pauli_string.rs:453-466): out = sum_k P_k psi (new state) */
 int qi_apply_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t count, qi_state** out);
-/* trotter_evolve_state (time_evolution.rs:140-167); order 1 = First (45-66), 2 = Second (89-115) */
+/* a run of apply_exp_factor calls (pauli_string.rs:237-262) applied in order, term k with factors[2k], factors[2k+1]:
+ * what the Trotter loops (time_evolution.rs:57-63, 102-111) and a run of Gate::PauliTimeEvolution gates
+ * (gate.rs:116-118) do.  Consecutive terms share register-window passes. */
+int qi_apply_pauli_exp_sequence(qi_state* s, const qi_pauli_term* terms, uint64_t count, const double* factors);
+/* trotter_evolve_state (time_evolution.rs:140-167); order 1 = First (45-66), 2 = Second (89-115); the whole
+ * evolution is one such sequence */
 int qi_trotter_evolve(qi_state* s, const qi_pauli_term* terms, uint64_t count, double dt, uint64_t steps, int order);
+/* host-only: passes the batching scheduler builds for `repeats` repetitions of the term list on a
+ * `num_qubits` state (terms per pass; 0 = a term that runs alone); no device access */
+int qi_debug_pauli_schedule(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, uint64_t repeats,
+                            int32_t* terms_per_pass, uint64_t max_passes, uint64_t* n_passes);
 
 /* ---- measurement (state.rs:525-784) --------------------------------------------------------- */
 typedef enum qi_basis { QI_BASIS_COMPUTATIONAL = 0, QI_BASIS_X = 1, QI_BASIS_Y = 2, QI_BASIS_CUSTOM = 3 } qi_basis;

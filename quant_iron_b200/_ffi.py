@@ -87,6 +87,8 @@ _sig("qi_apply_pauli_exp", [state_p, C.POINTER(QiPauliTerm), dp])
 _sig("qi_expect_pauli_sum", [state_p, C.POINTER(QiPauliTerm), C.c_uint64, dp])
 _sig("qi_apply_pauli_sum", [state_p, C.POINTER(QiPauliTerm), C.c_uint64, C.POINTER(state_p)])
 _sig("qi_trotter_evolve", [state_p, C.POINTER(QiPauliTerm), C.c_uint64, C.c_double, C.c_uint64, C.c_int])
+_sig("qi_apply_pauli_exp_sequence", [state_p, C.POINTER(QiPauliTerm), C.c_uint64, dp])
+_sig("qi_debug_pauli_schedule", [C.c_uint32, C.POINTER(QiPauliTerm), C.c_uint64, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, u64p])
 _sig("qi_probabilities", [state_p, u32p, C.c_uint32, dp])
 _sig("qi_sample", [state_p, u32p, C.c_uint32, C.c_uint64, C.c_uint64, u64p])
 _sig("qi_collapse", [state_p, u32p, C.c_uint32, C.c_uint64])

@@ -225,7 +225,8 @@ class Circuit:
 
     # ---- lowering to C-ABI records ----
     def _lower(self):
-        """Split the gate list into runs: ('ops', qi_gate[count], count, keepalive) | ('gate', Gate)."""
+        """Split the gate list into runs: ('ops', qi_gate[count], count, keepalive) |
+        ('evol', qi_pauli_term[count], count, keepalive, factors) | ('gate', Gate, index)."""
         if self._records is not None:
             return self._records
         runs = []
@@ -243,13 +244,35 @@ class Circuit:
             runs.append(("ops", arr, len(cur), keep))
             cur.clear()
 
+        evol: List[Gate] = []
+
+        def close_evol():
+            # consecutive PauliTimeEvolution gates = one apply_exp_factor sequence (fused passes on the device)
+            if not evol:
+                return
+            arr = (_ffi.QiPauliTerm * len(evol))()
+            keep, factors = [], []
+            for i, g in enumerate(evol):
+                rec, k = g.pauli_string.term()
+                arr[i] = rec
+                keep.append(k)
+                factors += [0.0, -g.time]
+            runs.append(("evol", arr, len(evol), (keep, list(evol)), _ffi.dbl_array(factors)))
+            evol.clear()
+
         for index, g in enumerate(self.gates):
             if g.kind == "Operator":
+                close_evol()
                 cur.append(g)
+            elif g.kind == "PauliTimeEvolution":
+                close()
+                evol.append(g)
             else:
                 close()
+                close_evol()
                 runs.append(("gate", g, index))
         close()
+        close_evol()
         self._records = runs
         return runs
 
@@ -260,6 +283,11 @@ class Circuit:
         for run in self._lower():
             if run[0] == "ops":
                 _ffi.check(_lib.qi_apply_circuit(state._h, run[1], run[2]))
+            elif run[0] == "evol":
+                for g in run[3][1]:                       # gate.rs:116-118 -> pauli_string.rs:281-284
+                    if g.pauli_string.coefficient().imag != 0.0:
+                        raise Error("InvalidPauliStringCoefficient", g.pauli_string.coefficient())
+                _ffi.check(_lib.qi_apply_pauli_exp_sequence(state._h, run[1], run[2], run[4]))
             else:
                 # gate k of the circuit draws from the stream seeded `seed + k` (shared-seed contract)
                 run[1].apply_(state, None if seed is None else seed + run[2])

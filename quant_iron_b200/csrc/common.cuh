@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* what);
 enum KernelFamily {
     KF_INIT = 0, KF_PAIR, KF_DIAG, KF_SWAP, KF_MATCH, KF_WINDOW, KF_PAULI, KF_PAULI_EXP, KF_EXPECT,
     KF_REDUCE, KF_ELEMENTWISE, KF_PROB, KF_SCAN, KF_SAMPLE, KF_COLLAPSE, KF_EXCHANGE, KF_BARRIER,
-    KF_COUNT
+    KF_PAULI_WINDOW, KF_COUNT
 };
 extern const char* const kFamilyNames[KF_COUNT];
 
@@ -182,6 +182,19 @@ struct PhysGate {
     uint64_t cmask;      // physical control bits that must be 1 (local bits only after rank filtering)
     double p[8];         // resolved numeric parameters (see resolve_gate)
 };
+
+// one exp(alpha P) factor, reduced to masks over PHYSICAL local bit positions (pauli.cu)
+struct PauliExp {
+    uint64_t x, z;       // flipped bits (X, Y factors) / sign bits (Y, Z factors), local bits only
+    int k0;              // (3 nY + 2 popc(rank bits & z)) & 3
+    amp_t ch, sh;        // cosh(alpha), sinh(alpha); an empty string is (exp(alpha), 0) with x = z = 0
+};
+// pauli.cu
+int pauli_exp_single(qi_state* s, const PauliExp& t);          // one term, one pass (per-term kernels)
+// pauli_window.cu
+bool pauli_window_supported(const qi_state* s);
+int run_pauli_exp_batch(qi_state* s, const std::vector<PauliExp>& seq);
+int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* terms_per_pass);
 
 // gates.cu
 int validate_gate(const qi_state* s, const qi_gate* g);

@@ -10,7 +10,7 @@ namespace qi {
 const char* const kFamilyNames[KF_COUNT] = {
     "init", "gate_pair", "gate_diag", "gate_swap", "gate_matchgate", "gate_window", "pauli_apply",
     "pauli_exp", "pauli_expect", "reduce", "elementwise", "probabilities", "scan", "sample",
-    "collapse", "exchange", "barrier"};
+    "collapse", "exchange", "barrier", "pauli_exp_window"};
 
 static thread_local uint64_t tl_payload[2] = {0, 0};
 static thread_local char tl_msg[256] = {0};

@@ -9,6 +9,8 @@
 // (each factor is a permutation times a power of i, all exact in floating point), so one fused
 // pass replaces the reference's clone + one sweep per factor; exp(alpha P) psi =
 // cosh(alpha) psi + sinh(alpha) P psi (pauli_string.rs:251-261) is one pass too.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace qi {
@@ -186,6 +188,67 @@ static int exp_masks(qi_state* s, Masks m, amp_t alpha) {
 
 int shard_localise_mask(qi_state* s, const qi_pauli_term* t);   // shard.cu: make every X/Y qubit local
 
+// one term on the per-term kernels (k0 already holds the rank-bit signs; 3*(3*k0) = k0 mod 4)
+int pauli_exp_single(qi_state* s, const PauliExp& t) {
+    Context& c = ctx();
+    Masks m{t.x, t.z, (3 * t.k0) & 3, 0};
+    LaunchScope ls(KF_PAULI_EXP, 32.0 * (double)s->len);
+    if (t.x == 0) {
+        k_pauli_exp_diag<<<grid_for(s->len, kBlock), kBlock, 0, c.stream>>>(s->d, s->len, m, t.ch, t.sh);
+    } else {
+        uint64_t pairs = s->len >> 1;
+        k_pauli_exp_pair<<<(unsigned)((pairs + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, pairs, highest_bit(t.x), m, t.ch, t.sh);
+    }
+    return check_launch("pauli_exp");
+}
+
+// reduce exp(factor * coefficient * P) to masks under the state's CURRENT layout
+static int make_exp(const qi_state* s, const qi_pauli_term& t, amp_t factor, PauliExp* e, bool* needs_exchange) {
+    Masks m;
+    QI_TRY(term_masks(s, &t, &m));
+    const amp_t alpha = cmul(make_double2(t.coefficient[0], t.coefficient[1]), factor);      // pauli_string.rs:239
+    *needs_exchange = false;
+    if (t.num_ops == 0) {            // pauli_string.rs:241-244: state * exp(alpha)
+        e->x = e->z = 0; e->k0 = 0; e->ch = h_cexp(alpha); e->sh = make_double2(0.0, 0.0);
+        return QI_OK;
+    }
+    const uint64_t local_mask = s->len - 1;
+    *needs_exchange = (m.x & ~local_mask) != 0;
+    e->x = m.x;
+    e->z = m.z & local_mask;
+    e->k0 = (3 * m.ny + 2 * __builtin_popcountll(m.high & m.z)) & 3;
+    e->ch = h_ccosh(alpha);
+    e->sh = h_csinh(alpha);
+    return QI_OK;
+}
+
+// state <- exp(f_k c_k P_k) state for the terms order[0], order[1], ... (apply_exp_factor in sequence).
+// Consecutive terms are fused into register-window passes (pauli_window.cu) unless the state is too small
+// or fusion is switched off; a term with an X/Y factor on a rank bit first flushes the pending batch and
+// exchanges that qubit into the local bits.
+static int exp_sequence(qi_state* s, const qi_pauli_term* terms, const std::vector<uint32_t>& order, const std::vector<amp_t>& factors) {
+    Context& c = ctx();
+    const bool batch = c.opt_fuse && c.opt_path != 1 && pauli_window_supported(s);
+    std::vector<PauliExp> pending;
+    for (size_t k = 0; k < order.size(); k++) {
+        const qi_pauli_term& t = terms[order[k]];
+        PauliExp e;
+        bool ex = false;
+        QI_TRY(make_exp(s, t, factors[k], &e, &ex));
+        if (ex) {
+            QI_TRY(run_pauli_exp_batch(s, pending));
+            pending.clear();
+            QI_TRY(shard_localise_mask(s, &t));
+            QI_TRY(make_exp(s, t, factors[k], &e, &ex));
+            if (ex) return fail(QI_ERR_PEER, 0, 0, "X/Y factor still on a global qubit after the exchange");
+        }
+        if (batch) { pending.push_back(e); continue; }
+        if (t.num_ops == 0) { double z[2] = {e.ch.x, e.ch.y}; QI_TRY(qi_scale(s, z)); }
+        else QI_TRY(pauli_exp_single(s, e));
+    }
+    return run_pauli_exp_batch(s, pending);
+}
+
 }  // namespace qi
 
 using namespace qi;
@@ -290,23 +353,70 @@ int qi_apply_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t c
     return check_launch("pauli_sum_apply");
 }
 
+int qi_apply_pauli_exp_sequence(qi_state* s, const qi_pauli_term* terms, uint64_t count, const double* factors) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    if (count == 0) return QI_OK;
+    if (!terms || !factors) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    Masks m;
+    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &m));      // validate before touching the state
+    QI_TRY(ensure_ctx());
+    std::vector<uint32_t> order(count);
+    std::vector<amp_t> f(count);
+    for (uint64_t k = 0; k < count; k++) { order[k] = (uint32_t)k; f[k] = make_double2(factors[2 * k], factors[2 * k + 1]); }
+    return exp_sequence(s, terms, order, f);
+}
+
 int qi_trotter_evolve(qi_state* s, const qi_pauli_term* terms, uint64_t count, double dt, uint64_t steps, int order) {
     if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
     if (count == 0) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, 0, 0, "empty Hamiltonian");   // time_evolution.rs:147-149
     if (!terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
     if (order != 1 && order != 2) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)order, 0, "order must be 1 or 2");
+    if (count > 0xffffffffull) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "too many terms");
     // validate every term once, before touching the state
     Masks m;
     for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &m));
-    const double f1[2] = {0.0, -dt}, f2[2] = {0.0, -dt / 2.0};
-    for (uint64_t step = 0; step < steps; step++) {
-        if (order == 1) {
-            for (uint64_t k = 0; k < count; k++) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f1));           // 57-63
-        } else {
-            for (uint64_t k = 0; k < count; k++) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f2));           // 102-105
-            for (uint64_t k = count; k-- > 0;) QI_TRY(qi_apply_pauli_exp(s, &terms[k], f2));             // 108-111
+    QI_TRY(ensure_ctx());
+    // the whole evolution is one sequence of apply_exp_factor calls; it is handed to the batching executor in
+    // chunks of whole steps so that passes can span step boundaries
+    const amp_t f1 = make_double2(0.0, -dt), f2 = make_double2(0.0, -dt / 2.0);
+    const uint64_t per_step = order == 1 ? count : 2 * count;
+    const uint64_t steps_per_chunk = std::max<uint64_t>(1, 16384 / per_step);
+    std::vector<uint32_t> seq;
+    std::vector<amp_t> f;
+    for (uint64_t step0 = 0; step0 < steps; step0 += steps_per_chunk) {
+        const uint64_t ns = std::min(steps_per_chunk, steps - step0);
+        seq.clear();
+        f.clear();
+        for (uint64_t st = 0; st < ns; st++) {
+            if (order == 1) {
+                for (uint64_t k = 0; k < count; k++) { seq.push_back((uint32_t)k); f.push_back(f1); }           // 57-63
+            } else {
+                for (uint64_t k = 0; k < count; k++) { seq.push_back((uint32_t)k); f.push_back(f2); }           // 102-105
+                for (uint64_t k = count; k-- > 0;) { seq.push_back((uint32_t)k); f.push_back(f2); }             // 108-111
+            }
         }
+        QI_TRY(exp_sequence(s, terms, seq, f));
     }
+    return QI_OK;
+}
+
+int qi_debug_pauli_schedule(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, uint64_t repeats,
+                            int32_t* terms_per_pass, uint64_t max_passes, uint64_t* n_passes) {
+    if (!terms || !n_passes || num_qubits == 0 || num_qubits > 62) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "bad argument");
+    qi_state host;                   // layout only: no device memory is touched
+    host.num_qubits = host.n_local = num_qubits;
+    host.len = 1ull << num_qubits;
+    for (int q = 0; q < 64; q++) host.phys[q] = (uint8_t)q;
+    std::vector<PauliExp> one(count), seq;
+    for (uint64_t k = 0; k < count; k++) {
+        bool ex = false;
+        QI_TRY(make_exp(&host, terms[k], make_double2(0.0, -0.01), &one[k], &ex));
+    }
+    for (uint64_t r = 0; r < repeats; r++) seq.insert(seq.end(), one.begin(), one.end());
+    std::vector<int> per;
+    QI_TRY(debug_pauli_schedule(seq, &per));
+    *n_passes = per.size();
+    for (size_t i = 0; i < per.size() && i < max_passes; i++) terms_per_pass[i] = per[i];
     return QI_OK;
 }
 

@@ -24,14 +24,13 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "window_layout.cuh"
 
 namespace qi {
 
 enum { WK_X = 1, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };   // pair kinds first (<= WK_U2)
-enum { CLS_NONE = 0, CLS_LANE = 1, CLS_REG = 2, CLS_TILE = 3 };
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 104 B + header < 16 KB)
-static const int kLaneQubits = 5;
 
 struct DOp {                 // device op, 104 bytes
     uint8_t kind;            // WK_*
@@ -446,46 +445,7 @@ static void lower_gate(Pass& ps, const PhysGate& g, bool merge) {
 }
 
 // ---- host: lowering a pass to device form -----------------------------------------------------------
-struct Layout {
-    int R;
-    std::vector<int> regs;              // sorted window qubits
-    int cls[64];                        // CLS_* per physical bit
-    int idx[64];                        // lane bit / slot bit / compact tile bit per physical bit
-    int ntile_bits;
-};
-
-static Layout make_layout(const qi_state* s, std::vector<int> regs, int R) {
-    Layout L;
-    L.R = R;
-    const int n = (int)s->n_local;
-    std::sort(regs.begin(), regs.end());
-    // pad the window with unused qubits (lowest free positions first: better locality)
-    for (int q = kLaneQubits; q < n && (int)regs.size() < R; q++)
-        if (std::find(regs.begin(), regs.end(), q) == regs.end()) regs.push_back(q);
-    std::sort(regs.begin(), regs.end());
-    L.regs = regs;
-    int t = 0;
-    for (int q = 0; q < 64; q++) {
-        L.cls[q] = CLS_NONE; L.idx[q] = 0;
-        if (q >= n) continue;
-        auto it = std::find(regs.begin(), regs.end(), q);
-        if (q < kLaneQubits) { L.cls[q] = CLS_LANE; L.idx[q] = q; }
-        else if (it != regs.end()) { L.cls[q] = CLS_REG; L.idx[q] = (int)(it - regs.begin()); }
-        else { L.cls[q] = CLS_TILE; L.idx[q] = t++; }
-    }
-    L.ntile_bits = t;
-    return L;
-}
-
-static void split_mask(const Layout& L, uint64_t phys, uint32_t* lane, uint32_t* reg, uint64_t* tile) {
-    *lane = 0; *reg = 0; *tile = 0;
-    for (int q = 0; q < 64; q++) {
-        if (!((phys >> q) & 1)) continue;
-        if (L.cls[q] == CLS_LANE) *lane |= 1u << L.idx[q];
-        else if (L.cls[q] == CLS_REG) *reg |= 1u << L.idx[q];
-        else if (L.cls[q] == CLS_TILE) *tile |= 1ull << L.idx[q];
-    }
-}
+// (Layout / make_layout / split_mask: window_layout.cuh)
 
 // build the tables of one group: [lane(32) | slot(2^R) | chunk0(256) | chunk1(256) ...]
 static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>& arena, DOp* d) {
@@ -560,12 +520,7 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
     Context& c = ctx();
     WProgram<R> P;
     memset(&P, 0, sizeof(P));
-    P.ins = make_insert(L.regs, {});
-    for (int sidx = 0; sidx < (1 << R); sidx++) {
-        uint64_t o = 0;
-        for (int j = 0; j < R; j++) if ((sidx >> j) & 1) o |= 1ull << L.regs[j];
-        P.off[sidx] = o;
-    }
+    fill_offsets<R>(L, &P.ins, P.off);
     P.tables = d_tables;
     const uint64_t ntiles = s->len >> (kLaneQubits + R);
     const int warps_per_block = 4;

@@ -127,6 +127,29 @@ class PauliString:
         return f"{self._coefficient} * {ops}"
 
 
+def apply_exp_sequence_(state, strings, factors):
+    """In place: state <- exp(factors[k] * c_k * P_k) state for k = 0, 1, ... — the same result as calling
+    apply_exp_factor (pauli_string.rs:237-262) once per string, but consecutive strings share fused
+    register-window passes on the device (qi_apply_pauli_exp_sequence)."""
+    strings = list(strings)
+    factors = [complex(f) for f in factors]
+    if len(strings) != len(factors):
+        raise Error("MismatchedNumberOfParameters", len(strings), len(factors))
+    if not strings:
+        return state
+    arr = (_ffi.QiPauliTerm * len(strings))()
+    keep = []
+    for i, ps in enumerate(strings):
+        rec, k = ps.term()
+        arr[i] = rec
+        keep.append(k)
+    flat = []
+    for f in factors:
+        flat += [f.real, f.imag]
+    _ffi.check(_lib.qi_apply_pauli_exp_sequence(state._h, arr, len(strings), _ffi.dbl_array(flat)))
+    return state
+
+
 class SumOp:
     """pauli_string.rs:398-507."""
 

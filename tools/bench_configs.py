@@ -80,6 +80,25 @@ if 3 in configs:
            "terms": h.num_terms(), "exp_applications": 50 * h.num_terms(), "trotter_ms": ms, "expectation_ms": ms_e,
            "expectation": [e.real, e.imag], "norm_sqr": st.norm_sqr(),
            "effective_gbs": 50 * h.num_terms() * 32.0 * (1 << n) / (ms * 1e-3) / 1e9}
+    # the same evolution on the per-term kernels (one pass per exp), and the pass statistics of the fused path
+    qi.engine.set_option("fuse", 0)
+    st_u = qi.State.new_plus(n)
+    rec["trotter_ms_per_term_kernels"] = timed(lambda: qi.trotter_evolve_state_(h, st_u, 0.01, 50, qi.TrotterOrder.First))
+    qi.engine.set_option("fuse", 1)
+    rec["fused_vs_per_term_diff_norm"] = (st - st_u).norm_sqr() ** 0.5
+    del st_u
+    qi.engine.stats_reset()
+    qi.engine.set_option("profile", 1)
+    st_p = qi.State.new_plus(n)
+    qi.trotter_evolve_state_(h, st_p, 0.01, 50, qi.TrotterOrder.First)
+    qi.engine.synchronize()
+    qi.engine.set_option("profile", 0)
+    rec["kernels"] = qi.engine.stats()
+    w = rec["kernels"].get("pauli_exp_window")
+    if w and w["launches"]:
+        rec["window_pass_ms"] = w["total_ms"] / w["launches"]
+        rec["window_pass_gbs"] = 32.0 * (1 << n) / (w["total_ms"] / w["launches"] * 1e-3) / 1e9
+    del st_p
     if a.with_oracle:
         from oracle import refapi as ref
         hr = ref.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1)
