@@ -58,6 +58,7 @@ struct Context {
     int opt_profile = 0;
     int opt_window_regs = 0;          // 0 = default
     int opt_lazy_swap = 1;            // uncontrolled SWAP = relabelling of the qubit map
+    int opt_tma = 0;                  // window passes: 1 = TMA-prefetched persistent kernel (measured 2.4% slower), 0 = direct loads
     // stats
     uint64_t launches[KF_COUNT] = {0};
     double alg_bytes[KF_COUNT] = {0};

@@ -175,10 +175,83 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
     }
 }
 
+// ---- the op program on one register tile -------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const WProgram<R>& P) {
+    constexpr int S = 1 << R;
+#pragma unroll 1
+    for (uint32_t o = 0; o < P.nops; o++) {
+        const DOp& op = P.ops[o];
+        const uint64_t c_tile = op.c_tile;
+        if ((tile & c_tile) != c_tile) continue;                      // warp-uniform control
+        const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
+        const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
+        if (kind <= WK_U2 && tpos < 5) {                              // pair gate across lanes
+            lane_pair_op<R>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
+            continue;
+        }
+        if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
+        if (kind == WK_DIAG) {
+            const amp_t ph = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((s & c_reg) == c_reg) v[s] = cmul(v[s], ph);
+        } else if (kind == WK_RZ) {
+            const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
+            const uint32_t t_reg = op.t_reg;
+            if (t_reg == 0 && c_reg == 0) {                           // target outside the registers: one phase per thread
+                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+                const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+                for (int s = 0; s < S; s++) v[s] = cmul(v[s], pt);
+            } else {
+                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+                const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((s & c_reg) == c_reg) {
+                        if (s & t_reg) v[s] = cmul(v[s], p1);
+                        else v[s] = cmul(v[s], pt);
+                    }
+            }
+        } else if (kind == WK_TABLE) {
+            const amp_t* __restrict__ tab = P.tables + (uint64_t)__double_as_longlong(op.m[0]);
+            const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
+            if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
+            if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) continue;
+            amp_t f = tab[lane];                                        // lane table (32 entries)
+            const uint32_t nch = op.nchunks;
+            for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
+                f = cmul(f, __ldg(tab + 32 + S + 256 * k + ((tile >> (8 * k)) & 255)));
+            const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
+            if (op.has_reg) {
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], f);
+            }
+        } else {
+            switch (tpos - 5) {
+                case 0: reg_pair_op<R, 0>(v, kind, c_reg, op.m); break;
+                case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, op.m); break;
+                case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, op.m); break;
+                case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, op.m); break;
+                default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, op.m); break;
+            }
+        }
+    }
+}
+
 // resident blocks per SM the register budget is tuned for: 8 amplitudes/thread -> 8 blocks,
 // 16 -> 4 blocks (128 registers), 32 -> 2 blocks
+#define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? 4 : 2))
+
+// direct variant: every thread loads its 2^R amplitudes itself (coalesced 512 B per warp access)
 template <int R>
-__global__ void __launch_bounds__(128, (R <= 3 ? 8 : (R == 4 ? 4 : 2))) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
+__global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -188,70 +261,78 @@ __global__ void __launch_bounds__(128, (R <= 3 ? 8 : (R == 4 ? 4 : 2))) k_window
         amp_t v[S];
 #pragma unroll
         for (int s = 0; s < S; s++) v[s] = QI_LD(a + base + P.off[s]);
-#pragma unroll 1
-        for (uint32_t o = 0; o < P.nops; o++) {
-            const DOp& op = P.ops[o];
-            const uint64_t c_tile = op.c_tile;
-            if ((tile & c_tile) != c_tile) continue;                      // warp-uniform control
-            const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
-            const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
-            if (kind <= WK_U2 && tpos < 5) {                              // pair gate across lanes
-                lane_pair_op<R>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
-                continue;
-            }
-            if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
-            if (kind == WK_DIAG) {
-                const amp_t ph = make_double2(op.m[0], op.m[1]);
+        run_ops<R>(v, tile, lane, P);
 #pragma unroll
-                for (int s = 0; s < S; s++)
-                    if ((s & c_reg) == c_reg) v[s] = cmul(v[s], ph);
-            } else if (kind == WK_RZ) {
-                const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
-                const uint32_t t_reg = op.t_reg;
-                if (t_reg == 0 && c_reg == 0) {                           // target outside the registers: one phase per thread
-                    const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
-                    const amp_t pt = t_thread ? p1 : p0;
-#pragma unroll
-                    for (int s = 0; s < S; s++) v[s] = cmul(v[s], pt);
-                } else {
-                    const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
-                    const amp_t pt = t_thread ? p1 : p0;
-#pragma unroll
-                    for (int s = 0; s < S; s++)
-                        if ((s & c_reg) == c_reg) {
-                            if (s & t_reg) v[s] = cmul(v[s], p1);
-                            else v[s] = cmul(v[s], pt);
-                        }
-                }
-            } else if (kind == WK_TABLE) {
-                const amp_t* __restrict__ tab = P.tables + (uint64_t)__double_as_longlong(op.m[0]);
-                const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
-                if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
-                if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) continue;
-                amp_t f = tab[lane];                                        // lane table (32 entries)
-                const uint32_t nch = op.nchunks;
-                for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
-                    f = cmul(f, __ldg(tab + 32 + S + 256 * k + ((tile >> (8 * k)) & 255)));
-                const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
-                if (op.has_reg) {
-#pragma unroll
-                    for (int s = 0; s < S; s++)
-                        if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
-                } else {
-#pragma unroll
-                    for (int s = 0; s < S; s++)
-                        if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], f);
-                }
-            } else {
-                switch (tpos - 5) {
-                    case 0: reg_pair_op<R, 0>(v, kind, c_reg, op.m); break;
-                    case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, op.m); break;
-                    case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, op.m); break;
-                    case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, op.m); break;
-                    default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, op.m); break;
-                }
-            }
+        for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
+    }
+}
+
+// ---- TMA-prefetched variant ------------------------------------------------------------------------------
+// Persistent grid (one block slot per SM and resident block).  Every warp owns an 8 KiB (2^R x 512 B) staging
+// buffer in shared memory and one mbarrier: while it works on tile t in registers, the 2^R bulk copies
+// (cp.async.bulk, 512 B each, L2 evict-first) of its NEXT tile are already in flight, so HBM stays busy during
+// the compute phase of a fused pass instead of only during the load phase of whichever warps happen to be there.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "QI_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra QI_DONE;\n\t"
+        "bra QI_WAIT;\n\t"
+        "QI_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)
+                 : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
+    constexpr int S = 1 << R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];     // [4 warps][S * 32 amplitudes] then 4 mbarriers
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    amp_t* buf = reinterpret_cast<amp_t*>(smem_raw) + w * (S * 32);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 4 * S * 32 * sizeof(amp_t)) + w;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t warp = (uint64_t)blockIdx.x * 4 + w;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 4;
+    // lane s (< 2^R) fetches slot s of the tile: 32 consecutive amplitudes = 512 B
+    auto issue = [&](uint64_t tile) {
+        if (lane == 0) mbar_expect_tx(bar, S * 512);
+        __syncwarp();
+        if (lane < S) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was last read through the generic proxy
+            bulk_load_evict_first(buf + lane * 32, a + expand_index(tile << 5, P.ins) + P.off[lane], 512, bar);
         }
+    };
+    uint64_t tile = warp;
+    uint32_t parity = 0;
+    if (tile < ntiles) issue(tile);
+    for (; tile < ntiles; tile += nwarps) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        amp_t v[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) v[s] = buf[s * 32 + lane];
+        __syncwarp();
+        if (tile + nwarps < ntiles) issue(tile + nwarps);
+        run_ops<R>(v, tile, lane, P);
+        const uint64_t base = expand_index((tile << 5) | (uint64_t)lane, P.ins);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
     }
@@ -532,7 +613,19 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
         P.nops = (uint32_t)cnt;
         memcpy(P.ops, ops + first, cnt * sizeof(DOp));
         LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
-        k_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+        if (c.opt_tma) {
+            uint64_t pblocks = (uint64_t)c.sm_count * QI_WINDOW_BLOCKS(R);       // persistent: every block resident
+            if (pblocks > blocks) pblocks = blocks;
+            const size_t smem = (size_t)warps_per_block * (32u << R) * sizeof(amp_t) + warps_per_block * sizeof(uint64_t);
+            static bool configured = false;      // per instantiation
+            if (!configured) {
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = true;
+            }
+            k_window_tma<R><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
+        } else {
+            k_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+        }
         QI_TRY(check_launch("k_window"));
     }
     return QI_OK;

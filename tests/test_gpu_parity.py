@@ -361,3 +361,25 @@ def test_trotter_24_sites_fused_vs_per_term(gpu):
     assert d.norm_sqr() < 1e-24
     ea, eb = h.expectation_value(a), h.expectation_value(b)
     assert abs(ea - eb) <= EXP_RTOL * abs(eb)
+
+
+@pytest.mark.parametrize("n,regs", [(9, 4), (13, 4), (16, 4), (12, 3), (14, 5)])
+def test_tma_prefetched_window_kernel_matches_oracle(gpu, ref, n, regs):
+    """k_window_tma (cp.async.bulk + mbarrier staging, option "tma" = 1) computes exactly what the direct
+    kernel computes: layered circuit and QFT vs the oracle, for every register-window width."""
+    from quant_iron_b200 import workloads as w
+    gpu.engine.set_option("tma", 1)
+    gpu.engine.set_option("window_regs", regs)
+    try:
+        specs = w.random_layered_circuit(n, 10)
+        out_g = w.build_circuit(gpu, n, specs).execute(gpu.State.new_zero(n))
+        out_r = w.build_circuit(ref, n, specs).execute(ref.State.new_zero(n))
+        assert_amps(out_g, vec(out_r), msg=f"tma layered n={n}")
+        qs = list(range(n))
+        cg = gpu.CircuitBuilder(n).add_subroutine(gpu.Subroutine.qft(qs, n)).build()
+        cr = ref.CircuitBuilder(n).add_subroutine(ref.Subroutine.qft(qs, n)).build()
+        g, r = _pair(gpu, ref, n, seed=77)
+        assert_amps(cg.execute(g), vec(cr.execute(r)), msg=f"tma qft n={n}")
+    finally:
+        gpu.engine.set_option("tma", 0)
+        gpu.engine.set_option("window_regs", 0)
