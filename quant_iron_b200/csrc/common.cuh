@@ -104,7 +104,6 @@ struct qi_state {
     unsigned long long epoch = 0;
     uint64_t bytes_sent = 0, bytes_recv = 0, exchanges = 0, exchanged_qubits = 0;
     uint64_t reduce_count = 0;          // parity selects the allreduce scratch buffer
-    uint64_t lookahead_remaining = 0;   // gates left in the current qi_apply_circuit call (eviction heuristic)
     bool attached = false;
     bool identity_layout() const { for (uint32_t q = 0; q < num_qubits; q++) if (phys[q] != q) return false; return true; }
 };
@@ -206,8 +205,8 @@ bool window_supported(const qi_state* s);
 int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<std::vector<int>>* summary);
 // shard.cu
 int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip);
-bool shard_needs_exchange(const qi_state* s, const qi_gate* g);
-int shard_do_exchange(qi_state* s, const qi_gate* g);
+int apply_circuit_sharded(qi_state* s, const qi_gate* gates, uint64_t count, bool use_window);   // staged around exchanges
+int prepare_gate(qi_state* s, const qi_gate* g, PhysGate* o, bool* skip);                        // gates.cu
 int shard_allreduce_sum(qi_state* s, double* host_vals, int count);
 int exchange_global_local(qi_state* s, int global_phys, int local_phys);
 // reduce.cu

@@ -337,8 +337,6 @@ int canonicalise(qi_state* s) {
 
 using namespace qi;
 
-namespace qi { int prepare_gate(qi_state* s, const qi_gate* g, PhysGate* o, bool* skip); }
-
 extern "C" {
 
 int qi_unitary2_check(const double m[8]) {
@@ -370,6 +368,7 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
     QI_TRY(ensure_ctx());
     Context& c = ctx();
     const bool use_window = (c.opt_path != 1) && window_supported(s);
+    if (s->world > 1) return apply_circuit_sharded(s, gates, count, use_window);     // staged around the exchanges (shard.cu)
     std::vector<PhysGate> run;
     run.reserve(count);
     auto flush = [&]() -> int {
@@ -388,12 +387,6 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
             // (gates queued before it were mapped with the old labels, later ones use the new ones)
             std::swap(s->phys[gates[i].targets[0]], s->phys[gates[i].targets[1]]);
             continue;
-        }
-        if (s->world > 1 && shard_needs_exchange(s, &gates[i])) {
-            // a global<->local qubit exchange changes the qubit map: queued gates must run first
-            QI_TRY(flush());
-            s->lookahead_remaining = count - i;
-            QI_TRY(shard_do_exchange(s, &gates[i]));
         }
         QI_TRY(prepare_gate(s, &gates[i], &pg, &skip));
         if (skip || pg.kind == IK_NOP) continue;

@@ -191,7 +191,6 @@ static uint64_t global_targets(const qi_state* s, const qi_gate* g) {
     return m;
 }
 
-bool shard_needs_exchange(const qi_state* s, const qi_gate* g) { return s->world > 1 && global_targets(s, g) != 0; }
 
 static uint64_t target_positions(const qi_state* s, const qi_gate* g) {
     uint64_t m = 1ull << s->phys[g->targets[0]];
@@ -243,12 +242,88 @@ static int plan_exchange(const qi_state* s, const qi_gate* g, uint64_t rem, std:
     return QI_OK;
 }
 
-int shard_do_exchange(qi_state* s, const qi_gate* g) {
-    // `g` points into the caller's gate array: what follows it is the lookahead for the eviction choice
-    const uint64_t rem = s->lookahead_remaining ? s->lookahead_remaining - 1 : 0;
-    std::vector<int> G, L;
-    QI_TRY(plan_exchange(s, g, rem, &G, &L));
-    return exchange_multi(s, G, L);
+
+// ---- staged execution of a gate list on a sharded state ------------------------------------------------
+// A global<->local exchange costs about as much as four fused passes over the shard, so the gate list is cut
+// into STAGES: under the current qubit layout a stage takes every gate that (a) has no non-diagonal target
+// on a rank bit and (b) commutes with every gate deferred so far (on each shared qubit both act diagonally --
+// the rule the window scheduler uses).  Gates behind a deferred gate keep flowing as long as they stay
+// outside its light cone, so one exchange serves a deep trapezoid of the circuit instead of one layer.
+// Then ONE multi-qubit exchange brings in what the first deferred gate needs (plus what the lookahead over
+// the deferred list says will be needed soon) and the next stage starts.  Host-only decisions that depend on
+// the gate list alone: every rank takes the same ones, and the planner (qi_shard_plan) replays them.
+static void logical_uses(const qi_gate& g, uint64_t* n_use, uint64_t* d_use) {
+    *n_use = 0;
+    *d_use = 0;
+    for (uint32_t c = 0; c < g.num_controls; c++) *d_use |= 1ull << g.controls[c];
+    if (is_diag_kind(g.kind)) { *d_use |= 1ull << g.targets[0]; return; }
+    *n_use |= 1ull << g.targets[0];
+    if (g.kind == QI_GATE_SWAP) *n_use |= 1ull << g.targets[1];
+    if (g.kind == QI_GATE_MATCHGATE) *n_use |= 1ull << (g.targets[0] + 1);
+}
+
+// run(take): execute gates[take[0]], gates[take[1]], ... under the current layout.  exchange(G, L): swap the
+// global positions G with the local positions L and update s->phys.
+template <typename RunFn, typename ExchangeFn>
+static int staged_walk(qi_state* s, const qi_gate* gates, uint64_t count, RunFn run, ExchangeFn exchange) {
+    std::vector<uint64_t> pending(count), rest, take;
+    for (uint64_t i = 0; i < count; i++) pending[i] = i;
+    std::vector<qi_gate> ahead;
+    while (!pending.empty()) {
+        take.clear();
+        rest.clear();
+        uint64_t def_any = 0, def_n = 0;
+        for (uint64_t i : pending) {
+            uint64_t n_use, d_use;
+            logical_uses(gates[i], &n_use, &d_use);
+            const bool ok = global_targets(s, &gates[i]) == 0 && (n_use & def_any) == 0 && (d_use & def_n) == 0;
+            if (ok) take.push_back(i);
+            else { rest.push_back(i); def_any |= n_use | d_use; def_n |= n_use; }
+        }
+        QI_TRY(run(take));
+        if (rest.empty()) break;
+        // the first deferred gate is deferred only because of a global target: bring it in (lookahead = the
+        // deferred list, in order)
+        ahead.clear();
+        for (uint64_t i : rest) ahead.push_back(gates[i]);
+        std::vector<int> G, L;
+        QI_TRY(plan_exchange(s, ahead.data(), ahead.size() - 1, &G, &L));
+        if (G.empty()) return fail(QI_ERR_PEER, 0, 0, "staged execution made no progress");
+        QI_TRY(exchange(G, L));
+        pending.swap(rest);
+    }
+    return QI_OK;
+}
+
+// engine entry (qi_apply_circuit on a sharded state): segments between lazily relabelled SWAPs are staged
+int apply_circuit_sharded(qi_state* s, const qi_gate* gates, uint64_t count, bool use_window) {
+    Context& c = ctx();
+    std::vector<PhysGate> phys_run;
+    auto run = [&](const std::vector<uint64_t>& take, const qi_gate* seg) -> int {
+        phys_run.clear();
+        for (uint64_t i : take) {
+            PhysGate pg;
+            bool skip = false;
+            QI_TRY(prepare_gate(s, &seg[i], &pg, &skip));
+            if (!skip && pg.kind != IK_NOP) phys_run.push_back(pg);
+        }
+        if (phys_run.empty()) return QI_OK;
+        if (use_window) return run_circuit_windowed(s, phys_run);
+        for (const PhysGate& g : phys_run) QI_TRY(launch_simple_gate(s, g));
+        return QI_OK;
+    };
+    uint64_t first = 0;
+    while (first < count) {
+        uint64_t end = first;
+        while (end < count && !(c.opt_lazy_swap && gates[end].kind == QI_GATE_SWAP && gates[end].num_controls == 0)) end++;
+        const qi_gate* seg = gates + first;
+        QI_TRY(staged_walk(s, seg, end - first,
+                           [&](const std::vector<uint64_t>& take) { return run(take, seg); },
+                           [&](const std::vector<int>& G, const std::vector<int>& L) { return exchange_multi(s, G, L); }));
+        if (end < count) std::swap(s->phys[gates[end].targets[0]], s->phys[gates[end].targets[1]]);    // the lazy SWAP itself
+        first = end + 1;
+    }
+    return QI_OK;
 }
 
 // logical record -> physical record on this rank
@@ -454,25 +529,34 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
     s.world = world;
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
     uint64_t ex = 0, exq = 0, freeg = 0;
-    for (uint64_t i = 0; i < count; i++) {
-        QI_TRY(validate_gate(&s, &gates[i]));
-        const qi_gate* g = &gates[i];
-        if (g->kind == QI_GATE_SWAP && g->num_controls == 0) { std::swap(s.phys[g->targets[0]], s.phys[g->targets[1]]); continue; }
-        if (global_targets(&s, g) != 0) {
-            std::vector<int> G, L;
-            QI_TRY(plan_exchange(&s, g, count - i - 1, &G, &L));
-            for (size_t k = 0; k < G.size(); k++) {
-                int qg = logical_at(&s, G[k]), ql = logical_at(&s, L[k]);
-                s.phys[qg] = (uint8_t)L[k];
-                s.phys[ql] = (uint8_t)G[k];
-            }
-            ex++;
-            exq += G.size();
-        }
-        bool touches_global = false;
-        for (uint32_t c = 0; c < g->num_controls; c++) touches_global |= s.phys[g->controls[c]] >= s.n_local;
-        touches_global |= s.phys[g->targets[0]] >= s.n_local;
-        if (touches_global) freeg++;
+    for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    uint64_t first = 0;
+    while (first < count) {
+        uint64_t end = first;
+        while (end < count && !(gates[end].kind == QI_GATE_SWAP && gates[end].num_controls == 0)) end++;
+        const qi_gate* seg = gates + first;
+        QI_TRY(staged_walk(&s, seg, end - first,
+            [&](const std::vector<uint64_t>& take) -> int {
+                for (uint64_t i : take) {
+                    const qi_gate* g = &seg[i];
+                    bool touches_global = s.phys[g->targets[0]] >= s.n_local;
+                    for (uint32_t c = 0; c < g->num_controls; c++) touches_global |= s.phys[g->controls[c]] >= s.n_local;
+                    if (touches_global) freeg++;
+                }
+                return QI_OK;
+            },
+            [&](const std::vector<int>& G, const std::vector<int>& L) -> int {
+                for (size_t k = 0; k < G.size(); k++) {
+                    int qg = logical_at(&s, G[k]), ql = logical_at(&s, L[k]);
+                    if (qg >= 0) s.phys[qg] = (uint8_t)L[k];
+                    if (ql >= 0) s.phys[ql] = (uint8_t)G[k];
+                }
+                ex++;
+                exq += G.size();
+                return QI_OK;
+            }));
+        if (end < count) std::swap(s.phys[gates[end].targets[0]], s.phys[gates[end].targets[1]]);
+        first = end + 1;
     }
     if (exchanges) *exchanges = ex;
     (void)exq;

@@ -247,7 +247,10 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 
 // resident blocks per SM the register budget is tuned for: 8 amplitudes/thread -> 8 blocks,
 // 16 -> 4 blocks (128 registers), 32 -> 2 blocks
-#define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? 4 : 2))
+#ifndef QI_WINDOW_BLOCKS4
+#define QI_WINDOW_BLOCKS4 4
+#endif
+#define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? QI_WINDOW_BLOCKS4 : 2))
 
 // direct variant: every thread loads its 2^R amplitudes itself (coalesced 512 B per warp access)
 template <int R>
