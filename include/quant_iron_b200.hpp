@@ -297,6 +297,19 @@ public:
         check(qi_expect_pauli_sum(s.handle(), arr.data(), arr.size(), o));
         return cplx(o[0], o[1]);
     }
+    // exp(f_k c_k P_k) for k = 0, 1, ... applied in order: one apply_exp_factor (pauli_string.rs:237-262) per term,
+    // fused into register-window passes on the device
+    State apply_exp_sequence(const State& s, const std::vector<cplx>& factors) const {
+        if (factors.size() != terms.size()) throw Error(QI_ERR_MISMATCHED_NUMBER_OF_PARAMETERS, "MismatchedNumberOfParameters", terms.size(), factors.size(), "factors");
+        std::vector<std::unique_ptr<PauliString::Term>> keep;
+        std::vector<qi_pauli_term> arr;
+        std::vector<double> f;
+        for (auto& t : terms) { keep.push_back(t.term()); arr.push_back(keep.back()->t); }
+        for (auto& z : factors) { f.push_back(z.real()); f.push_back(z.imag()); }
+        State o(s);
+        check(qi_apply_pauli_exp_sequence(o.handle(), arr.data(), arr.size(), f.data()));
+        return o;
+    }
     State trotter_evolve(const State& s, double dt, uint64_t steps, int order) const {   // time_evolution.rs:140-167
         std::vector<std::unique_ptr<PauliString::Term>> keep;
         std::vector<qi_pauli_term> arr;

@@ -194,6 +194,8 @@ int pauli_exp_single(qi_state* s, const PauliExp& t);          // one term, one 
 // pauli_window.cu
 bool pauli_window_supported(const qi_state* s);
 int run_pauli_exp_batch(qi_state* s, const std::vector<PauliExp>& seq);
+int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms, int grid, double2* partials, int max_groups,
+                           int* groups_used, std::vector<size_t>* leftover);      // ch = coefficient of each term
 int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* terms_per_pass);
 
 // gates.cu

@@ -290,43 +290,82 @@ int qi_expect_pauli_sum(const qi_state* s, const qi_pauli_term* terms, uint64_t 
     out[0] = out[1] = 0.0;
     if (count == 0) return QI_OK;     // pauli_string.rs:486-489
     if (!terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
-    std::vector<Masks> ms(count);
-    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &ms[k]));
+    Masks m;
+    for (uint64_t k = 0; k < count; k++) QI_TRY(term_masks(s, &terms[k], &m));
     QI_TRY(ensure_ctx());
-    if (s->world > 1) {
-        // a term with X/Y on a global qubit pairs amplitudes across ranks: bring that qubit into the local
-        // bits first (an exchange changes the layout, not the logical state), then re-derive every mask
-        // (done term by term below, right before each term's kernel is queued)
-    }
     Context& c = ctx();
     int g = c.sm_count * 4;
     uint64_t need = (s->len + kBlock - 1) / kBlock;
     if (need < (uint64_t)g) g = (int)need;
-    const uint64_t kBatch = 512;
+    // every launch (one window group of many terms, or one term on the per-term kernel) fills one SLOT of g block
+    // partials; k_expect_final adds the slots in order
+    const uint64_t kSlots = 512;
+    QI_TRY(ensure_partials((size_t)g * 2 * kSlots));
+    double2* partials = (double2*)c.d_partials;
     double tot[2] = {0.0, 0.0};
-    for (uint64_t base = 0; base < count; base += kBatch) {
-        uint64_t nb = count - base < kBatch ? count - base : kBatch;
-        QI_TRY(ensure_partials((size_t)g * 2 * nb));
-        for (uint64_t k = 0; k < nb; k++) {
-            const qi_pauli_term& t = terms[base + k];
-            if (s->world > 1) {
-                QI_TRY(term_masks(s, &t, &ms[base + k]));      // the layout may have changed since the first pass
-                if (ms[base + k].x & ~(s->len - 1)) {
-                    QI_TRY(shard_localise_mask(const_cast<qi_state*>(s), &t));
-                    QI_TRY(term_masks(s, &t, &ms[base + k]));
-                }
-            }
-            LaunchScope ls(KF_EXPECT, (ms[base + k].x ? 32.0 : 16.0) * (double)s->len);
-            k_pauli_expect<<<g, kBlock, 0, c.stream>>>(s->d, s->len, ms[base + k], make_double2(t.coefficient[0], t.coefficient[1]),
-                                                       (double2*)c.d_partials + (size_t)k * g);
-        }
-        k_expect_final<<<1, kBlock, nb * sizeof(double2), c.stream>>>((double2*)c.d_partials, g, (int)nb, (double2*)c.d_result);
+    uint64_t used = 0;
+    auto flush_slots = [&]() -> int {
+        if (!used) return QI_OK;
+        k_expect_final<<<1, kBlock, used * sizeof(double2), c.stream>>>(partials, g, (int)used, (double2*)c.d_result);
         QI_TRY(check_launch("pauli_expect"));
         QI_CUDA(cudaMemcpyAsync(c.h_result, c.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         QI_CUDA(cudaStreamSynchronize(c.stream));
         tot[0] += c.h_result[0];
         tot[1] += c.h_result[1];
+        used = 0;
+        return QI_OK;
+    };
+    auto single = [&](const PauliExp& e) -> int {
+        if (used == kSlots) QI_TRY(flush_slots());
+        Masks mk{e.x, e.z, (3 * e.k0) & 3, 0};
+        LaunchScope ls(KF_EXPECT, (e.x ? 32.0 : 16.0) * (double)s->len);
+        k_pauli_expect<<<g, kBlock, 0, c.stream>>>(s->d, s->len, mk, e.ch, partials + used * g);
+        used++;
+        return QI_OK;
+    };
+    // terms whose X/Y factors fit a register window share one read of the state (pauli_window.cu)
+    const bool batch = c.opt_fuse && c.opt_path != 1 && pauli_window_supported(s);
+    std::vector<PauliExp> pend;
+    auto flush_batch = [&]() -> int {
+        while (!pend.empty()) {
+            if (used == kSlots) QI_TRY(flush_slots());
+            std::vector<size_t> left;
+            int groups = 0;
+            QI_TRY(run_pauli_expect_batch(s, pend, g, partials + used * g, (int)(kSlots - used), &groups, &left));
+            used += (uint64_t)groups;
+            // terms that found no group: wider than a window -> per-term kernel; out of slots -> next round
+            std::vector<PauliExp> retry;
+            for (size_t idx : left) {
+                if (__builtin_popcountll(pend[idx].x & ~31ull) > 4) QI_TRY(single(pend[idx]));
+                else retry.push_back(pend[idx]);
+            }
+            pend.swap(retry);
+            if (!pend.empty()) QI_TRY(flush_slots());
+        }
+        return QI_OK;
+    };
+    const uint64_t local_mask = s->len - 1;
+    for (uint64_t k = 0; k < count; k++) {
+        const qi_pauli_term& t = terms[k];
+        QI_TRY(term_masks(s, &t, &m));
+        if (m.x & ~local_mask) {
+            // X/Y on a rank bit pairs amplitudes across ranks: bring that qubit into the local bits first.  The
+            // exchange changes the layout, so what is pending (masks under the old layout) is launched before it.
+            QI_TRY(flush_batch());
+            QI_TRY(shard_localise_mask(const_cast<qi_state*>(s), &t));
+            QI_TRY(term_masks(s, &t, &m));
+        }
+        PauliExp e;
+        e.x = m.x;
+        e.z = m.z & local_mask;
+        e.k0 = (3 * m.ny + 2 * __builtin_popcountll(m.high & m.z)) & 3;
+        e.ch = make_double2(t.coefficient[0], t.coefficient[1]);
+        e.sh = make_double2(0.0, 0.0);
+        if (batch) pend.push_back(e);
+        else QI_TRY(single(e));
     }
+    QI_TRY(flush_batch());
+    QI_TRY(flush_slots());
     if (s->world > 1) QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(s), tot, 2));
     out[0] = tot[0];
     out[1] = tot[1];

@@ -243,4 +243,138 @@ int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* ter
     });
 }
 
+// ---- SumOp::expectation_value: many terms per read-only pass ------------------------------------------------
+// <psi| c P |psi> = sum_i conj(psi[i]) c i^k(i) psi[i ^ x] (pauli_string.rs:491-502 for one term).  Terms whose X/Y
+// factors fit a window share one read of the state; no ordering constraint (nothing is written), so terms are
+// grouped first-fit.  Every thread adds its terms' contributions into one complex accumulator; the block sums
+// go to `partials` and are added by k_expect_final in a fixed order (deterministic; the association differs from
+// the reference's term-by-term sum, well inside the 1e-10 relative bar).
+template <int R, int M, bool SW>
+__device__ __forceinline__ void px_expect(const amp_t (&v)[1 << R], const uint32_t xl, const uint32_t zr, const bool nre, const bool nim,
+                                          double& tr, double& ti) {
+    constexpr int S = 1 << R;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        amp_t o = v[s ^ M];
+        if (xl) o = px_shfl(o, xl);
+        const bool par = __popc(s & zr) & 1;
+        double pre = SW ? o.y : o.x, pim = SW ? o.x : o.y;       // i^k o: component swap for odd k, then signs
+        pre = (nre != par) ? -pre : pre;
+        pim = (nim != par) ? -pim : pim;
+        tr += v[s].x * pre + v[s].y * pim;                       // conj(v) * (pre + i pim)
+        ti += v[s].x * pim - v[s].y * pre;
+    }
+}
+
+template <int R, bool SW>
+__device__ __forceinline__ void px_expect_dispatch(const amp_t (&v)[1 << R], const uint32_t xr, const uint32_t xl, const uint32_t zr,
+                                                   const bool nre, const bool nim, double& tr, double& ti) {
+    constexpr int S = 1 << R;
+#define QI_PX_CASE(m) case m: px_expect<R, ((m) < S ? (m) : 0), SW>(v, xl, zr, nre, nim, tr, ti); break;
+    switch (xr) {
+        QI_PX_CASE(0) QI_PX_CASE(1) QI_PX_CASE(2) QI_PX_CASE(3) QI_PX_CASE(4) QI_PX_CASE(5) QI_PX_CASE(6) QI_PX_CASE(7)
+        QI_PX_CASE(8) QI_PX_CASE(9) QI_PX_CASE(10) QI_PX_CASE(11) QI_PX_CASE(12) QI_PX_CASE(13) QI_PX_CASE(14) QI_PX_CASE(15)
+        default: break;
+    }
+#undef QI_PX_CASE
+}
+
+template <int R>
+__global__ void __launch_bounds__(128, 4) k_pauli_expect_window(const amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ PXProgram<R> P,
+                                                                 double2* __restrict__ partials) {
+    constexpr int S = 1 << R;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    double ax = 0.0, ay = 0.0;
+    for (uint64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const uint64_t base = expand_index((tile << 5) | (uint64_t)lane, P.ins);
+        amp_t v[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) v[s] = ld_amp(a + base + P.off[s]);
+#pragma unroll 1
+        for (uint32_t o = 0; o < P.nops; o++) {
+            const PXOp& op = P.ops[o];
+            const uint32_t k0 = op.k0;
+            const bool flip = (__popcll(tile & op.zt) + __popc((uint32_t)lane & op.zl)) & 1;
+            const bool nre = (((k0 & 3) == 1) || ((k0 & 3) == 2)) != flip;
+            const bool nim = ((k0 & 3) >= 2) != flip;
+            double tr = 0.0, ti = 0.0;
+            if (k0 & 1) px_expect_dispatch<R, true>(v, op.xr, op.xl, op.zr, nre, nim, tr, ti);
+            else px_expect_dispatch<R, false>(v, op.xr, op.xl, op.zr, nre, nim, tr, ti);
+            ax += op.c * tr - op.s * ti;                          // coefficient (c, s) = (re, im)
+            ay += op.c * ti + op.s * tr;
+        }
+    }
+    // block sum: shuffle tree, then one value per warp through shared memory (fixed order)
+    __shared__ double2 wsum[4];
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_down_sync(0xffffffffu, ax, o);
+        ay += __shfl_down_sync(0xffffffffu, ay, o);
+    }
+    if (lane == 0) wsum[threadIdx.x >> 5] = make_double2(ax, ay);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double2 t = wsum[0];
+        for (int w = 1; w < 4; w++) { t.x += wsum[w].x; t.y += wsum[w].y; }
+        partials[blockIdx.x] = t;
+    }
+}
+
+// terms: x/z/k0 as in PauliExp, ch = the term's coefficient.  Launches one kernel per window group with `grid`
+// blocks, group j writing partials[j * grid ..]; returns the number of groups.  Terms that do not fit a window
+// are returned in `leftover` (indices into `terms`) for the per-term kernel.
+int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms, int grid, double2* partials, int max_groups,
+                           int* groups_used, std::vector<size_t>* leftover) {
+    Context& c = ctx();
+    constexpr int R = kPauliR;
+    const uint64_t lane_mask = (1ull << kLaneQubits) - 1;
+    struct Group { uint64_t window = 0; int nregs = 0; std::vector<size_t> terms; };
+    std::vector<Group> groups;
+    for (size_t i = 0; i < terms.size(); i++) {
+        const uint64_t need = terms[i].x & ~lane_mask;
+        if (__builtin_popcountll(need) > R) { leftover->push_back(i); continue; }
+        Group* best = nullptr;
+        for (Group& g : groups) {
+            if (g.terms.size() >= (size_t)kMaxPX) continue;
+            if (g.nregs + __builtin_popcountll(need & ~g.window) <= R) { best = &g; break; }
+        }
+        if (!best) {
+            if ((int)groups.size() >= max_groups) { leftover->push_back(i); continue; }
+            groups.emplace_back();
+            best = &groups.back();
+        }
+        best->nregs += __builtin_popcountll(need & ~best->window);
+        best->window |= need;
+        best->terms.push_back(i);
+    }
+    const uint64_t ntiles = s->len >> (kLaneQubits + R);
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const Group& g = groups[gi];
+        std::vector<int> regs;
+        for (int q = kLaneQubits; q < 64; q++) if ((g.window >> q) & 1) regs.push_back(q);
+        Layout L = make_layout(s, regs, R);
+        PXProgram<R> P;
+        memset(&P, 0, sizeof(P));
+        fill_offsets<R>(L, &P.ins, P.off);
+        P.nops = (uint32_t)g.terms.size();
+        for (size_t k = 0; k < g.terms.size(); k++) {
+            const PauliExp& t = terms[g.terms[k]];
+            PXOp& d = P.ops[k];
+            uint64_t xt = 0;
+            split_mask(L, t.x, &d.xl, &d.xr, &xt);
+            if (xt) return fail(QI_ERR_UNKNOWN, 0, 0, "pauli window: X/Y factor outside the window");
+            split_mask(L, t.z, &d.zl, &d.zr, &d.zt);
+            d.k0 = (uint32_t)(t.k0 & 3);
+            d.c = t.ch.x;
+            d.s = t.ch.y;
+        }
+        LaunchScope ls(KF_EXPECT, 16.0 * (double)s->len);
+        k_pauli_expect_window<R><<<grid, 128, 0, c.stream>>>(s->d, ntiles, P, partials + (size_t)gi * grid);
+        QI_TRY(check_launch("k_pauli_expect_window"));
+    }
+    *groups_used = (int)groups.size();
+    return QI_OK;
+}
+
 }  // namespace qi

@@ -71,6 +71,10 @@ int main() {
     State ev = hs.trotter_evolve(State::new_plus(10), 0.01, 5, 1);
     EXPECT(std::fabs(ev.norm_sqr() - 1.0) < 1e-12);
     EXPECT(std::fabs(hs.expectation_value(ev).imag()) < 1e-12);
+    // one first-order step == the same terms as one fused apply_exp_factor sequence with factor -i*dt
+    State one = hs.trotter_evolve(State::new_plus(10), 0.01, 1, 1);
+    State seq = hs.apply_exp_sequence(State::new_plus(10), std::vector<cplx>(hs.num_terms(), cplx(0.0, -0.01)));
+    EXPECT(seq.approx_eq(one));
     std::printf(failures ? "C++ facade: %d FAILURES\n" : "C++ facade: ALL PASS\n", failures);
     return failures ? 1 : 0;
 }

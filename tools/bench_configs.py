@@ -73,11 +73,18 @@ if 3 in configs:
     qi.trotter_evolve_state_(h, st, 0.01, 1, qi.TrotterOrder.First)      # warm-up step
     st = qi.State.new_plus(n)
     ms = timed(lambda: qi.trotter_evolve_state_(h, st, 0.01, 50, qi.TrotterOrder.First))
+    h.expectation_value(st)                                                # warm-up (scratch allocation, module load)
     t0 = time.perf_counter()
     e = h.expectation_value(st)
     ms_e = (time.perf_counter() - t0) * 1e3
+    qi.engine.set_option("fuse", 0)
+    t0 = time.perf_counter()
+    e_u = h.expectation_value(st)
+    ms_e_u = (time.perf_counter() - t0) * 1e3
+    qi.engine.set_option("fuse", 1)
     rec = {"config": 3, "what": "heisenberg_1d(24,1,2,3,0.5,0.1), new_plus(24), 50 first-order Trotter steps dt=0.01, expectation",
-           "terms": h.num_terms(), "exp_applications": 50 * h.num_terms(), "trotter_ms": ms, "expectation_ms": ms_e,
+           "terms": h.num_terms(), "exp_applications": 50 * h.num_terms(), "trotter_ms": ms, "expectation_ms": ms_e, "expectation_ms_per_term_kernels": ms_e_u,
+           "expectation_fused_minus_per_term": abs(e - e_u),
            "expectation": [e.real, e.imag], "norm_sqr": st.norm_sqr(),
            "effective_gbs": 50 * h.num_terms() * 32.0 * (1 << n) / (ms * 1e-3) / 1e9}
     # the same evolution on the per-term kernels (one pass per exp), and the pass statistics of the fused path
