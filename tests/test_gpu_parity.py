@@ -420,3 +420,36 @@ def test_sumop_expectation_batched_vs_oracle(gpu, ref, n, seed):
     for pg, pr in list(zip(tg, tr))[:20]:
         a, b = gpu.SumOp([pg]).expectation_value(g), ref.SumOp([pr]).expectation_value(r)
         assert abs(a - b) <= 1e-12, (a, b)
+
+
+def test_pauli_sequences_longer_than_one_launch(gpu, ref):
+    """More terms than one window launch holds (192 ops) and more expectation terms than one group holds: the
+    scheduler must split, never truncate."""
+    from quant_iron_b200.pauli import apply_exp_sequence_
+    n = 10
+    rng = np.random.default_rng(9)
+    g, r = _pair(gpu, ref, n, seed=500)
+    sg, sr = [], []
+    for i in range(700):
+        q = int(rng.integers(0, n))
+        which = int(rng.integers(0, 3))
+        c = complex(rng.uniform(-1, 1), 0.0)
+        sg.append(gpu.PauliString.new(c).with_op(q, [gpu.Pauli.X, gpu.Pauli.Y, gpu.Pauli.Z][which]))
+        sr.append(ref.PauliString.new(c).with_op(q, [ref.Pauli.X, ref.Pauli.Y, ref.Pauli.Z][which]))
+    gpu.engine.stats_reset()
+    out = apply_exp_sequence_(g.clone(), sg, [complex(0.0, -0.01)] * len(sg))
+    launches = gpu.engine.stats()["pauli_exp_window"]["launches"]
+    assert 4 <= launches <= 40, launches
+    for p in sr:
+        r2 = p.apply_exp_factor(r, complex(0.0, -0.01)) if p is sr[0] else p.apply_exp_factor(r2, complex(0.0, -0.01))
+    assert_amps(out, vec(r2), msg="700-term sequence")
+    eg, er = gpu.SumOp(sg).expectation_value(out), ref.SumOp(sr).expectation_value(r2)
+    assert abs(eg - er) <= EXP_RTOL * max(1.0, abs(er)), (eg, er)
+    # argument errors leave the state untouched and report the reference's variant
+    bad = sg[:3] + [gpu.PauliString.new(1.0).with_op(n + 2, gpu.Pauli.X)]
+    before = vec(out).copy()
+    with pytest.raises(gpu.Error) as e:
+        apply_exp_sequence_(out, bad, [1.0] * 4)
+    assert e.value.variant == "InvalidQubitIndex"
+    assert np.array_equal(vec(out), before)
+    assert apply_exp_sequence_(out, [], []) is out
