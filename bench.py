@@ -307,8 +307,22 @@ def run_ours(args, rank, world, local_rank):
     try:
         if args.skip_e2e:
             raise RuntimeError("skipped (--skip-e2e)")
+        # one pinned buffer per rank, used for both directions (the final state of one step is the initial state
+        # of the next: any normalised state times the same); guarded so that N ranks never pin more than the
+        # host has
+        need = world * 16 * (1 << n_local)
+        avail = None
+        try:
+            with open("/proc/meminfo") as f:
+                for line in f:
+                    if line.startswith("MemAvailable:"):
+                        avail = int(line.split()[1]) * 1024
+        except OSError:
+            pass
+        if avail is not None and need * 1.25 > avail:
+            raise RuntimeError(f"host memory: e2e needs {need >> 30} GiB pinned, {avail >> 30} GiB available")
         host_in = torch.zeros(1 << n_local, dtype=torch.complex128).pin_memory()
-        host_out = torch.empty(1 << n_local, dtype=torch.complex128).pin_memory()
+        host_out = host_in
         if rank == 0:
             host_in[0] = 1.0
         hin, hout = host_in.numpy(), host_out.numpy()
