@@ -75,3 +75,21 @@ def test_host_side_validation_without_device():
     assert len(qi.heisenberg_1d(24, 1.0, 2.0, 3.0, 0.5, 0.1).terms) == 96
     specs = qi.workloads.random_layered_circuit(28, 40)
     assert len(specs) == 40 * 28 + 20 * 14 + 20 * 13
+
+
+def test_rust_sys_bindings_match_the_header():
+    """the Rust `-sys` crate source is generated from include/qiron_b200.h; the committed files must
+    be what the generator produces today and must declare every exported function."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lib_rs = open(os.path.join(root, "bindings", "rust", "quant-iron-b200-sys", "src", "lib.rs")).read()
+    header = open(os.path.join(root, "include", "qiron_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    names = set(re.findall(r"\b(qi_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 59
+    for n in names:
+        assert re.search(rf"pub fn {n}\(", lib_rs), n
