@@ -1228,6 +1228,113 @@ def heisenberg_1d(n: int, jx: float, jy: float, jz: float, h: float, mu: float) 
     return SumOp(terms)
 
 
+def heisenberg_2d(n_rows: int, m_cols: int, jx: float, jy: float, jz: float, h_field: float, mu: float) -> SumOp:
+    """models/heisenberg.rs:122-220 restated literally: for every site index (row-major) push the field term, the
+    three vertical-bond terms and the three horizontal-bond terms; field coefficient mu * (-0.5 h) (line 143)."""
+    if n_rows < 2:
+        raise Error("InvalidNumberOfInputs", n_rows, 2)
+    elif m_cols < 2:
+        raise Error("InvalidNumberOfInputs", m_cols, 2)
+    if jx == 0.0 and jy == 0.0 and jz == 0.0 and h_field == 0.0:
+        return SumOp([])
+    coeff_x, coeff_y, coeff_z = complex(-0.5 * jx, 0.0), complex(-0.5 * jy, 0.0), complex(-0.5 * jz, 0.0)
+    field_coeff = complex(mu * (-0.5 * h_field), mu * 0.0)
+    terms = []
+    for site in range(n_rows * m_cols):
+        r, c = site // m_cols, site % m_cols
+        if h_field != 0.0:
+            terms.append(PauliString(field_coeff).with_op(site, Pauli.Z))
+        down = ((r + 1) % n_rows) * m_cols + c
+        if jx != 0.0:
+            terms.append(PauliString(coeff_x).with_op(site, Pauli.X).with_op(down, Pauli.X))
+        if jy != 0.0:
+            terms.append(PauliString(coeff_y).with_op(site, Pauli.Y).with_op(down, Pauli.Y))
+        if jz != 0.0:
+            terms.append(PauliString(coeff_z).with_op(site, Pauli.Z).with_op(down, Pauli.Z))
+        right = r * m_cols + ((c + 1) % m_cols)
+        if jx != 0.0:
+            terms.append(PauliString(coeff_x).with_op(site, Pauli.X).with_op(right, Pauli.X))
+        if jy != 0.0:
+            terms.append(PauliString(coeff_y).with_op(site, Pauli.Y).with_op(right, Pauli.Y))
+        if jz != 0.0:
+            terms.append(PauliString(coeff_z).with_op(site, Pauli.Z).with_op(right, Pauli.Z))
+    return SumOp(terms)
+
+
+def ising_1d(h, j, mu: float) -> SumOp:
+    """models/ising.rs:27-75."""
+    n = len(h)
+    if len(j) != n:
+        raise Error("MismatchedNumberOfParameters", n, len(j))
+    if n < 2:
+        raise Error("InvalidNumberOfInputs", n, 2)
+    if all(v == 0.0 for v in h) and all(v == 0.0 for v in j):
+        return SumOp([])
+    terms = []
+    for i in range(n):
+        if j[i] != 0.0:
+            terms.append(PauliString(complex(j[i], 0.0) * -1.0).with_op(i, Pauli.Z).with_op((i + 1) % n, Pauli.Z))
+        if h[i] != 0.0:
+            terms.append(PauliString(-1.0 * mu * complex(h[i], 0.0)).with_op(i, Pauli.Z))
+    return SumOp(terms)
+
+
+def ising_1d_uniform(n: int, h: float, j: float, mu: float) -> SumOp:
+    """models/ising.rs:90-139."""
+    if n < 2:
+        raise Error("InvalidNumberOfInputs", n, 2)
+    if h == 0.0 and j == 0.0:
+        return SumOp([])
+    terms = []
+    for i in range(n):
+        if j != 0.0:
+            terms.append(PauliString(complex(j, 0.0) * -1.0).with_op(i, Pauli.Z).with_op((i + 1) % n, Pauli.Z))
+        if h != 0.0:
+            terms.append(PauliString(-1.0 * mu * complex(h, 0.0)).with_op(i, Pauli.Z))
+    return SumOp(terms)
+
+
+def ising_2d(h, j, mu: float) -> SumOp:
+    """models/ising.rs:161-244."""
+    n = len(h)
+    m = len(h[0]) if n else 0
+    if n < 2:
+        raise Error("InvalidNumberOfInputs", n, 2)
+    elif m < 2:
+        raise Error("InvalidNumberOfInputs", m, 2)
+    if all(h[r][c] == 0.0 and j[r][c][0] == 0.0 and j[r][c][1] == 0.0 for r in range(n) for c in range(m)):
+        return SumOp([])
+    terms = []
+    for idx in range(n * m):
+        r, c = idx // m, idx % m
+        if h[r][c] != 0.0:
+            terms.append(PauliString(-1.0 * mu * complex(h[r][c], 0.0)).with_op(idx, Pauli.Z))
+        if j[r][c][0] != 0.0:
+            terms.append(PauliString(complex(j[r][c][0], 0.0) * -1.0).with_op(idx, Pauli.Z).with_op(((r + 1) % n) * m + c, Pauli.Z))
+        if j[r][c][1] != 0.0:
+            terms.append(PauliString(complex(j[r][c][1], 0.0) * -1.0).with_op(idx, Pauli.Z).with_op(r * m + ((c + 1) % m), Pauli.Z))
+    return SumOp(terms)
+
+
+def ising_2d_uniform(n: int, m: int, h: float, j: float, mu: float) -> SumOp:
+    """models/ising.rs:259-324."""
+    if n < 2:
+        raise Error("InvalidNumberOfInputs", n, 2)
+    elif m < 2:
+        raise Error("InvalidNumberOfInputs", m, 2)
+    if h == 0.0 and j == 0.0:
+        return SumOp([])
+    terms = []
+    for idx in range(n * m):
+        r, c = idx // m, idx % m
+        if h != 0.0:
+            terms.append(PauliString(-1.0 * mu * complex(h, 0.0)).with_op(idx, Pauli.Z))
+        if j != 0.0:
+            terms.append(PauliString(complex(j, 0.0) * -1.0).with_op(idx, Pauli.Z).with_op(((r + 1) % n) * m + c, Pauli.Z))
+            terms.append(PauliString(complex(j, 0.0) * -1.0).with_op(idx, Pauli.Z).with_op(r * m + ((c + 1) % m), Pauli.Z))
+    return SumOp(terms)
+
+
 # ----------------------------------------------------------------------------
 # Synthetic workloads shared by oracle, CPU baseline and GPU engine (BASELINE.md section 4)
 def random_state(num_qubits: int, seed: int = 20260002) -> State:
