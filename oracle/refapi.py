@@ -116,6 +116,30 @@ class Error(Exception):
         self.variant = variant
         self.payload = tuple(payload)
 
+    # thiserror Display strings (errors.rs:10-98)
+    _DISPLAY = {
+        "InvalidNumberOfMeasurements": "Invalid number of measurements: {0}",
+        "OverlappingControlAndTargetQubits": "Control qubit index {0} overlaps with target qubit index {1}",
+        "InvalidNumberOfQubits": "Invalid number of qubits: {0}",
+        "InvalidQubitIndex": "Invalid qubit index: {0} for {1} qubits",
+        "StateVectorNotNormalised": "State vector is not normalised",
+        "NonUnitaryMatrix": "Non-unitary matrix",
+        "InvalidNumberOfInputs": "Unexpected number of inputs: expected {1}, got {0}",
+        "MismatchedNumberOfParameters": "Mismatched number of parameters: expected {0}, got {1}",
+        "UnknownError": "An unknown error occurred",
+        "CircuitMacroError": "Failed to create circuit from macro: {0}",
+        "InvalidInputValue": "Invalid input value for operation: {0}",
+        "ZeroNorm": "The state cannot be normalised because it has zero norm.",
+        "InvalidPauliStringCoefficient": "Invalid Pauli String coefficient: {0}",
+    }
+
+    def to_string(self) -> str:
+        fmt = self._DISPLAY.get(self.variant)
+        try:
+            return fmt.format(*self.payload) if fmt else str(self)
+        except IndexError:
+            return str(self)
+
     def __eq__(self, other):
         return isinstance(other, Error) and (self.variant, self.payload) == (other.variant, other.payload)
 
@@ -904,9 +928,25 @@ class Gate:
     def PauliTimeEvolution(ps, time):
         return Gate("PauliTimeEvolution", pauli_string=ps, time=float(time), targets=ps.get_targets(), controls=[])
 
+    @staticmethod
+    def Parametric(p_gate, targets, controls=()):
+        return Gate("Parametric", p_gate=p_gate, targets=list(targets), controls=list(controls))
+
+    def concrete(self):  # circuit.rs:205-217
+        if self.kind == "Parametric":
+            return self.p_gate.to_concrete_gates(self.targets, self.controls)
+        if self.kind == "PauliString":
+            return self.pauli_string.to_gates()
+        return [self]
+
     def apply(self, state: State, seed: Optional[int] = None) -> State:  # gate.rs:99-122
         if self.kind == "Operator":
             return self.op.apply(state, self.targets, self.controls)
+        if self.kind == "Parametric":                                     # gate.rs:107-114
+            cur = state.clone()
+            for g in self.p_gate.to_concrete_gates(self.targets, self.controls):
+                cur = g.apply(cur)
+            return cur
         if self.kind == "Measurement":
             return state.measure(self.basis, self.targets, seed=seed).new_state
         if self.kind == "PauliString":
@@ -917,7 +957,60 @@ class Gate:
         return self.targets
 
     def get_control_qubits(self):
-        return self.controls if self.kind == "Operator" else None
+        return self.controls if self.kind in ("Operator", "Parametric") else None
+
+
+class Parameter:
+    """parametric/parameter.rs:13-74: `clone` shares the values (Arc), `deep_clone` copies them."""
+
+    def __init__(self, initial_values, _shared=None):
+        self._v = _shared if _shared is not None else {"values": [float(x) for x in initial_values]}
+
+    @staticmethod
+    def new(initial_values):
+        return Parameter(initial_values)
+
+    def clone(self):
+        return Parameter((), _shared=self._v)
+
+    def deep_clone(self):
+        return Parameter(self.get())
+
+    def get(self):
+        return list(self._v["values"])
+
+    def set(self, new_values):
+        if len(new_values) != len(self._v["values"]):
+            raise ValueError("wrong number of parameter values")
+        self._v["values"] = [float(x) for x in new_values]
+
+    def __len__(self):
+        return len(self._v["values"])
+
+
+class ParametricGate:
+    """parametric/parametric_gate.rs: `kind` selects which concrete constructor the values feed."""
+    KINDS = {"ry_phase": 2, "ry_phase_dag": 2, "matchgate": 3, "rx": 1, "ry": 1, "rz": 1, "p": 1}
+
+    def __init__(self, kind, parameter):
+        assert len(parameter) == self.KINDS[kind]
+        self.kind, self.parameter = kind, parameter
+
+    def to_concrete_gates(self, targets, controls):
+        v = self.parameter.get()
+        if self.kind == "matchgate":                                   # parametric_gate.rs:95-104
+            return [Gate.controlled_matchgate(targets[0], list(controls), v[0], v[1], v[2])]
+        ctor = getattr(Gate, f"{self.kind}_controlled_gates")          # e.g. Gate::rx_controlled_gates (124-131)
+        return ctor(list(targets), list(controls), *v)
+
+
+def ParametricRyPhase(parameter): return ParametricGate("ry_phase", parameter)            # noqa: E704
+def ParametricRyPhaseDag(parameter): return ParametricGate("ry_phase_dag", parameter)     # noqa: E704
+def ParametricMatchgate(parameter): return ParametricGate("matchgate", parameter)         # noqa: E704
+def ParametricRx(parameter): return ParametricGate("rx", parameter)                       # noqa: E704
+def ParametricRy(parameter): return ParametricGate("ry", parameter)                       # noqa: E704
+def ParametricRz(parameter): return ParametricGate("rz", parameter)                       # noqa: E704
+def ParametricP(parameter): return ParametricGate("p", parameter)                         # noqa: E704
 
 
 def _install_gate_ctors():
@@ -943,6 +1036,14 @@ def _install_gate_ctors():
     Gate.ry_phase_gate = staticmethod(lambda q, th, ph: Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], []))
     Gate.ry_phase_dag_gate = staticmethod(
         lambda q, th, ph: Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], []))
+    Gate.ry_phase_multi_gate = staticmethod(
+        lambda qs, th, ph: [Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], []) for q in qs])
+    Gate.ry_phase_controlled_gates = staticmethod(
+        lambda ts, cs, th, ph: [Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], list(cs)) for q in ts])
+    Gate.ry_phase_dag_multi_gate = staticmethod(
+        lambda qs, th, ph: [Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], []) for q in qs])
+    Gate.ry_phase_dag_controlled_gates = staticmethod(
+        lambda ts, cs, th, ph: [Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], list(cs)) for q in ts])
     Gate.cnot_gate = staticmethod(lambda target, control: Gate.Operator(CNOT(), [target], [control]))  # gate.rs:1128
     Gate.swap_gate = staticmethod(lambda q1, q2: Gate.Operator(SWAP(), [q1, q2], []))
     Gate.swap_controlled_gate = staticmethod(lambda q1, q2, cs: Gate.Operator(SWAP(), [q1, q2], list(cs)))
@@ -1039,6 +1140,11 @@ class Circuit:
         for i, g in enumerate(self.gates):
             cur = g.apply(cur, None if seed is None else seed + i)
         return cur
+
+    def to_concrete_circuit(self):  # circuit.rs:204-221
+        c = Circuit(self.num_qubits)
+        c.gates = [cg for g in self.gates for cg in g.concrete()]
+        return c
 
     def trace_execution(self, initial_state: State) -> List[State]:  # circuit.rs:188-202
         if initial_state.num_qubits != self.num_qubits:
@@ -1162,6 +1268,24 @@ def _install_builder_methods():
         setattr(CircuitBuilder, f"{name}_gate", lambda self, q, a, _c=cls: self._each(_c(a), [q]))
         setattr(CircuitBuilder, f"{name}_gates", lambda self, qs, a, _c=cls: self._each(_c(a), qs))
         setattr(CircuitBuilder, f"c{name}_gates", lambda self, t, c, a, _c=cls: self._each(_c(a), t, c))
+
+    # parametric adders (circuit.rs:1226-1742)
+    def each(self, kind, targets, controls, parameters):
+        targets, parameters = list(targets), list(parameters)
+        if len(targets) != len(parameters):
+            raise Error("MismatchedNumberOfParameters", len(targets), len(parameters))
+        for t, prm in zip(targets, parameters):
+            self.add_gate(Gate.Parametric(ParametricGate(kind, prm), [t], list(controls)))
+        return self
+    for kind in ("ry_phase", "ry_phase_dag", "rx", "ry", "rz", "p"):
+        setattr(CircuitBuilder, f"parametric_{kind}_gate",
+                lambda self, t, prm, _k=kind: self.add_gate(Gate.Parametric(ParametricGate(_k, prm), [t], [])))
+        setattr(CircuitBuilder, f"parametric_{kind}_gates", lambda self, ts, prms, _k=kind: each(self, _k, ts, [], prms))
+        setattr(CircuitBuilder, f"parametric_c{kind}_gates", lambda self, ts, cs, prms, _k=kind: each(self, _k, ts, cs, prms))
+    CircuitBuilder.parametric_matchgate = lambda self, t, prm: self.add_gate(
+        Gate.Parametric(ParametricGate("matchgate", prm), [t], []))
+    CircuitBuilder.parametric_cmatchgate = lambda self, t, cs, prm: self.add_gate(
+        Gate.Parametric(ParametricGate("matchgate", prm), [t], list(cs)))
 
 
 _install_builder_methods()

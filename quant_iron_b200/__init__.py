@@ -15,6 +15,8 @@ from .measurement import MeasurementBasis, MeasurementResult
 from .models import heisenberg_1d, heisenberg_2d, ising_1d, ising_1d_uniform, ising_2d, ising_2d_uniform
 from .operators import (CNOT, SWAP, Hadamard, Identity, Matchgate, Operator, Pauli, PhaseS, PhaseSdag, PhaseShift,
                         PhaseT, PhaseTdag, RotateX, RotateY, RotateZ, Toffoli, Unitary2)
+from .parametric import (Parameter, ParametricGate, ParametricMatchgate, ParametricP, ParametricRx, ParametricRy,
+                         ParametricRyPhase, ParametricRyPhaseDag, ParametricRz)
 from .pauli import PauliString, SumOp
 from .state import State
 from . import workloads
@@ -25,5 +27,6 @@ __all__ = [
     "PhaseSdag", "PhaseTdag", "PhaseShift", "RotateX", "RotateY", "RotateZ", "Unitary2", "Matchgate",
     "Gate", "Circuit", "CircuitBuilder", "Subroutine", "PauliString", "SumOp", "MeasurementBasis",
     "MeasurementResult", "TrotterOrder", "first_order_trotter_step", "second_order_trotter_step",
-    "trotter_evolve_state", "trotter_evolve_state_", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "workloads", "engine",
+    "trotter_evolve_state", "trotter_evolve_state_", "Parameter", "ParametricGate", "ParametricMatchgate", "ParametricP", "ParametricRx", "ParametricRy", "ParametricRyPhase",
+    "ParametricRyPhaseDag", "ParametricRz", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "workloads", "engine",
 ]

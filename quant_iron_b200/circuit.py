@@ -18,6 +18,8 @@ from .errors import Error
 from .measurement import MeasurementBasis
 from .operators import (CNOT, SWAP, Hadamard, Identity, Matchgate, Operator, Pauli, PhaseS, PhaseSdag, PhaseShift,
                         PhaseT, PhaseTdag, RotateX, RotateY, RotateZ, Toffoli, Unitary2)
+from .parametric import (Parameter, ParametricGate, ParametricMatchgate, ParametricP, ParametricRx, ParametricRy,
+                         ParametricRyPhase, ParametricRyPhaseDag, ParametricRz)
 from .pauli import PauliString
 
 _lib = _ffi.lib
@@ -47,13 +49,30 @@ class Gate:
     def PauliTimeEvolution(ps, time):
         return Gate("PauliTimeEvolution", pauli_string=ps, time=float(time), targets=ps.get_targets(), controls=[])
 
+    @staticmethod
+    def Parametric(p_gate, targets, controls=()):
+        """gate.rs:34: resolved to concrete operator gates each time it is applied (gate.rs:107-114)."""
+        return Gate("Parametric", p_gate=p_gate, targets=list(targets), controls=list(controls))
+
     new_operator = Operator
     new_measurement = staticmethod(lambda indices, basis: Gate.Measurement(basis, indices))
+
+    def concrete(self) -> "List[Gate]":
+        """Circuit::to_concrete_circuit's per-gate rule (circuit.rs:205-217)."""
+        if self.kind == "Parametric":
+            return self.p_gate.to_concrete_gates(self.targets, self.controls)
+        if self.kind == "PauliString":
+            return self.pauli_string.to_gates()
+        return [self]
 
     def apply_(self, state, seed: Optional[int] = None):
         """gate.rs:99-122, in place."""
         if self.kind == "Operator":
             return state.apply_(self.op, self.targets, self.controls)
+        if self.kind == "Parametric":
+            for g in self.p_gate.to_concrete_gates(self.targets, self.controls):
+                g.apply_(state)
+            return state
         if self.kind == "Measurement":
             state.measure_(self.basis, self.targets, seed=seed)
             return state
@@ -71,11 +90,13 @@ class Gate:
         return self.targets
 
     def get_control_qubits(self):
-        return self.controls if self.kind == "Operator" else None
+        return self.controls if self.kind in ("Operator", "Parametric") else None
 
     def __repr__(self):
         if self.kind == "Operator":
             return f"Gate.Operator({self.op!r}, {self.targets}, {self.controls})"
+        if self.kind == "Parametric":
+            return f"Gate.Parametric({self.p_gate!r}, {self.targets}, {self.controls})"
         return f"Gate.{self.kind}({self.targets})"
 
 
@@ -101,6 +122,14 @@ def _install_gate_ctors():
     Gate.ry_phase_gate = staticmethod(lambda q, th, ph: Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], []))
     Gate.ry_phase_dag_gate = staticmethod(
         lambda q, th, ph: Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], []))
+    Gate.ry_phase_multi_gate = staticmethod(
+        lambda qs, th, ph: [Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], []) for q in qs])
+    Gate.ry_phase_controlled_gates = staticmethod(
+        lambda ts, cs, th, ph: [Gate.Operator(Unitary2.from_ry_phase(th, ph), [q], list(cs)) for q in ts])
+    Gate.ry_phase_dag_multi_gate = staticmethod(
+        lambda qs, th, ph: [Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], []) for q in qs])
+    Gate.ry_phase_dag_controlled_gates = staticmethod(
+        lambda ts, cs, th, ph: [Gate.Operator(Unitary2.from_ry_phase_dagger(th, ph), [q], list(cs)) for q in ts])
     Gate.cnot_gate = staticmethod(lambda target, control: Gate.Operator(CNOT(), [target], [control]))  # gate.rs:1128
     Gate.swap_gate = staticmethod(lambda q1, q2: Gate.Operator(SWAP(), [q1, q2], []))
     Gate.swap_controlled_gate = staticmethod(lambda q1, q2, cs: Gate.Operator(SWAP(), [q1, q2], list(cs)))
@@ -229,6 +258,7 @@ class Circuit:
         ('evol', qi_pauli_term[count], count, keepalive, factors) | ('gate', Gate, index)."""
         if self._records is not None:
             return self._records
+        has_parametric = any(g.kind == "Parametric" for g in self.gates)
         runs = []
         cur: List[Gate] = []
 
@@ -264,6 +294,10 @@ class Circuit:
             if g.kind == "Operator":
                 close_evol()
                 cur.append(g)
+            elif g.kind == "Parametric":
+                # resolved with the parameter values of THIS execution; the concrete gates join the fused run
+                close_evol()
+                cur.extend(g.p_gate.to_concrete_gates(g.targets, g.controls))
             elif g.kind == "PauliTimeEvolution":
                 close()
                 evol.append(g)
@@ -273,7 +307,8 @@ class Circuit:
                 runs.append(("gate", g, index))
         close()
         close_evol()
-        self._records = runs
+        if not has_parametric:
+            self._records = runs
         return runs
 
     def execute_(self, state, seed: Optional[int] = None):
@@ -297,6 +332,11 @@ class Circuit:
         if initial_state.num_qubits != self.num_qubits:
             raise Error("InvalidNumberOfQubits", initial_state.num_qubits)
         return self.execute_(initial_state.clone(), seed)
+
+    def to_concrete_circuit(self) -> "Circuit":  # circuit.rs:204-221
+        c = Circuit(self.num_qubits)
+        c.gates = [cg for g in self.gates for cg in g.concrete()]
+        return c
 
     def trace_execution(self, initial_state):  # circuit.rs:188-202
         if initial_state.num_qubits != self.num_qubits:
@@ -407,6 +447,21 @@ class CircuitBuilder:
     def measure_gate(self, basis: MeasurementBasis, qubits):
         return self.add_gate(Gate.Measurement(basis, qubits))
 
+    # ---- parametric gates (circuit.rs:1226-1742) ----
+    def _parametric_each(self, cls, targets, controls, parameters):
+        targets, parameters = list(targets), list(parameters)
+        if len(targets) != len(parameters):
+            raise Error("MismatchedNumberOfParameters", len(targets), len(parameters))
+        for t, prm in zip(targets, parameters):
+            self.add_gate(Gate.Parametric(cls(prm), [t], list(controls)))
+        return self
+
+    def parametric_matchgate(self, target_index, parameter):
+        return self.add_gate(Gate.Parametric(ParametricMatchgate(parameter), [target_index], []))
+
+    def parametric_cmatchgate(self, target_index, control_indices, parameter):
+        return self.add_gate(Gate.Parametric(ParametricMatchgate(parameter), [target_index], list(control_indices)))
+
 
 def _install_builder_methods():
     simple = {"h": Hadamard, "x": lambda: Pauli.X, "y": lambda: Pauli.Y, "z": lambda: Pauli.Z,
@@ -422,6 +477,16 @@ def _install_builder_methods():
         setattr(CircuitBuilder, f"{name}_gate", lambda self, q, a, _c=cls: self._each(_c(a), [q]))
         setattr(CircuitBuilder, f"{name}_gates", lambda self, qs, a, _c=cls: self._each(_c(a), qs))
         setattr(CircuitBuilder, f"c{name}_gates", lambda self, t, c, a, _c=cls: self._each(_c(a), t, c))
+    # parametric adders (circuit.rs:1226-1742): <name>_gate(target, parameter), <name>_gates(targets, parameters),
+    # c<name>_gates(targets, controls, parameters) -- one Parameter per target
+    for name, cls in {"ry_phase": ParametricRyPhase, "ry_phase_dag": ParametricRyPhaseDag, "rx": ParametricRx,
+                      "ry": ParametricRy, "rz": ParametricRz, "p": ParametricP}.items():
+        setattr(CircuitBuilder, f"parametric_{name}_gate",
+                lambda self, t, prm, _c=cls: self.add_gate(Gate.Parametric(_c(prm), [t], [])))
+        setattr(CircuitBuilder, f"parametric_{name}_gates",
+                lambda self, ts, prms, _c=cls: self._parametric_each(_c, ts, [], prms))
+        setattr(CircuitBuilder, f"parametric_c{name}_gates",
+                lambda self, ts, cs, prms, _c=cls: self._parametric_each(_c, ts, cs, prms))
 
 
 _install_builder_methods()

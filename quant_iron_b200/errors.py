@@ -12,6 +12,30 @@ class Error(Exception):
         self.payload = tuple(payload)
         self.message = ""
 
+    # thiserror Display strings (errors.rs:10-98)
+    _DISPLAY = {
+        "InvalidNumberOfMeasurements": "Invalid number of measurements: {0}",
+        "OverlappingControlAndTargetQubits": "Control qubit index {0} overlaps with target qubit index {1}",
+        "InvalidNumberOfQubits": "Invalid number of qubits: {0}",
+        "InvalidQubitIndex": "Invalid qubit index: {0} for {1} qubits",
+        "StateVectorNotNormalised": "State vector is not normalised",
+        "NonUnitaryMatrix": "Non-unitary matrix",
+        "InvalidNumberOfInputs": "Unexpected number of inputs: expected {1}, got {0}",
+        "MismatchedNumberOfParameters": "Mismatched number of parameters: expected {0}, got {1}",
+        "UnknownError": "An unknown error occurred",
+        "CircuitMacroError": "Failed to create circuit from macro: {0}",
+        "InvalidInputValue": "Invalid input value for operation: {0}",
+        "ZeroNorm": "The state cannot be normalised because it has zero norm.",
+        "InvalidPauliStringCoefficient": "Invalid Pauli String coefficient: {0}",
+    }
+
+    def to_string(self) -> str:
+        fmt = self._DISPLAY.get(self.variant)
+        try:
+            return fmt.format(*self.payload) if fmt else str(self)
+        except IndexError:
+            return str(self)
+
     def __eq__(self, other):
         return isinstance(other, Error) and (self.variant, self.payload) == (other.variant, other.payload)
 
