@@ -60,7 +60,10 @@ int qi_init(int device);                       /* bind the engine to a CUDA devi
 int qi_synchronize(void);                      /* wait for all queued work */
 int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_mem, uint64_t* free_mem);
 /* options: "path" = 0 auto | 1 force the simple per-gate kernels | 2 force the window kernels;
- *          "fuse" = 1/0 gate fusion in qi_apply_circuit; "profile" = 1/0 per-kernel event timing */
+ *          "fuse" = 1/0 fusion in qi_apply_circuit, Pauli-exp sequences and expectation values;
+ *          "profile" = 1/0 per-kernel event timing; "window_regs" = 3|4|5 register qubits per window pass
+ *          (default 4); "lazy_swap" = 1/0 uncontrolled SWAP as a relabelling; "absorb" = 1/0 fold CNOTs into the
+ *          neighbouring single-qubit gate; "tma" = 0/1 TMA-prefetched variant of the window kernel */
 int qi_set_option(const char* name, int64_t value);
 
 /* kernel accounting for bench.py (gpu_launches, roofline.achieved) */
@@ -213,8 +216,9 @@ int qi_state_layout(const qi_state* s, uint8_t* phys, uint32_t* n_local);
 int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* exchanges,
                   uint64_t* comm_free_global_gates, uint8_t* final_phys);
 
-/* host-only: how the fused executor splits a gate list into passes on one device; rows[6*i..] =
- * {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops} */
+/* host-only: how the fused executor splits a gate list into passes on one device; rows[8*i..] =
+ * {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops,
+ *  CNOTs absorbed into a neighbouring gate, 0} */
 int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int window_regs, int32_t* rows,
                       uint64_t max_rows, uint64_t* n_rows);
 

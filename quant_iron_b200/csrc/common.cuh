@@ -59,6 +59,7 @@ struct Context {
     int opt_window_regs = 0;          // 0 = default
     int opt_lazy_swap = 1;            // uncontrolled SWAP = relabelling of the qubit map
     int opt_tma = 0;                  // window passes: 1 = TMA-prefetched persistent kernel (measured 2.4% slower), 0 = direct loads
+    int opt_absorb = 1;               // fold a CNOT into the neighbouring single-qubit gate on its target (window.cu)
     // stats
     uint64_t launches[KF_COUNT] = {0};
     double alg_bytes[KF_COUNT] = {0};

@@ -185,6 +185,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "window_regs")) c.opt_window_regs = (int)value;
     else if (!strcmp(name, "lazy_swap")) c.opt_lazy_swap = (int)value;
     else if (!strcmp(name, "tma")) c.opt_tma = (int)value;
+    else if (!strcmp(name, "absorb")) c.opt_absorb = (int)value;
     else if (!strcmp(name, "profile")) { if (!value) drain_profile(); c.opt_profile = (int)value; }
     else return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "unknown option");
     return QI_OK;

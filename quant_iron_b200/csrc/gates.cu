@@ -396,7 +396,8 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
 }
 
 // Host-only: how the fused executor would split a gate list into passes on a single device (no device access).
-// rows[6*i..] = {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops}
+// rows[8*i..] = {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops,
+//               absorbed CNOTs, 0}
 int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int window_regs, int32_t* rows,
                       uint64_t max_rows, uint64_t* n_rows) {
     qi_state s;
@@ -418,7 +419,7 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
     uint64_t n = 0;
     for (auto& r : summary) {
         if (n >= max_rows) break;
-        for (int k = 0; k < 6; k++) rows[6 * n + k] = r[k];
+        for (int k = 0; k < 8; k++) rows[8 * n + k] = r[k];
         n++;
     }
     if (n_rows) *n_rows = summary.size();

@@ -28,11 +28,11 @@
 
 namespace qi {
 
-enum { WK_X = 1, WK_RX, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };   // pair kinds first (<= WK_U2)
+enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };   // pair kinds first (<= WK_U2); RXS = RX o X
 
-static const int kMaxOps = 120;      // per launch (parameter space: 120 * 104 B + header < 16 KB)
+static const int kMaxOps = 120;      // per launch (parameter space: 120 * 112 B + header < 16 KB)
 
-struct DOp {                 // device op, 104 bytes
+struct DOp {                 // device op, 112 bytes
     uint8_t kind;            // WK_*
     uint8_t tpos;            // pair ops: 0..4 lane bit, 5+j register bit j
     uint8_t hub_cls;         // WK_TABLE: class of the hub bit (CLS_*)
@@ -40,9 +40,11 @@ struct DOp {                 // device op, 104 bytes
     uint8_t nchunks;         // WK_TABLE: number of 8-bit tile chunks with a table
     uint8_t has_reg;         // WK_TABLE: register table is not all ones
     uint8_t pad[2];
-    uint32_t c_lane, c_reg;  // control bits in lane space / slot space (all must be 1)
+    uint32_t c_lane, c_reg;  // c_lane: control bits in lane space (all must be 1).  c_reg: SLOT MASK -- bit s is set iff
+                             // slot s passes the register-bit controls (positive and negative), expanded on the host
     uint32_t t_lane, t_reg;  // WK_RZ: target bit in lane space / slot space (0 if elsewhere)
-    uint64_t c_tile;         // control bits in compact tile-index space
+    uint64_t c_tile;         // control bits in compact tile-index space (positive and negative controls)
+    uint64_t c_tval;         // value those bits must have: (tile & c_tile) == c_tval
     uint64_t t_tile;         // WK_RZ: target bit in tile space
     double m[8];             // matrix / phases; WK_TABLE: m[0] holds the table offset (as integer bits)
 };
@@ -72,26 +74,30 @@ __device__ __forceinline__ amp_t shfl_xor_amp(amp_t v, int mask) {
 
 // ---- pair gate on register bit B --------------------------------------------------------------
 // COND = false: no register-bit controls, straight-line code.  COND = true: the slot predicate
-// (s0 & c_reg) == c_reg is warp-uniform (c_reg comes from the constant bank, s0 is a literal), so a
+// bit s0 of the slot mask c_reg is warp-uniform (c_reg comes from the constant bank, s0 is a literal), so a
 // controlled gate costs a uniform branch per pair, not a select per register.
-// Kinds: X (swap), RX ([[c,-is],[-is,c]]), REAL (real 2x2; H is REAL), U2 (complex 2x2; Y is U2).
+// Kinds: X (swap), RX ([[c,-is],[-is,c]]), RXS (RX with its inputs swapped = RX o X = X o RX), REAL (real 2x2;
+// H is REAL), U2 (complex 2x2; Y is U2).
 template <int R, int B, int KIND, bool COND>
 __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t c_reg, const double* __restrict__ m) {
     double k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, k7 = 0;
-    if (KIND == WK_RX) { k0 = m[0]; k1 = m[1]; }
+    if (KIND == WK_RX || KIND == WK_RXS) { k0 = m[0]; k1 = m[1]; }
     if (KIND == WK_REAL) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; }
     if (KIND == WK_U2) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; k4 = m[4]; k5 = m[5]; k6 = m[6]; k7 = m[7]; }
 #pragma unroll
     for (int p = 0; p < (1 << (R - 1)); p++) {
         const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int s1 = s0 | (1 << B);
-        if (!COND || ((s0 & c_reg) == c_reg)) {
+        if (!COND || ((c_reg >> s0) & 1u)) {
             const amp_t a0 = v[s0], a1 = v[s1];
             if (KIND == WK_X) {
                 v[s0] = a1; v[s1] = a0;
             } else if (KIND == WK_RX) {
                 v[s0] = make_double2(k0 * a0.x + k1 * a1.y, k0 * a0.y - k1 * a1.x);
                 v[s1] = make_double2(k0 * a1.x + k1 * a0.y, k0 * a1.y - k1 * a0.x);
+            } else if (KIND == WK_RXS) {
+                v[s0] = make_double2(k0 * a1.x + k1 * a0.y, k0 * a1.y - k1 * a0.x);
+                v[s1] = make_double2(k0 * a0.x + k1 * a1.y, k0 * a0.y - k1 * a1.x);
             } else if (KIND == WK_REAL) {
                 v[s0] = make_double2(k0 * a0.x + k1 * a1.x, k0 * a0.y + k1 * a1.y);
                 v[s1] = make_double2(k2 * a0.x + k3 * a1.x, k2 * a0.y + k3 * a1.y);
@@ -105,16 +111,26 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
     }
 }
 
+template <int R>
+constexpr uint32_t kAllSlots = (R >= 5) ? 0xffffffffu : ((1u << (1 << R)) - 1u);
+
 template <int R, int B>
 __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
-#ifdef QI_UNCOND_FAST
-    // uncontrolled H / RX / RY (the bulk of layered circuits): straight-line variant without slot predicates
-    if (c_reg == 0 && kind == WK_REAL) { reg_pair_kind<R, B, WK_REAL, false>(v, 0, m); return; }
-    if (c_reg == 0 && kind == WK_RX) { reg_pair_kind<R, B, WK_RX, false>(v, 0, m); return; }
-#endif
+    // no register-bit controls (the bulk of every circuit): straight-line variants without slot predicates -- the
+    // per-pair predicate regions keep the compiler from interleaving the pairs, which exposes the FP64 latency.
+    // (X and U2 stay predicated: their straight-line forms spill hundreds of bytes.)
+    if (c_reg == kAllSlots<R>) {
+        switch (kind) {
+            case WK_REAL: reg_pair_kind<R, B, WK_REAL, false>(v, 0, m); return;
+            case WK_RX: reg_pair_kind<R, B, WK_RX, false>(v, 0, m); return;
+            case WK_RXS: reg_pair_kind<R, B, WK_RXS, false>(v, 0, m); return;
+            default: break;
+        }
+    }
     switch (kind) {
         case WK_X: reg_pair_kind<R, B, WK_X, true>(v, c_reg, m); break;
         case WK_RX: reg_pair_kind<R, B, WK_RX, true>(v, c_reg, m); break;
+        case WK_RXS: reg_pair_kind<R, B, WK_RXS, true>(v, c_reg, m); break;
         case WK_REAL: reg_pair_kind<R, B, WK_REAL, true>(v, c_reg, m); break;
         default: reg_pair_kind<R, B, WK_U2, true>(v, c_reg, m); break;
     }
@@ -123,16 +139,19 @@ __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, u
 // ---- pair gate on lane bit tpos (warp shuffles; every lane takes part in the exchange) -----------
 // A lane whose lane-bit controls are off keeps its value: its coefficients become (1, 0); its partner
 // differs only in the target bit, so it sees the same controls.
-template <int R>
-__device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
-                                             const double* __restrict__ m, int lane) {
+// ALL = every slot takes part (no register-bit controls): straight-line code, so the shuffles of a gate are issued
+// back to back (one exposed latency per gate) instead of one latency-exposed shuffle group per predicated slot.
+template <int R, bool ALL>
+__device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
+                                               const double* __restrict__ m, int lane) {
+    constexpr int S = 1 << R;
     const int xm = 1 << tpos;
     const bool hi = (lane >> tpos) & 1;     // this lane holds the |1> member of the pair
     if (kind == WK_X) {
         const int src = thread_ok ? (lane ^ xm) : lane;
 #pragma unroll
-        for (int s = 0; s < (1 << R); s++)
-            if ((s & c_reg) == c_reg)
+        for (int s = 0; s < S; s++)
+            if (ALL || ((c_reg >> s) & 1u))
                 v[s] = make_double2(__shfl_sync(0xffffffffu, v[s].x, src), __shfl_sync(0xffffffffu, v[s].y, src));
         return;
     }
@@ -140,8 +159,8 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
         double cA = hi ? m[3] : m[0], cB = hi ? m[2] : m[1];
         if (!thread_ok) { cA = 1.0; cB = 0.0; }
 #pragma unroll
-        for (int s = 0; s < (1 << R); s++) {
-            if ((s & c_reg) == c_reg) {
+        for (int s = 0; s < S; s++) {
+            if (ALL || ((c_reg >> s) & 1u)) {
                 const amp_t mine = v[s];
                 const amp_t other = shfl_xor_amp(mine, xm);
                 v[s] = make_double2(cA * mine.x + cB * other.x, cA * mine.y + cB * other.y);
@@ -149,15 +168,18 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
         }
         return;
     }
-    if (kind == WK_RX) {       // mine' = c*mine - i*s*other
+    if (kind == WK_RX || kind == WK_RXS) {
+        // RX: mine' = c*mine - i*s*other.  RXS (inputs swapped): mine' = c*other - i*s*mine
+        const bool swapped = (kind == WK_RXS) && thread_ok;
         double c = m[0], sn = m[1];
         if (!thread_ok) { c = 1.0; sn = 0.0; }
 #pragma unroll
-        for (int s = 0; s < (1 << R); s++) {
-            if ((s & c_reg) == c_reg) {
+        for (int s = 0; s < S; s++) {
+            if (ALL || ((c_reg >> s) & 1u)) {
                 const amp_t mine = v[s];
                 const amp_t other = shfl_xor_amp(mine, xm);
-                v[s] = make_double2(c * mine.x + sn * other.y, c * mine.y - sn * other.x);
+                const amp_t P = swapped ? other : mine, Q = swapped ? mine : other;
+                v[s] = make_double2(c * P.x + sn * Q.y, c * P.y - sn * Q.x);
             }
         }
         return;
@@ -166,8 +188,8 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
     amp_t cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
     if (!thread_ok) { cA = make_double2(1.0, 0.0); cB = make_double2(0.0, 0.0); }
 #pragma unroll
-    for (int s = 0; s < (1 << R); s++) {
-        if ((s & c_reg) == c_reg) {
+    for (int s = 0; s < S; s++) {
+        if (ALL || ((c_reg >> s) & 1u)) {
             const amp_t mine = v[s];
             const amp_t other = shfl_xor_amp(mine, xm);
             v[s] = cadd(cmul(cA, mine), cmul(cB, other));
@@ -175,18 +197,26 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
     }
 }
 
-// ---- the op program on one register tile -------------------------------------------------------------
 template <int R>
+__device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
+                                             const double* __restrict__ m, int lane) {
+    if (c_reg == kAllSlots<R>) lane_pair_impl<R, true>(v, kind, tpos, c_reg, thread_ok, m, lane);
+    else lane_pair_impl<R, false>(v, kind, tpos, c_reg, thread_ok, m, lane);
+}
+
+// ---- the op program on one register tile -------------------------------------------------------------
+// LANES = the program contains pair gates on lane qubits; programs without them run an instantiation that does not
+// carry the shuffle code at all (smaller, fewer live registers).
+template <int R, bool LANES>
 __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const WProgram<R>& P) {
     constexpr int S = 1 << R;
 #pragma unroll 1
     for (uint32_t o = 0; o < P.nops; o++) {
         const DOp& op = P.ops[o];
-        const uint64_t c_tile = op.c_tile;
-        if ((tile & c_tile) != c_tile) continue;                      // warp-uniform control
+        if ((tile & op.c_tile) != op.c_tval) continue;                // warp-uniform control (positive and negative bits)
         const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
         const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
-        if (kind <= WK_U2 && tpos < 5) {                              // pair gate across lanes
+        if (LANES && kind <= WK_U2 && tpos < 5) {                     // pair gate across lanes
             lane_pair_op<R>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
             continue;
         }
@@ -195,11 +225,11 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
             const amp_t ph = make_double2(op.m[0], op.m[1]);
 #pragma unroll
             for (int s = 0; s < S; s++)
-                if ((s & c_reg) == c_reg) v[s] = cmul(v[s], ph);
+                if ((c_reg >> s) & 1u) v[s] = cmul(v[s], ph);
         } else if (kind == WK_RZ) {
             const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
             const uint32_t t_reg = op.t_reg;
-            if (t_reg == 0 && c_reg == 0) {                           // target outside the registers: one phase per thread
+            if (t_reg == 0 && c_reg == kAllSlots<R>) {                 // target outside the registers: one phase per thread
                 const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
                 const amp_t pt = t_thread ? p1 : p0;
 #pragma unroll
@@ -209,7 +239,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
                 const amp_t pt = t_thread ? p1 : p0;
 #pragma unroll
                 for (int s = 0; s < S; s++)
-                    if ((s & c_reg) == c_reg) {
+                    if ((c_reg >> s) & 1u) {
                         if (s & t_reg) v[s] = cmul(v[s], p1);
                         else v[s] = cmul(v[s], pt);
                     }
@@ -253,7 +283,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 #define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? QI_WINDOW_BLOCKS4 : 2))
 
 // direct variant: every thread loads its 2^R amplitudes itself (coalesced 512 B per warp access)
-template <int R>
+template <int R, bool LANES>
 __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
@@ -264,7 +294,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __re
         amp_t v[S];
 #pragma unroll
         for (int s = 0; s < S; s++) v[s] = QI_LD(a + base + P.off[s]);
-        run_ops<R>(v, tile, lane, P);
+        run_ops<R, LANES>(v, tile, lane, P);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
     }
@@ -300,7 +330,7 @@ __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void
                  : "memory");
 }
 
-template <int R>
+template <int R, bool LANES>
 __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     extern __shared__ __align__(128) unsigned char smem_raw[];     // [4 warps][S * 32 amplitudes] then 4 mbarriers
@@ -334,7 +364,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* 
         for (int s = 0; s < S; s++) v[s] = buf[s * 32 + lane];
         __syncwarp();
         if (tile + nwarps < ntiles) issue(tile + nwarps);
-        run_ops<R>(v, tile, lane, P);
+        run_ops<R, LANES>(v, tile, lane, P);
         const uint64_t base = expand_index((tile << 5) | (uint64_t)lane, P.ins);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
@@ -365,6 +395,7 @@ struct HOp {
     uint32_t kind = 0;
     int target = -1;            // pair ops: physical target
     uint64_t cmask = 0;         // physical bits that must be 1 (WK_DIAG: includes the target)
+    uint64_t nmask = 0;         // physical bits that must be 0 (the complement half of an absorbed CNOT)
     uint64_t tmask = 0;         // WK_RZ: physical target bit
     double m[8] = {0};
     int group = -1;             // WK_TABLE: index into Pass::groups
@@ -418,12 +449,100 @@ static void append_op(Pass& ps, const HOp& op, uint64_t n_use) {
     for (DiagGroup& g : ps.groups) g.blocked_since |= n_use;
 }
 
+// ---- CNOT absorption --------------------------------------------------------------------------------
+// A CNOT (X with one control c) next to an uncontrolled single-qubit gate G on the same target t costs a full
+// register-swap op of its own.  Since (G X)(a0, a1) = G(a1, a0) and X only permutes, the pair is replaced by
+//   [c = 1] G' = G X  (or X G)   and   [c = 0] G
+// two half-populated ops that together do the work of ONE G.  Exact: X permutes, G' has the columns (rows) of
+// G swapped.  Only controls on tile or register bits qualify (a lane-bit control would idle half the lanes in
+// both ops), and nothing between the two gates may touch t or change c.
+static bool absorbable_kind(uint32_t k) { return k == WK_REAL || k == WK_RX || k == WK_RXS || k == WK_U2; }
+
+// G' = G o X (swap_inputs) or X o G (swap outputs); for the kinds above both are again one of the kinds
+static void compose_with_x(HOp* g, bool x_first) {
+    double* m = g->m;
+    if (g->kind == WK_RX) { g->kind = WK_RXS; return; }          // RX is symmetric and persymmetric: RX X = X RX
+    if (g->kind == WK_RXS) { g->kind = WK_RX; return; }
+    if (g->kind == WK_REAL) {                                     // m = (k00, k01, k10, k11)
+        if (x_first) { std::swap(m[0], m[1]); std::swap(m[2], m[3]); }      // columns
+        else { std::swap(m[0], m[2]); std::swap(m[1], m[3]); }              // rows
+        return;
+    }
+    // WK_U2: m = (m00, m01, m10, m11) as (re, im)
+    if (x_first) { std::swap(m[0], m[2]); std::swap(m[1], m[3]); std::swap(m[4], m[6]); std::swap(m[5], m[7]); }
+    else { std::swap(m[0], m[4]); std::swap(m[1], m[5]); std::swap(m[2], m[6]); std::swap(m[3], m[7]); }
+}
+
+// index of the last op of the pass that touches qubit t, or -1; `clean` = no op after it n-uses `protect`
+static int last_touch(const Pass& ps, int t, uint64_t protect, bool* clean) {
+    *clean = true;
+    for (int i = (int)ps.ops.size() - 1; i >= 0; i--) {
+        const HOp& h = ps.ops[i];
+        if (h.kind == 0) continue;
+        uint64_t n = 0, d = 0;
+        if (h.kind == WK_TABLE) {
+            const DiagGroup& g = ps.groups[h.group];
+            if (g.hub >= 0) d |= 1ull << g.hub;
+            if (g.hub_alt >= 0) d |= 1ull << g.hub_alt;
+            for (int q : g.bits) d |= 1ull << q;
+            d |= h.cmask | h.tmask;
+        } else if (h.kind == WK_DIAG || h.kind == WK_RZ) d = h.cmask | h.tmask;
+        else { n = 1ull << h.target; d = h.cmask | h.nmask; }
+        if ((n | d) & (1ull << t)) return i;
+        if (n & protect) *clean = false;
+    }
+    return -1;
+}
+
+// `g` (uncontrolled pair op on t) is about to be appended: if the last op on t is a single-control X, fold it in
+static bool absorb_cnot_before(Pass& ps, HOp* g) {
+    if (!absorbable_kind(g->kind) || g->cmask || g->nmask) return false;
+    bool clean = false;
+    const int i = last_touch(ps, g->target, 0, &clean);
+    if (i < 0) return false;
+    HOp& x = ps.ops[i];
+    if (x.kind != WK_X || x.target != g->target || x.nmask || __builtin_popcountll(x.cmask) != 1) return false;
+    if (x.cmask & ((1ull << kLaneQubits) - 1)) return false;
+    // nothing after the X may have changed its control qubit
+    bool ctrl_clean = false;
+    (void)last_touch(ps, g->target, x.cmask, &ctrl_clean);
+    if (!ctrl_clean) return false;
+    const uint64_t c = x.cmask;
+    HOp on = *g;                 // control = 1: G X, takes the X's place
+    compose_with_x(&on, true);
+    on.cmask = c;
+    x = on;
+    g->nmask = c;                // control = 0: plain G, appended by the caller
+    return true;
+}
+
+// `x` (single-control X on t) is about to be appended: if the last op on t is an uncontrolled G, fold the X in
+static bool absorb_cnot_after(Pass& ps, const HOp& x, HOp* off_half) {
+    if (x.kind != WK_X || x.nmask || __builtin_popcountll(x.cmask) != 1) return false;
+    if (x.cmask & ((1ull << kLaneQubits) - 1)) return false;
+    bool clean = false;
+    const int i = last_touch(ps, x.target, x.cmask, &clean);
+    if (i < 0 || !clean) return false;
+    HOp& g = ps.ops[i];
+    if (!absorbable_kind(g.kind) || g.target != x.target || g.cmask || g.nmask) return false;
+    *off_half = g;               // control = 0: plain G, appended by the caller
+    off_half->nmask = x.cmask;
+    compose_with_x(&g, false);   // control = 1: X G, stays in G's place
+    g.cmask = x.cmask;
+    return true;
+}
+
 static void push_pair(Pass& ps, uint32_t kind, int target, uint64_t cmask, const double* m8) {
     HOp op;
     op.kind = kind;
     op.target = target;
     op.cmask = cmask;
     if (m8) memcpy(op.m, m8, 8 * sizeof(double));
+    if (ctx().opt_absorb) {
+        HOp off;
+        if (absorb_cnot_before(ps, &op)) { append_op(ps, op, 1ull << target); return; }     // op now carries nmask
+        if (absorb_cnot_after(ps, op, &off)) { append_op(ps, off, 1ull << target); return; }
+    }
     append_op(ps, op, 1ull << target);
 }
 
@@ -570,10 +689,19 @@ static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>
     memcpy(&d->m[0], &o, sizeof(o));
 }
 
+// bit sl set iff slot sl has every positive register-bit control on and every negative one off
+static uint32_t slot_mask(int R, uint32_t pos, uint32_t neg) {
+    uint32_t m = 0;
+    for (int sl = 0; sl < (1 << R); sl++)
+        if (((uint32_t)sl & pos) == pos && ((uint32_t)sl & neg) == 0) m |= 1u << sl;
+    return m;
+}
+
 static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp>& dops, std::vector<amp_t>& arena, Layout* Lout) {
     Layout L = make_layout(s, ps.regs, R);
     *Lout = L;
     for (const HOp& h : ps.ops) {
+        if (h.kind == 0) continue;              // absorbed into a neighbour (absorb_cnot)
         DOp d;
         memset(&d, 0, sizeof(d));
         HOp op = h;
@@ -588,7 +716,15 @@ static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp
             if (op.kind == WK_DIAG) { op.m[0] = h.m[0]; op.m[1] = h.m[1]; }
         }
         d.kind = (uint8_t)op.kind;
-        split_mask(L, op.cmask, &d.c_lane, &d.c_reg, &d.c_tile);
+        {
+            uint32_t pos_reg = 0, neg_lane = 0, neg_reg = 0;
+            uint64_t pos_tile = 0, neg_tile = 0;
+            split_mask(L, op.cmask, &d.c_lane, &pos_reg, &pos_tile);
+            split_mask(L, op.nmask, &neg_lane, &neg_reg, &neg_tile);      // neg_lane is always 0 (absorb_cnot refuses lane controls)
+            d.c_reg = slot_mask(L.R, pos_reg, neg_reg);
+            d.c_tile = pos_tile | neg_tile;
+            d.c_tval = pos_tile;
+        }
         if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
         memcpy(d.m, op.m, sizeof(d.m));
         if (op.kind != WK_DIAG && op.kind != WK_RZ) {
@@ -615,6 +751,8 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
         size_t cnt = std::min<size_t>(kMaxOps, nops - first);
         P.nops = (uint32_t)cnt;
         memcpy(P.ops, ops + first, cnt * sizeof(DOp));
+        bool lanes = false;
+        for (size_t k = 0; k < cnt; k++) lanes |= (P.ops[k].kind <= WK_U2 && P.ops[k].kind >= WK_X && P.ops[k].tpos < kLaneQubits);
         LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
         if (c.opt_tma) {
             uint64_t pblocks = (uint64_t)c.sm_count * QI_WINDOW_BLOCKS(R);       // persistent: every block resident
@@ -622,12 +760,16 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
             const size_t smem = (size_t)warps_per_block * (32u << R) * sizeof(amp_t) + warps_per_block * sizeof(uint64_t);
             static bool configured = false;      // per instantiation
             if (!configured) {
-                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = true;
             }
-            k_window_tma<R><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
+            if (lanes) k_window_tma<R, true><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
+            else k_window_tma<R, false><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
+        } else if (lanes) {
+            k_window<R, true><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
         } else {
-            k_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+            k_window<R, false><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
         }
         QI_TRY(check_launch("k_window"));
     }
@@ -752,14 +894,16 @@ int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R,
     std::vector<Step> steps;
     QI_TRY(schedule_passes(s, gates, true, R, steps));
     for (const Step& st : steps) {
-        int lane_ops = 0, reg_ops = 0, diag_ops = 0, table_ops = 0;
+        int lane_ops = 0, reg_ops = 0, diag_ops = 0, table_ops = 0, absorbed = 0;
         for (const HOp& h : st.pass.ops) {
+            if (h.kind == 0) continue;
+            if (h.nmask) absorbed++;
             if (h.kind == WK_TABLE) table_ops++;
             else if (h.kind == WK_DIAG || h.kind == WK_RZ) diag_ops++;
             else if (h.target < kLaneQubits) lane_ops++;
             else reg_ops++;
         }
-        summary->push_back({st.simple ? 1 : 0, (int)st.pass.regs.size(), lane_ops, reg_ops, diag_ops, table_ops});
+        summary->push_back({st.simple ? 1 : 0, (int)st.pass.regs.size(), lane_ops, reg_ops, diag_ops, table_ops, absorbed, 0});
     }
     return QI_OK;
 }

@@ -14,12 +14,14 @@ ap.add_argument("--qubits", type=int, default=30)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--tag", default="")
 ap.add_argument("--regs", type=int, default=0)
-ap.add_argument("--tma", type=int, default=1)
+ap.add_argument("--tma", type=int, default=0)
+ap.add_argument("--absorb", type=int, default=1)
 a = ap.parse_args()
 n = a.qubits
 if a.regs:
     qi.engine.set_option("window_regs", a.regs)
 qi.engine.set_option("tma", a.tma)
+qi.engine.set_option("absorb", a.absorb)
 st = qi.State.new_zero(n)
 for name, specs in (("layered", w.random_layered_circuit(n, 40)), ("qft", w.qft_specs(n))):
     c = w.build_circuit(qi, n, specs)

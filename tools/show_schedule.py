@@ -15,10 +15,10 @@ def schedule(n, specs, regs=4):
     arr = (_ffi.QiGate * len(recs))()
     for i, (r, _k) in enumerate(recs):
         arr[i] = r
-    rows = (C.c_int32 * (6 * 4096))()
+    rows = (C.c_int32 * (8 * 4096))()
     nrows = C.c_uint64()
     _ffi.check(_ffi.lib.qi_debug_schedule(n, arr, len(recs), regs, rows, 4096, C.byref(nrows)))
-    return [tuple(rows[6 * i + k] for k in range(6)) for i in range(min(4096, nrows.value))]
+    return [tuple(rows[8 * i + k] for k in range(7)) for i in range(min(4096, nrows.value))]
 
 
 if __name__ == "__main__":
@@ -30,6 +30,6 @@ if __name__ == "__main__":
     specs = w.random_layered_circuit(a.qubits, 40) if a.what == "layered" else w.qft_specs(a.qubits)
     rows = schedule(a.qubits, specs, a.regs)
     print(f"{len(specs)} gates -> {len(rows)} passes")
-    print("simple regs lane reg diag table")
+    print("simple regs lane reg diag table absorbed_cnots")
     for r in rows:
         print(*r)
