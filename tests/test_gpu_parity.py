@@ -453,3 +453,31 @@ def test_pauli_sequences_longer_than_one_launch(gpu, ref):
     assert e.value.variant == "InvalidQubitIndex"
     assert np.array_equal(vec(out), before)
     assert apply_exp_sequence_(out, [], []) is out
+
+
+@pytest.mark.parametrize("absorb", [1, 0])
+def test_cnot_absorption_matches_oracle(gpu, ref, absorb):
+    """Option "absorb": a CNOT next to a single-qubit gate on its target is folded into two half-populated ops
+    (G X / X G where the control is set, G where it is clear).  Random H / RX / RY / RZ / CNOT lists exercise both
+    composition orders, register, tile and lane controls, and targets on lanes and registers."""
+    gpu.engine.set_option("absorb", absorb)
+    try:
+        rng = np.random.default_rng(11)
+        for trial in range(6):
+            n = 9 + trial
+            bg, br = gpu.CircuitBuilder(n), ref.CircuitBuilder(n)
+            for _ in range(160):
+                k = int(rng.integers(0, 6))
+                t, c = [int(x) for x in rng.permutation(n)[:2]]
+                a = float(rng.uniform(-3, 3))
+                for b in (bg, br):
+                    if k == 0: b.h_gate(t)
+                    elif k == 1: b.rx_gate(t, a)
+                    elif k == 2: b.ry_gate(t, a)
+                    elif k == 3: b.cnot_gate(t, c)
+                    elif k == 4: b.rz_gate(t, a)
+                    else: b.y_gate(t)
+            g, r = _pair(gpu, ref, n, seed=600 + trial)
+            assert_amps(bg.build().execute(g), vec(br.build().execute(r)), msg=f"absorb={absorb} n={n}")
+    finally:
+        gpu.engine.set_option("absorb", 1)
