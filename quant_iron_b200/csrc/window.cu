@@ -114,7 +114,7 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
 template <int R>
 constexpr uint32_t kAllSlots = (R >= 5) ? 0xffffffffu : ((1u << (1 << R)) - 1u);
 
-template <int R, int B>
+template <int R, int B, bool U2K>
 __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
     // no register-bit controls (the bulk of every circuit): straight-line variants without slot predicates -- the
     // per-pair predicate regions keep the compiler from interleaving the pairs, which exposes the FP64 latency.
@@ -132,7 +132,7 @@ __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, u
         case WK_RX: reg_pair_kind<R, B, WK_RX, true>(v, c_reg, m); break;
         case WK_RXS: reg_pair_kind<R, B, WK_RXS, true>(v, c_reg, m); break;
         case WK_REAL: reg_pair_kind<R, B, WK_REAL, true>(v, c_reg, m); break;
-        default: reg_pair_kind<R, B, WK_U2, true>(v, c_reg, m); break;
+        default: if (U2K) reg_pair_kind<R, B, WK_U2, true>(v, c_reg, m); break;
     }
 }
 
@@ -141,7 +141,7 @@ __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, u
 // differs only in the target bit, so it sees the same controls.
 // ALL = every slot takes part (no register-bit controls): straight-line code, so the shuffles of a gate are issued
 // back to back (one exposed latency per gate) instead of one latency-exposed shuffle group per predicated slot.
-template <int R, bool ALL>
+template <int R, bool ALL, bool U2K>
 __device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
                                                const double* __restrict__ m, int lane) {
     constexpr int S = 1 << R;
@@ -184,6 +184,7 @@ __device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind
         }
         return;
     }
+    if (!U2K) return;
     amp_t cA = hi ? make_double2(m[6], m[7]) : make_double2(m[0], m[1]);
     amp_t cB = hi ? make_double2(m[4], m[5]) : make_double2(m[2], m[3]);
     if (!thread_ok) { cA = make_double2(1.0, 0.0); cB = make_double2(0.0, 0.0); }
@@ -197,17 +198,17 @@ __device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind
     }
 }
 
-template <int R>
+template <int R, bool U2K>
 __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
                                              const double* __restrict__ m, int lane) {
-    if (c_reg == kAllSlots<R>) lane_pair_impl<R, true>(v, kind, tpos, c_reg, thread_ok, m, lane);
-    else lane_pair_impl<R, false>(v, kind, tpos, c_reg, thread_ok, m, lane);
+    if (c_reg == kAllSlots<R>) lane_pair_impl<R, true, U2K>(v, kind, tpos, c_reg, thread_ok, m, lane);
+    else lane_pair_impl<R, false, U2K>(v, kind, tpos, c_reg, thread_ok, m, lane);
 }
 
 // ---- the op program on one register tile -------------------------------------------------------------
 // LANES = the program contains pair gates on lane qubits; programs without them run an instantiation that does not
 // carry the shuffle code at all (smaller, fewer live registers).
-template <int R, bool LANES>
+template <int R, bool LANES, bool U2K>
 __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const WProgram<R>& P) {
     constexpr int S = 1 << R;
 #pragma unroll 1
@@ -217,7 +218,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
         const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
         const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
         if (LANES && kind <= WK_U2 && tpos < 5) {                     // pair gate across lanes
-            lane_pair_op<R>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
+            lane_pair_op<R, U2K>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
             continue;
         }
         if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
@@ -265,11 +266,11 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
             }
         } else {
             switch (tpos - 5) {
-                case 0: reg_pair_op<R, 0>(v, kind, c_reg, op.m); break;
-                case 1: reg_pair_op<R, (R > 1 ? 1 : 0)>(v, kind, c_reg, op.m); break;
-                case 2: reg_pair_op<R, (R > 2 ? 2 : 0)>(v, kind, c_reg, op.m); break;
-                case 3: reg_pair_op<R, (R > 3 ? 3 : 0)>(v, kind, c_reg, op.m); break;
-                default: reg_pair_op<R, (R > 4 ? 4 : 0)>(v, kind, c_reg, op.m); break;
+                case 0: reg_pair_op<R, 0, U2K>(v, kind, c_reg, op.m); break;
+                case 1: reg_pair_op<R, (R > 1 ? 1 : 0), U2K>(v, kind, c_reg, op.m); break;
+                case 2: reg_pair_op<R, (R > 2 ? 2 : 0), U2K>(v, kind, c_reg, op.m); break;
+                case 3: reg_pair_op<R, (R > 3 ? 3 : 0), U2K>(v, kind, c_reg, op.m); break;
+                default: reg_pair_op<R, (R > 4 ? 4 : 0), U2K>(v, kind, c_reg, op.m); break;
             }
         }
     }
@@ -283,7 +284,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 #define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? QI_WINDOW_BLOCKS4 : 2))
 
 // direct variant: every thread loads its 2^R amplitudes itself (coalesced 512 B per warp access)
-template <int R, bool LANES>
+template <int R, bool LANES, bool U2K>
 __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __re
         amp_t v[S];
 #pragma unroll
         for (int s = 0; s < S; s++) v[s] = QI_LD(a + base + P.off[s]);
-        run_ops<R, LANES>(v, tile, lane, P);
+        run_ops<R, LANES, U2K>(v, tile, lane, P);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
     }
@@ -330,7 +331,7 @@ __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void
                  : "memory");
 }
 
-template <int R, bool LANES>
+template <int R, bool LANES, bool U2K>
 __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     extern __shared__ __align__(128) unsigned char smem_raw[];     // [4 warps][S * 32 amplitudes] then 4 mbarriers
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* 
         for (int s = 0; s < S; s++) v[s] = buf[s * 32 + lane];
         __syncwarp();
         if (tile + nwarps < ntiles) issue(tile + nwarps);
-        run_ops<R, LANES>(v, tile, lane, P);
+        run_ops<R, LANES, U2K>(v, tile, lane, P);
         const uint64_t base = expand_index((tile << 5) | (uint64_t)lane, P.ins);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
@@ -751,25 +752,36 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
         size_t cnt = std::min<size_t>(kMaxOps, nops - first);
         P.nops = (uint32_t)cnt;
         memcpy(P.ops, ops + first, cnt * sizeof(DOp));
-        bool lanes = false;
-        for (size_t k = 0; k < cnt; k++) lanes |= (P.ops[k].kind <= WK_U2 && P.ops[k].kind >= WK_X && P.ops[k].tpos < kLaneQubits);
+        // instantiation by content: programs without lane gates / without complex 2x2 gates run kernels that do not
+        // carry that code (smaller, fewer live registers)
+        bool lanes = false, u2k = false;
+        for (size_t k = 0; k < cnt; k++) {
+            const DOp& o = P.ops[k];
+            if (o.kind >= WK_X && o.kind <= WK_U2) { lanes |= o.tpos < kLaneQubits; u2k |= o.kind == WK_U2; }
+        }
         LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
+        const unsigned threads = warps_per_block * 32;
         if (c.opt_tma) {
             uint64_t pblocks = (uint64_t)c.sm_count * QI_WINDOW_BLOCKS(R);       // persistent: every block resident
             if (pblocks > blocks) pblocks = blocks;
             const size_t smem = (size_t)warps_per_block * (32u << R) * sizeof(amp_t) + warps_per_block * sizeof(uint64_t);
-            static bool configured = false;      // per instantiation
+            static bool configured = false;      // per instantiation of launch_program
             if (!configured) {
-                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                QI_CUDA(cudaFuncSetAttribute(k_window_tma<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = true;
             }
-            if (lanes) k_window_tma<R, true><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
-            else k_window_tma<R, false><<<(unsigned)pblocks, warps_per_block * 32, smem, c.stream>>>(s->d, ntiles, P);
-        } else if (lanes) {
-            k_window<R, true><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+            if (lanes && u2k) k_window_tma<R, true, true><<<(unsigned)pblocks, threads, smem, c.stream>>>(s->d, ntiles, P);
+            else if (lanes) k_window_tma<R, true, false><<<(unsigned)pblocks, threads, smem, c.stream>>>(s->d, ntiles, P);
+            else if (u2k) k_window_tma<R, false, true><<<(unsigned)pblocks, threads, smem, c.stream>>>(s->d, ntiles, P);
+            else k_window_tma<R, false, false><<<(unsigned)pblocks, threads, smem, c.stream>>>(s->d, ntiles, P);
         } else {
-            k_window<R, false><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+            if (lanes && u2k) k_window<R, true, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else if (lanes) k_window<R, true, false><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else if (u2k) k_window<R, false, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else k_window<R, false, false><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
         }
         QI_TRY(check_launch("k_window"));
     }
