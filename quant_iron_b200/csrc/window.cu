@@ -10,7 +10,8 @@
 // A gate whose target is a window qubit pairs two registers of the same thread (no data movement);
 // a target on qubits 0..4 pairs two lanes (warp shuffles); controls and diagonal gates can sit on
 // ANY qubit: a control on a tile bit is a warp-uniform skip, on a lane bit a per-thread predicate,
-// on a register bit a per-slot uniform predicate.  No shared memory, no block synchronisation.
+// on a register bit a per-slot uniform predicate (a host-expanded slot mask, which also carries
+// negative controls).  The default kernel uses no shared memory and no block synchronisation.
 // The op program of a pass travels in the kernel's parameter space (constant bank, uniform loads).
 //
 // Diagonal gates that meet in a pass are merged into PHASE-TABLE ops: a group "if hub bit set,
@@ -20,7 +21,15 @@
 //
 // The host scheduler walks the gate list greedily: a gate joins the current pass if it commutes
 // with every gate deferred so far (two gates commute when on each shared qubit both act diagonally)
-// and its non-diagonal targets fit the window (5 lane qubits + R free choices).
+// and its non-diagonal targets fit the window (5 lane qubits + R free choices).  A CNOT next to a
+// single-qubit gate on its target is absorbed into it (absorb_cnot_*).
+//
+// Performance notes that shaped the code (DESIGN.md 3.1 has the measurements):
+//   * gates without register-bit controls take straight-line variants: per-slot predicate regions
+//     serialise the slots and expose one shuffle / FP64 latency per slot;
+//   * the kernel is instantiated by pass content (k_window<R, LANES, U2K>): passes without lane
+//     gates / complex 2x2 gates run code that does not carry those paths;
+//   * k_window_tma is a TMA-prefetched persistent variant kept behind the "tma" option (slower).
 #include <algorithm>
 
 #include "common.cuh"
