@@ -60,6 +60,7 @@ struct Context {
     int opt_lazy_swap = 1;            // uncontrolled SWAP = relabelling of the qubit map
     int opt_tma = 0;                  // window passes: 1 = TMA-prefetched persistent kernel (measured 2.4% slower), 0 = direct loads
     int opt_absorb = 1;               // fold a CNOT into the neighbouring single-qubit gate on its target (window.cu)
+    int64_t opt_pool_mb = 4096;       // device-buffer cache: at most this many MiB are kept for reuse (0 = off)
     // stats
     uint64_t launches[KF_COUNT] = {0};
     double alg_bytes[KF_COUNT] = {0};
@@ -76,6 +77,12 @@ struct Context {
 Context& ctx();
 int ensure_ctx();
 int ensure_partials(size_t doubles);
+// Device buffers through a small size-keyed cache: cudaMalloc/cudaFree cost up to milliseconds each (and cudaFree
+// synchronises), which would dominate the reference's functional API (`&self -> State` clones once per gate) on small
+// states.  Everything runs on the one engine stream, so a cached buffer can be handed out again without a sync.
+int dev_alloc(void** p, size_t bytes);
+void dev_free(void* p, size_t bytes);
+void dev_pool_trim();                 // release every cached buffer
 
 // Kernel launch bookkeeping: counts launches, accumulates algorithmic bytes and, when the
 // "profile" option is on, brackets the launch with CUDA events on the engine stream.

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -72,6 +73,69 @@ int ensure_ctx() {
     if (g_ctx.ready) return cudaSetDevice(g_ctx.device) == cudaSuccess ? QI_OK : cuda_fail(cudaGetLastError(), "cudaSetDevice");
     std::lock_guard<std::mutex> lk(g_mutex);
     return init_locked(-1);
+}
+
+// ---- device-buffer cache ---------------------------------------------------------------------------
+namespace {
+struct DevPool {
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> free_by_size;
+    size_t cached_bytes = 0;
+};
+DevPool& pool() { static DevPool p; return p; }
+const size_t kMaxPooledBuffer = 1ull << 30;      // larger buffers go straight back to the driver
+}  // namespace
+
+int dev_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) return QI_OK;
+    {
+        DevPool& dp = pool();
+        std::lock_guard<std::mutex> lk(dp.mu);
+        auto it = dp.free_by_size.find(bytes);
+        if (it != dp.free_by_size.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            dp.cached_bytes -= bytes;
+            return QI_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        dev_pool_trim();                             // give the cache back and retry once
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    return QI_OK;
+}
+
+void dev_free(void* p, size_t bytes) {
+    if (!p) return;
+    Context& c = ctx();
+    const size_t cap = (size_t)(c.opt_pool_mb > 0 ? c.opt_pool_mb : 0) << 20;
+    if (bytes <= kMaxPooledBuffer) {
+        DevPool& dp = pool();
+        std::lock_guard<std::mutex> lk(dp.mu);
+        if (dp.cached_bytes + bytes <= cap) {
+            // work queued on the engine stream may still touch the buffer; the next user is queued behind it
+            dp.free_by_size[bytes].push_back(p);
+            dp.cached_bytes += bytes;
+            return;
+        }
+    }
+    if (c.ready) cudaStreamSynchronize(c.stream);
+    cudaFree(p);
+}
+
+void dev_pool_trim() {
+    DevPool& dp = pool();
+    std::lock_guard<std::mutex> lk(dp.mu);
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    for (auto& kv : dp.free_by_size)
+        for (void* p : kv.second) cudaFree(p);
+    dp.free_by_size.clear();
+    dp.cached_bytes = 0;
 }
 
 int ensure_partials(size_t doubles) {
@@ -186,6 +250,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "lazy_swap")) c.opt_lazy_swap = (int)value;
     else if (!strcmp(name, "tma")) c.opt_tma = (int)value;
     else if (!strcmp(name, "absorb")) c.opt_absorb = (int)value;
+    else if (!strcmp(name, "pool_mb")) { c.opt_pool_mb = value; if (value <= 0) dev_pool_trim(); }
     else if (!strcmp(name, "profile")) { if (!value) drain_profile(); c.opt_profile = (int)value; }
     else return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "unknown option");
     return QI_OK;

@@ -182,8 +182,8 @@ static int alloc_state(uint32_t num_qubits, uint64_t len, qi_state** out) {
     s->consistent = (num_qubits < 64) && (len == (1ull << num_qubits));
     for (int i = 0; i < 64; i++) s->phys[i] = (uint8_t)i;
     if (len) {
-        cudaError_t e = cudaMalloc(&s->d, len * sizeof(amp_t));
-        if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(state)"); }
+        int st = dev_alloc((void**)&s->d, len * sizeof(amp_t));
+        if (st != QI_OK) { delete s; return st; }
     }
     *out = s;
     return QI_OK;
@@ -337,9 +337,13 @@ void qi_shard_release(qi_state* s);
 
 void qi_state_free(qi_state* s) {
     if (!s) return;
-    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
-    if (s->world > 1) qi_shard_release(s);
-    if (s->d) cudaFree(s->d);
+    if (s->world > 1) {                  // shards are IPC-exported: never cached
+        if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+        qi_shard_release(s);
+        if (s->d) cudaFree(s->d);
+    } else {
+        dev_free(s->d, s->len * sizeof(amp_t));
+    }
     delete s;
 }
 

@@ -481,3 +481,28 @@ def test_cnot_absorption_matches_oracle(gpu, ref, absorb):
             assert_amps(bg.build().execute(g), vec(br.build().execute(r)), msg=f"absorb={absorb} n={n}")
     finally:
         gpu.engine.set_option("absorb", 1)
+
+
+def test_functional_api_clones_through_the_buffer_cache(gpu, ref):
+    """The reference's API is functional (`&self -> State`): every gate call clones.  Clones come from a size-keyed
+    device-buffer cache; states that die and are reborn in a tight loop must never alias live data."""
+    n = 12
+    g, r = _pair(gpu, ref, n, seed=700)
+    keep = [g]
+    for i in range(40):
+        q = i % n
+        g2 = g.h(q).rx((q + 3) % n, 0.1 * (i + 1)).cnot(q, (q + 1) % n)       # three clones, two die at once
+        r = r.h(q).rx((q + 3) % n, 0.1 * (i + 1)).cnot(q, (q + 1) % n)
+        if i % 7 == 0:
+            keep.append(g2)                                                    # some stay alive across iterations
+        g = g2
+    assert_amps(g, vec(r), msg="chain of functional gate calls")
+    first = vec(keep[0])
+    assert_amps(keep[0], vec(ref.random_state(n, 700)), msg="the original state is untouched")
+    gpu.engine.set_option("pool_mb", 0)            # trim and disable: same results without the cache
+    try:
+        h = keep[1].h(0).h(0)
+        assert_amps(h, vec(keep[1]), tol=1e-14, msg="cache off")
+    finally:
+        gpu.engine.set_option("pool_mb", 4096)
+    assert np.array_equal(vec(keep[0]), first)
