@@ -208,7 +208,7 @@ static int local_table(const qi_state* s, const std::vector<int>& pos, double** 
     if (m > 34) return fail(QI_ERR_INVALID_INPUT_VALUE, (uint64_t)m, 0, "probability table too large");
     const uint64_t nbins = 1ull << m;
     double* d_probs = nullptr;
-    QI_CUDA(cudaMalloc(&d_probs, nbins * sizeof(double)));
+    QI_TRY(dev_alloc((void**)&d_probs, nbins * sizeof(double)));
     BinMap bm;
     memset(&bm, 0, sizeof(bm));
     bm.m = m;
@@ -234,7 +234,7 @@ static int local_table(const qi_state* s, const std::vector<int>& pos, double** 
         k_prob_serial<<<(unsigned)((nbins + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(s->d, nbins, rest_total, ins, bm, d_probs);
     }
     if (st == QI_OK) st = check_launch("probabilities");
-    if (st != QI_OK) { cudaFree(d_probs); return st; }
+    if (st != QI_OK) { dev_free(d_probs, nbins * sizeof(double)); return st; }
     *d_probs_out = d_probs;
     return QI_OK;
 }
@@ -264,7 +264,7 @@ static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& 
     std::vector<double> hl(nloc), full(nbins, 0.0);
     cudaError_t e = cudaMemcpyAsync(hl.data(), d_local, nloc * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-    cudaFree(d_local);
+    dev_free(d_local, nloc * sizeof(double));
     if (e != cudaSuccess) return cuda_fail(e, "D2H local table");
     for (uint64_t b = 0; b < nbins; b++) {
         uint64_t lb = 0, seen = 0, val = 0;
@@ -282,10 +282,10 @@ static int device_probabilities(const qi_state* s, const std::vector<uint32_t>& 
         for (uint64_t off = 0; off < nbins; off += 512)
             QI_TRY(shard_allreduce_sum(const_cast<qi_state*>(s), full.data() + off, (int)std::min<uint64_t>(512, nbins - off)));
     double* d_probs = nullptr;
-    QI_CUDA(cudaMalloc(&d_probs, nbins * sizeof(double)));
+    QI_TRY(dev_alloc((void**)&d_probs, nbins * sizeof(double)));
     e = cudaMemcpyAsync(d_probs, full.data(), nbins * sizeof(double), cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-    if (e != cudaSuccess) { cudaFree(d_probs); return cuda_fail(e, "H2D full table"); }
+    if (e != cudaSuccess) { dev_free(d_probs, nbins * sizeof(double)); return cuda_fail(e, "H2D full table"); }
     *d_probs_out = d_probs;
     return QI_OK;
 }
@@ -313,10 +313,11 @@ static int sample_from_table(const double* d_probs, uint64_t nbins, uint64_t see
     uint64_t ntiles = (nbins + kScanTile - 1) / kScanTile;
     double* d_cdf = nullptr;
     uint64_t* d_bins = nullptr;
-    QI_CUDA(cudaMalloc(&d_cdf, nbins * sizeof(double)));
-    cudaError_t e = cudaMalloc(&d_bins, shots * sizeof(uint64_t));
-    if (e != cudaSuccess) { cudaFree(d_cdf); return cuda_fail(e, "cudaMalloc(bins)"); }
-    int st = ensure_partials(ntiles + 8);
+    QI_TRY(dev_alloc((void**)&d_cdf, nbins * sizeof(double)));
+    cudaError_t e = cudaSuccess;
+    int st = dev_alloc((void**)&d_bins, shots * sizeof(uint64_t));
+    if (st != QI_OK) { dev_free(d_cdf, nbins * sizeof(double)); return st; }
+    st = ensure_partials(ntiles + 8);
     if (st == QI_OK) {
         {
             LaunchScope ls(KF_SCAN, 24.0 * (double)nbins);
@@ -335,8 +336,8 @@ static int sample_from_table(const double* d_probs, uint64_t nbins, uint64_t see
         if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
         if (e != cudaSuccess) st = cuda_fail(e, "D2H bins");
     }
-    cudaFree(d_cdf);
-    cudaFree(d_bins);
+    dev_free(d_cdf, nbins * sizeof(double));
+    dev_free(d_bins, shots * sizeof(uint64_t));
     return st;
 }
 
@@ -412,7 +413,7 @@ int qi_probabilities(const qi_state* s, const uint32_t* qubits, uint32_t m, doub
     uint64_t nbins = 1ull << q.size();
     cudaError_t e = cudaMemcpyAsync(out, d_probs, nbins * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
-    cudaFree(d_probs);
+    dev_free(d_probs, nbins * sizeof(double));
     if (e != cudaSuccess) return cuda_fail(e, "D2H probabilities");
     return QI_OK;
 }
@@ -426,7 +427,7 @@ int qi_sample(const qi_state* s, const uint32_t* qubits, uint32_t m, uint64_t sh
     double* d_probs = nullptr;
     QI_TRY(device_probabilities(s, q, &d_probs));
     int st = sample_from_table(d_probs, 1ull << q.size(), seed, 0, shots, bins);
-    cudaFree(d_probs);
+    dev_free(d_probs, (1ull << q.size()) * sizeof(double));
     return st;
 }
 
@@ -467,7 +468,7 @@ int qi_measure(qi_state* s, int basis, const double* custom_u, const uint32_t* q
     QI_TRY(device_probabilities(s, q, &d_probs));
     uint64_t bin = 0;
     int st = sample_from_table(d_probs, 1ull << q.size(), seed, draw_index, 1, &bin);
-    cudaFree(d_probs);
+    dev_free(d_probs, (1ull << q.size()) * sizeof(double));
     QI_TRY(st);
     QI_TRY(collapse_impl(s, q, bin));
     switch (basis) {
