@@ -216,6 +216,11 @@ int qi_state_layout(const qi_state* s, uint8_t* phys, uint32_t* n_local);
 int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* exchanges,
                   uint64_t* comm_free_global_gates, uint8_t* final_phys);
 
+/* host-only planner for Pauli-exp sequences (`repeats` repetitions of the term list, e.g. Trotter steps) on `world`
+ * ranks: exchanges the engine performs and the number of stages it runs between them */
+int qi_shard_plan_pauli(uint32_t total_qubits, int world, const qi_pauli_term* terms, uint64_t count, uint64_t repeats,
+                        uint64_t* exchanges, uint64_t* stages);
+
 /* host-only: how the fused executor splits a gate list into passes on one device; rows[8*i..] =
  * {per-gate-kernel step?, window qubits used, lane-pair ops, register-pair ops, diagonal ops, phase-table ops,
  *  CNOTs absorbed into a neighbouring gate, 0} */

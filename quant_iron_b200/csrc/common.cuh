@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -230,5 +231,8 @@ int set_amplitude(qi_state* s, uint64_t local_index, amp_t v);
 // gates.cu: undo lazy SWAP relabelling (physical swaps until logical qubit q sits at bit q)
 int canonicalise(qi_state* s);
 int shard_localise_mask(qi_state* s, const qi_pauli_term* t);
+// staged execution of Pauli-exp sequences around exchanges (shard.cu); lx / lz = logical X-or-Y / Y-or-Z masks per term
+int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
+                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges);
 
 }  // namespace qi

@@ -229,24 +229,36 @@ static int make_exp(const qi_state* s, const qi_pauli_term& t, amp_t factor, Pau
 static int exp_sequence(qi_state* s, const qi_pauli_term* terms, const std::vector<uint32_t>& order, const std::vector<amp_t>& factors) {
     Context& c = ctx();
     const bool batch = c.opt_fuse && c.opt_path != 1 && pauli_window_supported(s);
-    std::vector<PauliExp> pending;
+    // apply the terms order[take[0]], order[take[1]], ... under the current layout (all their X/Y factors local)
+    auto run = [&](const std::vector<size_t>& take) -> int {
+        std::vector<PauliExp> pending;
+        for (size_t k : take) {
+            const qi_pauli_term& t = terms[order[k]];
+            PauliExp e;
+            bool ex = false;
+            QI_TRY(make_exp(s, t, factors[k], &e, &ex));
+            if (ex) return fail(QI_ERR_PEER, 0, 0, "X/Y factor on a global qubit inside a stage");
+            if (batch) { pending.push_back(e); continue; }
+            if (t.num_ops == 0) { double z[2] = {e.ch.x, e.ch.y}; QI_TRY(qi_scale(s, z)); }
+            else QI_TRY(pauli_exp_single(s, e));
+        }
+        return run_pauli_exp_batch(s, pending);
+    };
+    if (s->world == 1) {
+        std::vector<size_t> all(order.size());
+        for (size_t k = 0; k < all.size(); k++) all[k] = k;
+        return run(all);
+    }
+    // sharded: stages around the exchanges (shard_pauli_walk), on logical-qubit masks
+    std::vector<uint64_t> lx(order.size(), 0), lz(order.size(), 0);
     for (size_t k = 0; k < order.size(); k++) {
         const qi_pauli_term& t = terms[order[k]];
-        PauliExp e;
-        bool ex = false;
-        QI_TRY(make_exp(s, t, factors[k], &e, &ex));
-        if (ex) {
-            QI_TRY(run_pauli_exp_batch(s, pending));
-            pending.clear();
-            QI_TRY(shard_localise_mask(s, &t));
-            QI_TRY(make_exp(s, t, factors[k], &e, &ex));
-            if (ex) return fail(QI_ERR_PEER, 0, 0, "X/Y factor still on a global qubit after the exchange");
+        for (uint32_t i = 0; i < t.num_ops; i++) {
+            if (t.paulis[i] != 3) lx[k] |= 1ull << t.qubits[i];
+            if (t.paulis[i] != 1) lz[k] |= 1ull << t.qubits[i];
         }
-        if (batch) { pending.push_back(e); continue; }
-        if (t.num_ops == 0) { double z[2] = {e.ch.x, e.ch.y}; QI_TRY(qi_scale(s, z)); }
-        else QI_TRY(pauli_exp_single(s, e));
     }
-    return run_pauli_exp_batch(s, pending);
+    return shard_pauli_walk(s, lx, lz, run, false, nullptr);
 }
 
 }  // namespace qi

@@ -18,6 +18,7 @@
 //   * reductions: each rank publishes its partial in its flag block, all ranks read all partials
 //     and add them in rank order (deterministic, identical on every rank).
 #include <algorithm>
+#include <functional>
 
 #include "common.cuh"
 
@@ -375,6 +376,91 @@ int shard_localise_mask(qi_state* s, const qi_pauli_term* t) {
     }
 }
 
+// ---- staged execution of a sequence of Pauli exponentials on a sharded state ----------------------------
+// Same idea as staged_walk, with the exact Pauli commutation test: under the current layout a stage takes every
+// term whose X/Y factors are all local and that commutes with every term deferred so far (two strings commute
+// iff they anticommute on an even number of qubits); then ONE multi-qubit exchange brings in the global X/Y
+// qubits the deferred terms need next, evicting the local qubits whose next X/Y use is furthest away.
+// lx / lz: per term, LOGICAL qubit masks of its X-or-Y and Y-or-Z factors.  run(take) executes the terms take[..]
+// (indices into lx) under the current layout; dry = planner mode (relabel only, no device access).
+int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
+                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges) {
+    const int nl = (int)s->n_local;
+    const size_t kMaxDeferred = 512;
+    std::vector<size_t> pending(lx.size()), rest, take, deferred;
+    for (size_t i = 0; i < lx.size(); i++) pending[i] = i;
+    auto x_is_local = [&](uint64_t xm) {
+        for (uint32_t q = 0; q < s->num_qubits; q++)
+            if (((xm >> q) & 1) && s->phys[q] >= nl) return false;
+        return true;
+    };
+    while (!pending.empty()) {
+        take.clear(); rest.clear(); deferred.clear();
+        uint64_t def_support = 0;
+        bool saturated = false;
+        for (size_t k : pending) {
+            bool ok = !saturated && x_is_local(lx[k]);
+            if (ok && ((lx[k] | lz[k]) & def_support))
+                for (size_t d : deferred)
+                    if ((__builtin_popcountll(lx[d] & lz[k]) + __builtin_popcountll(lz[d] & lx[k])) & 1) { ok = false; break; }
+            if (ok) take.push_back(k);
+            else {
+                rest.push_back(k);
+                if (!saturated) {
+                    deferred.push_back(k);
+                    def_support |= lx[k] | lz[k];
+                    if (deferred.size() >= kMaxDeferred) saturated = true;       // keep the test cheap: defer the tail wholesale
+                }
+            }
+        }
+        QI_TRY(run(take));
+        if (rest.empty()) break;
+        if (x_is_local(lx[rest[0]])) { pending.swap(rest); continue; }          // deferred by the cap only: next stage takes it
+        // global positions to bring in: those of the first deferred term, plus the other global qubits the next
+        // deferred terms flip; local positions to evict: furthest next X/Y use (never a qubit the first term flips)
+        auto next_use = [&](int logical) -> size_t {
+            for (size_t j = 0; j < rest.size() && j < 4096; j++) if ((lx[rest[j]] >> logical) & 1) return j;
+            return ~(size_t)0;
+        };
+        std::vector<int> G, L;
+        uint64_t want = lx[rest[0]];
+        for (size_t j = 1; j < rest.size() && j < 64; j++) want |= lx[rest[j]];
+        uint64_t used_local = 0;
+        for (int gp = (int)s->num_qubits - 1; gp >= nl; gp--) {
+            const int qg = logical_at(s, gp);
+            if (qg < 0 || !((want >> qg) & 1)) continue;
+            const bool mandatory = (lx[rest[0]] >> qg) & 1;
+            int best = -1;
+            size_t best_next = 0;
+            for (int p = nl - 1; p >= 0; p--) {
+                if ((used_local >> p) & 1) continue;
+                const int ql = logical_at(s, p);
+                if (ql >= 0 && ((lx[rest[0]] >> ql) & 1)) continue;
+                const size_t nu = ql < 0 ? ~(size_t)0 : next_use(ql);
+                if (best < 0 || nu > best_next || (nu == best_next && p >= 5 && best < 5)) { best = p; best_next = nu; }
+            }
+            if (best < 0) { if (mandatory) return fail(QI_ERR_PEER, 0, 0, "no local qubit available for the exchange"); continue; }
+            if (!mandatory && best_next <= next_use(qg)) continue;              // the evicted qubit would be needed sooner
+            G.push_back(gp);
+            L.push_back(best);
+            used_local |= 1ull << best;
+        }
+        if (G.empty()) return fail(QI_ERR_PEER, 0, 0, "staged Pauli execution made no progress");
+        if (dry) {
+            for (size_t k = 0; k < G.size(); k++) {
+                int qg = logical_at(s, G[k]), ql = logical_at(s, L[k]);
+                if (qg >= 0) s->phys[qg] = (uint8_t)L[k];
+                if (ql >= 0) s->phys[ql] = (uint8_t)G[k];
+            }
+        } else {
+            QI_TRY(exchange_multi(s, G, L));
+        }
+        if (exchanges) (*exchanges)++;
+        pending.swap(rest);
+    }
+    return QI_OK;
+}
+
 // sum host values across ranks in rank order; every rank gets the identical result
 int shard_allreduce_sum(qi_state* s, double* vals, int count) {
     if (s->world == 1) return QI_OK;
@@ -562,6 +648,38 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
     (void)exq;
     if (comm_free_global_gates) *comm_free_global_gates = freeg;
     if (final_phys) memcpy(final_phys, s.phys, 64);
+    return QI_OK;
+}
+
+// Host-only planner for Pauli-exp sequences (`repeats` repetitions of the term list, e.g. Trotter steps): number of
+// exchanges the engine performs on `world` ranks (no device access; same decisions on every rank).
+int qi_shard_plan_pauli(uint32_t total_qubits, int world, const qi_pauli_term* terms, uint64_t count, uint64_t repeats,
+                        uint64_t* exchanges, uint64_t* stages) {
+    if (world != 1 && world != 2 && world != 4 && world != 8) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "world must be 1, 2, 4 or 8");
+    if ((count && !terms) || !exchanges) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "NULL argument");
+    qi_state s;
+    s.num_qubits = total_qubits;
+    s.n_local = total_qubits - log2i(world);
+    s.len = 1ull << s.n_local;
+    s.world = world;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    std::vector<uint64_t> lx, lz;
+    for (uint64_t r = 0; r < repeats; r++)
+        for (uint64_t k = 0; k < count; k++) {
+            uint64_t x = 0, z = 0;
+            for (uint32_t i = 0; i < terms[k].num_ops; i++) {
+                const uint32_t q = terms[k].qubits[i];
+                if (q >= total_qubits) return fail(QI_ERR_INVALID_QUBIT_INDEX, q, total_qubits, "Invalid qubit index");
+                if (terms[k].paulis[i] != 3) x |= 1ull << q;
+                if (terms[k].paulis[i] != 1) z |= 1ull << q;
+            }
+            lx.push_back(x);
+            lz.push_back(z);
+        }
+    *exchanges = 0;
+    uint64_t nst = 0;
+    QI_TRY(shard_pauli_walk(&s, lx, lz, [&](const std::vector<size_t>&) { nst++; return QI_OK; }, true, exchanges));
+    if (stages) *stages = nst;
     return QI_OK;
 }
 

@@ -110,3 +110,12 @@ def plan(num_qubits: int, world: int, circuit) -> dict:
     _ffi.check(_lib.qi_shard_plan(num_qubits, world, arr, len(records), C.byref(ex), C.byref(free), phys))
     return {"exchanges": int(ex.value), "comm_free_global_gates": int(free.value),
             "final_layout": [int(phys[q]) for q in range(num_qubits)]}
+
+
+def plan_pauli(total_qubits: int, world: int, hamiltonian, repeats: int = 1) -> dict:
+    """Host-only: exchanges / stages the engine needs for `repeats` repetitions of the term sequence of a SumOp
+    (e.g. first-order Trotter steps) on `world` ranks (qi_shard_plan_pauli; no device access)."""
+    arr, n, keep = hamiltonian.term_array()
+    ex, st = C.c_uint64(0), C.c_uint64(0)
+    _ffi.check(_ffi.lib.qi_shard_plan_pauli(total_qubits, world, arr, n, repeats, C.byref(ex), C.byref(st)))
+    return {"exchanges": int(ex.value), "stages": int(st.value)}

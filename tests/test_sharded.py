@@ -36,6 +36,21 @@ def test_planner_matches_survey_counts():
     assert sharded.plan(33, 1, w.build_circuit(qi, 33, w.qft_specs(33)))["exchanges"] == 0
 
 
+def test_pauli_planner_stages_trotter_steps():
+    """Sharded Trotter evolution is staged around the exchanges with the exact Pauli commutation test: the
+    Heisenberg chain needs about ONE exchange per Trotter step (one per term that flips a rank-bit qubit without
+    staging: 6-7 per step), and an unsharded state needs none."""
+    import quant_iron_b200 as qi
+    from quant_iron_b200 import sharded
+    h = qi.heisenberg_1d(33, 1.0, 2.0, 3.0, 0.5, 0.1)
+    p1, p10 = sharded.plan_pauli(33, 8, h, 1), sharded.plan_pauli(33, 8, h, 10)
+    assert p1["exchanges"] <= 2 and p10["exchanges"] <= 12, (p1, p10)
+    assert p10["stages"] == p10["exchanges"] + 1
+    assert sharded.plan_pauli(33, 1, h, 3) == {"exchanges": 0, "stages": 1}
+    # a purely diagonal Hamiltonian never communicates
+    assert sharded.plan_pauli(20, 8, qi.ising_1d_uniform(20, 1.0, 2.0, 0.1), 5)["exchanges"] == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_engine_vs_oracle(world):
