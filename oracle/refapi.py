@@ -1165,6 +1165,10 @@ class CircuitBuilder:
         self.gates: List[Gate] = []
         self.num_qubits = num_qubits
 
+    @staticmethod
+    def new(num_qubits: int):  # circuit.rs:296-301
+        return CircuitBuilder(num_qubits)
+
     def add_gate(self, gate):
         self.gates.append(gate)
         return self
