@@ -23,6 +23,10 @@ EXP_RTOL = 1e-10     # north star: relative error on expectation values
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once instead of failing at import
+    if not os.path.exists(os.path.join(ROOT, "quant_iron_b200", "lib", "libqiron_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _load(name):
