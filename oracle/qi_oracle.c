@@ -515,9 +515,21 @@ void orc_random_state(cplx* a, int n, uint64_t seed) {
         double r = sqrt(-2.0 * log(u1 + 1.1102230246251565e-16));
         a[i] = c_mk(r * cos(6.283185307179586 * u2), r * sin(6.283185307179586 * u2));
     }
+    /* norm in a FIXED association order (an OpenMP reduction combines the per-thread partials in whatever order the
+     * threads finish, and depends on the thread count): blocks of 4096 summed serially, block sums added in order,
+     * so the golden fixtures reproduce bit for bit on any machine */
+    const int64_t blk = 4096, nblk = (dim + blk - 1) / blk;
+    double* part = (double*)malloc((size_t)nblk * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < nblk; b++) {
+        const int64_t lo = b * blk, hi = lo + blk < dim ? lo + blk : dim;
+        double acc = 0.0;
+        for (int64_t i = lo; i < hi; i++) acc += c_norm_sqr(a[i]);
+        part[b] = acc;
+    }
     double nsq = 0.0;
-#pragma omp parallel for reduction(+ : nsq) schedule(static)
-    for (int64_t i = 0; i < dim; i++) nsq += c_norm_sqr(a[i]);
+    for (int64_t b = 0; b < nblk; b++) nsq += part[b];
+    free(part);
     const double f = 1.0 / sqrt(nsq);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < dim; i++) a[i] = c_scale(f, a[i]);
