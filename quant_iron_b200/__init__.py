@@ -10,7 +10,7 @@ from . import _ffi
 from .algorithms import (TrotterOrder, first_order_trotter_step, second_order_trotter_step, trotter_evolve_state,
                          trotter_evolve_state_)
 from .circuit import Circuit, CircuitBuilder, Gate, Subroutine
-from .errors import Error
+from .errors import CompilerError, Error
 from .measurement import MeasurementBasis, MeasurementResult
 from .models import heisenberg_1d, heisenberg_2d, ising_1d, ising_1d_uniform, ising_2d, ising_2d_uniform
 from .operators import (CNOT, SWAP, Hadamard, Identity, Matchgate, Operator, Pauli, PhaseS, PhaseSdag, PhaseShift,
@@ -28,5 +28,5 @@ __all__ = [
     "Gate", "Circuit", "CircuitBuilder", "Subroutine", "PauliString", "SumOp", "MeasurementBasis",
     "MeasurementResult", "TrotterOrder", "first_order_trotter_step", "second_order_trotter_step",
     "trotter_evolve_state", "trotter_evolve_state_", "Parameter", "ParametricGate", "ParametricMatchgate", "ParametricP", "ParametricRx", "ParametricRy", "ParametricRyPhase",
-    "ParametricRyPhaseDag", "ParametricRz", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "workloads", "engine",
+    "ParametricRyPhaseDag", "ParametricRz", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "CompilerError", "workloads", "engine",
 ]

@@ -338,6 +338,10 @@ class Circuit:
         c.gates = [cg for g in self.gates for cg in g.concrete()]
         return c
 
+    def to_qasm(self, to_dir=None) -> str:  # circuit.rs:244-278 (host-only string emission, qasm.py)
+        from .qasm import circuit_to_qasm
+        return circuit_to_qasm(self, to_dir)
+
     def trace_execution(self, initial_state):  # circuit.rs:188-202
         if initial_state.num_qubits != self.num_qubits:
             raise Error("InvalidNumberOfQubits", initial_state.num_qubits)

@@ -41,3 +41,23 @@ class Error(Exception):
 
     def __hash__(self):
         return hash((self.variant, self.payload))
+
+
+class CompilerError(Exception):
+    """`enum CompilerError { IOError, UnsupportedOperator, InvalidOperands }` (errors.rs:99-108)."""
+    _DISPLAY = {"IOError": "I/O error: {0}", "UnsupportedOperator": "An unsupported operation was encountered: {0}",
+                "InvalidOperands": "Invalid operands ({0}) for operator {1}"}
+
+    def __init__(self, variant: str, *payload):
+        super().__init__(f"{variant}{tuple(payload)}")
+        self.variant = variant
+        self.payload = tuple(payload)
+
+    def to_string(self) -> str:
+        return self._DISPLAY[self.variant].format(*self.payload)
+
+    def __eq__(self, other):
+        return isinstance(other, CompilerError) and (self.variant, self.payload) == (other.variant, other.payload)
+
+    def __hash__(self):
+        return hash((self.variant, self.payload))
