@@ -68,3 +68,31 @@ def test_gate_planner_layered_circuit_needs_two_exchanges(n, world):
     assert pl["exchanges"] <= 3, pl["exchanges"]
     assert sorted(pl["final_layout"]) == list(range(n))
     assert sharded.plan(n, 1, c)["exchanges"] == 0
+
+
+def test_circuit_lowering_splits_runs_by_gate_kind():
+    """Circuit._lower (host only): operator gates -> one qi_apply_circuit run, consecutive PauliTimeEvolution gates ->
+    one qi_apply_pauli_exp_sequence run, Measurement / PauliString gates alone; parametric gates are resolved at
+    every lowering (never cached) and join the operator run."""
+    import quant_iron_b200 as qi
+    P = qi.Pauli
+    zz = qi.PauliString.new(0.5).with_op(0, P.Z).with_op(1, P.Z)
+    xx = qi.PauliString.new(0.25).with_op(1, P.X).with_op(2, P.X)
+    prm = qi.Parameter.new([0.3])
+    c = (qi.CircuitBuilder(3).h_gate(0).cnot_gate(1, 0)                                  # run 0: ops (2 records)
+         .pauli_time_evolution_gate(zz, 0.1).pauli_time_evolution_gate(xx, 0.2)          # run 1: evol (2 terms)
+         .rx_gate(2, 0.4).parametric_ry_gate(1, prm).z_gate(0)                           # run 2: ops (3 records)
+         .measure_gate(qi.MeasurementBasis.Computational, [0])                           # run 3: gate (index 7)
+         .pauli_string_gate(xx)                                                          # run 4: gate (index 8)
+         .t_gate(2).build())                                                             # run 5: ops (1 record)
+    runs = c._lower()
+    assert [r[0] for r in runs] == ["ops", "evol", "ops", "gate", "gate", "ops"]
+    assert [r[2] for r in runs if r[0] == "ops"] == [2, 3, 1]
+    assert runs[1][2] == 2 and list(runs[1][4])[:4] == [0.0, -0.1, 0.0, -0.2]           # factors = (0, -t) per gate
+    assert runs[3][2] == 7 and runs[4][2] == 8                                           # gate index = seed offset
+    ry = runs[2][1][1]
+    assert ry.kind == 12 and abs(ry.params[0] - 0.3) < 1e-15 and ry.targets[0] == 1      # QI_GATE_RY with the parameter
+    prm.set([0.9])
+    assert abs(c._lower()[2][1][1].params[0] - 0.9) < 1e-15                              # re-resolved, not cached
+    plain = qi.CircuitBuilder(2).h_gate(0).cnot_gate(1, 0).build()
+    assert plain._lower() is plain._lower()                                              # cached when nothing is parametric
