@@ -3,7 +3,7 @@
 // The reference is compiled Rust and its toolchain is absent from this image, so the compiled-language
 // host side is C++: the same names, argument order and error behaviour as the crate's public surface
 // for the state-vector path (State gate methods, Operator, Gate/Circuit/CircuitBuilder, Subroutine::qft,
-// PauliString/SumOp, measure, Trotter, heisenberg_1d).  Citations are file:line under the reference root.
+// PauliString/SumOp, measure, Trotter, heisenberg_1d/2d, ising_1d/2d).  Citations are file:line under the reference root.
 // `&self -> State` methods are device clone + in-place kernel; methods with a trailing underscore act in place.
 #pragma once
 #include <cmath>
@@ -259,6 +259,7 @@ public:
     PauliString with_op(size_t q, Pauli p) const { PauliString r(*this); r.add_op(q, p); return r; }
     cplx coefficient() const { return coefficient_; }
     size_t len() const { return ops_.size(); }
+    const std::map<size_t, Pauli>& ops() const { return ops_; }
     struct Term { qi_pauli_term t; std::vector<uint32_t> q; std::vector<uint8_t> p; };
     std::unique_ptr<Term> term() const {
         auto r = std::make_unique<Term>();
@@ -332,6 +333,71 @@ inline SumOp heisenberg_1d(size_t n, double jx, double jy, double jz, double h, 
         if (h != 0.0) terms.push_back(PauliString(cplx(-mu * (-0.5 * h), 0.0)).with_op(i, Pauli::Z));   // code is ground truth, heisenberg.rs:49
     }
     return SumOp(terms);
+}
+
+// models/heisenberg.rs:122-220: site (r, c) -> qubit r*m_cols + c, periodic; per site: field Z, the vertical bond
+// (XX, YY, ZZ), the horizontal bond (XX, YY, ZZ); couplings -J/2, field coefficient mu * (-h/2) (line 143)
+inline SumOp heisenberg_2d(size_t n_rows, size_t m_cols, double jx, double jy, double jz, double h_field, double mu) {
+    if (n_rows < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n_rows, 2, "heisenberg_2d");
+    if (m_cols < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", m_cols, 2, "heisenberg_2d");
+    std::vector<PauliString> terms;
+    if (jx == 0.0 && jy == 0.0 && jz == 0.0 && h_field == 0.0) return SumOp(terms);
+    const double js[3] = {jx, jy, jz};
+    const Pauli ps[3] = {Pauli::X, Pauli::Y, Pauli::Z};
+    for (size_t site = 0; site < n_rows * m_cols; site++) {
+        const size_t r = site / m_cols, c = site % m_cols;
+        if (h_field != 0.0) terms.push_back(PauliString(cplx(mu * (-0.5 * h_field), 0.0)).with_op(site, Pauli::Z));
+        const size_t nb[2] = {((r + 1) % n_rows) * m_cols + c, r * m_cols + (c + 1) % m_cols};
+        for (size_t d = 0; d < 2; d++)
+            for (int k = 0; k < 3; k++)
+                if (js[k] != 0.0) terms.push_back(PauliString(cplx(-0.5 * js[k], 0.0)).with_op(site, ps[k]).with_op(nb[d], ps[k]));
+    }
+    return SumOp(terms);
+}
+
+// models/ising.rs:27-75: H = -sum_i J_i Z_i Z_{i+1} - mu sum_i h_i Z_i, periodic; per site coupling then field
+inline SumOp ising_1d(const std::vector<double>& h, const std::vector<double>& j, double mu) {
+    const size_t n = h.size();
+    if (j.size() != n) throw Error(QI_ERR_MISMATCHED_NUMBER_OF_PARAMETERS, "MismatchedNumberOfParameters", n, j.size(), "ising_1d");
+    if (n < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n, 2, "ising_1d");
+    std::vector<PauliString> terms;
+    bool all_zero = true;
+    for (size_t i = 0; i < n; i++) all_zero = all_zero && h[i] == 0.0 && j[i] == 0.0;
+    if (all_zero) return SumOp(terms);
+    for (size_t i = 0; i < n; i++) {
+        if (j[i] != 0.0) terms.push_back(PauliString(cplx(j[i] * -1.0, 0.0)).with_op(i, Pauli::Z).with_op((i + 1) % n, Pauli::Z));
+        if (h[i] != 0.0) terms.push_back(PauliString(cplx(-1.0 * mu * h[i], 0.0)).with_op(i, Pauli::Z));
+    }
+    return SumOp(terms);
+}
+inline SumOp ising_1d_uniform(size_t n, double h, double j, double mu) {   // ising.rs:90-139
+    if (n < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n, 2, "ising_1d_uniform");
+    return ising_1d(std::vector<double>(n, h), std::vector<double>(n, j), mu);
+}
+// models/ising.rs:161-244: h[r][c] field, jv[r][c] / jh[r][c] couplings to ((r+1)%N, c) / (r, (c+1)%M); per site field, vertical, horizontal
+inline SumOp ising_2d(const std::vector<std::vector<double>>& h, const std::vector<std::vector<double>>& jv,
+                      const std::vector<std::vector<double>>& jh, double mu) {
+    const size_t n = h.size(), m = n ? h[0].size() : 0;
+    if (n < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n, 2, "ising_2d");
+    if (m < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", m, 2, "ising_2d");
+    std::vector<PauliString> terms;
+    bool all_zero = true;
+    for (size_t r = 0; r < n; r++)
+        for (size_t c = 0; c < m; c++) all_zero = all_zero && h[r][c] == 0.0 && jv[r][c] == 0.0 && jh[r][c] == 0.0;
+    if (all_zero) return SumOp(terms);
+    for (size_t site = 0; site < n * m; site++) {
+        const size_t r = site / m, c = site % m;
+        if (h[r][c] != 0.0) terms.push_back(PauliString(cplx(-1.0 * mu * h[r][c], 0.0)).with_op(site, Pauli::Z));
+        if (jv[r][c] != 0.0) terms.push_back(PauliString(cplx(jv[r][c] * -1.0, 0.0)).with_op(site, Pauli::Z).with_op(((r + 1) % n) * m + c, Pauli::Z));
+        if (jh[r][c] != 0.0) terms.push_back(PauliString(cplx(jh[r][c] * -1.0, 0.0)).with_op(site, Pauli::Z).with_op(r * m + (c + 1) % m, Pauli::Z));
+    }
+    return SumOp(terms);
+}
+inline SumOp ising_2d_uniform(size_t n, size_t m, double h, double j, double mu) {   // ising.rs:259-324
+    if (n < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", n, 2, "ising_2d_uniform");
+    if (m < 2) throw Error(QI_ERR_INVALID_NUMBER_OF_INPUTS, "InvalidNumberOfInputs", m, 2, "ising_2d_uniform");
+    std::vector<std::vector<double>> hh(n, std::vector<double>(m, h)), jj(n, std::vector<double>(m, j));
+    return ising_2d(hh, jj, jj, mu);
 }
 
 // gate.rs:13-52 (operator gates), circuit.rs:27-202, circuit.rs:288-1742, subroutine.rs:90-160

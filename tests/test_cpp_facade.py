@@ -15,6 +15,17 @@ def test_facade_compiles_on_cpu_box():
     assert os.path.exists(BIN)
 
 
+def test_facade_host_logic_on_cpu():
+    """Model builders, builder validation, QFT gate counts and the unitarity check of the C++ facade: no device."""
+    host = os.path.join(ROOT, "tests", "cpp", "test_facade_host")
+    if not os.path.exists(host):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([host], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASS" in r.stdout
+
+
 @pytest.mark.gpu
 def test_facade_known_answers_on_gpu():
     if not os.path.exists(BIN):
