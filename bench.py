@@ -9,7 +9,10 @@ configs[1]'s generator) at the metric's 30 qubits per GPU, f64, plus the achieve
 dominant kernel against the measured roofline, plus single-gate passes at 30 qubits.
 A "step" is one execution of the whole circuit on a state that is already resident in HBM; `e2e`
 is the same circuit through the public API with HOST buffers (H2D of the initial state and D2H of the
-final state inside the timed region).  N > 1: the state is sharded (top log2 N qubits global),
+final state inside the timed region).  At N = 1 `e2e` goes through Circuit.execute_host_ (qi_execute_host:
+chunked copies overlapped with the circuit) once that entry has reproduced the plain upload / execute /
+download sequence on this box; `e2e.mode` says which one the value is, `e2e.serial_value` is the plain
+sequence either way.  N > 1: the state is sharded (top log2 N qubits global),
 30 local qubits per GPU (weak scaling).
 """
 import argparse
@@ -336,28 +339,64 @@ def run_ours(args, rank, world, local_rank):
             host_in[0] = 1.0
         hin, hout = host_in.numpy(), host_out.numpy()
         e2e_steps = max(1, min(args.steps, 3))
-        times = []
-        for i in range(1 + e2e_steps):
-            barrier()
-            t0 = time.perf_counter()
-            state.upload_(hin)                             # H2D of the initial state (pinned)
-            circuit.execute_(state)
-            if world > 1:
-                state.to_host(hout)                        # D2H of this rank's shard of the final state
+
+        def e2e_step(mode):
+            if mode == "pipelined":
+                # qi_execute_host: chunked upload / download overlapped with the circuit (csrc/host_pipeline.cu)
+                circuit.execute_host_(state, hin, hout)
             else:
-                state.to_host(hout)                        # D2H of the final state (logical order)
-            barrier()
-            dt = time.perf_counter() - t0
-            if i > 0:
-                times.append(dt)
-        tt = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_val = n_gates * world / float(tt.item())
+                state.upload_(hin)                         # H2D of the initial state (pinned)
+                circuit.execute_(state)
+                state.to_host(hout)                        # D2H of the final state (this rank's shard when sharded)
+
+        def e2e_time(mode):
+            times = []
+            for i in range(1 + e2e_steps):
+                barrier()
+                t0 = time.perf_counter()
+                e2e_step(mode)
+                barrier()
+                dt = time.perf_counter() - t0
+                if i > 0:
+                    times.append(dt)
+            tt = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        # the pipelined entry is used for the headline only if it reproduces the plain sequence on this box:
+        # both run once from |0..0>, a strided sample of the 2^n outputs (every chunk is hit) must agree to 1e-12
+        pipe = {"mode": "serial"}
+        if world == 1:
+            try:
+                def from_zero(mode):
+                    host_in.zero_()
+                    host_in[0] = 1.0
+                    e2e_step(mode)
+                    qi.engine.synchronize()
+                    return hout[::1021].copy()
+                a, b = from_zero("pipelined"), from_zero("serial")
+                diff = float(np.max(np.abs(a - b)))
+                pipe["pipelined_max_abs_diff_vs_serial"] = diff
+                if diff <= 1e-12 and float(np.max(np.abs(b))) > 0.0:
+                    pipe["mode"] = "pipelined"
+            except Exception as ex:  # noqa: BLE001
+                pipe["pipelined_error"] = repr(ex)[:200]
+        sec_serial = e2e_time("serial")
+        pipe["serial_value"] = n_gates * world / sec_serial
+        sec = sec_serial
+        if pipe["mode"] == "pipelined":
+            try:
+                sec = e2e_time("pipelined")
+                pipe["pipelined_value"] = n_gates * world / sec
+            except Exception as ex:  # noqa: BLE001
+                pipe["mode"], pipe["pipelined_error"], sec = "serial", repr(ex)[:200], sec_serial
+        e2e_val = n_gates * world / sec
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * (16 * (1 << n_local)) + 88 * n_gates,
                "d2h_bytes_per_step": world * 16 * (1 << n_local), "qubits": n, "steps": e2e_steps,
-               "seconds_per_step": float(tt.item()),
+               "seconds_per_step": sec,
                "checksum_norm_first_64k": float(np.vdot(hout[:1 << 16], hout[:1 << 16]).real)}
+        e2e.update(pipe)
         del host_in, host_out, hin, hout
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

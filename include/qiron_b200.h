@@ -63,7 +63,8 @@ int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_m
  *          "fuse" = 1/0 fusion in qi_apply_circuit, Pauli-exp sequences and expectation values;
  *          "profile" = 1/0 per-kernel event timing; "window_regs" = 3|4|5 register qubits per window pass
  *          (default 4); "lazy_swap" = 1/0 uncontrolled SWAP as a relabelling; "absorb" = 1/0 fold CNOTs into the
- *          neighbouring single-qubit gate; "tma" = 0/1 TMA-prefetched variant of the window kernel */
+ *          neighbouring single-qubit gate; "tma" = 0/1 TMA-prefetched variant of the window kernel;
+ *          "host_chunk_qubits", "host_min_qubits": see qi_execute_host */
 int qi_set_option(const char* name, int64_t value);
 
 /* kernel accounting for bench.py (gpu_launches, roofline.achieved) */
@@ -144,6 +145,20 @@ int qi_apply_gate(qi_state* s, const qi_gate* gate);
 /* Circuit::execute's gate loop (circuit.rs:160-172) over a run of operator gates.  All records are
  * validated first; then the run is scheduled into fused register-window passes. */
 int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count);
+/* Circuit::execute (circuit.rs:160-172) on a HOST-resident state vector, the form the reference's caller has
+ * (`State.state_vector` is a host Vec, state.rs:74-81): same result as qi_state_upload + qi_apply_circuit +
+ * qi_state_to_host on `s` (the device working buffer, len = 2^num_qubits amplitudes; it holds the final state
+ * afterwards), but the two PCIe copies overlap the circuit: the device buffer is cut into 2^k chunks by its top k
+ * qubits, the gates that commute ahead of everything touching those qubits non-diagonally run chunk by chunk behind
+ * the uploads, the gates that commute behind everything else run chunk by chunk ahead of the downloads
+ * (csrc/host_pipeline.cu).  amps_in and amps_out may be the same buffer; pinned memory is needed for the overlap,
+ * not for correctness.  Options: "host_chunk_qubits" = k (default 3, 0 = plain sequence), "host_min_qubits" (default
+ * 26: smaller states take the plain sequence).  Sharded states and lists with relabelled SWAPs take the plain sequence. */
+int qi_execute_host(qi_state* s, const qi_gate* gates, uint64_t count, const double* amps_in, double* amps_out, uint64_t len);
+/* host-only: the execution order qi_execute_host uses -- order[0 .. n_front) chunk by chunk behind the uploads,
+ * the next n_middle on the whole state, the last n_back chunk by chunk ahead of the downloads (no device access) */
+int qi_host_pipeline_plan(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int chunk_qubits, uint64_t* order,
+                          uint64_t* n_front, uint64_t* n_middle, uint64_t* n_back);
 /* Unitary2::new's unitarity check (operator.rs:2092-2118): QI_OK or QI_ERR_NON_UNITARY_MATRIX */
 int qi_unitary2_check(const double m[8]);
 

@@ -426,6 +426,17 @@ public:
         check(qi_apply_circuit(s.handle(), arr.data(), arr.size()));
     }
     State execute(const State& initial) const { State s(initial); execute_(s); return s; }   // circuit.rs:160-172
+    // Circuit::execute for a HOST-resident state vector (state.rs:74-81): in -> circuit -> out with `work` as the device
+    // buffer; the two PCIe copies overlap the circuit (qi_execute_host).  `out` may alias `in`.
+    void execute_host_(State& work, const std::complex<double>* in, std::complex<double>* out, size_t len) const {
+        if (work.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", work.num_qubits(), 0, "execute_host");
+        std::vector<GateRecord> recs;
+        recs.reserve(gates.size());
+        for (auto& g : gates) recs.push_back(make_record(*g.op, g.targets, g.controls));
+        std::vector<qi_gate> arr;
+        for (auto& r : recs) { r.g.controls = r.controls.data(); arr.push_back(r.g); }
+        check(qi_execute_host(work.handle(), arr.data(), arr.size(), reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), len));
+    }
 };
 class CircuitBuilder {
     std::vector<Gate> gates_;

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libqiron_b200.so")
-SOURCES = ["engine.cu", "state.cu", "gates.cu", "window.cu", "pauli.cu", "pauli_window.cu", "measure.cu", "shard.cu"]
+SOURCES = ["engine.cu", "state.cu", "gates.cu", "window.cu", "pauli.cu", "pauli_window.cu", "measure.cu", "shard.cu", "host_pipeline.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -81,6 +81,8 @@ _sig("qi_conj", [state_p])
 _sig("qi_tensor_product", [state_p, state_p, C.POINTER(state_p)])
 _sig("qi_apply_gate", [state_p, C.POINTER(QiGate)])
 _sig("qi_apply_circuit", [state_p, C.POINTER(QiGate), C.c_uint64])
+_sig("qi_execute_host", [state_p, C.POINTER(QiGate), C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64])
+_sig("qi_host_pipeline_plan", [C.c_uint32, C.POINTER(QiGate), C.c_uint64, C.c_int, u64p, u64p, u64p, u64p])
 _sig("qi_unitary2_check", [dp])
 _sig("qi_apply_pauli_string", [state_p, C.POINTER(QiPauliTerm), C.c_int])
 _sig("qi_apply_pauli_exp", [state_p, C.POINTER(QiPauliTerm), dp])

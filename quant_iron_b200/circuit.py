@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+
+import numpy as np
 from typing import List, Optional, Sequence
 
 from . import _ffi
@@ -327,6 +329,27 @@ class Circuit:
                 # gate k of the circuit draws from the stream seeded `seed + k` (shared-seed contract)
                 run[1].apply_(state, None if seed is None else seed + run[2])
         return state
+
+    def execute_host_(self, state, host_in: np.ndarray, host_out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Circuit::execute for a HOST-resident state vector (the reference's `State.state_vector`, state.rs:74-81):
+        `host_in` -> circuit -> `host_out` (default: a new array; may be `host_in` itself), with `state` as the device
+        working buffer.  A circuit that is one run of operator gates goes through qi_execute_host, which overlaps the
+        two PCIe copies with the circuit (csrc/host_pipeline.cu); anything else is upload, execute_, download."""
+        if state.num_qubits != self.num_qubits:
+            raise Error("InvalidNumberOfQubits", state.num_qubits)
+        hin = np.ascontiguousarray(host_in, dtype=np.complex128)
+        if host_out is None:
+            host_out = np.empty_like(hin)
+        if host_out.dtype != np.complex128 or not host_out.flags.c_contiguous or host_out.shape != hin.shape:
+            raise ValueError("host_out must be a contiguous complex128 array of the state's length")
+        runs = self._lower()
+        if len(runs) == 1 and runs[0][0] == "ops":
+            _ffi.check(_lib.qi_execute_host(state._h, runs[0][1], runs[0][2], hin.ctypes.data_as(C.c_void_p),
+                                            host_out.ctypes.data_as(C.c_void_p), hin.shape[0]))
+            return host_out
+        state.upload_(hin)
+        self.execute_(state)
+        return state.to_host(host_out)
 
     def execute(self, initial_state, seed: Optional[int] = None):  # circuit.rs:160-172
         if initial_state.num_qubits != self.num_qubits:

@@ -74,6 +74,12 @@ struct Context {
     void* d_ops = nullptr;
     size_t ops_cap = 0;
     cudaEvent_t ops_event = nullptr;
+    // host-resident execution (host_pipeline.cu): copy stream + per-chunk events
+    int opt_host_chunk_qubits = 3;    // the top k qubits index 2^k chunks that are uploaded / downloaded one by one (0 = no pipelining)
+    int opt_host_min_qubits = 26;     // smaller states take the plain upload / execute / download sequence
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_sync = nullptr;
+    cudaEvent_t chunk_in[16] = {nullptr}, chunk_out[16] = {nullptr};
 };
 Context& ctx();
 int ensure_ctx();
@@ -220,6 +226,7 @@ int apply_circuit_sharded(qi_state* s, const qi_gate* gates, uint64_t count, boo
 int prepare_gate(qi_state* s, const qi_gate* g, PhysGate* o, bool* skip);                        // gates.cu
 int shard_allreduce_sum(qi_state* s, double* host_vals, int count);
 int exchange_global_local(qi_state* s, int global_phys, int local_phys);
+void logical_uses(const qi_gate& g, uint64_t* n_use, uint64_t* d_use);      // LOGICAL qubits a gate uses non-diagonally / diagonally
 // reduce.cu
 int reduce_norm_sqr(const qi_state* s, double* out_local);
 int reduce_inner(const qi_state* a, const qi_state* b, double out_local[2]);

@@ -253,7 +253,7 @@ static int plan_exchange(const qi_state* s, const qi_gate* g, uint64_t rem, std:
 // Then ONE multi-qubit exchange brings in what the first deferred gate needs (plus what the lookahead over
 // the deferred list says will be needed soon) and the next stage starts.  Host-only decisions that depend on
 // the gate list alone: every rank takes the same ones, and the planner (qi_shard_plan) replays them.
-static void logical_uses(const qi_gate& g, uint64_t* n_use, uint64_t* d_use) {
+void logical_uses(const qi_gate& g, uint64_t* n_use, uint64_t* d_use) {
     *n_use = 0;
     *d_use = 0;
     for (uint32_t c = 0; c < g.num_controls; c++) *d_use |= 1ull << g.controls[c];

@@ -75,6 +75,23 @@ int main() {
     State one = hs.trotter_evolve(State::new_plus(10), 0.01, 1, 1);
     State seq = hs.apply_exp_sequence(State::new_plus(10), std::vector<cplx>(hs.num_terms(), cplx(0.0, -0.01)));
     EXPECT(seq.approx_eq(one));
+    // Circuit::execute on a host-resident vector (qi_execute_host, pipelined in 8 chunks): same state as execute()
+    {
+        const size_t m = 12;
+        CircuitBuilder b(m);
+        for (size_t layer = 0; layer < 6; layer++) {
+            for (size_t q = 0; q < m; q++) { if ((q + layer) % 3 == 0) b.h_gate(q); else if ((q + layer) % 3 == 1) b.rx_gate(q, 0.3 + 0.1 * q); else b.rz_gate(q, 0.7 - 0.05 * q); }
+            for (size_t q = layer & 1; q + 1 < m; q += 2) b.cnot_gate(q + 1, q);
+        }
+        Circuit lc = b.build();
+        State want = lc.execute(State::new_plus(m));
+        std::vector<cplx> host = State::new_plus(m).state_vector();
+        State work = State::new_zero(m);
+        qi_set_option("host_min_qubits", 0);
+        lc.execute_host_(work, host.data(), host.data(), host.size());
+        qi_set_option("host_min_qubits", 26);
+        EXPECT(State::from_vector(host).approx_eq(want) && work.approx_eq(want));
+    }
     std::printf(failures ? "C++ facade: %d FAILURES\n" : "C++ facade: ALL PASS\n", failures);
     return failures ? 1 : 0;
 }
