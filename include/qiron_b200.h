@@ -242,6 +242,13 @@ int qi_shard_plan_pauli(uint32_t total_qubits, int world, const qi_pauli_term* t
 int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count, int window_regs, int32_t* rows,
                       uint64_t max_rows, uint64_t* n_rows);
 
+/* host-only: the device programs (window passes with their op lists and phase tables, per-gate-kernel steps) the fused
+ * executor would launch for a gate list, serialised so that tests can interpret them on the CPU and compare with the
+ * oracle without a GPU (tests/test_window_lowering.py; blob layout: csrc/window.cu, debug_lower).  rank / world > 1:
+ * the programs of that shard (or host-pipeline chunk) under the identity layout.  *used = bytes written / needed. */
+int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gates, uint64_t count, int window_regs,
+                   uint8_t* blob, uint64_t capacity, uint64_t* used);
+
 #ifdef __cplusplus
 }
 #endif

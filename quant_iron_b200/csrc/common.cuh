@@ -220,6 +220,7 @@ int launch_simple_gate(qi_state* s, const PhysGate& g);      // one pass with th
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates);
 bool window_supported(const qi_state* s);
 int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<std::vector<int>>* summary);
+int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<uint8_t>* blob);
 // shard.cu
 int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip);
 int apply_circuit_sharded(qi_state* s, const qi_gate* gates, uint64_t count, bool use_window);   // staged around exchanges

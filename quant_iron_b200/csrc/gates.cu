@@ -426,4 +426,45 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
     return QI_OK;
 }
 
+// Host-only: the device programs the fused executor would launch for a gate list on one device (`rank`/`world` > 1: on
+// that shard of a sharded state, identity layout), serialised for a CPU interpreter (layout: window.cu, debug_lower).
+// *used = bytes needed; QI_ERR_INVALID_ARGUMENT with payload[0] = needed size when `capacity` is too small.
+int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gates, uint64_t count, int window_regs, uint8_t* blob,
+                   uint64_t capacity, uint64_t* used) {
+    if (count && !gates) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "gates is NULL");
+    if (world < 1 || (world & (world - 1)) || world > 16 || rank < 0 || rank >= world) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "bad rank / world");
+    int p = 0;
+    while ((1 << p) < world) p++;
+    qi_state s;
+    s.num_qubits = num_qubits;
+    s.n_local = num_qubits - (uint32_t)p;
+    s.len = 1ull << s.n_local;
+    s.rank = rank;
+    s.world = world;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    if (!window_supported(&s)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few local qubits for the window executor");
+    std::vector<PhysGate> run;
+    for (uint64_t i = 0; i < count; i++) {
+        QI_TRY(validate_gate(&s, &gates[i]));
+        if (world == 1 && ctx().opt_lazy_swap && gates[i].kind == QI_GATE_SWAP && gates[i].num_controls == 0) {
+            std::swap(s.phys[gates[i].targets[0]], s.phys[gates[i].targets[1]]);
+            continue;
+        }
+        PhysGate pg;
+        bool skip = false;
+        QI_TRY(prepare_gate(&s, &gates[i], &pg, &skip));
+        if (!skip && pg.kind != IK_NOP) run.push_back(pg);
+    }
+    int R = window_regs ? window_regs : 4;
+    while (R > 3 && (int)s.n_local < 5 + R) R--;
+    std::vector<uint8_t> out;
+    QI_TRY(debug_lower(&s, run, R, &out));
+    // the final logical -> physical map (lazy SWAPs), so the interpreter can undo it
+    out.insert(out.end(), s.phys, s.phys + 64);
+    if (used) *used = out.size();
+    if (out.size() > capacity || !blob) return fail(QI_ERR_INVALID_ARGUMENT, out.size(), capacity, "blob too small");
+    memcpy(blob, out.data(), out.size());
+    return QI_OK;
+}
+
 }  // extern "C"

@@ -58,6 +58,9 @@ struct DOp {                 // device op, 112 bytes
     double m[8];             // matrix / phases; WK_TABLE: m[0] holds the table offset (as integer bits)
 };
 
+static_assert(sizeof(DOp) == 112, "DOp layout (the CPU interpreter in tests/ parses it)");
+static_assert(sizeof(PhysGate) == 88, "PhysGate layout (the CPU interpreter in tests/ parses it)");
+
 template <int R>
 struct WProgram {
     BitInsert ins;              // zero-insert positions of the R window qubits (ascending)
@@ -926,6 +929,34 @@ int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R,
         }
         summary->push_back({st.simple ? 1 : 0, (int)st.pass.regs.size(), lane_ops, reg_ops, diag_ops, table_ops, absorbed, 0});
     }
+    return QI_OK;
+}
+
+// host-only: schedule AND lower a run of physical gates; the device programs are serialised into `blob` so that a test
+// can interpret them on the CPU (tests/test_window_lowering.py).  Layout (all fields 8-byte aligned):
+//   u64 nsteps, then per step: u64 simple;
+//     simple = 1: PhysGate (raw);   simple = 0: u64 R, u64 regs[8] (sorted window qubits), u64 nops, DOp[nops] (raw, 112 B each)
+//   then u64 arena_count and arena_count double2 phase-table entries (DOp::m[0] of a table op is an offset into it)
+int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<uint8_t>* blob) {
+    std::vector<Step> steps;
+    QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
+    std::vector<amp_t> arena;
+    auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };
+    auto put64 = [&](uint64_t v) { put(&v, 8); };
+    put64(steps.size());
+    for (const Step& st : steps) {
+        put64(st.simple ? 1 : 0);
+        if (st.simple) { put(&gates[st.gate], sizeof(PhysGate)); continue; }
+        std::vector<DOp> dops;
+        Layout L;
+        lower_pass(s, st.pass, st.R, dops, arena, &L);
+        put64((uint64_t)st.R);
+        for (int j = 0; j < 8; j++) put64(j < (int)L.regs.size() ? (uint64_t)L.regs[j] : 0ull);
+        put64(dops.size());
+        put(dops.data(), dops.size() * sizeof(DOp));
+    }
+    put64(arena.size());
+    put(arena.data(), arena.size() * sizeof(amp_t));
     return QI_OK;
 }
 

@@ -1,0 +1,110 @@
+"""The host half of the fused window executor, checked WITHOUT a GPU: `qi_debug_lower` serialises the device programs
+`qi_apply_circuit` would launch (scheduling, CNOT absorption, merged phase tables, slot masks, tile predicates, lazy SWAP
+relabelling, per-chunk / per-shard gate translation) and tests/window_interp.py interprets them with numpy.  The result
+must match the oracle to the north-star bar.  (The CUDA half -- that the kernels do what the ops mean -- is the `-m gpu`
+parity suite.)"""
+import numpy as np
+import pytest
+
+import window_interp as wi
+from conftest import AMP_TOL, vec
+from test_host_pipeline import _fuzz_builders, _plan
+
+
+def _run(circuit, n, start, regs=0):
+    v = np.array(start, dtype=np.complex128)
+    phys, steps = wi.execute(wi.lower(circuit, n, regs=regs), v, n)
+    return wi.to_logical(v, n, phys), steps
+
+
+@pytest.mark.parametrize("n,seed,regs", [(8, 1, 3), (9, 2, 4), (10, 3, 4), (10, 4, 5), (11, 5, 4), (12, 6, 4), (11, 7, 5), (9, 8, 3)])
+def test_fuzzed_gate_lists_lowered_programs_match_oracle(ref, n, seed, regs):
+    import quant_iron_b200 as gpu
+    cg, cr = _fuzz_builders([gpu, ref], n, seed, count=200, lazy_swaps=(seed % 2 == 0))
+    start = ref.random_state(n, 40 + seed)
+    got, steps = _run(cg, n, start.state_vector, regs)
+    want = vec(cr.execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    assert any(s[0] == "pass" for s in steps)
+
+
+@pytest.mark.parametrize("n,depth", [(10, 12), (13, 10), (14, 6)])
+def test_layered_circuit_lowered_programs_match_oracle(ref, n, depth):
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    specs = w.random_layered_circuit(n, depth)
+    start = ref.random_state(n, 3)
+    got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    ops = np.concatenate([s[3] for s in steps if s[0] == "pass"])
+    assert (ops["kind"] == wi.WK_TABLE).any()                      # merged RZ runs
+    assert ((ops["kind"] <= wi.WK_U2) & (ops["c_tval"] != ops["c_tile"])).any() or n < 12    # negative controls of absorbed CNOTs
+
+
+@pytest.mark.parametrize("n", [9, 12])
+def test_qft_lowered_programs_match_closed_form(ref, n):
+    """QFT|+..+> = |0..0> through the phase-table ops (one per Hadamard) and the relabelled final swaps."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    c = w.build_circuit(gpu, n, w.qft_specs(n))
+    plus = np.full(1 << n, 1.0 / np.sqrt(float(1 << n)), dtype=np.complex128)
+    got, steps = _run(c, n, plus)
+    assert abs(got[0] - 1.0) <= AMP_TOL and float(np.max(np.abs(got[1:]))) <= AMP_TOL
+    start = ref.random_state(n, 9)
+    got, _ = _run(c, n, start.state_vector)
+    want = vec(w.build_circuit(ref, n, w.qft_specs(n)).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+
+
+@pytest.mark.parametrize("absorb,fuse", [(0, 1), (1, 0), (0, 0)])
+def test_lowering_options(ref, absorb, fuse):
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    n = 11
+    specs = w.random_layered_circuit(n, 8)
+    start = ref.random_state(n, 4)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    gpu.engine.set_option("absorb", absorb)
+    gpu.engine.set_option("fuse", fuse)
+    try:
+        got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    finally:
+        gpu.engine.set_option("absorb", 1)
+        gpu.engine.set_option("fuse", 1)
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    if not fuse:
+        assert len(steps) == len(specs)
+
+
+@pytest.mark.parametrize("n,k,seed", [(11, 1, 1), (12, 2, 2), (12, 3, 3), (13, 3, 4)])
+def test_host_pipeline_chunk_programs_match_oracle(ref, n, k, seed):
+    """qi_execute_host on the CPU: front gates chunk by chunk (each chunk lowered as shard `c` of 2^k), middle on the
+    whole vector, back gates chunk by chunk -- the exact programs the device would run -- against the oracle."""
+    import quant_iron_b200 as gpu
+    cg, cr = _fuzz_builders([gpu, ref], n, seed, count=160)
+    order, nf, nm, nb = _plan(cg, n, k)
+    start = ref.random_state(n, 70 + seed)
+    want = vec(cr.execute(start))
+    v = np.array(start.state_vector, dtype=np.complex128)
+    clen = 1 << (n - k)
+
+    def sub(idx):
+        return gpu.Circuit.with_gates([cg.gates[i] for i in idx], n)
+
+    def per_chunk(idx):
+        if not idx:
+            return
+        c = sub(idx)
+        for ch in range(1 << k):
+            view = v[ch * clen:(ch + 1) * clen]
+            phys, _ = wi.execute(wi.lower(c, n, rank=ch, world=1 << k), view, n - k)
+            assert phys[:n] == list(range(n))
+
+    per_chunk(order[:nf])
+    if nm:
+        phys, _ = wi.execute(wi.lower(sub(order[nf:nf + nm]), n), v, n)
+        assert phys[:n] == list(range(n))
+    per_chunk(order[nf + nm:])
+    assert float(np.max(np.abs(v - want))) <= AMP_TOL
+    assert nf > 0 and nb > 0
