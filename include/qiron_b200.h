@@ -249,6 +249,11 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
 int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gates, uint64_t count, int window_regs,
                    uint8_t* blob, uint64_t capacity, uint64_t* used);
 
+/* host-only: the same for a sequence of apply_exp_factor calls (term k with factors[2k], factors[2k+1]): the fused
+ * Pauli-exp window passes and the terms that run alone (blob layout: csrc/pauli_window.cu, debug_pauli_lower) */
+int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, const double* factors, uint8_t* blob,
+                         uint64_t capacity, uint64_t* used);
+
 #ifdef __cplusplus
 }
 #endif

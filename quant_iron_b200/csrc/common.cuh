@@ -212,6 +212,7 @@ int run_pauli_exp_batch(qi_state* s, const std::vector<PauliExp>& seq);
 int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms, int grid, double2* partials, int max_groups,
                            int* groups_used, std::vector<size_t>* leftover);      // ch = coefficient of each term
 int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* terms_per_pass);
+int debug_pauli_lower(const qi_state* s, const std::vector<PauliExp>& seq, std::vector<uint8_t>* blob);
 
 // gates.cu
 int validate_gate(const qi_state* s, const qi_gate* g);

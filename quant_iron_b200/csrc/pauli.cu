@@ -471,4 +471,28 @@ int qi_debug_pauli_schedule(uint32_t num_qubits, const qi_pauli_term* terms, uin
     return QI_OK;
 }
 
+// Host-only: the device programs qi_apply_pauli_exp_sequence would launch on one device (fused register-window passes and
+// terms that run alone), serialised for the CPU interpreter in tests/ (layout: pauli_window.cu, debug_pauli_lower).
+int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, const double* factors, uint8_t* blob,
+                         uint64_t capacity, uint64_t* used) {
+    if (!terms || !factors || num_qubits == 0 || num_qubits > 62) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "bad argument");
+    qi_state host;                   // layout only: no device memory is touched
+    host.num_qubits = host.n_local = num_qubits;
+    host.len = 1ull << num_qubits;
+    for (int q = 0; q < 64; q++) host.phys[q] = (uint8_t)q;
+    if (!pauli_window_supported(&host)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few qubits for the window executor");
+    std::vector<PauliExp> seq(count);
+    for (uint64_t k = 0; k < count; k++) {
+        bool ex = false;
+        memset(&seq[k], 0, sizeof(PauliExp));
+        QI_TRY(make_exp(&host, terms[k], make_double2(factors[2 * k], factors[2 * k + 1]), &seq[k], &ex));
+    }
+    std::vector<uint8_t> out;
+    QI_TRY(debug_pauli_lower(&host, seq, &out));
+    if (used) *used = out.size();
+    if (out.size() > capacity || !blob) return fail(QI_ERR_INVALID_ARGUMENT, out.size(), capacity, "blob too small");
+    memcpy(blob, out.data(), out.size());
+    return QI_OK;
+}
+
 }  // extern "C"

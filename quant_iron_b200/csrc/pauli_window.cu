@@ -195,11 +195,11 @@ static int schedule_pauli(const std::vector<PauliExp>& seq, Emit emit) {
     return QI_OK;
 }
 
-static int launch_pauli_pass(qi_state* s, const std::vector<PauliExp>& seq, const PxPass& ps) {
-    Context& c = ctx();
+// device program of one pass (host only)
+static int build_px_program(const qi_state* s, const std::vector<PauliExp>& seq, const PxPass& ps, PXProgram<kPauliR>* Pout, Layout* Lout) {
     constexpr int R = kPauliR;
     Layout L = make_layout(s, ps.regs, R);
-    PXProgram<R> P;
+    PXProgram<R>& P = *Pout;
     memset(&P, 0, sizeof(P));
     fill_offsets<R>(L, &P.ins, P.off);
     P.nops = (uint32_t)ps.terms.size();
@@ -216,6 +216,15 @@ static int launch_pauli_pass(qi_state* s, const std::vector<PauliExp>& seq, cons
         d.c = t.ch.x;
         d.s = imag ? t.sh.y : t.sh.x;
     }
+    if (Lout) *Lout = L;
+    return QI_OK;
+}
+
+static int launch_pauli_pass(qi_state* s, const std::vector<PauliExp>& seq, const PxPass& ps) {
+    Context& c = ctx();
+    constexpr int R = kPauliR;
+    PXProgram<R> P;
+    QI_TRY(build_px_program(s, seq, ps, &P, nullptr));
     const uint64_t ntiles = s->len >> (kLaneQubits + R);
     const int warps_per_block = 4;
     uint64_t blocks = (ntiles + warps_per_block - 1) / warps_per_block;
@@ -241,6 +250,33 @@ int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* ter
         terms_per_pass->push_back((int)st.pass.terms.size());
         return QI_OK;
     });
+}
+
+// host-only: schedule AND lower a sequence; the device programs are serialised for the CPU interpreter in tests/
+// (tests/window_interp.py).  Layout: u64 nsteps, then per step: u64 single;
+//   single = 1: PauliExp (raw, 64 B);   single = 0: u64 R, u64 regs[8] (sorted window qubits), u64 nops, PXOp[nops] (raw, 48 B each)
+static_assert(sizeof(PXOp) == 48 && sizeof(PauliExp) == 64, "layouts parsed by the CPU interpreter in tests/");
+int debug_pauli_lower(const qi_state* s, const std::vector<PauliExp>& seq, std::vector<uint8_t>* blob) {
+    auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };
+    auto put64 = [&](uint64_t v) { put(&v, 8); };
+    const size_t head = blob->size();
+    put64(0);
+    uint64_t nsteps = 0;
+    QI_TRY(schedule_pauli(seq, [&](const PxStep& st) -> int {
+        nsteps++;
+        if (st.pass.terms.empty()) { put64(1); put(&seq[st.single], sizeof(PauliExp)); return QI_OK; }
+        PXProgram<kPauliR> P;
+        Layout L;
+        QI_TRY(build_px_program(s, seq, st.pass, &P, &L));
+        put64(0);
+        put64((uint64_t)kPauliR);
+        for (int j = 0; j < 8; j++) put64(j < (int)L.regs.size() ? (uint64_t)L.regs[j] : 0ull);
+        put64(P.nops);
+        put(P.ops, P.nops * sizeof(PXOp));
+        return QI_OK;
+    }));
+    memcpy(blob->data() + head, &nsteps, 8);
+    return QI_OK;
 }
 
 // ---- SumOp::expectation_value: many terms per read-only pass ------------------------------------------------

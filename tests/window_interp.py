@@ -208,3 +208,95 @@ def to_logical(v, n, phys):
     for q in range(n):
         P |= ((L >> np.uint64(q)) & np.uint64(1)) << np.uint64(phys[q])
     return v[P]
+
+
+# ---- fused Pauli-exponential sequences (csrc/pauli_window.cu) ---------------------------------------------------
+PXOP = np.dtype([("xl", "<u4"), ("xr", "<u4"), ("zl", "<u4"), ("zr", "<u4"), ("zt", "<u8"), ("k0", "<u4"), ("pad", "<u4"),
+                 ("c", "<f8"), ("s", "<f8")])
+PEXP = np.dtype([("x", "<u8"), ("z", "<u8"), ("k0", "<i4"), ("pad", "u1", 12), ("ch", "<f8", 2), ("sh", "<f8", 2)])
+assert PXOP.itemsize == 48 and PEXP.itemsize == 64
+
+
+def lower_pauli(strings, factors, n):
+    """Serialised programs of qi_apply_pauli_exp_sequence for PauliStrings of this package."""
+    from quant_iron_b200 import _ffi
+    arr = (_ffi.QiPauliTerm * len(strings))()
+    keep = []
+    for i, ps in enumerate(strings):
+        rec, k = ps.term()
+        arr[i] = rec
+        keep.append(k)
+    flat = []
+    for f in factors:
+        flat += [complex(f).real, complex(f).imag]
+    used = C.c_uint64()
+    cap = 1 << 20
+    while True:
+        blob = (C.c_uint8 * cap)()
+        st = _ffi.lib.qi_debug_pauli_lower(n, arr, len(strings), _ffi.dbl_array(flat), blob, cap, C.byref(used))
+        if st == 0:
+            return bytes(blob[:used.value])
+        if used.value > cap:
+            cap = used.value
+            continue
+        _ffi.check(st)
+
+
+def _parity(x):
+    x = x.copy()
+    for sh in (32, 16, 8, 4, 2, 1):
+        x ^= x >> np.uint64(sh)
+    return (x & np.uint64(1)).astype(np.int64)
+
+
+_IPOW = np.array([1, 1j, -1, -1j], dtype=np.complex128)
+
+
+def execute_pauli(blob, v, n):
+    """psi <- cosh(a) psi + sinh(a) P psi per term, (P psi)[i] = i^(k0 + 2 popc(i & z)) psi[i ^ x], in place on `v`."""
+    off = 0
+
+    def u64():
+        nonlocal off
+        val = struct.unpack_from("<Q", blob, off)[0]
+        off += 8
+        return val
+
+    idx = np.arange(1 << n, dtype=np.uint64)
+    lane = idx & np.uint64(31)
+    passes, singles = 0, 0
+    for _ in range(u64()):
+        if u64():
+            e = np.frombuffer(blob, PEXP, 1, off)[0]
+            off += PEXP.itemsize
+            singles += 1
+            k = (int(e["k0"]) + 2 * _parity(idx & np.uint64(e["z"]))) & 3
+            ch, sh = complex(*e["ch"]), complex(*e["sh"])
+            v[:] = ch * v + sh * (_IPOW[k] * v[idx ^ np.uint64(e["x"])])
+            continue
+        R = u64()
+        regs = [u64() for _ in range(8)][:R]
+        nops = u64()
+        ops = np.frombuffer(blob, PXOP, nops, off)
+        off += nops * PXOP.itemsize
+        passes += 1
+        slot = np.zeros(1 << n, dtype=np.uint64)
+        for j, q in enumerate(regs):
+            slot |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)
+        tile = np.zeros(1 << n, dtype=np.uint64)
+        t = 0
+        for q in range(5, n):
+            if q in regs:
+                continue
+            tile |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(t)
+            t += 1
+        for op in ops:
+            x = int(op["xl"])
+            for j, q in enumerate(regs):
+                if (int(op["xr"]) >> j) & 1:
+                    x |= 1 << q
+            flip = _parity(tile & np.uint64(op["zt"])) + _parity(lane & np.uint64(op["zl"])) + _parity(slot & np.uint64(op["zr"]))
+            k = (int(op["k0"]) + 2 * flip) & 3
+            v[:] = float(op["c"]) * v + float(op["s"]) * (_IPOW[k] * v[idx ^ np.uint64(x)])
+    assert off == len(blob)
+    return passes, singles
