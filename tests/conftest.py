@@ -23,10 +23,20 @@ EXP_RTOL = 1e-10     # north star: relative error on expectation values
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+    config.addinivalue_line("markers", "unproven: GPU test of a path that has not run on hardware yet; ordered last")
     # a fresh checkout has no built artefacts (they are git-ignored): build them once instead of failing at import
     if not os.path.exists(os.path.join(ROOT, "quant_iron_b200", "lib", "libqiron_b200.so")):
         import __graft_entry__
         __graft_entry__.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests of code that has not yet run on hardware (built after a round's GPU budget was spent) carry the
+    `unproven` marker and are moved to the end of the run: the driver runs the suite with -x, and a failure in brand-new
+    code must not hide the established parity results behind it."""
+    tail = [it for it in items if it.get_closest_marker("unproven")]
+    if tail:
+        items[:] = [it for it in items if not it.get_closest_marker("unproven")] + tail
 
 
 def _load(name):

@@ -34,3 +34,15 @@ def test_facade_known_answers_on_gpu():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.unproven
+def test_facade_execute_host_on_gpu():
+    """Circuit::execute_host_ (qi_execute_host, pipelined) through the C++ facade: same state as execute()."""
+    if not os.path.exists(BIN):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([BIN, "--execute-host"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASS" in r.stdout

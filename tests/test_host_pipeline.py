@@ -113,6 +113,7 @@ def small_pipeline(gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.unproven
 @pytest.mark.parametrize("n,k,seed", [(11, 1, 1), (11, 3, 2), (12, 2, 3), (12, 3, 4), (13, 3, 5), (13, 4, 6), (14, 3, 7)])
 def test_execute_host_pipelined_vs_oracle(gpu, ref, small_pipeline, n, k, seed):
     gpu.engine.set_option("host_chunk_qubits", k)
@@ -129,6 +130,7 @@ def test_execute_host_pipelined_vs_oracle(gpu, ref, small_pipeline, n, k, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.unproven
 @pytest.mark.parametrize("n", [11, 13])
 def test_execute_host_plain_sequence_paths(gpu, ref, small_pipeline, n):
     """Lists with relabelled SWAPs (the QFT) and k = 0 take upload / execute / download: same answers."""
@@ -147,6 +149,7 @@ def test_execute_host_plain_sequence_paths(gpu, ref, small_pipeline, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.unproven
 @pytest.mark.parametrize("n,depth", [(16, 12), (20, 40)])
 def test_execute_host_layered_circuit_vs_resident_path(gpu, ref, small_pipeline, n, depth):
     from quant_iron_b200 import workloads as w
@@ -164,6 +167,7 @@ def test_execute_host_layered_circuit_vs_resident_path(gpu, ref, small_pipeline,
 
 
 @pytest.mark.gpu
+@pytest.mark.unproven
 def test_execute_host_default_options_26_qubits(gpu):
     """Default options: a 26-qubit state (1 GiB) is pipelined in 8 chunks of 128 MiB; the result equals the plain
     upload / execute / download sequence on the same device buffer."""
