@@ -234,6 +234,11 @@ def run_ours(args, rank, world, local_rank):
         os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's "NCCL version ..." banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     qi.engine.init(local_rank)
+    options = {}
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        qi.engine.set_option(name, int(val))
+        options[name] = int(val)
     peak_gbs, peak_src = load_peaks()
     n_local = args.qubits
     n = n_local + (world.bit_length() - 1)
@@ -446,7 +451,7 @@ def run_ours(args, rank, world, local_rank):
                    "qubits": n, "gates_per_step": n_gates, "state_bytes_per_gpu": 16 * (1 << n_local),
                    "unit_of_work": "one gate applied to one 2^30-amplitude shard; a gate on the N-GPU state counts N "
                                    "(value = gates/s x N; raw_gates_per_sec is the literal circuit-gate rate)",
-                   "raw_gates_per_sec": raw_gates_per_sec,
+                   "raw_gates_per_sec": raw_gates_per_sec, "options": options,
                    "l2": "inputs (16 GiB state per GPU) far larger than the 126 MB L2; no flush needed",
                    "unfused_algorithmic_bytes_per_step": w.algorithmic_bytes(n, specs),
                    "effective_gbs_per_gpu_vs_unfused_bytes": w.algorithmic_bytes(n, specs) / world / (ms_per_step * 1e-3) / 1e9},
@@ -471,6 +476,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine option for an A/B run (qi_set_option), e.g. --opt lean=1; recorded in config.options")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -37,7 +37,14 @@
 
 namespace qi {
 
-enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE };   // pair kinds first (<= WK_U2); RXS = RX o X
+// pair kinds first (<= kLastPairKind); RXS = RX o X.  The *U kinds are the LEAN forms (option "lean", off by default, not yet
+// measured): the gate divided by its top-left entry g, so that two of the four coefficients are +-1 and a pair costs 4 DFMA
+// instead of 4 DMUL + 4 DFMA; the g of all lean gates of a pass are multiplied on the host and applied once (folded into a
+// phase table when the pass has an unconditional one, else one WK_SCALE op).
+//   REALUP = [[1, p], [q, 1]]   REALUM = [[1, p], [q, -1]]   (m[0] = p, m[1] = q; H / g = REALUM with p = q = 1)
+//   RXU = [[1, -i t], [-i t, 1]]   RXSU = RXU with its inputs swapped   (m[0] = t = tan(theta / 2))
+enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE };
+static const int kLastPairKind = WK_RXSU;
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 112 B + header < 16 KB)
 
@@ -96,6 +103,7 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
     if (KIND == WK_RX || KIND == WK_RXS) { k0 = m[0]; k1 = m[1]; }
     if (KIND == WK_REAL) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; }
     if (KIND == WK_U2) { k0 = m[0]; k1 = m[1]; k2 = m[2]; k3 = m[3]; k4 = m[4]; k5 = m[5]; k6 = m[6]; k7 = m[7]; }
+    if (KIND == WK_REALUP || KIND == WK_REALUM || KIND == WK_RXU || KIND == WK_RXSU) { k0 = m[0]; k1 = m[1]; }
 #pragma unroll
     for (int p = 0; p < (1 << (R - 1)); p++) {
         const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
@@ -113,6 +121,18 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
             } else if (KIND == WK_REAL) {
                 v[s0] = make_double2(k0 * a0.x + k1 * a1.x, k0 * a0.y + k1 * a1.y);
                 v[s1] = make_double2(k2 * a0.x + k3 * a1.x, k2 * a0.y + k3 * a1.y);
+            } else if (KIND == WK_REALUP) {
+                v[s0] = make_double2(fma(k0, a1.x, a0.x), fma(k0, a1.y, a0.y));
+                v[s1] = make_double2(fma(k1, a0.x, a1.x), fma(k1, a0.y, a1.y));
+            } else if (KIND == WK_REALUM) {
+                v[s0] = make_double2(fma(k0, a1.x, a0.x), fma(k0, a1.y, a0.y));
+                v[s1] = make_double2(fma(k1, a0.x, -a1.x), fma(k1, a0.y, -a1.y));
+            } else if (KIND == WK_RXU) {
+                v[s0] = make_double2(fma(k0, a1.y, a0.x), fma(-k0, a1.x, a0.y));
+                v[s1] = make_double2(fma(k0, a0.y, a1.x), fma(-k0, a0.x, a1.y));
+            } else if (KIND == WK_RXSU) {
+                v[s0] = make_double2(fma(k0, a0.y, a1.x), fma(-k0, a0.x, a1.y));
+                v[s1] = make_double2(fma(k0, a1.y, a0.x), fma(-k0, a1.x, a0.y));
             } else {
                 const amp_t m00 = make_double2(k0, k1), m01 = make_double2(k2, k3);
                 const amp_t m10 = make_double2(k4, k5), m11 = make_double2(k6, k7);
@@ -126,8 +146,24 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
 template <int R>
 constexpr uint32_t kAllSlots = (R >= 5) ? 0xffffffffu : ((1u << (1 << R)) - 1u);
 
-template <int R, int B, bool U2K>
+template <int R, int B, bool U2K, bool LEAN>
 __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
+    if (LEAN && kind >= WK_REALUP) {       // lean forms: uncontrolled ones straight-line, halves of an absorbed CNOT predicated
+        if (c_reg == kAllSlots<R>) {
+            switch (kind) {
+                case WK_REALUP: reg_pair_kind<R, B, WK_REALUP, false>(v, 0, m); return;
+                case WK_REALUM: reg_pair_kind<R, B, WK_REALUM, false>(v, 0, m); return;
+                case WK_RXU: reg_pair_kind<R, B, WK_RXU, false>(v, 0, m); return;
+                default: reg_pair_kind<R, B, WK_RXSU, false>(v, 0, m); return;
+            }
+        }
+        switch (kind) {
+            case WK_REALUP: reg_pair_kind<R, B, WK_REALUP, true>(v, c_reg, m); return;
+            case WK_REALUM: reg_pair_kind<R, B, WK_REALUM, true>(v, c_reg, m); return;
+            case WK_RXU: reg_pair_kind<R, B, WK_RXU, true>(v, c_reg, m); return;
+            default: reg_pair_kind<R, B, WK_RXSU, true>(v, c_reg, m); return;
+        }
+    }
     // no register-bit controls (the bulk of every circuit): straight-line variants without slot predicates -- the
     // per-pair predicate regions keep the compiler from interleaving the pairs, which exposes the FP64 latency.
     // (X and U2 stay predicated: their straight-line forms spill hundreds of bytes.)
@@ -153,12 +189,43 @@ __device__ __forceinline__ void reg_pair_op(amp_t (&v)[1 << R], uint32_t kind, u
 // differs only in the target bit, so it sees the same controls.
 // ALL = every slot takes part (no register-bit controls): straight-line code, so the shuffles of a gate are issued
 // back to back (one exposed latency per gate) instead of one latency-exposed shuffle group per predicated slot.
-template <int R, bool ALL, bool U2K>
+template <int R, bool ALL, bool U2K, bool LEAN>
 __device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
                                                const double* __restrict__ m, int lane) {
     constexpr int S = 1 << R;
     const int xm = 1 << tpos;
     const bool hi = (lane >> tpos) & 1;     // this lane holds the |1> member of the pair
+    if (LEAN && kind >= WK_REALUP) {
+        if (kind == WK_REALUP || kind == WK_REALUM) {
+            // [[1, p], [q, r]], r = +-1: |0> lane: mine + p other; |1> lane: r mine + q other
+            double cB = hi ? m[1] : m[0];
+            const bool neg = hi && kind == WK_REALUM && thread_ok;
+            if (!thread_ok) cB = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (ALL || ((c_reg >> s) & 1u)) {
+                    const amp_t mine = v[s];
+                    const amp_t other = shfl_xor_amp(mine, xm);
+                    const amp_t base = neg ? cneg(mine) : mine;
+                    v[s] = make_double2(fma(cB, other.x, base.x), fma(cB, other.y, base.y));
+                }
+            }
+            return;
+        }
+        // RXU: mine' = mine - i t other.  RXSU (inputs swapped): mine' = other - i t mine
+        const bool swapped = (kind == WK_RXSU) && thread_ok;
+        const double t = thread_ok ? m[0] : 0.0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            if (ALL || ((c_reg >> s) & 1u)) {
+                const amp_t mine = v[s];
+                const amp_t other = shfl_xor_amp(mine, xm);
+                const amp_t P = swapped ? other : mine, Q = swapped ? mine : other;
+                v[s] = make_double2(fma(t, Q.y, P.x), fma(-t, Q.x, P.y));
+            }
+        }
+        return;
+    }
     if (kind == WK_X) {
         const int src = thread_ok ? (lane ^ xm) : lane;
 #pragma unroll
@@ -210,17 +277,17 @@ __device__ __forceinline__ void lane_pair_impl(amp_t (&v)[1 << R], uint32_t kind
     }
 }
 
-template <int R, bool U2K>
+template <int R, bool U2K, bool LEAN>
 __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, uint32_t tpos, uint32_t c_reg, bool thread_ok,
                                              const double* __restrict__ m, int lane) {
-    if (c_reg == kAllSlots<R>) lane_pair_impl<R, true, U2K>(v, kind, tpos, c_reg, thread_ok, m, lane);
-    else lane_pair_impl<R, false, U2K>(v, kind, tpos, c_reg, thread_ok, m, lane);
+    if (c_reg == kAllSlots<R>) lane_pair_impl<R, true, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, m, lane);
+    else lane_pair_impl<R, false, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, m, lane);
 }
 
 // ---- the op program on one register tile -------------------------------------------------------------
 // LANES = the program contains pair gates on lane qubits; programs without them run an instantiation that does not
 // carry the shuffle code at all (smaller, fewer live registers).
-template <int R, bool LANES, bool U2K>
+template <int R, bool LANES, bool U2K, bool LEAN = false>
 __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const WProgram<R>& P) {
     constexpr int S = 1 << R;
 #pragma unroll 1
@@ -229,8 +296,8 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
         if ((tile & op.c_tile) != op.c_tval) continue;                // warp-uniform control (positive and negative bits)
         const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
         const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
-        if (LANES && kind <= WK_U2 && tpos < 5) {                     // pair gate across lanes
-            lane_pair_op<R, U2K>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
+        if (LANES && kind <= kLastPairKind && tpos < 5) {             // pair gate across lanes
+            lane_pair_op<R, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
             continue;
         }
         if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
@@ -276,13 +343,17 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
                 for (int s = 0; s < S; s++)
                     if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], f);
             }
+        } else if (LEAN && kind == WK_SCALE) {                          // the product of the pass's deferred gate scales
+            const double g = op.m[0];
+#pragma unroll
+            for (int s = 0; s < S; s++) v[s] = make_double2(v[s].x * g, v[s].y * g);
         } else {
             switch (tpos - 5) {
-                case 0: reg_pair_op<R, 0, U2K>(v, kind, c_reg, op.m); break;
-                case 1: reg_pair_op<R, (R > 1 ? 1 : 0), U2K>(v, kind, c_reg, op.m); break;
-                case 2: reg_pair_op<R, (R > 2 ? 2 : 0), U2K>(v, kind, c_reg, op.m); break;
-                case 3: reg_pair_op<R, (R > 3 ? 3 : 0), U2K>(v, kind, c_reg, op.m); break;
-                default: reg_pair_op<R, (R > 4 ? 4 : 0), U2K>(v, kind, c_reg, op.m); break;
+                case 0: reg_pair_op<R, 0, U2K, LEAN>(v, kind, c_reg, op.m); break;
+                case 1: reg_pair_op<R, (R > 1 ? 1 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+                case 2: reg_pair_op<R, (R > 2 ? 2 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+                case 3: reg_pair_op<R, (R > 3 ? 3 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+                default: reg_pair_op<R, (R > 4 ? 4 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
             }
         }
     }
@@ -296,7 +367,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 #define QI_WINDOW_BLOCKS(R) ((R) <= 3 ? 8 : ((R) == 4 ? QI_WINDOW_BLOCKS4 : 2))
 
 // direct variant: every thread loads its 2^R amplitudes itself (coalesced 512 B per warp access)
-template <int R, bool LANES, bool U2K>
+template <int R, bool LANES, bool U2K, bool LEAN = false>
 __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ WProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
@@ -307,7 +378,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __re
         amp_t v[S];
 #pragma unroll
         for (int s = 0; s < S; s++) v[s] = QI_LD(a + base + P.off[s]);
-        run_ops<R, LANES, U2K>(v, tile, lane, P);
+        run_ops<R, LANES, U2K, LEAN>(v, tile, lane, P);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
     }
@@ -412,6 +483,7 @@ struct HOp {
     uint64_t tmask = 0;         // WK_RZ: physical target bit
     double m[8] = {0};
     int group = -1;             // WK_TABLE: index into Pass::groups
+    int pair = -1;              // the two halves of an absorbed CNOT share an id (lean lowering treats them as one gate)
 };
 
 // a mergeable diagonal group: [hub set] * prod_j (bit_j ? f1_j : f0_j)
@@ -429,6 +501,7 @@ struct Pass {
     std::vector<int> regs;               // window qubits (physical positions >= 5)
     std::vector<HOp> ops;
     std::vector<DiagGroup> groups;
+    int next_pair = 0;
 };
 
 static void classify_u2(const double* p, HOp* op) {
@@ -524,6 +597,7 @@ static bool absorb_cnot_before(Pass& ps, HOp* g) {
     HOp on = *g;                 // control = 1: G X, takes the X's place
     compose_with_x(&on, true);
     on.cmask = c;
+    on.pair = g->pair = ps.next_pair++;
     x = on;
     g->nmask = c;                // control = 0: plain G, appended by the caller
     return true;
@@ -542,6 +616,7 @@ static bool absorb_cnot_after(Pass& ps, const HOp& x, HOp* off_half) {
     off_half->nmask = x.cmask;
     compose_with_x(&g, false);   // control = 1: X G, stays in G's place
     g.cmask = x.cmask;
+    g.pair = off_half->pair = ps.next_pair++;
     return true;
 }
 
@@ -664,7 +739,7 @@ static void lower_gate(Pass& ps, const PhysGate& g, bool merge) {
 // (Layout / make_layout / split_mask: window_layout.cuh)
 
 // build the tables of one group: [lane(32) | slot(2^R) | chunk0(256) | chunk1(256) ...]
-static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>& arena, DOp* d) {
+static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>& arena, DOp* d, double scale = 1.0) {
     const int S = 1 << L.R;
     const int nch_total = (L.ntile_bits + 7) / 8;
     int used_chunks = 0;
@@ -692,6 +767,8 @@ static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>
             for (int i = 0; i < 256; i++) chunk_t[256 * ch + i] = cmul(chunk_t[256 * ch + i], ((i >> b) & 1) ? f1 : f0);
         }
     }
+    if (scale != 1.0)                      // lean lowering: the pass's deferred gate scale rides on an unconditional table
+        for (int i = 0; i < 32; i++) lane_t[i] = make_double2(lane_t[i].x * scale, lane_t[i].y * scale);
     d->kind = WK_TABLE;
     d->nchunks = (uint8_t)used_chunks;
     d->has_reg = has_reg ? 1 : 0;
@@ -710,10 +787,70 @@ static uint32_t slot_mask(int R, uint32_t pos, uint32_t neg) {
     return m;
 }
 
+// ---- lean lowering (option "lean") --------------------------------------------------------------------
+// G = g * G' with G' in one of the unit forms of the WK_*U kinds.  Only gates that act on the WHOLE state qualify, so that
+// g is a global scalar: uncontrolled REAL / RX / RXS ops, and the two halves of an absorbed CNOT when both give the same g
+// (they act on complementary halves of the state).  Returns the product of the g (1.0 = nothing converted).
+static bool lean_form(const HOp& h, double* g, HOp* lean) {
+    const double kMin = 0.3;                 // keep p, q, t = O(1): below this the scaled form is used
+    *lean = h;
+    memset(lean->m, 0, sizeof(lean->m));
+    if (h.kind == WK_RX || h.kind == WK_RXS) {
+        if (std::fabs(h.m[0]) < kMin) return false;
+        *g = h.m[0];
+        lean->kind = h.kind == WK_RX ? WK_RXU : WK_RXSU;
+        lean->m[0] = h.m[1] / h.m[0];
+        return true;
+    }
+    if (h.kind == WK_REAL) {                 // (k00, k01, k10, k11)
+        if (std::fabs(h.m[0]) < kMin) return false;
+        if (h.m[3] == h.m[0]) lean->kind = WK_REALUP;
+        else if (h.m[3] == -h.m[0]) lean->kind = WK_REALUM;
+        else return false;
+        *g = h.m[0];
+        lean->m[0] = h.m[1] / h.m[0];
+        lean->m[1] = h.m[2] / h.m[0];
+        return true;
+    }
+    return false;
+}
+
+static double lean_convert(std::vector<HOp>& ops) {
+    const size_t n = ops.size();
+    std::vector<char> ok(n, 0);
+    std::vector<double> g(n, 1.0);
+    std::vector<HOp> lean(n);
+    for (size_t i = 0; i < n; i++) ok[i] = ops[i].kind != 0 && lean_form(ops[i], &g[i], &lean[i]);
+    size_t converted = 0;
+    std::vector<char> take(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (!ok[i]) continue;
+        const HOp& h = ops[i];
+        if (h.pair < 0) { if (h.cmask == 0 && h.nmask == 0) { take[i] = 1; converted++; } continue; }
+        for (size_t j = i + 1; j < n; j++)
+            if (ops[j].kind != 0 && ops[j].pair == h.pair) {
+                const bool halves = (h.cmask && !h.nmask && ops[j].nmask == h.cmask && !ops[j].cmask) ||
+                                    (h.nmask && !h.cmask && ops[j].cmask == h.nmask && !ops[j].nmask);
+                if (ok[j] && halves && g[j] == g[i]) { take[i] = 1; take[j] = 2; converted++; }     // 2 = its g is already counted
+                break;
+            }
+    }
+    if (converted < 3) return 1.0;           // the scale op would cost more than the lean forms save
+    double scale = 1.0;
+    for (size_t i = 0; i < n; i++) {
+        if (!take[i]) continue;
+        if (take[i] == 1) scale *= g[i];
+        ops[i] = lean[i];
+    }
+    return scale;
+}
+
 static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp>& dops, std::vector<amp_t>& arena, Layout* Lout) {
     Layout L = make_layout(s, ps.regs, R);
     *Lout = L;
-    for (const HOp& h : ps.ops) {
+    std::vector<HOp> ops(ps.ops);
+    double scale = ctx().opt_lean ? lean_convert(ops) : 1.0;
+    for (const HOp& h : ops) {
         if (h.kind == 0) continue;              // absorbed into a neighbour (absorb_cnot)
         DOp d;
         memset(&d, 0, sizeof(d));
@@ -721,7 +858,9 @@ static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp
         if (op.kind == WK_TABLE) {
             const DiagGroup& g = ps.groups[op.group];
             if (g.members >= 2) {
-                build_tables(L, g, arena, &d);
+                const bool carries = scale != 1.0 && g.hub < 0 && g.hub_alt < 0;      // unconditional: touches every amplitude
+                build_tables(L, g, arena, &d, carries ? scale : 1.0);
+                if (carries) scale = 1.0;
                 dops.push_back(d);
                 continue;
             }
@@ -746,6 +885,14 @@ static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp
         }
         dops.push_back(d);
     }
+    if (scale != 1.0) {                         // no table to ride on: one real scale op
+        DOp d;
+        memset(&d, 0, sizeof(d));
+        d.kind = WK_SCALE;
+        d.c_reg = slot_mask(L.R, 0, 0);
+        d.m[0] = scale;
+        dops.push_back(d);
+    }
 }
 
 template <int R>
@@ -766,14 +913,20 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
         memcpy(P.ops, ops + first, cnt * sizeof(DOp));
         // instantiation by content: programs without lane gates / without complex 2x2 gates run kernels that do not
         // carry that code (smaller, fewer live registers)
-        bool lanes = false, u2k = false;
+        bool lanes = false, u2k = false, lean = false;
         for (size_t k = 0; k < cnt; k++) {
             const DOp& o = P.ops[k];
-            if (o.kind >= WK_X && o.kind <= WK_U2) { lanes |= o.tpos < kLaneQubits; u2k |= o.kind == WK_U2; }
+            if (o.kind >= WK_X && o.kind <= kLastPairKind) { lanes |= o.tpos < kLaneQubits; u2k |= o.kind == WK_U2; lean |= o.kind >= WK_REALUP; }
+            lean |= o.kind == WK_SCALE;
         }
         LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
         const unsigned threads = warps_per_block * 32;
-        if (c.opt_tma) {
+        if (lean) {      // programs with lean forms (option "lean"): their own instantiations, the default ones stay as they are
+            if (lanes && u2k) k_window<R, true, true, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else if (lanes) k_window<R, true, false, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else if (u2k) k_window<R, false, true, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+            else k_window<R, false, false, true><<<(unsigned)blocks, threads, 0, c.stream>>>(s->d, ntiles, P);
+        } else if (c.opt_tma) {
             uint64_t pblocks = (uint64_t)c.sm_count * QI_WINDOW_BLOCKS(R);       // persistent: every block resident
             if (pblocks > blocks) pblocks = blocks;
             const size_t smem = (size_t)warps_per_block * (32u << R) * sizeof(amp_t) + warps_per_block * sizeof(uint64_t);

@@ -39,7 +39,7 @@ def test_layered_circuit_lowered_programs_match_oracle(ref, n, depth):
     assert float(np.max(np.abs(got - want))) <= AMP_TOL
     ops = np.concatenate([s[3] for s in steps if s[0] == "pass"])
     assert (ops["kind"] == wi.WK_TABLE).any()                      # merged RZ runs
-    assert ((ops["kind"] <= wi.WK_U2) & (ops["c_tval"] != ops["c_tile"])).any() or n < 12    # negative controls of absorbed CNOTs
+    assert ((ops["kind"] <= wi.LAST_PAIR) & (ops["c_tval"] != ops["c_tile"])).any() or n < 12    # negative controls of absorbed CNOTs
 
 
 @pytest.mark.parametrize("n", [9, 12])
@@ -55,6 +55,43 @@ def test_qft_lowered_programs_match_closed_form(ref, n):
     got, _ = _run(c, n, start.state_vector)
     want = vec(w.build_circuit(ref, n, w.qft_specs(n)).execute(start))
     assert float(np.max(np.abs(got - want))) <= AMP_TOL
+
+
+@pytest.fixture
+def lean():
+    import quant_iron_b200 as gpu
+    gpu.engine.set_option("lean", 1)
+    yield
+    gpu.engine.set_option("lean", 0)
+
+
+@pytest.mark.parametrize("n,seed,regs", [(9, 11, 3), (10, 12, 4), (11, 13, 4), (12, 14, 5), (10, 15, 4)])
+def test_lean_lowering_fuzz_matches_oracle(ref, lean, n, seed, regs):
+    """Option "lean": unit-form H / RX / real 2x2 ops with ONE deferred scale per pass (folded into a phase table or a
+    scale op) -- every operator kind, controls, absorbed CNOTs, relabelled SWAPs."""
+    import quant_iron_b200 as gpu
+    cg, cr = _fuzz_builders([gpu, ref], n, seed, count=240, lazy_swaps=(seed % 2 == 0))
+    start = ref.random_state(n, 40 + seed)
+    got, steps = _run(cg, n, start.state_vector, regs)
+    assert float(np.max(np.abs(got - vec(cr.execute(start))))) <= AMP_TOL
+
+
+@pytest.mark.parametrize("n,depth", [(12, 12), (14, 8)])
+def test_lean_lowering_layered_circuit(ref, lean, n, depth):
+    """The benchmark generator: most H / RX gates (and absorbed-CNOT pairs) take the lean forms; the scale rides on the
+    pass's RZ phase table where there is one."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    specs = w.random_layered_circuit(n, depth)
+    start = ref.random_state(n, 3)
+    got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    ops = np.concatenate([s[3] for s in steps if s[0] == "pass"])
+    n_lean = int(((ops["kind"] >= wi.WK_REALUP) & (ops["kind"] <= wi.WK_RXSU)).sum())
+    n_scaled = int(((ops["kind"] >= wi.WK_RX) & (ops["kind"] <= wi.WK_REAL)).sum())
+    assert n_lean > 2 * n_scaled, (n_lean, n_scaled)
+    assert int((ops["kind"] == wi.WK_SCALE).sum()) <= len([s for s in steps if s[0] == "pass"])
 
 
 @pytest.mark.parametrize("absorb,fuse", [(0, 1), (1, 0), (0, 0)])

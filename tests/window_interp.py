@@ -12,7 +12,8 @@ import struct
 
 import numpy as np
 
-WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_DIAG, WK_RZ, WK_TABLE = 1, 2, 3, 4, 5, 6, 7, 8
+WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE = range(1, 14)
+LAST_PAIR = WK_RXSU
 IK_H, IK_X, IK_Y, IK_U2, IK_DIAG, IK_RZ, IK_SWAP, IK_MATCH = 1, 2, 3, 4, 5, 6, 7, 8
 CLS_LANE, CLS_REG, CLS_TILE = 1, 2, 3
 
@@ -81,9 +82,17 @@ def _pair(v, idx0, tb, kind, m):
         n0, n1 = m[0] * a1 - 1j * m[1] * a0, m[0] * a0 - 1j * m[1] * a1
     elif kind == WK_REAL:
         n0, n1 = m[0] * a0 + m[1] * a1, m[2] * a0 + m[3] * a1
-    else:
+    elif kind == WK_U2:
         m00, m01, m10, m11 = (complex(m[0], m[1]), complex(m[2], m[3]), complex(m[4], m[5]), complex(m[6], m[7]))
         n0, n1 = m00 * a0 + m01 * a1, m10 * a0 + m11 * a1
+    elif kind in (WK_REALUP, WK_REALUM):      # lean forms (option "lean"): [[1, p], [q, +-1]]
+        n0, n1 = a0 + m[0] * a1, m[1] * a0 + (a1 if kind == WK_REALUP else -a1)
+    elif kind == WK_RXU:                      # [[1, -i t], [-i t, 1]]
+        n0, n1 = a0 - 1j * m[0] * a1, a1 - 1j * m[0] * a0
+    elif kind == WK_RXSU:                     # the same with its inputs swapped
+        n0, n1 = a1 - 1j * m[0] * a0, a0 - 1j * m[0] * a1
+    else:
+        raise AssertionError(f"unknown pair kind {kind}")
     v[idx0] = n0
     v[idx0 | tb] = n1
 
@@ -109,7 +118,7 @@ def run_pass(v, nl, R, regs, ops, arena):
         lane_ok = (lane & np.uint32(op["c_lane"])) == np.uint32(op["c_lane"])
         c_reg = int(op["c_reg"])
         slot_ok = ((np.uint32(c_reg) >> slot) & np.uint32(1)).astype(bool)
-        if kind <= WK_U2:
+        if kind <= LAST_PAIR:
             tpos = int(op["tpos"])
             tbit = tpos if tpos < 5 else regs[tpos - 5]
             tb = np.uint64(1 << tbit)
@@ -118,7 +127,9 @@ def run_pass(v, nl, R, regs, ops, arena):
             _pair(v, idx[sel], tb, kind, m)
             continue
         active = tile_ok & lane_ok
-        if kind == WK_DIAG:
+        if kind == WK_SCALE:                  # product of the deferred scales of the pass's lean gates (real)
+            v[active & slot_ok] *= float(m[0])
+        elif kind == WK_DIAG:
             v[active & slot_ok] *= complex(m[0], m[1])
         elif kind == WK_RZ:
             p0, p1 = complex(m[0], m[1]), complex(m[2], m[3])
