@@ -139,7 +139,17 @@ def cpu_baseline(num_qubits: int, specs, budget_s: float = 20.0):
     f_rate, f_done = run("faithful")
     i_rate, i_done = run("inplace")
     scale = float(1 << (num_qubits - n))
+    cpu_model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    cpu_model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
     return {
+        "cpu_model": cpu_model, "nproc": os.cpu_count(),
         # `value` is in the headline's terms (gates/s on the bench-size state): the rate measured on the
         # sample divided by 2^(bench qubits - sample qubits) (a gate's cost is proportional to the state size)
         "value": f_rate / scale, "unit": UNIT, "cores": cores, "kind": "port",
