@@ -247,9 +247,15 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
 /* host-only: the device programs (window passes with their op lists and phase tables, per-gate-kernel steps) the fused
  * executor would launch for a gate list, serialised so that tests can interpret them on the CPU and compare with the
  * oracle without a GPU (tests/test_window_lowering.py; blob layout: csrc/window.cu, debug_lower).  rank / world > 1:
- * the programs of that shard (or host-pipeline chunk) under the identity layout.  *used = bytes written / needed. */
-int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gates, uint64_t count, int window_regs,
-                   uint8_t* blob, uint64_t capacity, uint64_t* used);
+ * the programs of that shard (or host-pipeline chunk); phys = the logical -> physical qubit map (64 entries, NULL =
+ * identity).  *used = bytes written / needed. */
+int qi_debug_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys, const qi_gate* gates, uint64_t count,
+                   int window_regs, uint8_t* blob, uint64_t capacity, uint64_t* used);
+/* host-only: the stages the sharded executor runs for a gate list on `world` ranks (the gates of each stage, the qubit map
+ * it runs under, the global<->local exchange that follows), as a u64 stream a test replays on the CPU together with
+ * qi_debug_lower (tests/test_sharded_emulation.py; record layout: csrc/shard.cu) */
+int qi_debug_shard_stages(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* out,
+                          uint64_t capacity, uint64_t* used);
 
 /* host-only: the same for a sequence of apply_exp_factor calls (term k with factors[2k], factors[2k+1]): the fused
  * Pauli-exp window passes and the terms that run alone (blob layout: csrc/pauli_window.cu, debug_pauli_lower) */

@@ -427,10 +427,11 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
 }
 
 // Host-only: the device programs the fused executor would launch for a gate list on one device (`rank`/`world` > 1: on
-// that shard of a sharded state, identity layout), serialised for a CPU interpreter (layout: window.cu, debug_lower).
+// that shard of a sharded state; `phys` = logical -> physical qubit map it runs under, NULL = identity), serialised for
+// a CPU interpreter (layout: window.cu, debug_lower).
 // *used = bytes needed; QI_ERR_INVALID_ARGUMENT with payload[0] = needed size when `capacity` is too small.
-int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gates, uint64_t count, int window_regs, uint8_t* blob,
-                   uint64_t capacity, uint64_t* used) {
+int qi_debug_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys, const qi_gate* gates, uint64_t count, int window_regs,
+                   uint8_t* blob, uint64_t capacity, uint64_t* used) {
     if (count && !gates) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "gates is NULL");
     if (world < 1 || (world & (world - 1)) || world > 16 || rank < 0 || rank >= world) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "bad rank / world");
     int p = 0;
@@ -441,7 +442,7 @@ int qi_debug_lower(uint32_t num_qubits, int rank, int world, const qi_gate* gate
     s.len = 1ull << s.n_local;
     s.rank = rank;
     s.world = world;
-    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    for (int i = 0; i < 64; i++) s.phys[i] = phys ? phys[i] : (uint8_t)i;
     if (!window_supported(&s)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few local qubits for the window executor");
     std::vector<PhysGate> run;
     for (uint64_t i = 0; i < count; i++) {

@@ -651,6 +651,65 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
     return QI_OK;
 }
 
+// Host-only: the stages apply_circuit_sharded runs for a gate list on `world` ranks, as a u64 stream a test can replay
+// on the CPU (tests/test_sharded_emulation.py): nstages, then per stage
+//   phys[64] (logical -> physical map the stage runs under), ntake, take[ntake] (gate indices, circuit order),
+//   nex, G[nex], L[nex] (the exchange after the stage: global positions G swapped with local positions L; 0 = none)
+// and finally phys[64] after the last stage.  Same decisions as the engine (staged_walk, plan_exchange, lazy SWAPs).
+int qi_debug_shard_stages(uint32_t total_qubits, int world, const qi_gate* gates, uint64_t count, uint64_t* out, uint64_t capacity,
+                          uint64_t* used) {
+    if (world != 1 && world != 2 && world != 4 && world != 8) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "world must be 1, 2, 4 or 8");
+    if (count && !gates) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "gates is NULL");
+    qi_state s;
+    s.num_qubits = total_qubits;
+    s.n_local = total_qubits - log2i(world);
+    s.len = 1ull << s.n_local;
+    s.world = world;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<uint64_t> rec;
+    rec.push_back(0);
+    uint64_t nstages = 0;
+    auto put_phys = [&]() { for (int i = 0; i < 64; i++) rec.push_back(s.phys[i]); };
+    const bool lazy = ctx().opt_lazy_swap != 0;
+    uint64_t first = 0;
+    while (first < count) {
+        uint64_t end = first;
+        while (end < count && !(lazy && gates[end].kind == QI_GATE_SWAP && gates[end].num_controls == 0)) end++;
+        const qi_gate* seg = gates + first;
+        size_t ex_slot = 0;            // where the pending stage's exchange record starts
+        QI_TRY(staged_walk(&s, seg, end - first,
+            [&](const std::vector<uint64_t>& take) -> int {
+                nstages++;
+                put_phys();
+                rec.push_back(take.size());
+                for (uint64_t i : take) rec.push_back(first + i);
+                ex_slot = rec.size();
+                rec.push_back(0);                      // no exchange unless one follows
+                return QI_OK;
+            },
+            [&](const std::vector<int>& G, const std::vector<int>& L) -> int {
+                rec[ex_slot] = G.size();
+                for (int g : G) rec.push_back((uint64_t)g);
+                for (int l : L) rec.push_back((uint64_t)l);
+                for (size_t k = 0; k < G.size(); k++) {
+                    int qg = logical_at(&s, G[k]), ql = logical_at(&s, L[k]);
+                    if (qg >= 0) s.phys[qg] = (uint8_t)L[k];
+                    if (ql >= 0) s.phys[ql] = (uint8_t)G[k];
+                }
+                return QI_OK;
+            }));
+        if (end < count) std::swap(s.phys[gates[end].targets[0]], s.phys[gates[end].targets[1]]);
+        first = end + 1;
+    }
+    put_phys();
+    rec[0] = nstages;
+    if (used) *used = rec.size();
+    if (rec.size() > capacity || !out) return fail(QI_ERR_INVALID_ARGUMENT, rec.size(), capacity, "buffer too small");
+    memcpy(out, rec.data(), rec.size() * sizeof(uint64_t));
+    return QI_OK;
+}
+
 // Host-only planner for Pauli-exp sequences (`repeats` repetitions of the term list, e.g. Trotter steps): number of
 // exchanges the engine performs on `world` ranks (no device access; same decisions on every rank).
 int qi_shard_plan_pauli(uint32_t total_qubits, int world, const qi_pauli_term* terms, uint64_t count, uint64_t repeats,

@@ -24,16 +24,18 @@ PHYS = np.dtype([("kind", "<i4"), ("t0", "<i4"), ("t1", "<i4"), ("pad", "<i4"), 
 assert DOP.itemsize == 112 and PHYS.itemsize == 88
 
 
-def lower(circuit, n, rank=0, world=1, regs=0):
-    """Serialised programs for a Circuit of this package (one run of operator gates)."""
+def lower(circuit, n, rank=0, world=1, regs=0, phys=None):
+    """Serialised programs for a Circuit of this package (one run of operator gates); `phys` = the logical -> physical
+    qubit map the run starts under (64 entries, default identity)."""
     from quant_iron_b200 import _ffi
     runs = circuit._lower()
     assert len(runs) == 1 and runs[0][0] == "ops"
     used = C.c_uint64()
     cap = 1 << 20
+    pmap = (C.c_uint8 * 64)(*phys) if phys is not None else None
     while True:
         blob = (C.c_uint8 * cap)()
-        st = _ffi.lib.qi_debug_lower(n, rank, world, runs[0][1], runs[0][2], regs, blob, cap, C.byref(used))
+        st = _ffi.lib.qi_debug_lower(n, rank, world, pmap, runs[0][1], runs[0][2], regs, blob, cap, C.byref(used))
         if st == 0:
             return bytes(blob[:used.value])
         if used.value > cap:
