@@ -735,6 +735,75 @@ static void lower_gate(Pass& ps, const PhysGate& g, bool merge) {
     }
 }
 
+// ---- late placement of unconditional phase tables ----------------------------------------------------------------
+// merge_diag puts a diagonal gate into the latest open group that no later op blocks, else opens a new group at the
+// current end of the pass; a pass that spans several layers ends up with several unconditional tables although a table
+// op costs as much as two Hadamards.  Every uncontrolled single-qubit diagonal gate commutes with every op that does
+// not use its qubit non-diagonally, so inside the pass it may sit anywhere between the previous and the next such op:
+// an interval.  The fewest tables that serve all gates is the minimum piercing set of those intervals -- greedy by
+// the earliest right end, i.e. every table is placed as LATE as its most urgent member allows.
+static void repack_unconditional_tables(Pass& ps) {
+    const size_t n = ps.ops.size();
+    struct Item { int q; amp_t f0, f1; size_t lo, hi; };
+    std::vector<Item> items;
+    std::vector<char> drop(n, 0);
+    auto n_uses = [&](const HOp& h, int q) { return h.kind >= WK_X && h.kind <= kLastPairKind && h.target == q; };
+    size_t tables = 0;
+    for (size_t i = 0; i < n; i++) {
+        const HOp& h = ps.ops[i];
+        if (h.kind != WK_TABLE) continue;
+        const DiagGroup& g = ps.groups[h.group];
+        if (g.hub >= 0 || g.hub_alt >= 0) continue;
+        drop[i] = 1;
+        tables++;
+        for (size_t k = 0; k < g.bits.size(); k++) {
+            Item it{g.bits[k], g.f0[k], g.f1[k], 0, n};
+            for (size_t j = i; j-- > 0;) if (n_uses(ps.ops[j], it.q)) { it.lo = j + 1; break; }
+            for (size_t j = i + 1; j < n; j++) if (n_uses(ps.ops[j], it.q)) { it.hi = j; break; }
+            items.push_back(it);
+        }
+    }
+    if (tables < 2) return;
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.hi < b.hi; });
+    std::vector<std::vector<HOp>> insert_at(n + 1);
+    std::vector<char> used(items.size(), 0);
+    size_t new_tables = 0;
+    for (size_t a = 0; a < items.size(); a++) {
+        if (used[a]) continue;
+        const size_t point = items[a].hi;           // the table sits just before op `point`
+        DiagGroup grp;
+        for (size_t b = a; b < items.size(); b++) {
+            if (used[b] || items[b].lo > point) continue;
+            used[b] = 1;
+            grp.members++;
+            bool found = false;
+            for (size_t k = 0; k < grp.bits.size(); k++)
+                if (grp.bits[k] == items[b].q) { grp.f0[k] = cmul(grp.f0[k], items[b].f0); grp.f1[k] = cmul(grp.f1[k], items[b].f1); found = true; break; }
+            if (!found) { grp.bits.push_back(items[b].q); grp.f0.push_back(items[b].f0); grp.f1.push_back(items[b].f1); }
+        }
+        HOp op;
+        op.kind = WK_TABLE;
+        op.group = (int)ps.groups.size();
+        op.target = -2;                              // a single-member group falls back to the plain RZ form diag(f0, f1)
+        op.tmask = 1ull << grp.bits[0];
+        op.m[0] = grp.f0[0].x; op.m[1] = grp.f0[0].y; op.m[2] = grp.f1[0].x; op.m[3] = grp.f1[0].y;
+        if (grp.bits.size() == 1) grp.members = 1;   // several gates on ONE qubit are one plain op
+        ps.groups.push_back(grp);
+        insert_at[point].push_back(op);
+        new_tables++;
+    }
+    if (new_tables >= tables) return;                // nothing gained: keep the pass as it was built
+    std::vector<HOp> out;
+    out.reserve(n + new_tables);
+    for (size_t i = 0; i <= n; i++) {
+        for (const HOp& t : insert_at[i]) out.push_back(t);
+        if (i < n && !drop[i]) out.push_back(ps.ops[i]);
+    }
+    for (size_t i = 0; i < out.size(); i++)
+        if (out[i].kind == WK_TABLE) ps.groups[out[i].group].op_index = i;
+    ps.ops.swap(out);
+}
+
 // ---- host: lowering a pass to device form -----------------------------------------------------------
 // (Layout / make_layout / split_mask: window_layout.cuh)
 
@@ -1034,6 +1103,7 @@ static int schedule_passes(const qi_state* s, const std::vector<PhysGate>& gates
             steps.push_back(Step{true, last_taken, Pass(), R});
             continue;
         }
+        if (fuse && ctx().opt_late_tables) repack_unconditional_tables(ps);
         steps.push_back(Step{false, 0, std::move(ps), R});   // (measured: the 8-amplitude kernel streams ~6% slower than R = 4)
     }
     return QI_OK;
