@@ -64,6 +64,7 @@ int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_m
  *          "profile" = 1/0 per-kernel event timing; "window_regs" = 3|4|5 register qubits per window pass
  *          (default 4); "lazy_swap" = 1/0 uncontrolled SWAP as a relabelling; "absorb" = 1/0 fold CNOTs into the
  *          neighbouring single-qubit gate; "tma" = 0/1 TMA-prefetched variant of the window kernel;
+ *          "late_tables" = 1/0 unconditional phase tables placed as late as their members allow (fewest per pass);
  *          "lean" = 0/1 window passes apply H / RX / real 2x2 gates in unit form with one deferred scale per pass
  *          (half the FP64 instructions per gate; results differ from the default by rounding only; off until measured);
  *          "host_chunk_qubits", "host_min_qubits": see qi_execute_host */
