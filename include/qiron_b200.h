@@ -263,6 +263,11 @@ int qi_debug_shard_stages(uint32_t total_qubits, int world, const qi_gate* gates
 int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, const double* factors, uint8_t* blob,
                          uint64_t capacity, uint64_t* used);
 
+/* host-only: the read-only window programs of a batched SumOp expectation value (groups of terms sharing one read of the
+ * state) and the indices of the terms left to the per-term kernel (blob layout: csrc/pauli_window.cu, debug_expect_lower) */
+int qi_debug_expect_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, uint8_t* blob, uint64_t capacity,
+                          uint64_t* used);
+
 #ifdef __cplusplus
 }
 #endif

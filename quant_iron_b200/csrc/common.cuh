@@ -215,6 +215,7 @@ int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms
                            int* groups_used, std::vector<size_t>* leftover);      // ch = coefficient of each term
 int debug_pauli_schedule(const std::vector<PauliExp>& seq, std::vector<int>* terms_per_pass);
 int debug_pauli_lower(const qi_state* s, const std::vector<PauliExp>& seq, std::vector<uint8_t>* blob);
+int debug_expect_lower(const qi_state* s, const std::vector<PauliExp>& terms, std::vector<uint8_t>* blob);
 
 // gates.cu
 int validate_gate(const qi_state* s, const qi_gate* g);

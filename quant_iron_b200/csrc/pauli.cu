@@ -495,4 +495,32 @@ int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64
     return QI_OK;
 }
 
+// Host-only: the read-only window programs qi_expect_pauli_sum would launch on one device (first-fit groups of terms that
+// share a register window) and the terms left to the per-term kernel (layout: pauli_window.cu, debug_expect_lower).
+int qi_debug_expect_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, uint8_t* blob, uint64_t capacity,
+                          uint64_t* used) {
+    if (!terms || num_qubits == 0 || num_qubits > 62) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "bad argument");
+    qi_state host;                   // layout only: no device memory is touched
+    host.num_qubits = host.n_local = num_qubits;
+    host.len = 1ull << num_qubits;
+    for (int q = 0; q < 64; q++) host.phys[q] = (uint8_t)q;
+    if (!pauli_window_supported(&host)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few qubits for the window executor");
+    std::vector<PauliExp> seq(count);
+    Masks m;
+    for (uint64_t k = 0; k < count; k++) {
+        QI_TRY(term_masks(&host, &terms[k], &m));
+        memset(&seq[k], 0, sizeof(PauliExp));
+        seq[k].x = m.x;
+        seq[k].z = m.z;
+        seq[k].k0 = (3 * m.ny) & 3;
+        seq[k].ch = make_double2(terms[k].coefficient[0], terms[k].coefficient[1]);
+    }
+    std::vector<uint8_t> out;
+    QI_TRY(debug_expect_lower(&host, seq, &out));
+    if (used) *used = out.size();
+    if (out.size() > capacity || !blob) return fail(QI_ERR_INVALID_ARGUMENT, out.size(), capacity, "blob too small");
+    memcpy(blob, out.data(), out.size());
+    return QI_OK;
+}
+
 }  // extern "C"

@@ -360,18 +360,19 @@ __global__ void __launch_bounds__(128, 4) k_pauli_expect_window(const amp_t* __r
 // terms: x/z/k0 as in PauliExp, ch = the term's coefficient.  Launches one kernel per window group with `grid`
 // blocks, group j writing partials[j * grid ..]; returns the number of groups.  Terms that do not fit a window
 // are returned in `leftover` (indices into `terms`) for the per-term kernel.
-int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms, int grid, double2* partials, int max_groups,
-                           int* groups_used, std::vector<size_t>* leftover) {
-    Context& c = ctx();
+struct ExpectGroup { uint64_t window = 0; int nregs = 0; std::vector<size_t> terms; };
+
+// first-fit grouping of the terms by the window their X/Y factors need (host only)
+static void plan_expect_groups(const std::vector<PauliExp>& terms, int max_groups, std::vector<ExpectGroup>* groups_out,
+                               std::vector<size_t>* leftover) {
     constexpr int R = kPauliR;
     const uint64_t lane_mask = (1ull << kLaneQubits) - 1;
-    struct Group { uint64_t window = 0; int nregs = 0; std::vector<size_t> terms; };
-    std::vector<Group> groups;
+    std::vector<ExpectGroup>& groups = *groups_out;
     for (size_t i = 0; i < terms.size(); i++) {
         const uint64_t need = terms[i].x & ~lane_mask;
         if (__builtin_popcountll(need) > R) { leftover->push_back(i); continue; }
-        Group* best = nullptr;
-        for (Group& g : groups) {
+        ExpectGroup* best = nullptr;
+        for (ExpectGroup& g : groups) {
             if (g.terms.size() >= (size_t)kMaxPX) continue;
             if (g.nregs + __builtin_popcountll(need & ~g.window) <= R) { best = &g; break; }
         }
@@ -384,32 +385,73 @@ int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms
         best->window |= need;
         best->terms.push_back(i);
     }
+}
+
+// device program of one group (host only): (c, s) = the term's coefficient (re, im)
+static int build_expect_program(const qi_state* s, const std::vector<PauliExp>& terms, const ExpectGroup& g, PXProgram<kPauliR>* Pout,
+                                Layout* Lout) {
+    constexpr int R = kPauliR;
+    std::vector<int> regs;
+    for (int q = kLaneQubits; q < 64; q++) if ((g.window >> q) & 1) regs.push_back(q);
+    Layout L = make_layout(s, regs, R);
+    PXProgram<R>& P = *Pout;
+    memset(&P, 0, sizeof(P));
+    fill_offsets<R>(L, &P.ins, P.off);
+    P.nops = (uint32_t)g.terms.size();
+    for (size_t k = 0; k < g.terms.size(); k++) {
+        const PauliExp& t = terms[g.terms[k]];
+        PXOp& d = P.ops[k];
+        uint64_t xt = 0;
+        split_mask(L, t.x, &d.xl, &d.xr, &xt);
+        if (xt) return fail(QI_ERR_UNKNOWN, 0, 0, "pauli window: X/Y factor outside the window");
+        split_mask(L, t.z, &d.zl, &d.zr, &d.zt);
+        d.k0 = (uint32_t)(t.k0 & 3);
+        d.c = t.ch.x;
+        d.s = t.ch.y;
+    }
+    if (Lout) *Lout = L;
+    return QI_OK;
+}
+
+int run_pauli_expect_batch(const qi_state* s, const std::vector<PauliExp>& terms, int grid, double2* partials, int max_groups,
+                           int* groups_used, std::vector<size_t>* leftover) {
+    Context& c = ctx();
+    constexpr int R = kPauliR;
+    std::vector<ExpectGroup> groups;
+    plan_expect_groups(terms, max_groups, &groups, leftover);
     const uint64_t ntiles = s->len >> (kLaneQubits + R);
     for (size_t gi = 0; gi < groups.size(); gi++) {
-        const Group& g = groups[gi];
-        std::vector<int> regs;
-        for (int q = kLaneQubits; q < 64; q++) if ((g.window >> q) & 1) regs.push_back(q);
-        Layout L = make_layout(s, regs, R);
         PXProgram<R> P;
-        memset(&P, 0, sizeof(P));
-        fill_offsets<R>(L, &P.ins, P.off);
-        P.nops = (uint32_t)g.terms.size();
-        for (size_t k = 0; k < g.terms.size(); k++) {
-            const PauliExp& t = terms[g.terms[k]];
-            PXOp& d = P.ops[k];
-            uint64_t xt = 0;
-            split_mask(L, t.x, &d.xl, &d.xr, &xt);
-            if (xt) return fail(QI_ERR_UNKNOWN, 0, 0, "pauli window: X/Y factor outside the window");
-            split_mask(L, t.z, &d.zl, &d.zr, &d.zt);
-            d.k0 = (uint32_t)(t.k0 & 3);
-            d.c = t.ch.x;
-            d.s = t.ch.y;
-        }
+        QI_TRY(build_expect_program(s, terms, groups[gi], &P, nullptr));
         LaunchScope ls(KF_EXPECT, 16.0 * (double)s->len);
         k_pauli_expect_window<R><<<grid, 128, 0, c.stream>>>(s->d, ntiles, P, partials + (size_t)gi * grid);
         QI_TRY(check_launch("k_pauli_expect_window"));
     }
     *groups_used = (int)groups.size();
+    return QI_OK;
+}
+
+// host-only: the read-only window programs of a batched expectation value, serialised for the CPU interpreter in tests/:
+// u64 ngroups, per group: u64 R, u64 regs[8], u64 nops, PXOp[nops]; then u64 nleft and the indices of the terms that
+// found no group (they run on the per-term kernel)
+int debug_expect_lower(const qi_state* s, const std::vector<PauliExp>& terms, std::vector<uint8_t>* blob) {
+    auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };
+    auto put64 = [&](uint64_t v) { put(&v, 8); };
+    std::vector<ExpectGroup> groups;
+    std::vector<size_t> left;
+    plan_expect_groups(terms, 512, &groups, &left);
+    put64(groups.size());
+    for (const ExpectGroup& g : groups) {
+        PXProgram<kPauliR> P;
+        Layout L;
+        QI_TRY(build_expect_program(s, terms, g, &P, &L));
+        put64((uint64_t)kPauliR);
+        for (int j = 0; j < 8; j++) put64(j < (int)L.regs.size() ? (uint64_t)L.regs[j] : 0ull);
+        put64(P.nops);
+        put(P.ops, P.nops * sizeof(PXOp));
+    }
+    put64(left.size());
+    for (size_t i : left) put64(i);
     return QI_OK;
 }
 

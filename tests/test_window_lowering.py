@@ -222,3 +222,31 @@ def test_late_table_placement_fewer_diagonal_ops_same_state(ref):
     steps, _, _ = wi.parse(wi.lower(w.build_circuit(gpu, 30, w.random_layered_circuit(30, 40)), 30))
     per = [int(((s[3]["kind"] == wi.WK_TABLE) | (s[3]["kind"] == wi.WK_RZ)).sum()) for s in steps if s[0] == "pass"]
     assert max(per) <= 3 and sum(per) <= 130, (max(per), sum(per))
+
+
+@pytest.mark.parametrize("n,seed", [(9, 0), (11, 1), (12, 2)])
+def test_expectation_groups_match_oracle(ref, n, seed):
+    """SumOp::expectation_value batching: first-fit groups of terms sharing one register window, interpreted on the CPU,
+    plus the terms left to the per-term kernel (evaluated here with the oracle), vs the oracle's term-by-term sum."""
+    import quant_iron_b200 as gpu
+    (sg, sr), _ = _random_strings([gpu, ref], n, 50 + seed, 70)
+    psi = ref.random_state(n, 60 + seed)
+    v = np.array(psi.state_vector, dtype=np.complex128)
+    got, ngroups, left = wi.expect_groups(wi.lower_expect(sg, n), v, n)
+    for i in left:
+        got += ref.SumOp([sr[i]]).expectation_value(psi)
+    want = ref.SumOp(sr).expectation_value(psi)
+    assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+    assert 1 <= ngroups < len(sg) - len(left)
+
+
+def test_heisenberg_expectation_groups(ref):
+    """The 96 terms of the 24-site chain (BASELINE config 3) share a handful of read passes; value checked at 12 sites."""
+    import quant_iron_b200 as gpu
+    n = 12
+    hg, hr = gpu.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1), ref.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1)
+    psi = ref.random_state(n, 77)
+    got, ngroups, left = wi.expect_groups(wi.lower_expect(list(hg.terms), n), np.array(psi.state_vector), n)
+    want = hr.expectation_value(psi)
+    assert not left and ngroups <= 6
+    assert abs(got - want) <= 1e-10 * max(1.0, abs(want))

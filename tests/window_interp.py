@@ -313,3 +313,69 @@ def execute_pauli(blob, v, n):
             v[:] = float(op["c"]) * v + float(op["s"]) * (_IPOW[k] * v[idx ^ np.uint64(x)])
     assert off == len(blob)
     return passes, singles
+
+
+# ---- batched SumOp expectation (csrc/pauli_window.cu, k_pauli_expect_window) ---------------------------------------
+def lower_expect(strings, n):
+    from quant_iron_b200 import _ffi
+    arr = (_ffi.QiPauliTerm * len(strings))()
+    keep = []
+    for i, ps in enumerate(strings):
+        rec, k = ps.term()
+        arr[i] = rec
+        keep.append(k)
+    used = C.c_uint64()
+    cap = 1 << 20
+    while True:
+        blob = (C.c_uint8 * cap)()
+        st = _ffi.lib.qi_debug_expect_lower(n, arr, len(strings), blob, cap, C.byref(used))
+        if st == 0:
+            return bytes(blob[:used.value])
+        if used.value > cap:
+            cap = used.value
+            continue
+        _ffi.check(st)
+
+
+def expect_groups(blob, v, n):
+    """sum over the grouped terms of <psi| c P |psi> = sum_i conj(psi[i]) c i^(k0 + 2 popc(i & z)) psi[i ^ x]; returns
+    (value, number of groups, indices of the terms left to the per-term kernel)."""
+    off = 0
+
+    def u64():
+        nonlocal off
+        val = struct.unpack_from("<Q", blob, off)[0]
+        off += 8
+        return val
+
+    idx = np.arange(1 << n, dtype=np.uint64)
+    lane = idx & np.uint64(31)
+    total = 0j
+    ngroups = u64()
+    for _ in range(ngroups):
+        R = u64()
+        regs = [u64() for _ in range(8)][:R]
+        nops = u64()
+        ops = np.frombuffer(blob, PXOP, nops, off)
+        off += nops * PXOP.itemsize
+        slot = np.zeros(1 << n, dtype=np.uint64)
+        for j, q in enumerate(regs):
+            slot |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)
+        tile = np.zeros(1 << n, dtype=np.uint64)
+        t = 0
+        for q in range(5, n):
+            if q in regs:
+                continue
+            tile |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(t)
+            t += 1
+        for op in ops:
+            x = int(op["xl"])
+            for j, q in enumerate(regs):
+                if (int(op["xr"]) >> j) & 1:
+                    x |= 1 << q
+            flip = _parity(tile & np.uint64(op["zt"])) + _parity(lane & np.uint64(op["zl"])) + _parity(slot & np.uint64(op["zr"]))
+            k = (int(op["k0"]) + 2 * flip) & 3
+            total += complex(op["c"], op["s"]) * np.vdot(v, _IPOW[k] * v[idx ^ np.uint64(x)])
+    left = [u64() for _ in range(u64())]
+    assert off == len(blob)
+    return total, ngroups, left
