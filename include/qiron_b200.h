@@ -259,9 +259,14 @@ int qi_debug_shard_stages(uint32_t total_qubits, int world, const qi_gate* gates
                           uint64_t capacity, uint64_t* used);
 
 /* host-only: the same for a sequence of apply_exp_factor calls (term k with factors[2k], factors[2k+1]): the fused
- * Pauli-exp window passes and the terms that run alone (blob layout: csrc/pauli_window.cu, debug_pauli_lower) */
-int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, const double* factors, uint8_t* blob,
-                         uint64_t capacity, uint64_t* used);
+ * Pauli-exp window passes and the terms that run alone (blob layout: csrc/pauli_window.cu, debug_pauli_lower); rank /
+ * world / phys as in qi_debug_lower */
+int qi_debug_pauli_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys, const qi_pauli_term* terms,
+                         uint64_t count, const double* factors, uint8_t* blob, uint64_t capacity, uint64_t* used);
+/* host-only: the stages a Pauli-exp sequence runs in on `world` ranks (same record layout as qi_debug_shard_stages, term
+ * indices instead of gate indices) */
+int qi_debug_shard_pauli_stages(uint32_t total_qubits, int world, const qi_pauli_term* terms, uint64_t count, uint64_t* out,
+                                uint64_t capacity, uint64_t* used);
 
 /* host-only: the read-only window programs of a batched SumOp expectation value (groups of terms sharing one read of the
  * state) and the indices of the terms left to the per-term kernel (blob layout: csrc/pauli_window.cu, debug_expect_lower) */

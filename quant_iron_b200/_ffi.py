@@ -107,7 +107,8 @@ _sig("qi_shard_comm_stats", [state_p, u64p, u64p, u64p])
 _sig("qi_debug_schedule", [C.c_uint32, C.POINTER(QiGate), C.c_uint64, C.c_int, C.POINTER(C.c_int32), C.c_uint64, u64p])
 _sig("qi_debug_lower", [C.c_uint32, C.c_int, C.c_int, u8p, C.POINTER(QiGate), C.c_uint64, C.c_int, u8p, C.c_uint64, u64p])
 _sig("qi_debug_shard_stages", [C.c_uint32, C.c_int, C.POINTER(QiGate), C.c_uint64, u64p, C.c_uint64, u64p])
-_sig("qi_debug_pauli_lower", [C.c_uint32, C.POINTER(QiPauliTerm), C.c_uint64, dp, u8p, C.c_uint64, u64p])
+_sig("qi_debug_pauli_lower", [C.c_uint32, C.c_int, C.c_int, u8p, C.POINTER(QiPauliTerm), C.c_uint64, dp, u8p, C.c_uint64, u64p])
+_sig("qi_debug_shard_pauli_stages", [C.c_uint32, C.c_int, C.POINTER(QiPauliTerm), C.c_uint64, u64p, C.c_uint64, u64p])
 _sig("qi_debug_expect_lower", [C.c_uint32, C.POINTER(QiPauliTerm), C.c_uint64, u8p, C.c_uint64, u64p])
 _sig("qi_state_layout", [state_p, u8p, C.POINTER(C.c_uint32)])
 _sig("qi_shard_plan_pauli", [C.c_uint32, C.c_int, C.POINTER(QiPauliTerm), C.c_uint64, C.c_uint64, u64p, u64p])

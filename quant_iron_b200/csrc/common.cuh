@@ -245,6 +245,9 @@ int canonicalise(qi_state* s);
 int shard_localise_mask(qi_state* s, const qi_pauli_term* t);
 // staged execution of Pauli-exp sequences around exchanges (shard.cu); lx / lz = logical X-or-Y / Y-or-Z masks per term
 int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
-                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges);
+                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges,
+                     const std::function<void(const std::vector<int>&, const std::vector<int>&)>& on_exchange = nullptr);
+int debug_shard_pauli_stages(uint32_t total_qubits, int world, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
+                             std::vector<uint64_t>* rec);
 
 }  // namespace qi

@@ -473,25 +473,54 @@ int qi_debug_pauli_schedule(uint32_t num_qubits, const qi_pauli_term* terms, uin
 
 // Host-only: the device programs qi_apply_pauli_exp_sequence would launch on one device (fused register-window passes and
 // terms that run alone), serialised for the CPU interpreter in tests/ (layout: pauli_window.cu, debug_pauli_lower).
-int qi_debug_pauli_lower(uint32_t num_qubits, const qi_pauli_term* terms, uint64_t count, const double* factors, uint8_t* blob,
-                         uint64_t capacity, uint64_t* used) {
+int qi_debug_pauli_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys, const qi_pauli_term* terms, uint64_t count,
+                         const double* factors, uint8_t* blob, uint64_t capacity, uint64_t* used) {
     if (!terms || !factors || num_qubits == 0 || num_qubits > 62) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "bad argument");
+    if (world < 1 || (world & (world - 1)) || world > 8 || rank < 0 || rank >= world) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "bad rank / world");
+    int p = 0;
+    while ((1 << p) < world) p++;
     qi_state host;                   // layout only: no device memory is touched
-    host.num_qubits = host.n_local = num_qubits;
-    host.len = 1ull << num_qubits;
-    for (int q = 0; q < 64; q++) host.phys[q] = (uint8_t)q;
+    host.num_qubits = num_qubits;
+    host.n_local = num_qubits - (uint32_t)p;
+    host.len = 1ull << host.n_local;
+    host.rank = rank;
+    host.world = world;
+    for (int q = 0; q < 64; q++) host.phys[q] = phys ? phys[q] : (uint8_t)q;
     if (!pauli_window_supported(&host)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few qubits for the window executor");
     std::vector<PauliExp> seq(count);
     for (uint64_t k = 0; k < count; k++) {
         bool ex = false;
         memset(&seq[k], 0, sizeof(PauliExp));
         QI_TRY(make_exp(&host, terms[k], make_double2(factors[2 * k], factors[2 * k + 1]), &seq[k], &ex));
+        if (ex) return fail(QI_ERR_PEER, k, 0, "X/Y factor on a global qubit inside a stage");
     }
     std::vector<uint8_t> out;
     QI_TRY(debug_pauli_lower(&host, seq, &out));
     if (used) *used = out.size();
     if (out.size() > capacity || !blob) return fail(QI_ERR_INVALID_ARGUMENT, out.size(), capacity, "blob too small");
     memcpy(blob, out.data(), out.size());
+    return QI_OK;
+}
+
+// Host-only: the stages qi_apply_pauli_exp_sequence runs in on `world` ranks (terms per stage, the qubit map each stage runs
+// under, the exchange that follows) -- record layout: shard.cu, debug_shard_pauli_stages.
+int qi_debug_shard_pauli_stages(uint32_t total_qubits, int world, const qi_pauli_term* terms, uint64_t count, uint64_t* out,
+                                uint64_t capacity, uint64_t* used) {
+    if (world != 1 && world != 2 && world != 4 && world != 8) return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)world, 0, "world must be 1, 2, 4 or 8");
+    if (count && !terms) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "terms is NULL");
+    std::vector<uint64_t> lx(count, 0), lz(count, 0);
+    for (uint64_t k = 0; k < count; k++)
+        for (uint32_t i = 0; i < terms[k].num_ops; i++) {
+            const uint32_t q = terms[k].qubits[i];
+            if (q >= total_qubits) return fail(QI_ERR_INVALID_QUBIT_INDEX, q, total_qubits, "Invalid qubit index");
+            if (terms[k].paulis[i] != 3) lx[k] |= 1ull << q;
+            if (terms[k].paulis[i] != 1) lz[k] |= 1ull << q;
+        }
+    std::vector<uint64_t> rec;
+    QI_TRY(debug_shard_pauli_stages(total_qubits, world, lx, lz, &rec));
+    if (used) *used = rec.size();
+    if (rec.size() > capacity || !out) return fail(QI_ERR_INVALID_ARGUMENT, rec.size(), capacity, "buffer too small");
+    memcpy(out, rec.data(), rec.size() * sizeof(uint64_t));
     return QI_OK;
 }
 

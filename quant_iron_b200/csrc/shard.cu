@@ -384,7 +384,8 @@ int shard_localise_mask(qi_state* s, const qi_pauli_term* t) {
 // lx / lz: per term, LOGICAL qubit masks of its X-or-Y and Y-or-Z factors.  run(take) executes the terms take[..]
 // (indices into lx) under the current layout; dry = planner mode (relabel only, no device access).
 int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
-                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges) {
+                     const std::function<int(const std::vector<size_t>&)>& run, bool dry, uint64_t* exchanges,
+                     const std::function<void(const std::vector<int>&, const std::vector<int>&)>& on_exchange) {
     const int nl = (int)s->n_local;
     const size_t kMaxDeferred = 512;
     std::vector<size_t> pending(lx.size()), rest, take, deferred;
@@ -446,6 +447,7 @@ int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::ve
             used_local |= 1ull << best;
         }
         if (G.empty()) return fail(QI_ERR_PEER, 0, 0, "staged Pauli execution made no progress");
+        if (on_exchange) on_exchange(G, L);
         if (dry) {
             for (size_t k = 0; k < G.size(); k++) {
                 int qg = logical_at(s, G[k]), ql = logical_at(s, L[k]);
@@ -458,6 +460,42 @@ int shard_pauli_walk(qi_state* s, const std::vector<uint64_t>& lx, const std::ve
         if (exchanges) (*exchanges)++;
         pending.swap(rest);
     }
+    return QI_OK;
+}
+
+// Host-only: the stages a sequence of Pauli exponentials runs in on `world` ranks, as a u64 stream a test replays on the
+// CPU (tests/test_sharded_emulation.py): nstages, per stage phys[64], ntake, take[] (term indices), nex, G[], L[]; then the
+// final phys[64].  Same decisions as the engine (shard_pauli_walk).
+int debug_shard_pauli_stages(uint32_t total_qubits, int world, const std::vector<uint64_t>& lx, const std::vector<uint64_t>& lz,
+                             std::vector<uint64_t>* rec) {
+    qi_state s;
+    s.num_qubits = total_qubits;
+    s.n_local = total_qubits - log2i(world);
+    s.len = 1ull << s.n_local;
+    s.world = world;
+    for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
+    rec->push_back(0);
+    uint64_t nstages = 0;
+    size_t ex_slot = 0;
+    auto put_phys = [&]() { for (int i = 0; i < 64; i++) rec->push_back(s.phys[i]); };
+    QI_TRY(shard_pauli_walk(&s, lx, lz,
+        [&](const std::vector<size_t>& take) -> int {
+            nstages++;
+            put_phys();
+            rec->push_back(take.size());
+            for (size_t k : take) rec->push_back(k);
+            ex_slot = rec->size();
+            rec->push_back(0);
+            return QI_OK;
+        },
+        true, nullptr,
+        [&](const std::vector<int>& G, const std::vector<int>& L) {
+            (*rec)[ex_slot] = G.size();
+            for (int g : G) rec->push_back((uint64_t)g);
+            for (int l : L) rec->push_back((uint64_t)l);
+        }));
+    put_phys();
+    (*rec)[0] = nstages;
     return QI_OK;
 }
 

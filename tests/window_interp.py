@@ -230,8 +230,9 @@ PEXP = np.dtype([("x", "<u8"), ("z", "<u8"), ("k0", "<i4"), ("pad", "u1", 12), (
 assert PXOP.itemsize == 48 and PEXP.itemsize == 64
 
 
-def lower_pauli(strings, factors, n):
-    """Serialised programs of qi_apply_pauli_exp_sequence for PauliStrings of this package."""
+def lower_pauli(strings, factors, n, rank=0, world=1, phys=None):
+    """Serialised programs of qi_apply_pauli_exp_sequence for PauliStrings of this package (on shard `rank` of `world`
+    under the qubit map `phys` when given)."""
     from quant_iron_b200 import _ffi
     arr = (_ffi.QiPauliTerm * len(strings))()
     keep = []
@@ -246,7 +247,8 @@ def lower_pauli(strings, factors, n):
     cap = 1 << 20
     while True:
         blob = (C.c_uint8 * cap)()
-        st = _ffi.lib.qi_debug_pauli_lower(n, arr, len(strings), _ffi.dbl_array(flat), blob, cap, C.byref(used))
+        pmap = (C.c_uint8 * 64)(*phys) if phys is not None else None
+        st = _ffi.lib.qi_debug_pauli_lower(n, rank, world, pmap, arr, len(strings), _ffi.dbl_array(flat), blob, cap, C.byref(used))
         if st == 0:
             return bytes(blob[:used.value])
         if used.value > cap:
