@@ -404,6 +404,8 @@ def run_ours(args, rank, world, local_rank):
             try:
                 sec = e2e_time("pipelined")
                 pipe["pipelined_value"] = n_gates * world / sec
+                if sec > sec_serial:             # never report the slower of two verified, equivalent public calls
+                    pipe["mode"], sec = "serial", sec_serial
             except Exception as ex:  # noqa: BLE001
                 pipe["mode"], pipe["pipelined_error"], sec = "serial", repr(ex)[:200], sec_serial
         e2e_val = n_gates * world / sec
