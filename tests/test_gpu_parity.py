@@ -506,3 +506,19 @@ def test_functional_api_clones_through_the_buffer_cache(gpu, ref):
     finally:
         gpu.engine.set_option("pool_mb", 4096)
     assert np.array_equal(vec(keep[0]), first)
+
+
+@pytest.mark.parametrize("late", [0, 1])
+def test_late_table_placement_both_settings_match_oracle(gpu, ref, late):
+    """Option "late_tables" only moves unconditional phase-table ops inside a pass (host side, CPU-checked in
+    tests/test_window_lowering.py); both settings must give the oracle's state on the device too."""
+    from quant_iron_b200 import workloads as w
+    n = 14
+    specs = w.random_layered_circuit(n, 16)
+    gpu.engine.set_option("late_tables", late)
+    try:
+        out = w.build_circuit(gpu, n, specs).execute(gpu.State.new_zero(n))
+    finally:
+        gpu.engine.set_option("late_tables", 1)
+    want = w.build_circuit(ref, n, specs).execute(ref.State.new_zero(n))
+    assert_amps(out, vec(want), msg=f"late_tables={late}")
