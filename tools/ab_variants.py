@@ -15,7 +15,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "quant_iron_b200", "csrc")
 OUT = os.path.join(ROOT, "quant_iron_b200", "lib", "variants")
-SOURCES = ["engine", "state", "gates", "window", "pauli", "pauli_window", "measure", "shard"]
+SOURCES = ["engine", "state", "gates", "window", "pauli", "pauli_window", "measure", "shard", "host_pipeline"]
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
         "--expt-relaxed-constexpr", "-shared"]
 
