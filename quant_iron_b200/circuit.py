@@ -438,8 +438,8 @@ class CircuitBuilder:
     def matchgate(self, target, theta, phi1, phi2):
         return self.add_gate(Gate.Operator(Matchgate(theta, phi1, phi2), [target], []))
 
-    def cmatchgate(self, target, theta, phi1, phi2, controls):
-        return self.add_gate(Gate.Operator(Matchgate(theta, phi1, phi2), [target], controls))
+    def cmatchgate(self, target, controls, theta, phi1, phi2):  # circuit.rs:1194-1200: controls SECOND (State::cmatchgate has them last)
+        return self.add_gate(Gate.Operator(Matchgate(theta, phi1, phi2), [target], list(controls)))
 
     def add_operator_gate(self, op, targets, controls=()):  # circuit.rs:1215-1224
         return self.add_gate(Gate.Operator(op, targets, controls))

@@ -43,7 +43,7 @@ def _fuzz_builders(apis, n, seed, count=120, lazy_swaps=False):
             elif kind == 10: b.cswap_gate(t, t2, [c1])
             elif kind == 11: b.toffoli_gate(c1, c2, t)
             elif kind == 12: b.ry_phase_gate(t, ang, 0.5 * ang)
-            elif kind == 13: b.cmatchgate(mt, ang, 0.3 * ang, -0.7 * ang, mc) if mc else b.matchgate(mt, ang, 0.3 * ang, -0.7 * ang)
+            elif kind == 13: b.cmatchgate(mt, mc, ang, 0.3 * ang, -0.7 * ang) if mc else b.matchgate(mt, ang, 0.3 * ang, -0.7 * ang)
             elif kind == 14: b.rz_gate(t, ang)
             else: b.cnot_gate(t, c1)
     return [b.build() for b in builders]

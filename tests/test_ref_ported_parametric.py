@@ -62,7 +62,7 @@ def test_parametric_matchgate(qi):
     same(qi, qi.CircuitBuilder(2).parametric_matchgate(0, p.clone()).build_final(),
          qi.CircuitBuilder(2).matchgate(0, a, b, c).build_final(), 2)
     same(qi, qi.CircuitBuilder(3).parametric_cmatchgate(0, [2], p.clone()).build_final(),
-         qi.CircuitBuilder(3).cmatchgate(0, a, b, c, [2]).build_final(), 3)
+         qi.CircuitBuilder(3).cmatchgate(0, [2], a, b, c).build_final(), 3)
 
 
 def test_parametric_change_parameter_value_after_build(qi):
