@@ -2,8 +2,10 @@
 //
 // The reference is compiled Rust and its toolchain is absent from this image, so the compiled-language
 // host side is C++: the same names, argument order and error behaviour as the crate's public surface
-// for the state-vector path (State gate methods, Operator, Gate/Circuit/CircuitBuilder, Subroutine::qft,
-// PauliString/SumOp, measure, Trotter, heisenberg_1d/2d, ising_1d/2d).  Citations are file:line under the reference root.
+// for the state-vector path: every State constructor, metric and gate method (state.rs:99-2345), Operator and the built-in
+// operators, Gate (all four kinds) / Circuit / CircuitBuilder with the full adder set (circuit.rs:288-1742), Subroutine::qft,
+// PauliString / SumOp, measure / measure_n with custom bases, Trotter, heisenberg_1d/2d, ising_1d/2d.  Not mirrored here:
+// the parametric gates and the QASM emitter (Python host mirror only).  Citations are file:line under the reference root.
 // `&self -> State` methods are device clone + in-place kernel; methods with a trailing underscore act in place.
 #pragma once
 #include <cmath>
@@ -100,6 +102,14 @@ struct Unitary2 : Operator {   // operator.rs:2058-2275
         r.m[1][0] = cplx(s, 0.0); r.m[1][1] = cplx(e.real() * c, e.imag() * c);
         return r;
     }
+    static Unitary2 from_ry_phase_dagger(double theta, double phi) {   // operator.rs:2173-2192: [[c, s], [-e^{-i phi} s, e^{-i phi} c]]
+        Unitary2 r;
+        double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+        cplx e(std::cos(phi), -std::sin(phi));
+        r.m[0][0] = cplx(c, 0.0); r.m[0][1] = cplx(s, 0.0);
+        r.m[1][0] = cplx(-e.real() * s, -e.imag() * s); r.m[1][1] = cplx(e.real() * c, e.imag() * c);
+        return r;
+    }
 };
 struct Matchgate : Operator {   // operator.rs:852-1019
     double theta, phi1, phi2;
@@ -109,7 +119,21 @@ struct Matchgate : Operator {   // operator.rs:852-1019
     std::vector<double> params() const override { return {theta, phi1, phi2}; }
 };
 
-enum class MeasurementBasis { Computational = 0, X = 1, Y = 2 };   // measurement.rs:76-86 (Custom: State::measure_custom_)
+enum class MeasurementBasis { Computational = 0, X = 1, Y = 2, Custom = 3 };   // measurement.rs:76-86
+// `MeasurementBasis::Custom([[Complex<f64>; 2]; 2])`: the enum above plus its payload
+struct Basis {
+    MeasurementBasis kind = MeasurementBasis::Computational;
+    cplx u[2][2] = {{1.0, 0.0}, {0.0, 1.0}};
+    Basis() = default;
+    Basis(MeasurementBasis k) : kind(k) {}   // implicit: plain variants
+    static Basis custom(const cplx (&m)[2][2]) { Basis b; b.kind = MeasurementBasis::Custom; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) b.u[i][j] = m[i][j]; return b; }
+};
+// measurement.rs:15-60
+struct MeasurementResult {
+    Basis basis;
+    std::vector<size_t> indices;
+    std::vector<uint8_t> outcomes;
+};
 
 struct GateRecord {   // owns the control list a qi_gate points into
     qi_gate g;
@@ -143,6 +167,7 @@ public:
     State& operator=(State o) { std::swap(h_, o.h_); return *this; }
     ~State() { if (h_) qi_state_free(h_); }
     qi_state* handle() const { return h_; }
+    static State adopt(qi_state* h) { return State(h); }   // takes ownership of a handle the C ABI returned
 
     static State from_vector(const std::vector<cplx>& v) {   // State::new, state.rs:99-127
         qi_state* h = nullptr;
@@ -154,8 +179,23 @@ public:
     static State new_plus(size_t n) { qi_state* h = nullptr; check(qi_state_new_plus((uint32_t)n, &h)); return State(h); }
     static State new_minus(size_t n) { qi_state* h = nullptr; check(qi_state_new_minus((uint32_t)n, &h)); return State(h); }
     static State new_ghz(size_t n) { qi_state* h = nullptr; check(qi_state_new_ghz((uint32_t)n, &h)); return State(h); }
+    static State new_hartree_fock(size_t num_electrons, size_t num_orbitals) {   // state.rs:140-151
+        if (num_orbitals == 0 || num_orbitals < num_electrons) throw Error(QI_ERR_INVALID_INPUT_VALUE, "InvalidInputValue", num_orbitals, 0, "new_hartree_fock");
+        return new_basis_n(num_orbitals, ((1ull << num_electrons) - 1ull) << (num_orbitals - num_electrons));
+    }
+    // Bell states, state.rs:28-66 / 330-373
+    static State new_phi_plus() { const double a = std::sqrt(0.5); return from_vector({a, 0.0, 0.0, a}); }
+    static State new_phi_minus() { const double a = std::sqrt(0.5); return from_vector({a, 0.0, 0.0, -a}); }
+    static State new_psi_plus() { const double a = std::sqrt(0.5); return from_vector({0.0, a, a, 0.0}); }
+    static State new_psi_minus() { const double a = std::sqrt(0.5); return from_vector({0.0, a, -a, 0.0}); }
 
     size_t num_qubits() const { return qi_state_num_qubits(h_); }
+    State conj() const { State s(*this); check(qi_conj(s.h_)); return s; }                                  // state.rs:397-403
+    bool equals_without_phase(const State& o) const {                                                        // state.rs:384-390
+        return num_qubits() == o.num_qubits() && std::fabs(std::abs(inner_product(o)) - 1.0) < 1.1920928955078125e-07;
+    }
+    double fs_dist(const State& o) const { return std::acos(std::abs(normalise().inner_product(o.normalise()))); }          // state.rs:470-480
+    double fs_fidelity(const State& o) const { double a = std::abs(normalise().inner_product(o.normalise())); return a * a; } // state.rs:492-498
     std::vector<cplx> state_vector() const {
         std::vector<cplx> v(qi_state_len(h_));
         check(qi_state_to_host(h_, reinterpret_cast<double*>(v.data()), v.size()));
@@ -220,6 +260,72 @@ public:
     State x_multi(const std::vector<size_t>& qs) const { return multi(PauliX(), qs); }
     State cx_multi(const std::vector<size_t>& t, const std::vector<size_t>& c) const { return multi(PauliX(), t, c); }
     State cp_multi(const std::vector<size_t>& t, const std::vector<size_t>& c, double a) const { return multi(PhaseShift(a), t, c); }
+    // the rest of the family (state.rs:1019-2345): <g>_multi(qubits), c<g>_multi(targets, controls)
+    using Q = std::vector<size_t>;
+    State ch_multi(const Q& t, const Q& c) const { return multi(Hadamard(), t, c); }
+    State y_multi(const Q& q) const { return multi(PauliY(), q); }
+    State cy_multi(const Q& t, const Q& c) const { return multi(PauliY(), t, c); }
+    State z_multi(const Q& q) const { return multi(PauliZ(), q); }
+    State cz_multi(const Q& t, const Q& c) const { return multi(PauliZ(), t, c); }
+    State i_multi(const Q& q) const { return multi(Identity(), q); }
+    State ci_multi(const Q& t, const Q& c) const { return multi(Identity(), t, c); }
+    State s_multi(const Q& q) const { return multi(PhaseS(), q); }
+    State cs_multi(const Q& t, const Q& c) const { return multi(PhaseS(), t, c); }
+    State t_multi(const Q& q) const { return multi(PhaseT(), q); }
+    State ct_multi(const Q& t, const Q& c) const { return multi(PhaseT(), t, c); }
+    State s_dag_multi(const Q& q) const { return multi(PhaseSdag(), q); }
+    State cs_dag_multi(const Q& t, const Q& c) const { return multi(PhaseSdag(), t, c); }
+    State t_dag_multi(const Q& q) const { return multi(PhaseTdag(), q); }
+    State ct_dag_multi(const Q& t, const Q& c) const { return multi(PhaseTdag(), t, c); }
+    State p_multi(const Q& q, double a) const { return multi(PhaseShift(a), q); }
+    State rx_multi(const Q& q, double a) const { return multi(RotateX(a), q); }
+    State crx_multi(const Q& t, const Q& c, double a) const { return multi(RotateX(a), t, c); }
+    State ry_multi(const Q& q, double a) const { return multi(RotateY(a), q); }
+    State cry_multi(const Q& t, const Q& c, double a) const { return multi(RotateY(a), t, c); }
+    State rz_multi(const Q& q, double a) const { return multi(RotateZ(a), q); }
+    State crz_multi(const Q& t, const Q& c, double a) const { return multi(RotateZ(a), t, c); }
+    State unitary(size_t q, const cplx (&u)[2][2]) const { return Unitary2::make(u).apply(*this, {q}); }
+    State unitary_multi(const Q& q, const cplx (&u)[2][2]) const { return multi(Unitary2::make(u), q); }
+    State cunitary_multi(const Q& t, const Q& c, const cplx (&u)[2][2]) const { return multi(Unitary2::make(u), t, c); }
+    State ry_phase_multi(const Q& q, double th, double ph) const { return multi(Unitary2::from_ry_phase(th, ph), q); }
+    State cry_phase_gates(const Q& t, const Q& c, double th, double ph) const { return multi(Unitary2::from_ry_phase(th, ph), t, c); }
+    State ry_phase_dag(size_t q, double th, double ph) const { return Unitary2::from_ry_phase_dagger(th, ph).apply(*this, {q}); }
+    State ry_phase_dag_multi(const Q& q, double th, double ph) const { return multi(Unitary2::from_ry_phase_dagger(th, ph), q); }
+    State cry_phase_dag_gates(const Q& t, const Q& c, double th, double ph) const { return multi(Unitary2::from_ry_phase_dagger(th, ph), t, c); }
+    State cswap(size_t t1, size_t t2, const Q& controls) const { return SWAP().apply(*this, {t1, t2}, controls); }
+    State cmatchgate(size_t q, double th, double p1, double p2, const Q& controls) const { return Matchgate(th, p1, p2).apply(*this, {q}, controls); }   // state.rs:2317-2324
+
+    // State::measure (state.rs:525-730) with the crate's return type; the shared-seed contract replaces rand::rng()
+    // (draw `draw` of the stream seeded `seed`).  An empty qubit list measures every qubit (531-541).
+    std::pair<MeasurementResult, State> measure(const Basis& basis, const Q& qubits, uint64_t seed, uint64_t draw = 0) const {
+        State out(*this);
+        std::vector<uint32_t> q(qubits.begin(), qubits.end());
+        MeasurementResult r;
+        r.basis = basis;
+        r.indices = qubits;
+        if (qubits.empty()) for (size_t k = 0; k < num_qubits(); k++) r.indices.push_back(k);
+        r.outcomes.assign(r.indices.size(), 0);
+        uint64_t bin = 0;
+        double u[8];
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) { u[4 * a + 2 * b] = basis.u[a][b].real(); u[4 * a + 2 * b + 1] = basis.u[a][b].imag(); }
+        check(qi_measure(out.h_, (int)basis.kind, basis.kind == MeasurementBasis::Custom ? u : nullptr, q.data(), (uint32_t)q.size(), seed, draw,
+                         r.outcomes.data(), &bin));
+        return {r, out};
+    }
+    // State::measure_n (state.rs:750-784): n independent measurements of the same state; measurement k uses draw k
+    std::vector<std::pair<MeasurementResult, State>> measure_n(const Basis& basis, const Q& qubits, size_t n, uint64_t seed) const {
+        if (n == 0) throw Error(QI_ERR_INVALID_NUMBER_OF_MEASUREMENTS, "InvalidNumberOfMeasurements", 0, 0, "measure_n");
+        std::vector<std::pair<MeasurementResult, State>> out;
+        out.reserve(n);
+        for (size_t k = 0; k < n; k++) out.push_back(measure(basis, qubits, seed, k));
+        return out;
+    }
+    std::vector<double> probabilities(const Q& qubits) const {   // un-normalised marginal table, state.rs:559-588
+        std::vector<uint32_t> q(qubits.begin(), qubits.end());
+        std::vector<double> out((size_t)1 << qubits.size());
+        check(qi_probabilities(h_, q.data(), (uint32_t)q.size(), out.data()));
+        return out;
+    }
 
     // State::measure (state.rs:525-730), in place; returns outcomes[j] = bit j of the sampled bin
     std::vector<uint8_t> measure_(MeasurementBasis basis, const std::vector<size_t>& qubits, uint64_t seed, uint64_t draw = 0) {
@@ -290,6 +396,15 @@ public:
     std::vector<PauliString> terms;
     explicit SumOp(std::vector<PauliString> t = {}) : terms(std::move(t)) {}
     size_t num_terms() const { return terms.size(); }
+    SumOp with_term(const PauliString& t) const { SumOp r(*this); r.terms.push_back(t); return r; }
+    State apply(const State& s) const {   // pauli_string.rs:453-466: sum_k P_k psi (a new state; empty sum = 0 * psi)
+        std::vector<std::unique_ptr<PauliString::Term>> keep;
+        std::vector<qi_pauli_term> arr;
+        for (auto& t : terms) { keep.push_back(t.term()); arr.push_back(keep.back()->t); }
+        qi_state* h = nullptr;
+        check(qi_apply_pauli_sum(s.handle(), arr.data(), arr.size(), &h));
+        return State::adopt(h);
+    }
     cplx expectation_value(const State& s) const {
         std::vector<std::unique_ptr<PauliString::Term>> keep;
         std::vector<qi_pauli_term> arr;
@@ -400,10 +515,29 @@ inline SumOp ising_2d_uniform(size_t n, size_t m, double h, double j, double mu)
     return ising_2d(hh, jj, jj, mu);
 }
 
-// gate.rs:13-52 (operator gates), circuit.rs:27-202, circuit.rs:288-1742, subroutine.rs:90-160
+// gate.rs:13-52, circuit.rs:27-202, circuit.rs:288-1742, subroutine.rs:90-160
 struct Gate {
-    std::shared_ptr<Operator> op;
-    std::vector<size_t> targets, controls;
+    enum class Kind { Operator, Measurement, PauliString, PauliTimeEvolution };
+    Kind kind = Kind::Operator;
+    std::shared_ptr<Operator> op;                    // Operator
+    std::vector<size_t> targets, controls;           // Operator: targets / controls; Measurement: measured qubits in `targets`
+    Basis basis;                                     // Measurement (gate.rs:26)
+    std::shared_ptr<PauliString> pauli_string;       // PauliString / PauliTimeEvolution (gate.rs:38, 46)
+    double time = 0.0;                               // PauliTimeEvolution
+    Gate() = default;
+    Gate(std::shared_ptr<Operator> o, std::vector<size_t> t, std::vector<size_t> c) : op(std::move(o)), targets(std::move(t)), controls(std::move(c)) {}
+    static Gate measurement(const Basis& b, std::vector<size_t> qubits) { Gate g; g.kind = Kind::Measurement; g.basis = b; g.targets = std::move(qubits); return g; }
+    static Gate pauli_string_gate(const PauliString& ps) { Gate g; g.kind = Kind::PauliString; g.pauli_string = std::make_shared<PauliString>(ps); for (auto& kv : ps.ops()) g.targets.push_back(kv.first); return g; }
+    static Gate pauli_time_evolution(const PauliString& ps, double t) { Gate g = pauli_string_gate(ps); g.kind = Kind::PauliTimeEvolution; g.time = t; return g; }
+    // Gate::apply (gate.rs:99-122), in place; `seed` feeds a Measurement gate's draw (shared-seed contract)
+    void apply_(State& s, uint64_t seed = 0) const {
+        switch (kind) {
+            case Kind::Operator: s.apply_(*op, targets, controls); break;
+            case Kind::Measurement: s = s.measure(basis, targets, seed).second; break;
+            case Kind::PauliString: s = pauli_string->apply_normalised(s); break;     // coefficient dropped, gate.rs:115-117
+            case Kind::PauliTimeEvolution: s = pauli_string->apply_exp_neg_i_dt(s, time); break;
+        }
+    }
 };
 struct Subroutine {
     std::vector<Gate> gates;
@@ -412,27 +546,75 @@ struct Subroutine {
     static Subroutine iqft(const std::vector<size_t>& qubits, size_t num_qubits);
 };
 class Circuit {
+    static void validate(const Gate& g, size_t n) {   // circuit.rs:35-52
+        for (size_t q : g.targets) if (q >= n) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n, "circuit");
+        for (size_t q : g.controls) if (q >= n) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n, "circuit");
+    }
+
 public:
     std::vector<Gate> gates;
     size_t num_qubits;
     explicit Circuit(size_t n) : num_qubits(n) {}
-    void execute_(State& s) const {   // Circuit::execute's loop -> one fused run
+    static Circuit with_gates(std::vector<Gate> gs, size_t n) { Circuit c(n); for (auto& g : gs) validate(g, n); c.gates = std::move(gs); return c; }   // circuit.rs:66-82
+    void add_gate(const Gate& g) { validate(g, num_qubits); gates.push_back(g); }                                       // circuit.rs:97-111
+    size_t get_num_qubits() const { return num_qubits; }
+    const std::vector<Gate>& get_gates() const { return gates; }
+    // Circuit::execute's loop (circuit.rs:160-172), in place: consecutive operator gates = ONE fused run (qi_apply_circuit),
+    // consecutive PauliTimeEvolution gates = ONE fused exp sequence; measurement / PauliString gates run on their own.
+    // Gate k of the circuit draws from the stream seeded `seed + k`.
+    void execute_(State& s, uint64_t seed = 0) const {
         if (s.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", s.num_qubits(), 0, "execute");
-        std::vector<GateRecord> recs;
-        recs.reserve(gates.size());
-        for (auto& g : gates) recs.push_back(make_record(*g.op, g.targets, g.controls));
-        std::vector<qi_gate> arr;
-        for (auto& r : recs) { r.g.controls = r.controls.data(); arr.push_back(r.g); }
-        check(qi_apply_circuit(s.handle(), arr.data(), arr.size()));
+        size_t i = 0;
+        while (i < gates.size()) {
+            const Gate::Kind k = gates[i].kind;
+            size_t j = i;
+            while (j < gates.size() && gates[j].kind == k && (k == Gate::Kind::Operator || k == Gate::Kind::PauliTimeEvolution)) j++;
+            if (k == Gate::Kind::Operator) {
+                std::vector<GateRecord> recs;
+                recs.reserve(j - i);
+                for (size_t g = i; g < j; g++) recs.push_back(make_record(*gates[g].op, gates[g].targets, gates[g].controls));
+                std::vector<qi_gate> arr;
+                for (auto& r : recs) { r.g.controls = r.controls.data(); arr.push_back(r.g); }
+                check(qi_apply_circuit(s.handle(), arr.data(), arr.size()));
+            } else if (k == Gate::Kind::PauliTimeEvolution) {
+                std::vector<std::unique_ptr<PauliString::Term>> keep;
+                std::vector<qi_pauli_term> arr;
+                std::vector<double> f;
+                for (size_t g = i; g < j; g++) {
+                    if (gates[g].pauli_string->coefficient().imag() != 0.0)      // gate.rs:116-118 -> pauli_string.rs:281-284
+                        throw Error(QI_ERR_INVALID_PAULI_STRING_COEFFICIENT, "InvalidPauliStringCoefficient", 0, 0, "imaginary coefficient");
+                    keep.push_back(gates[g].pauli_string->term());
+                    arr.push_back(keep.back()->t);
+                    f.push_back(0.0);
+                    f.push_back(-gates[g].time);
+                }
+                check(qi_apply_pauli_exp_sequence(s.handle(), arr.data(), arr.size(), f.data()));
+            } else {
+                gates[i].apply_(s, seed + i);
+                j = i + 1;
+            }
+            i = j;
+        }
     }
-    State execute(const State& initial) const { State s(initial); execute_(s); return s; }   // circuit.rs:160-172
+    State execute(const State& initial, uint64_t seed = 0) const { State s(initial); execute_(s, seed); return s; }   // circuit.rs:160-172
+    std::vector<State> trace_execution(const State& initial, uint64_t seed = 0) const {   // circuit.rs:188-202
+        if (initial.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", initial.num_qubits(), 0, "trace_execution");
+        std::vector<State> out;
+        State cur(initial);
+        out.push_back(cur);
+        for (size_t k = 0; k < gates.size(); k++) { gates[k].apply_(cur, seed + k); out.push_back(cur); }
+        return out;
+    }
     // Circuit::execute for a HOST-resident state vector (state.rs:74-81): in -> circuit -> out with `work` as the device
-    // buffer; the two PCIe copies overlap the circuit (qi_execute_host).  `out` may alias `in`.
+    // buffer; the two PCIe copies overlap the circuit (qi_execute_host).  `out` may alias `in`.  Operator gates only.
     void execute_host_(State& work, const std::complex<double>* in, std::complex<double>* out, size_t len) const {
         if (work.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", work.num_qubits(), 0, "execute_host");
         std::vector<GateRecord> recs;
         recs.reserve(gates.size());
-        for (auto& g : gates) recs.push_back(make_record(*g.op, g.targets, g.controls));
+        for (auto& g : gates) {
+            if (g.kind != Gate::Kind::Operator) throw Error(QI_ERR_INVALID_ARGUMENT, "InvalidArgument", 0, 0, "execute_host_ takes operator gates only");
+            recs.push_back(make_record(*g.op, g.targets, g.controls));
+        }
         std::vector<qi_gate> arr;
         for (auto& r : recs) { r.g.controls = r.controls.data(); arr.push_back(r.g); }
         check(qi_execute_host(work.handle(), arr.data(), arr.size(), reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), len));
@@ -441,7 +623,8 @@ public:
 class CircuitBuilder {
     std::vector<Gate> gates_;
     size_t n_;
-    template <class Op> CircuitBuilder& each(Op op, const std::vector<size_t>& ts, const std::vector<size_t>& cs = {}) {
+    using Q = std::vector<size_t>;
+    template <class Op> CircuitBuilder& each(Op op, const Q& ts, const Q& cs = {}) {
         auto sp = std::make_shared<Op>(op);
         for (size_t q : ts) gates_.push_back(Gate{sp, {q}, cs});
         return *this;
@@ -449,29 +632,58 @@ class CircuitBuilder {
 
 public:
     explicit CircuitBuilder(size_t n) : n_(n) {}
-    CircuitBuilder& h_gate(size_t q) { return each(Hadamard(), {q}); }
-    CircuitBuilder& h_gates(const std::vector<size_t>& qs) { return each(Hadamard(), qs); }
-    CircuitBuilder& x_gate(size_t q) { return each(PauliX(), {q}); }
-    CircuitBuilder& rx_gate(size_t q, double a) { return each(RotateX(a), {q}); }
-    CircuitBuilder& ry_gate(size_t q, double a) { return each(RotateY(a), {q}); }
-    CircuitBuilder& rz_gate(size_t q, double a) { return each(RotateZ(a), {q}); }
-    CircuitBuilder& p_gate(size_t q, double a) { return each(PhaseShift(a), {q}); }
-    CircuitBuilder& cp_gates(const std::vector<size_t>& ts, const std::vector<size_t>& cs, double a) { return each(PhaseShift(a), ts, cs); }
-    CircuitBuilder& cx_gates(const std::vector<size_t>& ts, const std::vector<size_t>& cs) { return each(PauliX(), ts, cs); }
+    CircuitBuilder& add_gate(const Gate& g) { gates_.push_back(g); return *this; }                     // circuit.rs:311-314
+    CircuitBuilder& add_gates(const std::vector<Gate>& gs) { gates_.insert(gates_.end(), gs.begin(), gs.end()); return *this; }
+    // <g>_gate(qubit), <g>_gates(qubits), c<g>_gates(targets, controls)  (circuit.rs:378-870)
+#define QI_BUILDER_FAMILY(NAME, OP)                                                              \
+    CircuitBuilder& NAME##_gate(size_t q) { return each(OP(), {q}); }                             \
+    CircuitBuilder& NAME##_gates(const Q& qs) { return each(OP(), qs); }                          \
+    CircuitBuilder& c##NAME##_gates(const Q& ts, const Q& cs) { return each(OP(), ts, cs); }
+    QI_BUILDER_FAMILY(h, Hadamard)
+    QI_BUILDER_FAMILY(x, PauliX)
+    QI_BUILDER_FAMILY(y, PauliY)
+    QI_BUILDER_FAMILY(z, PauliZ)
+    QI_BUILDER_FAMILY(s, PhaseS)
+    QI_BUILDER_FAMILY(sdag, PhaseSdag)
+    QI_BUILDER_FAMILY(t, PhaseT)
+    QI_BUILDER_FAMILY(tdag, PhaseTdag)
+#undef QI_BUILDER_FAMILY
+    CircuitBuilder& id_gate(size_t q) { return each(Identity(), {q}); }
+    CircuitBuilder& id_gates(const Q& qs) { return each(Identity(), qs); }
+    CircuitBuilder& ci_gates(const Q& ts, const Q& cs) { return each(Identity(), ts, cs); }
+#define QI_BUILDER_ANGLE(NAME, OP)                                                                         \
+    CircuitBuilder& NAME##_gate(size_t q, double a) { return each(OP(a), {q}); }                            \
+    CircuitBuilder& NAME##_gates(const Q& qs, double a) { return each(OP(a), qs); }                         \
+    CircuitBuilder& c##NAME##_gates(const Q& ts, const Q& cs, double a) { return each(OP(a), ts, cs); }
+    QI_BUILDER_ANGLE(p, PhaseShift)
+    QI_BUILDER_ANGLE(rx, RotateX)
+    QI_BUILDER_ANGLE(ry, RotateY)
+    QI_BUILDER_ANGLE(rz, RotateZ)
+#undef QI_BUILDER_ANGLE
+    // circuit.rs:875-945: the unitarity check fires here (Result in the crate, exception here)
+    CircuitBuilder& unitary_gate(size_t q, const cplx (&u)[2][2]) { return each(Unitary2::make(u), {q}); }
+    CircuitBuilder& unitary_gates(const Q& qs, const cplx (&u)[2][2]) { return each(Unitary2::make(u), qs); }
+    CircuitBuilder& cunitary_gates(const Q& ts, const Q& cs, const cplx (&u)[2][2]) { return each(Unitary2::make(u), ts, cs); }
+    CircuitBuilder& ry_phase_gate(size_t q, double th, double ph) { return each(Unitary2::from_ry_phase(th, ph), {q}); }
+    CircuitBuilder& ry_phase_gates(const Q& qs, double th, double ph) { return each(Unitary2::from_ry_phase(th, ph), qs); }
+    CircuitBuilder& cry_phase_gates(const Q& ts, const Q& cs, double th, double ph) { return each(Unitary2::from_ry_phase(th, ph), ts, cs); }
+    CircuitBuilder& ry_phase_dag_gate(size_t q, double th, double ph) { return each(Unitary2::from_ry_phase_dagger(th, ph), {q}); }
+    CircuitBuilder& ry_phase_dag_gates(const Q& qs, double th, double ph) { return each(Unitary2::from_ry_phase_dagger(th, ph), qs); }
+    CircuitBuilder& cry_phase_dag_gates(const Q& ts, const Q& cs, double th, double ph) { return each(Unitary2::from_ry_phase_dagger(th, ph), ts, cs); }
     CircuitBuilder& cnot_gate(size_t target, size_t control) { gates_.push_back(Gate{std::make_shared<CNOT>(), {target}, {control}}); return *this; }   // circuit.rs:1071
     CircuitBuilder& swap_gate(size_t a, size_t b) { gates_.push_back(Gate{std::make_shared<SWAP>(), {a, b}, {}}); return *this; }
+    CircuitBuilder& cswap_gate(size_t a, size_t b, const Q& cs) { gates_.push_back(Gate{std::make_shared<SWAP>(), {a, b}, cs}); return *this; }          // circuit.rs:1096
     CircuitBuilder& toffoli_gate(size_t c1, size_t c2, size_t t) { gates_.push_back(Gate{std::make_shared<Toffoli>(), {t}, {c1, c2}}); return *this; }   // circuit.rs:1118
+    CircuitBuilder& matchgate(size_t q, double th, double p1, double p2) { gates_.push_back(Gate{std::make_shared<Matchgate>(th, p1, p2), {q}, {}}); return *this; }   // circuit.rs:1169
+    CircuitBuilder& cmatchgate(size_t q, const Q& cs, double th, double p1, double p2) { gates_.push_back(Gate{std::make_shared<Matchgate>(th, p1, p2), {q}, cs}); return *this; }   // circuit.rs:1194: controls second
+    CircuitBuilder& pauli_string_gate(const PauliString& ps) { gates_.push_back(Gate::pauli_string_gate(ps)); return *this; }                            // circuit.rs:1130
+    CircuitBuilder& pauli_time_evolution_gate(const PauliString& ps, double t) { gates_.push_back(Gate::pauli_time_evolution(ps, t)); return *this; }
+    template <class Op> CircuitBuilder& add_operator_gate(const Op& op, const Q& ts, const Q& cs = {}) { gates_.push_back(Gate{std::make_shared<Op>(op), ts, cs}); return *this; }   // circuit.rs:1215-1224
+    CircuitBuilder& measure_gate(const Basis& basis, const Q& qubits) { gates_.push_back(Gate::measurement(basis, qubits)); return *this; }              // circuit.rs:1737
     CircuitBuilder& add_subroutine(const Subroutine& s) { gates_.insert(gates_.end(), s.gates.begin(), s.gates.end()); return *this; }
     Subroutine build_subroutine() { Subroutine s{gates_, n_}; gates_.clear(); return s; }
-    Circuit build() const {   // Circuit::with_gates validation, circuit.rs:35-52
-        Circuit c(n_);
-        for (auto& g : gates_) {
-            for (size_t q : g.targets) if (q >= n_) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n_, "build");
-            for (size_t q : g.controls) if (q >= n_) throw Error(QI_ERR_INVALID_QUBIT_INDEX, "InvalidQubitIndex", q, n_, "build");
-        }
-        c.gates = gates_;
-        return c;
-    }
+    Circuit build() const { return Circuit::with_gates(gates_, n_); }   // circuit.rs:340-343 (validation: circuit.rs:35-52)
+    Circuit build_final() { Circuit c = Circuit::with_gates(gates_, n_); gates_.clear(); return c; }   // circuit.rs:352-358
 };
 inline Subroutine Subroutine::qft(const std::vector<size_t>& q, size_t num_qubits) {   // subroutine.rs:90-112
     CircuitBuilder b(num_qubits);

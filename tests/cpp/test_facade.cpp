@@ -93,6 +93,50 @@ int main(int argc, char** argv) {
         qi_set_option("host_min_qubits", 26);
         EXPECT(State::from_vector(host).approx_eq(want) && work.approx_eq(want));
     }
+    // the wider surface added late in round 1 (run with --surface until it has run on hardware once)
+    if (argc > 1 && std::string(argv[1]) == "--surface") {
+        using Q = std::vector<size_t>;
+        // Bell constructors (state.rs:330-373) vs the circuit that prepares them; metrics (state.rs:384-498)
+        State bell = State::new_zero(2).h(0).cnot(0, 1);
+        EXPECT(bell.approx_eq(State::new_phi_plus()) && bell.equals_without_phase(State::new_phi_plus() * cplx(0.0, 1.0)));
+        EXPECT(std::fabs(bell.fs_fidelity(State::new_phi_minus())) < 1e-12 && std::fabs(bell.fs_dist(State::new_phi_minus()) - M_PI / 2) < 1e-9);
+        EXPECT(State::new_hartree_fock(2, 4).approx_eq(State::new_basis_n(4, 12)));
+        // State families vs the builder's (state.rs:1019-2345 vs circuit.rs:378-1224)
+        State p3 = State::new_plus(3);
+        EXPECT(p3.cs_multi({0}, {1}).approx_eq(CircuitBuilder(3).cs_gates({0}, {1}).build().execute(p3)));
+        EXPECT(p3.crx_multi({0, 2}, {1}, 0.7).approx_eq(CircuitBuilder(3).crx_gates({0, 2}, {1}, 0.7).build().execute(p3)));
+        EXPECT(p3.ry_phase_dag(1, 0.7, 0.3).ry_phase(1, 0.7, 0.3).approx_eq(p3));
+        EXPECT(p3.cswap(0, 1, {2}).approx_eq(CircuitBuilder(3).cswap_gate(0, 1, {2}).build().execute(p3)));
+        EXPECT(p3.cmatchgate(0, 0.4, 0.2, 0.1, {2}).approx_eq(CircuitBuilder(3).cmatchgate(0, {2}, 0.4, 0.2, 0.1).build().execute(p3)));
+        const cplx xm[2][2] = {{0.0, 1.0}, {1.0, 0.0}};
+        EXPECT(State::new_zero(2).unitary(1, xm).approx_eq(State::new_basis_n(2, 2)));
+        // SumOp::apply (pauli_string.rs:453-466): (X0 + Z0)|0> = |1> + |0>
+        auto sv = SumOp({PauliString(1.0).with_op(0, Pauli::X), PauliString(1.0).with_op(0, Pauli::Z)}).apply(State::new_zero(1)).state_vector();
+        EXPECT(std::abs(sv[0] - cplx(1.0, 0.0)) < 1e-12 && std::abs(sv[1] - cplx(1.0, 0.0)) < 1e-12);
+        // a circuit with every gate kind (gate.rs:99-122): runs of operator gates, a PauliString gate (normalised, coefficient
+        // dropped), time-evolution gates, a measurement
+        PauliString zx = PauliString(cplx(0.5 * M_PI, 0.0)).with_op(0, Pauli::Z).with_op(1, Pauli::X);
+        Circuit mixed = CircuitBuilder(2).h_gate(0).pauli_time_evolution_gate(zx, 0.5).pauli_string_gate(PauliString(3.0).with_op(0, Pauli::Z))
+                            .h_gate(0).measure_gate(MeasurementBasis::Computational, {0}).build();
+        State direct = PauliString(3.0).with_op(0, Pauli::Z).apply_normalised(zx.apply_exp_neg_i_dt(State::new_zero(2).h(0), 0.5)).h(0);
+        auto trace = mixed.trace_execution(State::new_zero(2), 7);
+        EXPECT(trace.size() == 6 && trace[4].approx_eq(direct));
+        State fin = mixed.execute(State::new_zero(2), 7);
+        EXPECT(std::fabs(fin.norm_sqr() - 1.0) < 1e-12 && fin.approx_eq(trace[5]));
+        // measure / measure_n with the crate's return shape (state.rs:525-784): Bell outcomes are perfectly correlated
+        auto shots = State::new_phi_plus().measure_n(MeasurementBasis::Computational, Q{}, 16, 20260003);
+        EXPECT(shots.size() == 16);
+        for (auto& sh : shots) EXPECT(sh.first.outcomes.size() == 2 && sh.first.outcomes[0] == sh.first.outcomes[1] &&
+                                      sh.second.approx_eq(State::new_basis_n(2, sh.first.outcomes[0] ? 3 : 0)));
+        EXPECT(throws("InvalidNumberOfMeasurements", 0, 0, [] { State::new_zero(1).measure_n(MeasurementBasis::X, {0}, 0, 1); }));
+        // measuring |0> in the custom basis U = H is measuring |+>... the outcome state is U^dagger |b> (state.rs:708-720)
+        const double r = 1.0 / std::sqrt(2.0);
+        const cplx hm[2][2] = {{r, r}, {r, -r}};
+        auto mr = State::new_zero(1).measure(Basis::custom(hm), {0}, 5);
+        EXPECT(std::fabs(mr.second.norm_sqr() - 1.0) < 1e-12 && std::fabs(std::abs(mr.second.amplitude(0)) - r) < 1e-12);
+        auto pr = State::new_phi_plus().probabilities({0, 1});
+        EXPECT(pr.size() == 4 && std::fabs(pr[0] - 0.5) < 1e-12 && std::fabs(pr[3] - 0.5) < 1e-12 && pr[1] < 1e-12);
+    }
     std::printf(failures ? "C++ facade: %d FAILURES\n" : "C++ facade: ALL PASS\n", failures);
     return failures ? 1 : 0;
 }

@@ -73,6 +73,65 @@ int main() {
     const cplx good[2][2] = {{cplx(0, 0), cplx(1, 0)}, {cplx(1, 0), cplx(0, 0)}};
     EXPECT(Unitary2::make(good).kind() == QI_GATE_U2);
     EXPECT(rejected);
+    // the builder's full adder surface (circuit.rs:378-1224, 1737), counted as the reference's macro tests count it
+    // (macros_tests.rs:47-74, 134-211, 231-247, 267-305): one gate per target, validation in build / build_final
+    {
+        using Q = std::vector<size_t>;
+        const cplx xm[2][2] = {{0.0, 1.0}, {1.0, 0.0}};
+        CircuitBuilder b(3);
+        b.h_gate(0).h_gates({0, 1}).x_gate(1).x_gates({1, 2}).y_gate(2).y_gates({0, 2}).z_gate(0).z_gates({0, 1}).s_gate(1).s_gates({1, 2})
+            .t_gate(2).t_gates({0, 2}).id_gate(0).id_gates({0, 1}).sdag_gate(1).sdag_gates({1, 2}).tdag_gate(2).tdag_gates({0, 2});
+        EXPECT(b.build().gates.size() == 27);
+        EXPECT(throws("InvalidQubitIndex", 3, 3, [&] { CircuitBuilder(3).tdag_gates({0, 3}).build_final(); }));
+        CircuitBuilder c4(4);
+        auto four = [&](auto add) { add(Q{0}, Q{1}); add(Q{0, 1}, Q{2}); add(Q{0}, Q{1, 2}); add(Q{0, 1}, Q{2, 3}); };
+        four([&](Q t, Q c) { c4.ch_gates(t, c); });
+        four([&](Q t, Q c) { c4.cx_gates(t, c); });
+        four([&](Q t, Q c) { c4.cy_gates(t, c); });
+        four([&](Q t, Q c) { c4.cz_gates(t, c); });
+        four([&](Q t, Q c) { c4.cs_gates(t, c); });
+        four([&](Q t, Q c) { c4.ct_gates(t, c); });
+        four([&](Q t, Q c) { c4.csdag_gates(t, c); });
+        four([&](Q t, Q c) { c4.ctdag_gates(t, c); });
+        four([&](Q t, Q c) { c4.crx_gates(t, c, M_PI / 4); });
+        four([&](Q t, Q c) { c4.cry_gates(t, c, M_PI / 4); });
+        four([&](Q t, Q c) { c4.cry_phase_gates(t, c, M_PI / 4, M_PI / 2); });
+        c4.cmatchgate(0, {1}, M_PI / 4, M_PI / 2, M_PI / 3).cmatchgate(0, {1, 2}, M_PI / 4, M_PI / 2, M_PI / 3);
+        four([&](Q t, Q c) { c4.crz_gates(t, c, M_PI / 4); });
+        four([&](Q t, Q c) { c4.cp_gates(t, c, M_PI / 4); });
+        EXPECT(c4.build().gates.size() == 6 * 13 + 2);
+        EXPECT(throws("InvalidQubitIndex", 6, 4, [&] { CircuitBuilder(4).cx_gates({0, 1}, {2, 6}).build(); }));
+        CircuitBuilder u(4);
+        u.unitary_gate(0, xm).unitary_gates({0, 1}, xm).cunitary_gates({0}, {1}, xm).cunitary_gates({0, 1}, {2}, xm).cunitary_gates({0}, {1, 2}, xm)
+            .cunitary_gates({0, 1}, {2, 3}, xm);
+        EXPECT(u.build().gates.size() == 9);
+        const cplx bad[2][2] = {{1.0, 1.0}, {0.0, 1.0}};
+        EXPECT(throws("NonUnitaryMatrix", 0, 0, [&] { CircuitBuilder(2).unitary_gate(0, bad); }));
+        CircuitBuilder m(3);
+        m.measure_gate(MeasurementBasis::X, {0}).measure_gate(MeasurementBasis::X, {1, 2}).measure_gate(MeasurementBasis::Y, {0})
+            .measure_gate(MeasurementBasis::Computational, {1, 2}).measure_gate(Basis::custom(xm), {0}).measure_gate(Basis::custom(xm), {1, 2});
+        Circuit mc = m.build();
+        EXPECT(mc.gates.size() == 6 && mc.gates[4].kind == Gate::Kind::Measurement && mc.gates[4].basis.kind == MeasurementBasis::Custom);
+        CircuitBuilder a(3);
+        a.rx_gate(0, 1.0).ry_gate(1, 1.0).rz_gate(2, 1.0).p_gate(0, 1.0).ry_phase_gate(1, 1.0, 0.5).matchgate(0, 1.0, 0.5, 0.25).rx_gates({0, 1}, 1.0)
+            .ry_gates({1, 2}, 1.0).rz_gates({0, 2}, 1.0).ry_phase_gates({0, 1}, 1.0, 0.5).p_gates({0, 1, 2}, 1.0);
+        EXPECT(a.build().gates.size() == 4 + 2 + 2 + 2 + 3 + 4);
+        CircuitBuilder t5(5);
+        t5.cnot_gate(0, 1).swap_gate(1, 2).cswap_gate(0, 1, {2}).cswap_gate(0, 1, {2, 3}).toffoli_gate(0, 1, 2);
+        EXPECT(t5.build().gates.size() == 5);
+        EXPECT(throws("InvalidQubitIndex", 6, 5, [&] { CircuitBuilder(5).cswap_gate(0, 1, {2, 6}).build(); }));
+        // Pauli gates carry their targets (gate.rs:38-52); build_final empties the builder (circuit.rs:352-358)
+        PauliString ps = PauliString(cplx(0.5, 0.0)).with_op(0, Pauli::X).with_op(2, Pauli::Z);
+        CircuitBuilder pb(3);
+        pb.pauli_string_gate(ps).pauli_time_evolution_gate(ps, 0.1);
+        Circuit pc = pb.build_final();
+        EXPECT(pc.gates.size() == 2 && pc.gates[0].kind == Gate::Kind::PauliString && pc.gates[1].kind == Gate::Kind::PauliTimeEvolution);
+        EXPECT(pc.gates[1].targets.size() == 2 && pc.gates[1].time == 0.1 && pb.build().gates.empty());
+        EXPECT(throws("InvalidQubitIndex", 5, 3, [&] { CircuitBuilder(3).pauli_string_gate(PauliString(cplx(1.0, 0.0)).with_op(5, Pauli::Y)).build(); }));
+        // ry_phase / ry_phase_dagger are inverses of each other (operator.rs:2140-2192): U^dagger = dagger form
+        Unitary2 f = Unitary2::from_ry_phase(0.7, 0.3), d = Unitary2::from_ry_phase_dagger(0.7, 0.3);
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) EXPECT(std::abs(std::conj(f.m[j][i]) - d.m[i][j]) < 1e-15);
+    }
     std::printf(failures ? "C++ facade host logic: %d FAILURES\n" : "C++ facade host logic: ALL PASS\n", failures);
     return failures ? 1 : 0;
 }

@@ -46,3 +46,16 @@ def test_facade_execute_host_on_gpu():
     r = subprocess.run([BIN, "--execute-host"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.unproven
+def test_facade_wider_surface_on_gpu():
+    """State gate families, Bell / Hartree-Fock constructors, metrics, SumOp::apply, circuits with measurement and Pauli
+    gates, measure / measure_n with custom bases through the C++ facade."""
+    if not os.path.exists(BIN):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([BIN, "--surface"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASS" in r.stdout
