@@ -4,15 +4,17 @@
 // host side is C++: the same names, argument order and error behaviour as the crate's public surface
 // for the state-vector path: every State constructor, metric and gate method (state.rs:99-2345), Operator and the built-in
 // operators, Gate (all four kinds) / Circuit / CircuitBuilder with the full adder set (circuit.rs:288-1742), Subroutine::qft,
-// PauliString / SumOp, measure / measure_n with custom bases, Trotter, heisenberg_1d/2d, ising_1d/2d.  Not mirrored here:
-// the parametric gates and the QASM emitter (Python host mirror only).  Citations are file:line under the reference root.
+// PauliString / SumOp, measure / measure_n with custom bases, Trotter, heisenberg_1d/2d, ising_1d/2d, Parameter and the
+// parametric gates.  Not mirrored here: the QASM emitter (Python host mirror only).  Citations are file:line under the reference root.
 // `&self -> State` methods are device clone + in-place kernel; methods with a trailing underscore act in place.
 #pragma once
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <array>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -366,6 +368,7 @@ public:
     cplx coefficient() const { return coefficient_; }
     size_t len() const { return ops_.size(); }
     const std::map<size_t, Pauli>& ops() const { return ops_; }
+    std::vector<struct Gate> to_gates() const;   // pauli_string.rs:118-122: one Pauli operator gate per factor
     struct Term { qi_pauli_term t; std::vector<uint32_t> q; std::vector<uint8_t> p; };
     std::unique_ptr<Term> term() const {
         auto r = std::make_unique<Term>();
@@ -515,20 +518,51 @@ inline SumOp ising_2d_uniform(size_t n, size_t m, double h, double j, double mu)
     return ising_2d(hh, jj, jj, mu);
 }
 
+// components/parametric/parameter.rs:13-74: a shared, mutable cell of N values.  Copying shares the cell (Rust's Arc
+// clone); deep_clone copies it.
+template <size_t N>
+class Parameter {
+    struct Cell { std::array<double, N> v; std::mutex mu; };
+    std::shared_ptr<Cell> cell_;
+
+public:
+    explicit Parameter(const std::array<double, N>& initial) : cell_(std::make_shared<Cell>()) { cell_->v = initial; }
+    Parameter clone() const { return *this; }
+    Parameter deep_clone() const { return Parameter(get()); }
+    std::array<double, N> get() const { std::lock_guard<std::mutex> lk(cell_->mu); return cell_->v; }
+    void set(const std::array<double, N>& v) { std::lock_guard<std::mutex> lk(cell_->mu); cell_->v = v; }
+};
+// components/parametric/parametric_gate.rs:6-24: resolved to concrete operator gates every time it is applied
+struct Gate;
+struct ParametricGate {
+    virtual ~ParametricGate() = default;
+    virtual std::vector<Gate> to_concrete_gates(const std::vector<size_t>& targets, const std::vector<size_t>& controls) const = 0;
+};
+
 // gate.rs:13-52, circuit.rs:27-202, circuit.rs:288-1742, subroutine.rs:90-160
 struct Gate {
-    enum class Kind { Operator, Measurement, PauliString, PauliTimeEvolution };
+    enum class Kind { Operator, Measurement, PauliString, PauliTimeEvolution, Parametric };
     Kind kind = Kind::Operator;
     std::shared_ptr<Operator> op;                    // Operator
     std::vector<size_t> targets, controls;           // Operator: targets / controls; Measurement: measured qubits in `targets`
     Basis basis;                                     // Measurement (gate.rs:26)
     std::shared_ptr<PauliString> pauli_string;       // PauliString / PauliTimeEvolution (gate.rs:38, 46)
     double time = 0.0;                               // PauliTimeEvolution
+    std::shared_ptr<ParametricGate> p_gate;          // Parametric (gate.rs:30): targets / controls as for Operator
     Gate() = default;
     Gate(std::shared_ptr<Operator> o, std::vector<size_t> t, std::vector<size_t> c) : op(std::move(o)), targets(std::move(t)), controls(std::move(c)) {}
     static Gate measurement(const Basis& b, std::vector<size_t> qubits) { Gate g; g.kind = Kind::Measurement; g.basis = b; g.targets = std::move(qubits); return g; }
     static Gate pauli_string_gate(const PauliString& ps) { Gate g; g.kind = Kind::PauliString; g.pauli_string = std::make_shared<PauliString>(ps); for (auto& kv : ps.ops()) g.targets.push_back(kv.first); return g; }
     static Gate pauli_time_evolution(const PauliString& ps, double t) { Gate g = pauli_string_gate(ps); g.kind = Kind::PauliTimeEvolution; g.time = t; return g; }
+    static Gate parametric(std::shared_ptr<ParametricGate> pg, std::vector<size_t> t, std::vector<size_t> c) {
+        Gate g; g.kind = Kind::Parametric; g.p_gate = std::move(pg); g.targets = std::move(t); g.controls = std::move(c); return g;
+    }
+    // Circuit::to_concrete_circuit's per-gate rule (circuit.rs:205-217)
+    std::vector<Gate> concrete() const {
+        if (kind == Kind::Parametric) return p_gate->to_concrete_gates(targets, controls);
+        if (kind == Kind::PauliString) return pauli_string->to_gates();
+        return {*this};
+    }
     // Gate::apply (gate.rs:99-122), in place; `seed` feeds a Measurement gate's draw (shared-seed contract)
     void apply_(State& s, uint64_t seed = 0) const {
         switch (kind) {
@@ -536,9 +570,45 @@ struct Gate {
             case Kind::Measurement: s = s.measure(basis, targets, seed).second; break;
             case Kind::PauliString: s = pauli_string->apply_normalised(s); break;     // coefficient dropped, gate.rs:115-117
             case Kind::PauliTimeEvolution: s = pauli_string->apply_exp_neg_i_dt(s, time); break;
+            case Kind::Parametric: for (const Gate& g : p_gate->to_concrete_gates(targets, controls)) g.apply_(s, seed); break;   // gate.rs:107-114
         }
     }
 };
+inline std::vector<Gate> PauliString::to_gates() const {
+    std::vector<Gate> out;
+    for (auto& kv : ops_) {
+        std::shared_ptr<Operator> op;
+        if (kv.second == Pauli::X) op = std::make_shared<PauliX>(); else if (kv.second == Pauli::Y) op = std::make_shared<PauliY>(); else op = std::make_shared<PauliZ>();
+        out.push_back(Gate{op, {kv.first}, {}});
+    }
+    return out;
+}
+// parametric_gate.rs:35-211: one concrete gate per target (the matchgate: its single target)
+template <class MakeOp, size_t N>
+struct ParametricOf : ParametricGate {
+    Parameter<N> parameter;
+    explicit ParametricOf(Parameter<N> p) : parameter(std::move(p)) {}
+    std::vector<Gate> to_concrete_gates(const std::vector<size_t>& targets, const std::vector<size_t>& controls) const override {
+        auto sp = MakeOp::make(parameter.get());
+        std::vector<Gate> out;
+        for (size_t t : targets) out.push_back(Gate{sp, {t}, controls});
+        return out;
+    }
+};
+struct MakeRyPhase { static std::shared_ptr<Operator> make(const std::array<double, 2>& v) { return std::make_shared<Unitary2>(Unitary2::from_ry_phase(v[0], v[1])); } };
+struct MakeRyPhaseDag { static std::shared_ptr<Operator> make(const std::array<double, 2>& v) { return std::make_shared<Unitary2>(Unitary2::from_ry_phase_dagger(v[0], v[1])); } };
+struct MakeMatchgate { static std::shared_ptr<Operator> make(const std::array<double, 3>& v) { return std::make_shared<Matchgate>(v[0], v[1], v[2]); } };
+struct MakeRx { static std::shared_ptr<Operator> make(const std::array<double, 1>& v) { return std::make_shared<RotateX>(v[0]); } };
+struct MakeRy { static std::shared_ptr<Operator> make(const std::array<double, 1>& v) { return std::make_shared<RotateY>(v[0]); } };
+struct MakeRz { static std::shared_ptr<Operator> make(const std::array<double, 1>& v) { return std::make_shared<RotateZ>(v[0]); } };
+struct MakeP { static std::shared_ptr<Operator> make(const std::array<double, 1>& v) { return std::make_shared<PhaseShift>(v[0]); } };
+using ParametricRyPhase = ParametricOf<MakeRyPhase, 2>;        // parametric_gate.rs:35-52
+using ParametricRyPhaseDag = ParametricOf<MakeRyPhaseDag, 2>;  // 63-80
+using ParametricMatchgate = ParametricOf<MakeMatchgate, 3>;    // 92-110
+using ParametricRx = ParametricOf<MakeRx, 1>;                  // 120-136
+using ParametricRy = ParametricOf<MakeRy, 1>;                  // 146-162
+using ParametricRz = ParametricOf<MakeRz, 1>;                  // 172-188
+using ParametricP = ParametricOf<MakeP, 1>;                    // 198-211
 struct Subroutine {
     std::vector<Gate> gates;
     size_t num_qubits;
@@ -564,6 +634,23 @@ public:
     // Gate k of the circuit draws from the stream seeded `seed + k`.
     void execute_(State& s, uint64_t seed = 0) const {
         if (s.num_qubits() != num_qubits) throw Error(QI_ERR_INVALID_NUMBER_OF_QUBITS, "InvalidNumberOfQubits", s.num_qubits(), 0, "execute");
+        bool has_parametric = false;
+        for (auto& g : gates) has_parametric |= g.kind == Gate::Kind::Parametric;
+        if (has_parametric) {      // resolved with the parameter values of THIS execution; the concrete gates join the fused runs
+            Circuit flat(num_qubits);
+            std::vector<size_t> origin;
+            for (size_t k = 0; k < gates.size(); k++) {
+                if (gates[k].kind != Gate::Kind::Parametric) { flat.gates.push_back(gates[k]); origin.push_back(k); continue; }
+                for (const Gate& g : gates[k].p_gate->to_concrete_gates(gates[k].targets, gates[k].controls)) { flat.gates.push_back(g); origin.push_back(k); }
+            }
+            flat.execute_runs(s, seed, &origin);
+            return;
+        }
+        execute_runs(s, seed, nullptr);
+    }
+
+private:
+    void execute_runs(State& s, uint64_t seed, const std::vector<size_t>* origin) const {
         size_t i = 0;
         while (i < gates.size()) {
             const Gate::Kind k = gates[i].kind;
@@ -590,11 +677,18 @@ public:
                 }
                 check(qi_apply_pauli_exp_sequence(s.handle(), arr.data(), arr.size(), f.data()));
             } else {
-                gates[i].apply_(s, seed + i);
+                gates[i].apply_(s, seed + (origin ? (*origin)[i] : i));
                 j = i + 1;
             }
             i = j;
         }
+    }
+
+public:
+    Circuit to_concrete_circuit() const {   // circuit.rs:204-221
+        Circuit c(num_qubits);
+        for (auto& g : gates) for (const Gate& cg : g.concrete()) c.gates.push_back(cg);
+        return c;
     }
     State execute(const State& initial, uint64_t seed = 0) const { State s(initial); execute_(s, seed); return s; }   // circuit.rs:160-172
     std::vector<State> trace_execution(const State& initial, uint64_t seed = 0) const {   // circuit.rs:188-202
@@ -679,6 +773,25 @@ public:
     CircuitBuilder& pauli_string_gate(const PauliString& ps) { gates_.push_back(Gate::pauli_string_gate(ps)); return *this; }                            // circuit.rs:1130
     CircuitBuilder& pauli_time_evolution_gate(const PauliString& ps, double t) { gates_.push_back(Gate::pauli_time_evolution(ps, t)); return *this; }
     template <class Op> CircuitBuilder& add_operator_gate(const Op& op, const Q& ts, const Q& cs = {}) { gates_.push_back(Gate{std::make_shared<Op>(op), ts, cs}); return *this; }   // circuit.rs:1215-1224
+    // parametric adders (circuit.rs:1226-1735): one Parameter per target
+    template <class PG, size_t N> CircuitBuilder& parametric_each(const Q& ts, const Q& cs, const std::vector<Parameter<N>>& ps) {
+        if (ts.size() != ps.size()) throw Error(QI_ERR_MISMATCHED_NUMBER_OF_PARAMETERS, "MismatchedNumberOfParameters", ts.size(), ps.size(), "parametric gates");
+        for (size_t k = 0; k < ts.size(); k++) gates_.push_back(Gate::parametric(std::make_shared<PG>(ps[k]), {ts[k]}, cs));
+        return *this;
+    }
+#define QI_BUILDER_PARAMETRIC(NAME, PG, N)                                                                                                              \
+    CircuitBuilder& parametric_##NAME##_gate(size_t t, const Parameter<N>& p) { return parametric_each<PG, N>({t}, {}, {p}); }                           \
+    CircuitBuilder& parametric_##NAME##_gates(const Q& ts, const std::vector<Parameter<N>>& ps) { return parametric_each<PG, N>(ts, {}, ps); }           \
+    CircuitBuilder& parametric_c##NAME##_gates(const Q& ts, const Q& cs, const std::vector<Parameter<N>>& ps) { return parametric_each<PG, N>(ts, cs, ps); }
+    QI_BUILDER_PARAMETRIC(ry_phase, ParametricRyPhase, 2)
+    QI_BUILDER_PARAMETRIC(ry_phase_dag, ParametricRyPhaseDag, 2)
+    QI_BUILDER_PARAMETRIC(rx, ParametricRx, 1)
+    QI_BUILDER_PARAMETRIC(ry, ParametricRy, 1)
+    QI_BUILDER_PARAMETRIC(rz, ParametricRz, 1)
+    QI_BUILDER_PARAMETRIC(p, ParametricP, 1)
+#undef QI_BUILDER_PARAMETRIC
+    CircuitBuilder& parametric_matchgate(size_t t, const Parameter<3>& p) { gates_.push_back(Gate::parametric(std::make_shared<ParametricMatchgate>(p), {t}, {})); return *this; }
+    CircuitBuilder& parametric_cmatchgate(size_t t, const Q& cs, const Parameter<3>& p) { gates_.push_back(Gate::parametric(std::make_shared<ParametricMatchgate>(p), {t}, cs)); return *this; }
     CircuitBuilder& measure_gate(const Basis& basis, const Q& qubits) { gates_.push_back(Gate::measurement(basis, qubits)); return *this; }              // circuit.rs:1737
     CircuitBuilder& add_subroutine(const Subroutine& s) { gates_.insert(gates_.end(), s.gates.begin(), s.gates.end()); return *this; }
     Subroutine build_subroutine() { Subroutine s{gates_, n_}; gates_.clear(); return s; }

@@ -134,6 +134,12 @@ int main(int argc, char** argv) {
         const cplx hm[2][2] = {{r, r}, {r, -r}};
         auto mr = State::new_zero(1).measure(Basis::custom(hm), {0}, 5);
         EXPECT(std::fabs(mr.second.norm_sqr() - 1.0) < 1e-12 && std::fabs(std::abs(mr.second.amplitude(0)) - r) < 1e-12);
+        // a parametric circuit re-resolves at every execution (gate.rs:107-114; parametric_tests.rs:238-283)
+        Parameter<1> ang({0.0});
+        Circuit prx = CircuitBuilder(2).parametric_rx_gate(0, ang).cnot_gate(1, 0).build();
+        EXPECT(prx.execute(State::new_zero(2)).approx_eq(State::new_zero(2)));
+        ang.set({M_PI});
+        EXPECT(prx.execute(State::new_zero(2)).approx_eq(State::new_zero(2).rx(0, M_PI).cnot(0, 1)));
         auto pr = State::new_phi_plus().probabilities({0, 1});
         EXPECT(pr.size() == 4 && std::fabs(pr[0] - 0.5) < 1e-12 && std::fabs(pr[3] - 0.5) < 1e-12 && pr[1] < 1e-12);
     }

@@ -132,6 +132,26 @@ int main() {
         Unitary2 f = Unitary2::from_ry_phase(0.7, 0.3), d = Unitary2::from_ry_phase_dagger(0.7, 0.3);
         for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) EXPECT(std::abs(std::conj(f.m[j][i]) - d.m[i][j]) < 1e-15);
     }
+    // Parameter / parametric gates (components/parametric/*.rs; parametric_tests.rs:9-60, 238-283): a clone shares the cell,
+    // a deep clone does not; a parametric gate resolves with the values of the moment it is resolved
+    {
+        Parameter<1> th({0.25});
+        Parameter<1> shared = th.clone(), copy = th.deep_clone();
+        th.set({0.75});
+        EXPECT(shared.get()[0] == 0.75 && copy.get()[0] == 0.25);
+        Circuit pc = CircuitBuilder(3).parametric_rx_gate(0, th).parametric_cry_phase_gates({1, 2}, {0}, {Parameter<2>({0.1, 0.2}), Parameter<2>({0.3, 0.4})})
+                         .parametric_cmatchgate(0, {2}, Parameter<3>({0.5, 0.6, 0.7})).h_gate(1).build();
+        EXPECT(pc.gates.size() == 5 && pc.gates[0].kind == Gate::Kind::Parametric);
+        Circuit cc = pc.to_concrete_circuit();
+        EXPECT(cc.gates.size() == 5 && cc.gates[0].kind == Gate::Kind::Operator && cc.gates[0].op->kind() == QI_GATE_RX && cc.gates[0].op->params()[0] == 0.75);
+        EXPECT(cc.gates[3].op->kind() == QI_GATE_MATCHGATE && cc.gates[3].controls == std::vector<size_t>{2} && cc.gates[3].op->params()[2] == 0.7);
+        th.set({1.5});
+        EXPECT(pc.to_concrete_circuit().gates[0].op->params()[0] == 1.5 && cc.gates[0].op->params()[0] == 0.75);
+        EXPECT(throws("MismatchedNumberOfParameters", 2, 1, [&] { CircuitBuilder(3).parametric_rx_gates({0, 1}, {th}); }));
+        // a PauliString gate becomes its factors' Pauli gates (circuit.rs:205-217, pauli_string.rs:118-122)
+        Circuit ps = CircuitBuilder(3).pauli_string_gate(PauliString(cplx(2.0, 0.0)).with_op(0, Pauli::X).with_op(2, Pauli::Y)).build().to_concrete_circuit();
+        EXPECT(ps.gates.size() == 2 && ps.gates[0].op->kind() == QI_GATE_X && ps.gates[1].op->kind() == QI_GATE_Y && ps.gates[1].targets[0] == 2);
+    }
     std::printf(failures ? "C++ facade host logic: %d FAILURES\n" : "C++ facade host logic: ALL PASS\n", failures);
     return failures ? 1 : 0;
 }
