@@ -67,6 +67,7 @@ int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_m
  *          "late_tables" = 1/0 unconditional phase tables placed as late as their members allow (fewest per pass);
  *          "lean" = 0/1 window passes apply H / RX / real 2x2 gates in unit form with one deferred scale per pass
  *          (half the FP64 instructions per gate; results differ from the default by rounding only; off until measured);
+ *          "prefetch" = 0/1 (with "lean" = 1 only) L2 prefetch of every warp's next tile (off until measured);
  *          "host_chunk_qubits", "host_min_qubits": see qi_execute_host */
 int qi_set_option(const char* name, int64_t value);
 

@@ -62,6 +62,7 @@ struct Context {
     int opt_tma = 0;                  // window passes: 1 = TMA-prefetched persistent kernel (measured 2.4% slower), 0 = direct loads
     int opt_absorb = 1;               // fold a CNOT into the neighbouring single-qubit gate on its target (window.cu)
     int opt_late_tables = 1;          // window passes: unconditional phase tables placed as late as possible (fewest tables per pass)
+    int opt_prefetch = 0;             // lean instantiations only: L2 prefetch of the warp's next tile (unmeasured: off)
     int opt_lean = 0;                 // window passes: unit-form H / RX / real 2x2 with one deferred scale per pass (unmeasured: off)
     int64_t opt_pool_mb = 4096;       // device-buffer cache: at most this many MiB are kept for reuse (0 = off)
     // stats

@@ -73,7 +73,7 @@ struct WProgram {
     BitInsert ins;              // zero-insert positions of the R window qubits (ascending)
     uint64_t off[1 << R];       // slot -> index offset
     uint32_t nops;
-    uint32_t pad;
+    uint32_t flags;             // bit 0: prefetch the warp's next tile into L2 (option "prefetch"; lean instantiations only)
     const amp_t* tables;        // phase-table arena
     DOp ops[kMaxOps];
 };
@@ -378,6 +378,13 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __re
         amp_t v[S];
 #pragma unroll
         for (int s = 0; s < S; s++) v[s] = QI_LD(a + base + P.off[s]);
+        if (LEAN && (P.flags & 1u) && (lane & 7) == 0 && tile + nwarps < ntiles) {
+            // experimental (unmeasured): pull the warp's NEXT tile into L2 while this one is computed -- costs no registers,
+            // unlike a second tile in flight; one prefetch per 128-byte line (lanes 0, 8, 16, 24)
+            const uint64_t nbase = expand_index(((tile + nwarps) << 5) | (uint64_t)lane, P.ins);
+#pragma unroll
+            for (int s = 0; s < S; s++) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + nbase + P.off[s]));
+        }
         run_ops<R, LANES, U2K, LEAN>(v, tile, lane, P);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
@@ -979,6 +986,7 @@ static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t n
     for (size_t first = 0; first < nops; first += kMaxOps) {
         size_t cnt = std::min<size_t>(kMaxOps, nops - first);
         P.nops = (uint32_t)cnt;
+        P.flags = c.opt_prefetch ? 1u : 0u;
         memcpy(P.ops, ops + first, cnt * sizeof(DOp));
         // instantiation by content: programs without lane gates / without complex 2x2 gates run kernels that do not
         // carry that code (smaller, fewer live registers)

@@ -15,6 +15,7 @@ def lean(gpu):
     gpu.engine.set_option("lean", 1)
     yield
     gpu.engine.set_option("lean", 0)
+    gpu.engine.set_option("prefetch", 0)
     gpu.engine.set_option("window_regs", 0)
 
 
@@ -48,3 +49,17 @@ def test_lean_matches_default_at_26_qubits(gpu, lean):
     assert abs(ip - 1.0) <= 1e-10
     for i in (0, 1, 12345, (1 << n) - 1):
         assert abs(a.amplitude(i) - b.amplitude(i)) <= AMP_TOL
+
+
+@pytest.mark.parametrize("n,depth", [(14, 20), (22, 12)])
+def test_lean_with_l2_prefetch_vs_default(gpu, ref, lean, n, depth):
+    """Option "prefetch" (lean instantiations only) is a pure cache hint: the state must be bit-identical to lean alone."""
+    from quant_iron_b200 import workloads as w
+    c = w.build_circuit(gpu, n, w.random_layered_circuit(n, depth))
+    a = vec(c.execute(gpu.State.new_zero(n)))
+    gpu.engine.set_option("prefetch", 1)
+    b = vec(c.execute(gpu.State.new_zero(n)))
+    assert np.array_equal(a, b)
+    if n <= 16:
+        want = vec(w.build_circuit(ref, n, w.random_layered_circuit(n, depth)).execute(ref.State.new_zero(n)))
+        assert float(np.max(np.abs(b - want))) <= AMP_TOL

@@ -22,6 +22,7 @@ for rep in 1 2; do
 done
 python bench.py --skip-cpu --skip-extras --skip-e2e --opt lean=1 --opt window_regs=5 > "$OUT/bench_lean_r5.json" 2> "$OUT/bench_lean_r5.err"
 python bench.py --skip-cpu --skip-extras --skip-e2e --opt lean=1 --opt tma=1         > "$OUT/bench_lean_tma.json" 2> "$OUT/bench_lean_tma.err"
+python bench.py --skip-cpu --skip-extras --skip-e2e --opt lean=1 --opt prefetch=1    > "$OUT/bench_lean_prefetch.json" 2> "$OUT/bench_lean_prefetch.err"
 
 # 3. the full default line (cpu baseline, single-gate table, e2e) and the reference arm
 python bench.py > "$OUT/bench_full.json" 2> "$OUT/bench_full.err"
