@@ -21,6 +21,8 @@ from .pauli import PauliString, SumOp
 from .state import State
 from . import workloads
 from . import engine
+from . import macros
+from .macros import circuit as circuit_macro
 
 __all__ = [
     "State", "Operator", "Hadamard", "Pauli", "CNOT", "SWAP", "Toffoli", "Identity", "PhaseS", "PhaseT",
@@ -28,5 +30,5 @@ __all__ = [
     "Gate", "Circuit", "CircuitBuilder", "Subroutine", "PauliString", "SumOp", "MeasurementBasis",
     "MeasurementResult", "TrotterOrder", "first_order_trotter_step", "second_order_trotter_step",
     "trotter_evolve_state", "trotter_evolve_state_", "Parameter", "ParametricGate", "ParametricMatchgate", "ParametricP", "ParametricRx", "ParametricRy", "ParametricRyPhase",
-    "ParametricRyPhaseDag", "ParametricRz", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "CompilerError", "workloads", "engine",
+    "ParametricRyPhaseDag", "ParametricRz", "heisenberg_1d", "heisenberg_2d", "ising_1d", "ising_1d_uniform", "ising_2d", "ising_2d_uniform", "Error", "CompilerError", "workloads", "engine", "macros", "circuit_macro",
 ]
