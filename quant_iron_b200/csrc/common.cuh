@@ -220,6 +220,7 @@ int debug_expect_lower(const qi_state* s, const std::vector<PauliExp>& terms, st
 
 // gates.cu
 int validate_gate(const qi_state* s, const qi_gate* g);
+const qi_gate* normalise_gates(const qi_gate* gates, uint64_t count, std::vector<qi_gate>* own);   // gates.cu: aliased-control Matchgates -> P
 int launch_simple_gate(qi_state* s, const PhysGate& g);      // one pass with the per-gate kernels
 // window.cu
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates);

@@ -174,6 +174,31 @@ int validate_gate(const qi_state* s, const qi_gate* g) {
     return QI_OK;
 }
 
+// A Matchgate whose control list names its own partner qubit t+1 passes the reference's validation (controls are only
+// checked against the target, operator.rs:214-273) and means something definite there: check_controls(i01) fails for
+// every pair (bit t+1 of i01 is 0), so the 01/10 rotation never runs, and only `amp11 * e^{i phi2}` is applied where the
+// remaining controls are set (operator.rs:940-1007).  That is exactly PhaseShift(phi2) on t under the same control list
+// (both evaluate (cos phi2, sin phi2) and one complex multiply), so such records are rewritten once at the ABI entry
+// and nothing below ever sees a Matchgate whose control aliases its partner.
+const qi_gate* normalise_gates(const qi_gate* gates, uint64_t count, std::vector<qi_gate>* own) {
+    auto aliased = [](const qi_gate& g) {
+        if (g.kind != QI_GATE_MATCHGATE) return false;
+        for (uint32_t c = 0; c < g.num_controls; c++) if (g.controls[c] == g.targets[0] + 1) return true;
+        return false;
+    };
+    uint64_t first = 0;
+    while (first < count && !aliased(gates[first])) first++;
+    if (first == count) return gates;
+    own->assign(gates, gates + count);
+    for (uint64_t i = first; i < count; i++) {
+        if (!aliased(gates[i])) continue;
+        qi_gate& g = (*own)[i];
+        g.kind = QI_GATE_P;
+        g.params[0] = gates[i].params[2];
+    }
+    return own->data();
+}
+
 // numeric parameters, computed on the host with the reference's expressions
 static void resolve_params(const qi_gate* g, PhysGate* o) {
     const double is2 = 1.0 / std::sqrt(2.0);   // operator.rs:316, 1288
@@ -365,6 +390,8 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
     // Gate::apply validates as it goes (circuit.rs:167-169); the first failing gate aborts the run.
     // Here the whole run is validated up front, so a failure leaves the state untouched.
     for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     QI_TRY(ensure_ctx());
     Context& c = ctx();
     const bool use_window = (c.opt_path != 1) && window_supported(s);
@@ -406,8 +433,10 @@ int qi_debug_schedule(uint32_t num_qubits, const qi_gate* gates, uint64_t count,
     s.len = 1ull << num_qubits;
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
     std::vector<PhysGate> run;
+    for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     for (uint64_t i = 0; i < count; i++) {
-        QI_TRY(validate_gate(&s, &gates[i]));
         if (gates[i].kind == QI_GATE_SWAP && gates[i].num_controls == 0) { std::swap(s.phys[gates[i].targets[0]], s.phys[gates[i].targets[1]]); continue; }
         PhysGate pg;
         bool skip = false;
@@ -445,8 +474,10 @@ int qi_debug_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys
     for (int i = 0; i < 64; i++) s.phys[i] = phys ? phys[i] : (uint8_t)i;
     if (!window_supported(&s)) return fail(QI_ERR_INVALID_NUMBER_OF_QUBITS, num_qubits, 0, "too few local qubits for the window executor");
     std::vector<PhysGate> run;
+    for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     for (uint64_t i = 0; i < count; i++) {
-        QI_TRY(validate_gate(&s, &gates[i]));
         if (world == 1 && ctx().opt_lazy_swap && gates[i].kind == QI_GATE_SWAP && gates[i].num_controls == 0) {
             std::swap(s.phys[gates[i].targets[0]], s.phys[gates[i].targets[1]]);
             continue;

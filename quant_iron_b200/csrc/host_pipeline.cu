@@ -147,6 +147,8 @@ int qi_execute_host(qi_state* s, const qi_gate* gates, uint64_t count, const dou
     if (len != s->len) return fail(QI_ERR_INVALID_ARGUMENT, len, s->len, "length mismatch");
     if (len && (!amps_in || !amps_out)) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "host buffer is NULL");
     for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     QI_TRY(ensure_ctx());
     Context& c = ctx();
     const int k = c.opt_host_chunk_qubits;
@@ -181,6 +183,8 @@ int qi_host_pipeline_plan(uint32_t num_qubits, const qi_gate* gates, uint64_t co
     s.len = 1ull << num_qubits;
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
     for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     HostPlan plan;
     plan_host_pipeline(num_qubits, chunk_qubits, gates, count, &plan);
     uint64_t o = 0;

@@ -654,6 +654,8 @@ int qi_shard_plan(uint32_t total_qubits, int world, const qi_gate* gates, uint64
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
     uint64_t ex = 0, exq = 0, freeg = 0;
     for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     uint64_t first = 0;
     while (first < count) {
         uint64_t end = first;
@@ -705,6 +707,8 @@ int qi_debug_shard_stages(uint32_t total_qubits, int world, const qi_gate* gates
     s.world = world;
     for (int i = 0; i < 64; i++) s.phys[i] = (uint8_t)i;
     for (uint64_t i = 0; i < count; i++) QI_TRY(validate_gate(&s, &gates[i]));
+    std::vector<qi_gate> own;
+    gates = normalise_gates(gates, count, &own);
     std::vector<uint64_t> rec;
     rec.push_back(0);
     uint64_t nstages = 0;

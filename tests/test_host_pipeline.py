@@ -28,7 +28,7 @@ def _fuzz_builders(apis, n, seed, count=120, lazy_swaps=False):
         nc = int(rng.integers(0, 3))
         ctrls = [c1, c2][:nc]
         mt = int(rng.integers(0, n - 1))
-        mc = [q for q in ctrls if q not in (mt, mt + 1)]
+        mc = [q for q in ctrls if q != mt]           # a control on the partner qubit mt + 1 is legal in the reference (operator.rs:940-1007)
         for b in builders:
             if kind == 0: b.ch_gates([t], ctrls) if nc else b.h_gate(t)
             elif kind == 1: b.cx_gates([t], ctrls) if nc else b.x_gate(t)
@@ -67,7 +67,10 @@ def _nondiag_targets(rec):
         return set()
     t = {int(rec.targets[j]) for j in range(rec.num_targets)}
     if rec.kind == 18:                          # Matchgate acts on (q, q + 1)
-        t.add(int(rec.targets[0]) + 1)
+        partner = int(rec.targets[0]) + 1
+        if any(int(rec.controls[j]) == partner for j in range(rec.num_controls)):
+            return set()                        # control on the partner: only the phase on |11> survives (a diagonal gate)
+        t.add(partner)
     return t
 
 
