@@ -63,6 +63,9 @@ struct Context {
     int opt_absorb = 1;               // fold a CNOT into the neighbouring single-qubit gate on its target (window.cu)
     int opt_late_tables = 1;          // window passes: unconditional phase tables placed as late as possible (fewest tables per pass)
     int opt_prefetch = 0;             // lean instantiations only: L2 prefetch of the warp's next tile (unmeasured: off)
+    int opt_cz_rewrite = 1;           // fused executor: a controlled X next to a Hadamard on its target becomes a controlled Z (bit-exact)
+    int opt_tile = 1;                 // window passes on the CTA-tile kernel (k_tile: 11 qubits per pass, rounds regrouped through shared memory)
+    int opt_tile_min_qubits = 18;     // ... for states with at least this many local qubits (>= 11)
     int opt_lean = 0;                 // window passes: unit-form H / RX / real 2x2 with one deferred scale per pass (unmeasured: off)
     int64_t opt_pool_mb = 4096;       // device-buffer cache: at most this many MiB are kept for reuse (0 = off)
     // stats

@@ -251,6 +251,9 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "tma")) c.opt_tma = (int)value;
     else if (!strcmp(name, "absorb")) c.opt_absorb = (int)value;
     else if (!strcmp(name, "lean")) c.opt_lean = (int)value;
+    else if (!strcmp(name, "tile")) c.opt_tile = (int)value;
+    else if (!strcmp(name, "cz_rewrite")) c.opt_cz_rewrite = (int)value;
+    else if (!strcmp(name, "tile_min_qubits")) c.opt_tile_min_qubits = (int)value;
     else if (!strcmp(name, "prefetch")) c.opt_prefetch = (int)value;
     else if (!strcmp(name, "late_tables")) c.opt_late_tables = (int)value;
     else if (!strcmp(name, "host_chunk_qubits")) c.opt_host_chunk_qubits = (int)(value < 0 ? 0 : (value > 4 ? 4 : value));

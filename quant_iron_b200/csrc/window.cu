@@ -43,7 +43,8 @@ namespace qi {
 // phase table when the pass has an unconditional one, else one WK_SCALE op).
 //   REALUP = [[1, p], [q, 1]]   REALUM = [[1, p], [q, -1]]   (m[0] = p, m[1] = q; H / g = REALUM with p = q = 1)
 //   RXU = [[1, -i t], [-i t, 1]]   RXSU = RXU with its inputs swapped   (m[0] = t = tan(theta / 2))
-enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE };
+enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE,
+       WK_NEG /* WK_DIAG with phase -1 (Z, CZ): sign flips, no FP64 work */ };
 static const int kLastPairKind = WK_RXSU;
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 112 B + header < 16 KB)
@@ -55,9 +56,11 @@ struct DOp {                 // device op, 112 bytes
     uint8_t hub_bit;         // WK_TABLE: lane bit / slot bit / compact tile bit index
     uint8_t nchunks;         // WK_TABLE: number of 8-bit tile chunks with a table
     uint8_t has_reg;         // WK_TABLE: register table is not all ones
-    uint8_t pad[2];
-    uint32_t c_lane, c_reg;  // c_lane: control bits in lane space (all must be 1).  c_reg: SLOT MASK -- bit s is set iff
-                             // slot s passes the register-bit controls (positive and negative), expanded on the host
+    uint8_t c_lval;          // value the c_lane bits of the lane / thread index must have: (idx & c_lane) == c_lval
+    uint8_t pad;
+    uint32_t c_lane, c_reg;  // c_lane: control bits in lane space (k_window: lane bits 0..4; k_tile: the 7 thread-index bits).
+                             // c_reg: SLOT MASK -- bit s is set iff slot s passes the register-bit controls (positive and
+                             // negative), expanded on the host
     uint32_t t_lane, t_reg;  // WK_RZ: target bit in lane space / slot space (0 if elsewhere)
     uint64_t c_tile;         // control bits in compact tile-index space (positive and negative controls)
     uint64_t c_tval;         // value those bits must have: (tile & c_tile) == c_tval
@@ -91,6 +94,72 @@ __device__ __forceinline__ amp_t shfl_xor_amp(amp_t v, int mask) {
     return make_double2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
 }
 
+// ---- in-place 2x2 updates -------------------------------------------------------------------------------
+// Written as PTX with tied ("+d") operands: every amplitude keeps its virtual register across an op, so the op loop has no
+// phi nodes at its merge points.  The plain C++ forms made ptxas finish every variant in its own register assignment and
+// restore the canonical one with ~64 MOVs per op at the loop back-edge (17 % of all executed instructions, ncu r02b).
+// Same operation order as the C++ forms after FMA contraction: one product rounded, then one fused multiply-add.
+// REAL: a0' = k0 a0 + k1 a1, a1' = k2 a0 + k3 a1 (real coefficients, applied to .x and .y alike)
+__device__ __forceinline__ void upd_real(amp_t& a0, amp_t& a1, double k0, double k1, double k2, double k3) {
+    asm("{\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+        "mul.f64 t0, %4, %0;\n\tmul.f64 t1, %6, %0;\n\tmul.f64 t2, %4, %1;\n\tmul.f64 t3, %6, %1;\n\t"
+        "fma.rn.f64 %0, %5, %2, t0;\n\tfma.rn.f64 %1, %5, %3, t2;\n\tfma.rn.f64 %2, %7, %2, t1;\n\tfma.rn.f64 %3, %7, %3, t3;\n\t}"
+        : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(k0), "d"(k1), "d"(k2), "d"(k3));
+}
+// RX: a0' = c a0 - i s a1, a1' = c a1 - i s a0      (x' = c x + s y_other, y' = c y - s x_other)
+__device__ __forceinline__ void upd_rx(amp_t& a0, amp_t& a1, double c, double sn) {
+    asm("{\n\t.reg .f64 t0, t1, t2, t3, ns;\n\tneg.f64 ns, %5;\n\t"
+        "mul.f64 t0, %5, %3;\n\tmul.f64 t1, ns, %2;\n\tmul.f64 t2, %5, %1;\n\tmul.f64 t3, ns, %0;\n\t"      // s a1y, -s a1x, s a0y, -s a0x
+        "fma.rn.f64 %0, %4, %0, t0;\n\tfma.rn.f64 %1, %4, %1, t1;\n\tfma.rn.f64 %2, %4, %2, t2;\n\tfma.rn.f64 %3, %4, %3, t3;\n\t}"
+        : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(c), "d"(sn));
+}
+// RXS = RX with its inputs swapped: a0' = c a1 - i s a0, a1' = c a0 - i s a1
+__device__ __forceinline__ void upd_rxs(amp_t& a0, amp_t& a1, double c, double sn) {
+    asm("{\n\t.reg .f64 t0, t1, t2, t3, ns;\n\tneg.f64 ns, %5;\n\t"
+        "mul.f64 t0, %5, %1;\n\tmul.f64 t1, ns, %0;\n\tmul.f64 t2, %5, %3;\n\tmul.f64 t3, ns, %2;\n\t"      // s a0y, -s a0x, s a1y, -s a1x
+        "fma.rn.f64 t0, %4, %2, t0;\n\tfma.rn.f64 t1, %4, %3, t1;\n\tfma.rn.f64 %2, %4, %0, t2;\n\tfma.rn.f64 %3, %4, %1, t3;\n\t"
+        "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+        : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(c), "d"(sn));
+}
+// lean unit forms: [[1, p], [q, +-1]]
+template <bool MINUS>
+__device__ __forceinline__ void upd_realu(amp_t& a0, amp_t& a1, double p, double q) {
+    if (MINUS)
+        asm("{\n\t.reg .f64 t0, t1, n2, n3;\n\tneg.f64 n2, %2;\n\tneg.f64 n3, %3;\n\t"
+            "fma.rn.f64 t0, %4, %2, %0;\n\tfma.rn.f64 t1, %4, %3, %1;\n\tfma.rn.f64 %2, %5, %0, n2;\n\tfma.rn.f64 %3, %5, %1, n3;\n\t"
+            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+            : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(p), "d"(q));
+    else
+        asm("{\n\t.reg .f64 t0, t1;\n\t"
+            "fma.rn.f64 t0, %4, %2, %0;\n\tfma.rn.f64 t1, %4, %3, %1;\n\tfma.rn.f64 %2, %5, %0, %2;\n\tfma.rn.f64 %3, %5, %1, %3;\n\t"
+            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+            : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(p), "d"(q));
+}
+// RXU = [[1, -i t], [-i t, 1]]: a0' = a0 - i t a1, a1' = a1 - i t a0;  SWAPPED (RXSU): a0' = a1 - i t a0, a1' = a0 - i t a1
+template <bool SWAPPED>
+__device__ __forceinline__ void upd_rxu(amp_t& a0, amp_t& a1, double t) {
+    if (!SWAPPED)
+        asm("{\n\t.reg .f64 t0, t1, nt;\n\tneg.f64 nt, %4;\n\t"
+            "fma.rn.f64 t0, %4, %3, %0;\n\tfma.rn.f64 t1, nt, %2, %1;\n\tfma.rn.f64 %2, %4, %1, %2;\n\tfma.rn.f64 %3, nt, %0, %3;\n\t"
+            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+            : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(t));
+    else
+        asm("{\n\t.reg .f64 t0, t1, nt;\n\tneg.f64 nt, %4;\n\t"
+            "fma.rn.f64 t0, %4, %1, %2;\n\tfma.rn.f64 t1, nt, %0, %3;\n\tfma.rn.f64 %2, %4, %3, %0;\n\tfma.rn.f64 %3, nt, %2, %1;\n\t"
+            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+            : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(t));
+}
+
+// a *= f (complex): x' = x fx - y fy, y' = x fy + y fx
+__device__ __forceinline__ void upd_cmul(amp_t& a, const amp_t f) {
+    asm("{\n\t.reg .f64 t0, t1, t2;\n\t"
+        "mul.f64 t0, %1, %3;\n\tneg.f64 t0, t0;\n\tmul.f64 t1, %1, %2;\n\tfma.rn.f64 t2, %0, %3, t1;\n\tfma.rn.f64 %0, %0, %2, t0;\n\tmov.f64 %1, t2;\n\t}"
+        : "+d"(a.x), "+d"(a.y) : "d"(f.x), "d"(f.y));
+}
+__device__ __forceinline__ void upd_scale(amp_t& a, const double g) {
+    asm("mul.f64 %0, %0, %2;\n\tmul.f64 %1, %1, %2;" : "+d"(a.x), "+d"(a.y) : "d"(g));
+}
+
 // ---- pair gate on register bit B --------------------------------------------------------------
 // COND = false: no register-bit controls, straight-line code.  COND = true: the slot predicate
 // bit s0 of the slot mask c_reg is warp-uniform (c_reg comes from the constant bank, s0 is a literal), so a
@@ -109,31 +178,18 @@ __device__ __forceinline__ void reg_pair_kind(amp_t (&v)[1 << R], const uint32_t
         const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int s1 = s0 | (1 << B);
         if (!COND || ((c_reg >> s0) & 1u)) {
-            const amp_t a0 = v[s0], a1 = v[s1];
             if (KIND == WK_X) {
+                const amp_t a0 = v[s0], a1 = v[s1];
                 v[s0] = a1; v[s1] = a0;
-            } else if (KIND == WK_RX) {
-                v[s0] = make_double2(k0 * a0.x + k1 * a1.y, k0 * a0.y - k1 * a1.x);
-                v[s1] = make_double2(k0 * a1.x + k1 * a0.y, k0 * a1.y - k1 * a0.x);
-            } else if (KIND == WK_RXS) {
-                v[s0] = make_double2(k0 * a1.x + k1 * a0.y, k0 * a1.y - k1 * a0.x);
-                v[s1] = make_double2(k0 * a0.x + k1 * a1.y, k0 * a0.y - k1 * a1.x);
-            } else if (KIND == WK_REAL) {
-                v[s0] = make_double2(k0 * a0.x + k1 * a1.x, k0 * a0.y + k1 * a1.y);
-                v[s1] = make_double2(k2 * a0.x + k3 * a1.x, k2 * a0.y + k3 * a1.y);
-            } else if (KIND == WK_REALUP) {
-                v[s0] = make_double2(fma(k0, a1.x, a0.x), fma(k0, a1.y, a0.y));
-                v[s1] = make_double2(fma(k1, a0.x, a1.x), fma(k1, a0.y, a1.y));
-            } else if (KIND == WK_REALUM) {
-                v[s0] = make_double2(fma(k0, a1.x, a0.x), fma(k0, a1.y, a0.y));
-                v[s1] = make_double2(fma(k1, a0.x, -a1.x), fma(k1, a0.y, -a1.y));
-            } else if (KIND == WK_RXU) {
-                v[s0] = make_double2(fma(k0, a1.y, a0.x), fma(-k0, a1.x, a0.y));
-                v[s1] = make_double2(fma(k0, a0.y, a1.x), fma(-k0, a0.x, a1.y));
-            } else if (KIND == WK_RXSU) {
-                v[s0] = make_double2(fma(k0, a0.y, a1.x), fma(-k0, a0.x, a1.y));
-                v[s1] = make_double2(fma(k0, a1.y, a0.x), fma(-k0, a1.x, a0.y));
-            } else {
+            } else if (KIND == WK_RX) upd_rx(v[s0], v[s1], k0, k1);
+            else if (KIND == WK_RXS) upd_rxs(v[s0], v[s1], k0, k1);
+            else if (KIND == WK_REAL) upd_real(v[s0], v[s1], k0, k1, k2, k3);
+            else if (KIND == WK_REALUP) upd_realu<false>(v[s0], v[s1], k0, k1);
+            else if (KIND == WK_REALUM) upd_realu<true>(v[s0], v[s1], k0, k1);
+            else if (KIND == WK_RXU) upd_rxu<false>(v[s0], v[s1], k0);
+            else if (KIND == WK_RXSU) upd_rxu<true>(v[s0], v[s1], k0);
+            else {
+                const amp_t a0 = v[s0], a1 = v[s1];
                 const amp_t m00 = make_double2(k0, k1), m01 = make_double2(k2, k3);
                 const amp_t m10 = make_double2(k4, k5), m11 = make_double2(k6, k7);
                 v[s0] = cadd(cmul(m00, a0), cmul(m01, a1));
@@ -287,14 +343,16 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
 // ---- the op program on one register tile -------------------------------------------------------------
 // LANES = the program contains pair gates on lane qubits; programs without them run an instantiation that does not
 // carry the shuffle code at all (smaller, fewer live registers).
-template <int R, bool LANES, bool U2K, bool LEAN = false>
-__device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const WProgram<R>& P) {
+// NT = entries of a phase table's lane part: 32 (k_window: lanes) or 128 (k_tile: the thread index of the round's layout)
+template <int R, bool LANES, bool U2K, bool LEAN = false, int NT = 32>
+__device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const DOp* __restrict__ ops, const uint32_t nops,
+                                        const amp_t* __restrict__ tables) {
     constexpr int S = 1 << R;
 #pragma unroll 1
-    for (uint32_t o = 0; o < P.nops; o++) {
-        const DOp& op = P.ops[o];
+    for (uint32_t o = 0; o < nops; o++) {
+        const DOp& op = ops[o];
         if ((tile & op.c_tile) != op.c_tval) continue;                // warp-uniform control (positive and negative bits)
-        const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lane;
+        const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lval;
         const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
         if (LANES && kind <= kLastPairKind && tpos < 5) {             // pair gate across lanes
             lane_pair_op<R, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
@@ -305,7 +363,7 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
             const amp_t ph = make_double2(op.m[0], op.m[1]);
 #pragma unroll
             for (int s = 0; s < S; s++)
-                if ((c_reg >> s) & 1u) v[s] = cmul(v[s], ph);
+                if ((c_reg >> s) & 1u) upd_cmul(v[s], ph);
         } else if (kind == WK_RZ) {
             const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
             const uint32_t t_reg = op.t_reg;
@@ -313,40 +371,44 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
                 const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
                 const amp_t pt = t_thread ? p1 : p0;
 #pragma unroll
-                for (int s = 0; s < S; s++) v[s] = cmul(v[s], pt);
+                for (int s = 0; s < S; s++) upd_cmul(v[s], pt);
             } else {
                 const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
                 const amp_t pt = t_thread ? p1 : p0;
 #pragma unroll
                 for (int s = 0; s < S; s++)
                     if ((c_reg >> s) & 1u) {
-                        if (s & t_reg) v[s] = cmul(v[s], p1);
-                        else v[s] = cmul(v[s], pt);
+                        if (s & t_reg) upd_cmul(v[s], p1);
+                        else upd_cmul(v[s], pt);
                     }
             }
         } else if (kind == WK_TABLE) {
-            const amp_t* __restrict__ tab = P.tables + (uint64_t)__double_as_longlong(op.m[0]);
+            const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
             const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
             if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
             if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) continue;
-            amp_t f = tab[lane];                                        // lane table (32 entries)
+            amp_t f = tab[lane];                                        // lane table (NT entries)
             const uint32_t nch = op.nchunks;
             for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
-                f = cmul(f, __ldg(tab + 32 + S + 256 * k + ((tile >> (8 * k)) & 255)));
+                f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
             const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
             if (op.has_reg) {
 #pragma unroll
                 for (int s = 0; s < S; s++)
-                    if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], cmul(f, __ldg(tab + 32 + s)));
+                    if ((s & hub_slot) == hub_slot) upd_cmul(v[s], cmul(f, __ldg(tab + NT + s)));
             } else {
 #pragma unroll
                 for (int s = 0; s < S; s++)
-                    if ((s & hub_slot) == hub_slot) v[s] = cmul(v[s], f);
+                    if ((s & hub_slot) == hub_slot) upd_cmul(v[s], f);
             }
+        } else if (kind == WK_NEG) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
         } else if (LEAN && kind == WK_SCALE) {                          // the product of the pass's deferred gate scales
             const double g = op.m[0];
 #pragma unroll
-            for (int s = 0; s < S; s++) v[s] = make_double2(v[s].x * g, v[s].y * g);
+            for (int s = 0; s < S; s++) upd_scale(v[s], g);
         } else {
             switch (tpos - 5) {
                 case 0: reg_pair_op<R, 0, U2K, LEAN>(v, kind, c_reg, op.m); break;
@@ -385,7 +447,7 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window(amp_t* __re
 #pragma unroll
             for (int s = 0; s < S; s++) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + nbase + P.off[s]));
         }
-        run_ops<R, LANES, U2K, LEAN>(v, tile, lane, P);
+        run_ops<R, LANES, U2K, LEAN>(v, tile, lane, P.ops, P.nops, P.tables);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
     }
@@ -455,10 +517,106 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* 
         for (int s = 0; s < S; s++) v[s] = buf[s * 32 + lane];
         __syncwarp();
         if (tile + nwarps < ntiles) issue(tile + nwarps);
-        run_ops<R, LANES, U2K>(v, tile, lane, P);
+        run_ops<R, LANES, U2K>(v, tile, lane, P.ops, P.nops, P.tables);
         const uint64_t base = expand_index((tile << 5) | (uint64_t)lane, P.ins);
 #pragma unroll
         for (int s = 0; s < S; s++) QI_ST(a + base + P.off[s], v[s]);
+    }
+}
+
+// ---- CTA-tile variant (k_tile): two-level pass --------------------------------------------------------------
+// The warp-tile kernel above holds 9 qubits per pass (5 lane qubits whose gates cost shuffles + 4 register qubits), so a
+// deep circuit needs one HBM pass per ~10 gates, and the passes that carry lane-qubit gates run at 2-5x the HBM floor.
+// k_tile makes the unit of a pass a CTA TILE of 2^11 amplitudes: physical qubits 0..4 (so that every global access is a
+// coalesced 512-byte row) plus SIX window qubits chosen per pass.  128 threads hold 16 amplitudes each in registers and
+// work in ROUNDS: in a round, 4 of the 11 tile qubits are register qubits (every gate on them pairs two registers of one
+// thread, no data movement, no shuffles, low qubits included); between rounds the registers are regrouped through a
+// 32 KiB shared-memory image of the tile (one 16-byte store + one 16-byte load per amplitude, XOR-swizzled, ONE
+// __syncthreads per regroup: a thread writes the locations it owns under the current layout -- the ones it read last --
+// and reads the ones it owns under the next layout, so consecutive regroups cannot race).  The first and the last round
+// use the IO layout (register qubits = 4 of the window qubits), the only one whose global accesses coalesce.
+// Measured on the prototype (tools/micro/tile_proto.cu, profiles/r02_tile_proto_microbench.txt): a regroup costs ~0.3 ms
+// at 30 qubits against 5.5 ms for the HBM pass it replaces; a register gate costs 0.15-0.2 ms (the FP64 pipe).
+static const int kTileBits = 11;            // local bits of a CTA tile
+static const int kTileThreads = 128;        // 2^(kTileBits - 4)
+static const int kTileThrBits = 7;
+static const int kTileWindow = kTileBits - kLaneQubits;   // window qubits per pass (6)
+static const int kMaxRounds = 24;
+static const int kMaxTileOps = 232;         // parameter space: 232 * 112 B + rounds + header < 32 KiB
+
+struct TRound {                 // 64 bytes
+    uint16_t sswz[16];          // swizzled tile-local offset of slot s (register bits of this round)
+    uint8_t thr_pos[kTileThrBits];   // tile-local bit of thread-index bit k
+    uint8_t pad;
+    uint16_t first_op, nops;
+    uint32_t pad2[5];
+};
+static_assert(sizeof(TRound) == 64, "TRound layout");
+
+struct TProgram {
+    uint8_t tpos[kTileBits];    // physical qubit of tile-local bit j (ascending; tpos[0..4] = 0..4)
+    uint8_t nrounds;
+    uint32_t flags;
+    uint64_t goff_in[16];       // slot -> global index offset under the first round's layout (loads)
+    uint64_t goff_out[16];      // ... under the last round's layout (stores)
+    const amp_t* tables;        // phase-table arena
+    TRound rounds[kMaxRounds];
+    DOp ops[kMaxTileOps];
+};
+static_assert(sizeof(TProgram) <= 32000, "kernel parameter space");
+
+// XOR-fold of the 16-byte-unit index: a quarter warp (8 lanes, thread bits 0..2) hits 8 distinct 16-byte bank groups whenever
+// the three tile-local bits behind thread bits 0..2 fall into three different classes mod 3 (the host orders them so)
+__host__ __device__ __forceinline__ uint32_t tile_swz(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 3u); }
+
+template <bool U2K, bool LEAN>
+__global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ TProgram P) {
+    __shared__ __align__(16) amp_t sm[1 << kTileBits];
+    __shared__ uint16_t lbs[kMaxRounds][kTileThreads];       // swizzled tile-local base of thread t in round r
+    const int t = threadIdx.x;
+    const int nr = P.nrounds;
+    for (int r = 0; r < nr; r++) {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 0; k < kTileThrBits; k++) b |= ((t >> k) & 1u) << P.rounds[r].thr_pos[k];
+        lbs[r][t] = (uint16_t)tile_swz(b);
+    }
+    // IO layouts (first round: loads, last round: stores): thread bit k <-> tile-local bit thr_pos[k] <-> physical tpos[...]
+    uint64_t g_in = 0, g_out = 0;
+#pragma unroll
+    for (int k = 0; k < kTileThrBits; k++) {
+        g_in |= (uint64_t)((t >> k) & 1u) << P.tpos[P.rounds[0].thr_pos[k]];
+        g_out |= (uint64_t)((t >> k) & 1u) << P.tpos[P.rounds[nr - 1].thr_pos[k]];
+    }
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint64_t tb = tile;
+#pragma unroll 1
+        for (int j = 0; j < kTileBits; j++) tb = insert_zero(tb, P.tpos[j]);
+        amp_t v[16];
+        {
+            const amp_t* __restrict__ g = a + tb + g_in;
+#pragma unroll
+            for (int s = 0; s < 16; s++) v[s] = QI_LD(g + P.goff_in[s]);
+        }
+        run_ops<4, false, U2K, LEAN, kTileThreads>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
+#pragma unroll 1
+        for (int r = 1; r < nr; r++) {
+            const TRound& prev = P.rounds[r - 1];
+            const TRound& cur = P.rounds[r];
+            const uint32_t wb = lbs[r - 1][t], rb = lbs[r][t];
+#pragma unroll
+            for (int s = 0; s < 16; s++) sm[wb ^ prev.sswz[s]] = v[s];
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < 16; s++) v[s] = sm[rb ^ cur.sswz[s]];
+            run_ops<4, false, U2K, LEAN, kTileThreads>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
+        }
+        {
+            amp_t* __restrict__ g = a + tb + g_out;
+#pragma unroll
+            for (int s = 0; s < 16; s++) QI_ST(g + P.goff_out[s], v[s]);
+        }
     }
 }
 
@@ -827,15 +985,16 @@ static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>
     }
     (void)nch_total;
     const size_t off = arena.size();
-    arena.resize(off + 32 + S + 256 * (size_t)used_chunks, make_double2(1.0, 0.0));
+    const int NT = L.nt;
+    arena.resize(off + NT + S + 256 * (size_t)used_chunks, make_double2(1.0, 0.0));
     amp_t* lane_t = arena.data() + off;
-    amp_t* slot_t = lane_t + 32;
+    amp_t* slot_t = lane_t + NT;
     amp_t* chunk_t = slot_t + S;
     for (size_t k = 0; k < g.bits.size(); k++) {
         const int q = g.bits[k];
         const amp_t f0 = g.f0[k], f1 = g.f1[k];
         if (L.cls[q] == CLS_LANE) {
-            for (int i = 0; i < 32; i++) lane_t[i] = cmul(lane_t[i], ((i >> L.idx[q]) & 1) ? f1 : f0);
+            for (int i = 0; i < NT; i++) lane_t[i] = cmul(lane_t[i], ((i >> L.idx[q]) & 1) ? f1 : f0);
         } else if (L.cls[q] == CLS_REG) {
             for (int i = 0; i < S; i++) slot_t[i] = cmul(slot_t[i], ((i >> L.idx[q]) & 1) ? f1 : f0);
         } else {
@@ -844,7 +1003,7 @@ static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>
         }
     }
     if (scale != 1.0)                      // lean lowering: the pass's deferred gate scale rides on an unconditional table
-        for (int i = 0; i < 32; i++) lane_t[i] = make_double2(lane_t[i].x * scale, lane_t[i].y * scale);
+        for (int i = 0; i < NT; i++) lane_t[i] = make_double2(lane_t[i].x * scale, lane_t[i].y * scale);
     d->kind = WK_TABLE;
     d->nchunks = (uint8_t)used_chunks;
     d->has_reg = has_reg ? 1 : 0;
@@ -921,6 +1080,55 @@ static double lean_convert(std::vector<HOp>& ops) {
     return scale;
 }
 
+// one host op -> one device op under layout L (`scale`: the pass's deferred lean scale, consumed by the first
+// unconditional table)
+static void lower_op(const Layout& L, const Pass& ps, const HOp& h, double* scale, std::vector<DOp>& dops, std::vector<amp_t>& arena) {
+    DOp d;
+    memset(&d, 0, sizeof(d));
+    HOp op = h;
+    if (op.kind == WK_TABLE) {
+        const DiagGroup& g = ps.groups[op.group];
+        if (g.members >= 2) {
+            const bool carries = *scale != 1.0 && g.hub < 0 && g.hub_alt < 0;      // unconditional: touches every amplitude
+            build_tables(L, g, arena, &d, carries ? *scale : 1.0);
+            if (carries) *scale = 1.0;
+            dops.push_back(d);
+            return;
+        }
+        op.kind = (op.target == -2) ? WK_RZ : WK_DIAG;      // single member: plain op is cheaper
+        if (op.kind == WK_DIAG) { op.m[0] = h.m[0]; op.m[1] = h.m[1]; }
+    }
+    if (op.kind == WK_DIAG && op.m[0] == -1.0 && op.m[1] == 0.0) op.kind = WK_NEG;
+    d.kind = (uint8_t)op.kind;
+    {
+        uint32_t pos_lane = 0, pos_reg = 0, neg_lane = 0, neg_reg = 0;
+        uint64_t pos_tile = 0, neg_tile = 0;
+        split_mask(L, op.cmask, &pos_lane, &pos_reg, &pos_tile);
+        split_mask(L, op.nmask, &neg_lane, &neg_reg, &neg_tile);      // k_window: neg_lane is always 0 (absorb_cnot refuses lane controls)
+        d.c_lane = pos_lane | neg_lane;
+        d.c_lval = (uint8_t)pos_lane;
+        d.c_reg = slot_mask(L.R, pos_reg, neg_reg);
+        d.c_tile = pos_tile | neg_tile;
+        d.c_tval = pos_tile;
+    }
+    if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
+    memcpy(d.m, op.m, sizeof(d.m));
+    if (op.kind != WK_DIAG && op.kind != WK_RZ && op.kind != WK_NEG) {
+        const int t = op.target;
+        d.tpos = (uint8_t)(L.cls[t] == CLS_LANE ? L.idx[t] : kLaneQubits + L.idx[t]);
+    }
+    dops.push_back(d);
+}
+
+static void push_scale_op(const Layout& L, double scale, std::vector<DOp>& dops) {      // no table to ride on: one real scale op
+    DOp d;
+    memset(&d, 0, sizeof(d));
+    d.kind = WK_SCALE;
+    d.c_reg = slot_mask(L.R, 0, 0);
+    d.m[0] = scale;
+    dops.push_back(d);
+}
+
 static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp>& dops, std::vector<amp_t>& arena, Layout* Lout) {
     Layout L = make_layout(s, ps.regs, R);
     *Lout = L;
@@ -928,47 +1136,234 @@ static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp
     double scale = ctx().opt_lean ? lean_convert(ops) : 1.0;
     for (const HOp& h : ops) {
         if (h.kind == 0) continue;              // absorbed into a neighbour (absorb_cnot)
-        DOp d;
-        memset(&d, 0, sizeof(d));
-        HOp op = h;
-        if (op.kind == WK_TABLE) {
-            const DiagGroup& g = ps.groups[op.group];
-            if (g.members >= 2) {
-                const bool carries = scale != 1.0 && g.hub < 0 && g.hub_alt < 0;      // unconditional: touches every amplitude
-                build_tables(L, g, arena, &d, carries ? scale : 1.0);
-                if (carries) scale = 1.0;
-                dops.push_back(d);
-                continue;
+        lower_op(L, ps, h, &scale, dops, arena);
+    }
+    if (scale != 1.0) push_scale_op(L, scale, dops);
+}
+
+// ---- host: a tile pass = rounds ---------------------------------------------------------------------------
+struct TileRoundHost {
+    int regs[4];                 // tile-local bits held in registers (ascending)
+    int thr[kTileThrBits];       // tile-local bit of thread-index bit k
+    size_t first_op = 0, nops = 0;
+};
+struct TileLaunch {
+    int tile_qubits[kTileBits];  // physical qubit of tile-local bit j (ascending)
+    std::vector<TileRoundHost> rounds;
+    std::vector<DOp> dops;
+    bool u2k = false, lean = false;
+};
+
+static GateUse uses_of_hop(const Pass& ps, const HOp& h) {
+    GateUse u{0, 0};
+    if (h.kind == WK_TABLE) {
+        const DiagGroup& g = ps.groups[h.group];
+        if (g.hub >= 0) u.d_use |= 1ull << g.hub;
+        if (g.hub_alt >= 0) u.d_use |= 1ull << g.hub_alt;
+        for (int q : g.bits) u.d_use |= 1ull << q;
+        u.d_use |= h.cmask | h.tmask;
+    } else if (h.kind == WK_DIAG || h.kind == WK_RZ) u.d_use = h.cmask | h.tmask;
+    else if (h.kind >= WK_X && h.kind <= kLastPairKind) { u.n_use = 1ull << h.target; u.d_use = h.cmask | h.nmask; }
+    return u;
+}
+
+// Split the ops of a pass into rounds of <= 4 register qubits.  Same commutation rule as the pass scheduler: an op may
+// move ahead of the ops skipped before it when on every shared qubit both act diagonally; a pair op needs its target
+// among the round's register qubits.  Returns op indices per round and the register qubits (physical) of each round.
+static void form_rounds(const Pass& ps, const std::vector<HOp>& ops, std::vector<std::vector<size_t>>* round_ops,
+                        std::vector<std::vector<int>>* round_regs) {
+    std::vector<size_t> rest;
+    for (size_t i = 0; i < ops.size(); i++) if (ops[i].kind != 0) rest.push_back(i);
+    while (!rest.empty()) {
+        std::vector<size_t> take, keep;
+        std::vector<int> Q;
+        uint64_t qmask = 0, blocked_any = 0, blocked_n = 0;
+        for (size_t i : rest) {
+            const HOp& h = ops[i];
+            const GateUse u = uses_of_hop(ps, h);
+            bool ok = ((u.n_use & blocked_any) == 0) && ((u.d_use & blocked_n) == 0);
+            if (ok && u.n_use && !(u.n_use & qmask)) {
+                if ((int)Q.size() < 4) { Q.push_back(h.target); qmask |= u.n_use; }
+                else ok = false;
             }
-            op.kind = (op.target == -2) ? WK_RZ : WK_DIAG;      // single member: plain op is cheaper
-            if (op.kind == WK_DIAG) { op.m[0] = h.m[0]; op.m[1] = h.m[1]; }
+            if (ok) take.push_back(i);
+            else { keep.push_back(i); blocked_any |= u.n_use | u.d_use; blocked_n |= u.n_use; }
         }
-        d.kind = (uint8_t)op.kind;
-        {
-            uint32_t pos_reg = 0, neg_lane = 0, neg_reg = 0;
-            uint64_t pos_tile = 0, neg_tile = 0;
-            split_mask(L, op.cmask, &d.c_lane, &pos_reg, &pos_tile);
-            split_mask(L, op.nmask, &neg_lane, &neg_reg, &neg_tile);      // neg_lane is always 0 (absorb_cnot refuses lane controls)
-            d.c_reg = slot_mask(L.R, pos_reg, neg_reg);
-            d.c_tile = pos_tile | neg_tile;
-            d.c_tval = pos_tile;
-        }
-        if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
-        memcpy(d.m, op.m, sizeof(d.m));
-        if (op.kind != WK_DIAG && op.kind != WK_RZ) {
-            const int t = op.target;
-            d.tpos = (uint8_t)(L.cls[t] == CLS_LANE ? L.idx[t] : kLaneQubits + L.idx[t]);
-        }
-        dops.push_back(d);
+        round_ops->push_back(take);
+        round_regs->push_back(Q);
+        rest.swap(keep);
     }
-    if (scale != 1.0) {                         // no table to ride on: one real scale op
-        DOp d;
-        memset(&d, 0, sizeof(d));
-        d.kind = WK_SCALE;
-        d.c_reg = slot_mask(L.R, 0, 0);
-        d.m[0] = scale;
-        dops.push_back(d);
+}
+
+// thread-bit order of a round: bank-conflict-free regroups need the tile-local bits behind thread bits 0..2 in three
+// different classes of the swizzle (tile_swz folds bits 3-5, 6-8, 9-10 onto 0-2)
+static void order_thread_bits(const int regs[4], bool io, int thr[kTileThrBits]) {
+    std::vector<int> free_bits;
+    for (int j = 0; j < kTileBits; j++)
+        if (j != regs[0] && j != regs[1] && j != regs[2] && j != regs[3]) free_bits.push_back(j);
+    if (!io) {
+        auto cls = [](int j) { return j < 9 ? j % 3 : j - 9; };
+        std::vector<int> first;
+        bool have[3] = {false, false, false};
+        for (int j : free_bits) if (!have[cls(j)]) { have[cls(j)] = true; first.push_back(j); }
+        std::vector<int> out(first);
+        for (int j : free_bits) if (std::find(first.begin(), first.end(), j) == first.end()) out.push_back(j);
+        free_bits.swap(out);
     }
+    for (int k = 0; k < kTileThrBits; k++) thr[k] = free_bits[k];
+}
+
+static Layout round_layout(const qi_state* s, const int tile_qubits[kTileBits], const TileRoundHost& r) {
+    Layout L;
+    L.R = 4;
+    L.nt = kTileThreads;
+    const int n = (int)s->n_local;
+    int local_of[64];
+    for (int q = 0; q < 64; q++) local_of[q] = -1;
+    for (int j = 0; j < kTileBits; j++) local_of[tile_qubits[j]] = j;
+    int t = 0;
+    for (int q = 0; q < 64; q++) {
+        L.cls[q] = CLS_NONE; L.idx[q] = 0;
+        if (q >= n) continue;
+        const int j = local_of[q];
+        if (j < 0) { L.cls[q] = CLS_TILE; L.idx[q] = t++; continue; }
+        int slot = -1;
+        for (int k = 0; k < 4; k++) if (r.regs[k] == j) slot = k;
+        if (slot >= 0) { L.cls[q] = CLS_REG; L.idx[q] = slot; L.regs.push_back(q); continue; }
+        for (int k = 0; k < kTileThrBits; k++) if (r.thr[k] == j) { L.cls[q] = CLS_LANE; L.idx[q] = k; }
+    }
+    L.ntile_bits = t;
+    return L;
+}
+
+// lower one pass to one or more k_tile launches
+static void lower_tile_pass(const qi_state* s, const Pass& ps, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
+    const int n = (int)s->n_local;
+    // tile qubits: 0..4 + the pass's window qubits, padded with the lowest free positions
+    std::vector<int> win(ps.regs);
+    std::sort(win.begin(), win.end());
+    for (int q = kLaneQubits; q < n && (int)win.size() < kTileWindow; q++)
+        if (std::find(win.begin(), win.end(), q) == win.end()) win.push_back(q);
+    std::sort(win.begin(), win.end());
+    int tile_qubits[kTileBits], local_of[64];
+    for (int q = 0; q < 64; q++) local_of[q] = -1;
+    for (int j = 0; j < kLaneQubits; j++) tile_qubits[j] = j;
+    for (int j = 0; j < kTileWindow; j++) tile_qubits[kLaneQubits + j] = win[j];
+    for (int j = 0; j < kTileBits; j++) local_of[tile_qubits[j]] = j;
+
+    std::vector<HOp> ops(ps.ops);
+    double scale = ctx().opt_lean ? lean_convert(ops) : 1.0;
+    std::vector<std::vector<size_t>> round_ops;
+    std::vector<std::vector<int>> round_regs;
+    form_rounds(ps, ops, &round_ops, &round_regs);
+
+    auto make_round = [&](const std::vector<int>& Q, bool force_io) {
+        TileRoundHost r;
+        std::vector<int> loc;
+        bool io = true;
+        for (int q : Q) { loc.push_back(local_of[q]); io &= local_of[q] >= kLaneQubits; }
+        io |= force_io;
+        // pad to 4 register bits: IO rounds from the window bits (highest first), others from any free tile bit (highest first)
+        for (int j = kTileBits - 1; j >= (io ? kLaneQubits : 0) && (int)loc.size() < 4; j--)
+            if (std::find(loc.begin(), loc.end(), j) == loc.end()) loc.push_back(j);
+        std::sort(loc.begin(), loc.end());
+        for (int k = 0; k < 4; k++) r.regs[k] = loc[k];
+        order_thread_bits(r.regs, io, r.thr);
+        return std::make_pair(r, io);
+    };
+
+    // a round never carries more ops than one launch holds
+    {
+        std::vector<std::vector<size_t>> ro;
+        std::vector<std::vector<int>> rq;
+        const size_t kChunk = 192;
+        for (size_t r = 0; r < round_ops.size(); r++)
+            for (size_t first = 0; first < std::max<size_t>(1, round_ops[r].size()); first += kChunk) {
+                ro.emplace_back(round_ops[r].begin() + first, round_ops[r].begin() + std::min(round_ops[r].size(), first + kChunk));
+                rq.push_back(round_regs[r]);
+            }
+        if (ro.empty()) { ro.emplace_back(); rq.emplace_back(); }
+        round_ops.swap(ro);
+        round_regs.swap(rq);
+    }
+    const size_t nrounds = round_ops.size();
+    size_t ri = 0;
+    while (ri < nrounds) {
+        TileLaunch tl;
+        memcpy(tl.tile_qubits, tile_qubits, sizeof(tile_qubits));
+        bool last_io = false;
+        while (ri < nrounds) {
+            const std::vector<size_t>& idx = round_ops[ri];
+            if (!tl.rounds.empty() && (tl.dops.size() + idx.size() + 1 > (size_t)kMaxTileOps || (int)tl.rounds.size() + 2 > kMaxRounds)) break;
+            auto rr = make_round(round_regs[ri], false);
+            if (tl.rounds.empty() && !rr.second) {          // a launch starts in an IO layout: empty IO round first
+                TileRoundHost io = make_round(std::vector<int>(), true).first;
+                io.first_op = tl.dops.size();
+                tl.rounds.push_back(io);
+            }
+            TileRoundHost r = rr.first;
+            r.first_op = tl.dops.size();
+            const Layout L = round_layout(s, tile_qubits, r);
+            for (size_t i : idx) lower_op(L, ps, ops[i], &scale, tl.dops, arena);
+            if (ri + 1 == nrounds && scale != 1.0) { push_scale_op(L, scale, tl.dops); scale = 1.0; }
+            r.nops = tl.dops.size() - r.first_op;
+            tl.rounds.push_back(r);
+            last_io = rr.second;
+            ri++;
+        }
+        if (!last_io) {                                      // ... and ends in one
+            TileRoundHost io = make_round(std::vector<int>(), true).first;
+            io.first_op = tl.dops.size();
+            tl.rounds.push_back(io);
+        }
+        for (const DOp& d : tl.dops) {
+            if (d.kind >= WK_X && d.kind <= kLastPairKind) { tl.u2k |= d.kind == WK_U2; tl.lean |= d.kind >= WK_REALUP; }
+            tl.lean |= d.kind == WK_SCALE;
+        }
+        launches.push_back(std::move(tl));
+    }
+}
+
+static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables) {
+    Context& c = ctx();
+    static TProgram P;            // 30 KB: not on the stack
+    memset(&P, 0, sizeof(P));
+    for (int j = 0; j < kTileBits; j++) P.tpos[j] = (uint8_t)tl.tile_qubits[j];
+    P.nrounds = (uint8_t)tl.rounds.size();
+    P.tables = d_tables;
+    for (size_t r = 0; r < tl.rounds.size(); r++) {
+        const TileRoundHost& h = tl.rounds[r];
+        TRound& d = P.rounds[r];
+        for (int sl = 0; sl < 16; sl++) {
+            uint32_t o = 0;
+            for (int k = 0; k < 4; k++) if ((sl >> k) & 1) o |= 1u << h.regs[k];
+            d.sswz[sl] = (uint16_t)tile_swz(o);
+        }
+        for (int k = 0; k < kTileThrBits; k++) d.thr_pos[k] = (uint8_t)h.thr[k];
+        d.first_op = (uint16_t)h.first_op;
+        d.nops = (uint16_t)h.nops;
+    }
+    const TileRoundHost& in = tl.rounds.front();
+    const TileRoundHost& out = tl.rounds.back();
+    for (int sl = 0; sl < 16; sl++) {
+        uint64_t oi = 0, oo = 0;
+        for (int k = 0; k < 4; k++)
+            if ((sl >> k) & 1) { oi |= 1ull << tl.tile_qubits[in.regs[k]]; oo |= 1ull << tl.tile_qubits[out.regs[k]]; }
+        P.goff_in[sl] = oi;
+        P.goff_out[sl] = oo;
+    }
+    memcpy(P.ops, tl.dops.data(), tl.dops.size() * sizeof(DOp));
+    const uint64_t ntiles = s->len >> kTileBits;
+    uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
+    LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
+    if (tl.lean) {
+        if (tl.u2k) k_tile<true, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+        else k_tile<false, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+    } else {
+        if (tl.u2k) k_tile<true, false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+        else k_tile<false, false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+    }
+    return check_launch("k_tile");
 }
 
 template <int R>
@@ -1117,17 +1512,101 @@ static int schedule_passes(const qi_state* s, const std::vector<PhysGate>& gates
     return QI_OK;
 }
 
-int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
+// ---- peephole: a controlled X next to a Hadamard on its target becomes a controlled Z --------------------------------
+// H X = Z H and X H = H Z hold bit for bit in the reference's arithmetic (X only permutes, Z only negates, and
+// s*(a1 + a0) == s*(a0 + a1)), so  [C..X(t), H(t)] == [H(t), C..Z(t)]  and  [H(t), C..X(t)] == [C..Z(t), H(t)]  exactly.
+// The controlled Z is diagonal: it merges into the phase table the pass carries anyway, whereas the X costs a register
+// swap op of its own or (absorbed) turns the neighbouring gate into two predicated half-populated ops.  An X also slides
+// past gates that commute with it bit for bit: RX-form 2x2 gates on its target (RX X = X RX: both orders evaluate the
+// same products) and anything diagonal on its controls.  Random H/RX/RZ + CNOT layers: 5 of 9 CNOTs are rewritten.
+static bool is_rx_form(const PhysGate& g) {
+    const double* p = g.p;
+    return g.kind == IK_U2 && g.cmask == 0 && p[1] == 0.0 && p[2] == 0.0 && p[4] == 0.0 && p[7] == 0.0 && p[0] == p[6] && p[3] == p[5];
+}
+
+static void rewrite_cx_next_to_h(std::vector<PhysGate>& gates) {
+    const int G = (int)gates.size();
+    if (G < 2) return;
+    const int kWindow = 256;                       // gates scanned on either side of an X
+    std::vector<PhysGate> pool(gates);             // nodes 0..G-1: original gates; node G: list sentinel; then the inserted controlled-Z gates
+    pool.reserve(G + 1 + G / 2);
+    pool.push_back(PhysGate());
+    std::vector<int> next(G + 1), prev(G + 1);     // doubly linked list through the sentinel
+    for (int i = 0; i <= G; i++) { next[i] = i == G ? 0 : i + 1; prev[i] = i == 0 ? G : i - 1; }
+    auto unlink = [&](int i) { next[prev[i]] = next[i]; prev[next[i]] = prev[i]; };
+    auto insert_after = [&](int at, const PhysGate& g) {
+        const int id = (int)pool.size();
+        pool.push_back(g);
+        next.push_back(next[at]); prev.push_back(at);
+        prev[next[at]] = id; next[at] = id;
+    };
+    bool any = false;
+    for (int i = 0; i < G; i++) {
+        const PhysGate x = pool[i];
+        if (x.kind != IK_X) continue;
+        const uint64_t tb = 1ull << x.t0, cm = x.cmask;
+        PhysGate cz;
+        memset(&cz, 0, sizeof(cz));
+        cz.kind = IK_DIAG; cz.t0 = x.t0; cz.t1 = -1; cz.cmask = cm; cz.p[0] = -1.0; cz.p[1] = 0.0;
+        bool done = false;
+        // forward: [X ... H] -> [... H, CZ]
+        int j = next[i];
+        for (int k = 0; k < kWindow && j != G; k++, j = next[j]) {
+            const PhysGate& g = pool[j];
+            const GateUse u = uses_of(g);
+            if (u.n_use & cm) break;                                   // a control changes: the X cannot move past it
+            if ((u.n_use | u.d_use) & tb) {
+                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) { insert_after(j, cz); unlink(i); done = any = true; }
+                else if (is_rx_form(g) && g.t0 == x.t0) continue;     // commutes bit for bit
+                break;
+            }
+        }
+        if (done) continue;
+        // backward: [H ... X] -> [CZ, H ...]
+        j = prev[i];
+        for (int k = 0; k < kWindow && j != G; k++, j = prev[j]) {
+            const PhysGate& g = pool[j];
+            const GateUse u = uses_of(g);
+            if (u.n_use & cm) break;
+            if ((u.n_use | u.d_use) & tb) {
+                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) { insert_after(prev[j], cz); unlink(i); any = true; }
+                else if (is_rx_form(g) && g.t0 == x.t0) continue;
+                break;
+            }
+        }
+    }
+    if (!any) return;
+    std::vector<PhysGate> out;
+    out.reserve(pool.size());
+    for (int i = next[G]; i != G; i = next[i]) out.push_back(pool[i]);
+    gates.swap(out);
+}
+
+// passes run on the CTA-tile kernel (k_tile) when the state has enough local qubits; option "tile" = 0 keeps the warp-tile kernel
+static bool tile_mode(const qi_state* s) {
+    const Context& c = ctx();
+    return c.opt_tile && !c.opt_tma && (int)s->n_local >= std::max(kTileBits, c.opt_tile_min_qubits);
+}
+
+int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in) {
     Context& c = ctx();
-    const int R = window_regs(s);
+    std::vector<PhysGate> rewritten;
+    if (c.opt_cz_rewrite && c.opt_fuse) { rewritten = gates_in; rewrite_cx_next_to_h(rewritten); }
+    const std::vector<PhysGate>& gates = (c.opt_cz_rewrite && c.opt_fuse) ? rewritten : gates_in;
+    const bool tile = tile_mode(s);
+    const int R = tile ? kTileWindow : window_regs(s);
     std::vector<Step> steps;
     QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
     // lower every pass, upload all phase tables in one copy, then launch back to back
     std::vector<std::vector<DOp>> dops(steps.size());
     std::vector<Layout> layouts(steps.size());
+    std::vector<std::vector<TileLaunch>> tiles(steps.size());
     std::vector<amp_t> arena;
-    for (size_t i = 0; i < steps.size(); i++)
-        if (!steps[i].simple) lower_pass(s, steps[i].pass, steps[i].R, dops[i], arena, &layouts[i]);
+    for (size_t i = 0; i < steps.size(); i++) {
+        if (steps[i].simple) continue;
+        if (tile) lower_tile_pass(s, steps[i].pass, tiles[i], arena);
+        else lower_pass(s, steps[i].pass, steps[i].R, dops[i], arena, &layouts[i]);
+    }
     if (!arena.empty()) {
         QI_TRY(ensure_tables(arena.size()));
         QI_CUDA(cudaEventSynchronize(c.ops_event));      // the previous run's copy has left the pinned buffer
@@ -1137,6 +1616,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates) {
     }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, gates[steps[i].gate]));
+        else if (tile) { for (const TileLaunch& tl : tiles[i]) QI_TRY(launch_tile(s, tl, (const amp_t*)c.d_ops)); }
         else if (steps[i].R == 3) QI_TRY(launch_program<3>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else if (steps[i].R == 4) QI_TRY(launch_program<4>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else QI_TRY(launch_program<5>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
@@ -1168,13 +1648,47 @@ int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R,
 //   u64 nsteps, then per step: u64 simple;
 //     simple = 1: PhysGate (raw);   simple = 0: u64 R, u64 regs[8] (sorted window qubits), u64 nops, DOp[nops] (raw, 112 B each)
 //   then u64 arena_count and arena_count double2 phase-table entries (DOp::m[0] of a table op is an offset into it)
-int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<uint8_t>* blob) {
+//     simple = 2 (CTA-tile pass, one record per k_tile launch): u64 tile_qubits[11], u64 nrounds, then per round
+//                 u64 regs[4] (physical qubits of slot bits 0..3), u64 thr[7] (physical qubit of thread-index bit k), u64 nops, DOp[nops]
+int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R, std::vector<uint8_t>* blob) {
+    std::vector<PhysGate> gates(gates_in);
+    if (ctx().opt_cz_rewrite && ctx().opt_fuse) rewrite_cx_next_to_h(gates);
     std::vector<Step> steps;
+    const bool tile = tile_mode(s);
+    if (tile) R = kTileWindow;
     QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
     std::vector<amp_t> arena;
     auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };
     auto put64 = [&](uint64_t v) { put(&v, 8); };
     put64(steps.size());
+    if (tile) {
+        uint64_t nrec = 0;
+        std::vector<std::vector<TileLaunch>> tiles(steps.size());
+        for (size_t i = 0; i < steps.size(); i++) {
+            if (steps[i].simple) { nrec++; continue; }
+            lower_tile_pass(s, steps[i].pass, tiles[i], arena);
+            nrec += tiles[i].size();
+        }
+        blob->clear();
+        put64(nrec);
+        for (size_t i = 0; i < steps.size(); i++) {
+            if (steps[i].simple) { put64(1); put(&gates[steps[i].gate], sizeof(PhysGate)); continue; }
+            for (const TileLaunch& tl : tiles[i]) {
+                put64(2);
+                for (int j = 0; j < kTileBits; j++) put64((uint64_t)tl.tile_qubits[j]);
+                put64(tl.rounds.size());
+                for (const TileRoundHost& r : tl.rounds) {
+                    for (int k = 0; k < 4; k++) put64((uint64_t)tl.tile_qubits[r.regs[k]]);
+                    for (int k = 0; k < kTileThrBits; k++) put64((uint64_t)tl.tile_qubits[r.thr[k]]);
+                    put64(r.nops);
+                    put(tl.dops.data() + r.first_op, r.nops * sizeof(DOp));
+                }
+            }
+        }
+        put64(arena.size());
+        put(arena.data(), arena.size() * sizeof(amp_t));
+        return QI_OK;
+    }
     for (const Step& st : steps) {
         put64(st.simple ? 1 : 0);
         if (st.simple) { put(&gates[st.gate], sizeof(PhysGate)); continue; }

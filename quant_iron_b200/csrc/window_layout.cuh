@@ -14,6 +14,7 @@ static const int kLaneQubits = 5;    // lanes <-> physical qubits 0..4
 
 struct Layout {
     int R;
+    int nt = 32;                        // entries of the lane part of a phase table (32 lanes; k_tile rounds: 128 threads)
     std::vector<int> regs;              // sorted window qubits
     int cls[64];                        // CLS_* per physical bit
     int idx[64];                        // lane bit / slot bit / compact tile bit per physical bit

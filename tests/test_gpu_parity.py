@@ -16,6 +16,17 @@ pytestmark = pytest.mark.gpu
 PI = math.pi
 
 
+@pytest.fixture(autouse=True, params=[18, 11], ids=["tile_from_18q", "tile_from_11q"])
+def _tile_threshold(request):
+    """Every test runs twice: with the default split between the warp-tile kernel (k_window, < 18 local qubits) and the
+    CTA-tile kernel (k_tile), and with k_tile taking every state it can hold (>= 11 qubits), so that the small oracle-sized
+    cases exercise the kernel the benchmark sizes run on."""
+    import quant_iron_b200
+    quant_iron_b200.engine.set_option("tile_min_qubits", request.param)
+    yield
+    quant_iron_b200.engine.set_option("tile_min_qubits", 18)
+
+
 def _pair(gpu, ref, n, seed=20260002):
     r = ref.random_state(n, seed)
     return gpu.State(r.state_vector, n), r

@@ -28,18 +28,50 @@ def test_fuzzed_gate_lists_lowered_programs_match_oracle(ref, n, seed, regs):
     assert any(s[0] == "pass" for s in steps)
 
 
+@pytest.mark.parametrize("cz", [0, 1])
 @pytest.mark.parametrize("n,depth", [(10, 12), (13, 10), (14, 6)])
-def test_layered_circuit_lowered_programs_match_oracle(ref, n, depth):
+def test_layered_circuit_lowered_programs_match_oracle(ref, n, depth, cz):
     import quant_iron_b200 as gpu
     from quant_iron_b200 import workloads as w
     specs = w.random_layered_circuit(n, depth)
     start = ref.random_state(n, 3)
-    got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    gpu.engine.set_option("cz_rewrite", cz)
+    try:
+        got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    finally:
+        gpu.engine.set_option("cz_rewrite", 1)
     want = vec(w.build_circuit(ref, n, specs).execute(start))
     assert float(np.max(np.abs(got - want))) <= AMP_TOL
     ops = np.concatenate([s[3] for s in steps if s[0] == "pass"])
     assert (ops["kind"] == wi.WK_TABLE).any()                      # merged RZ runs
-    assert ((ops["kind"] <= wi.LAST_PAIR) & (ops["c_tval"] != ops["c_tile"])).any() or n < 12    # negative controls of absorbed CNOTs
+    if not cz:
+        assert ((ops["kind"] <= wi.LAST_PAIR) & (ops["c_tval"] != ops["c_tile"])).any() or n < 12    # negative controls of absorbed CNOTs
+
+
+def test_cx_next_to_h_becomes_cz_bit_exact(ref):
+    """[CX(c,t), H(t)] == [H(t), CZ(c,t)] and [H(t), CX(c,t)] == [CZ(c,t), H(t)] hold bit for bit in the reference's arithmetic;
+    the executor uses them (option cz_rewrite) to turn register-swap ops into phase-table members.  The rewritten programs
+    must reproduce the programs without the rewrite EXACTLY, and hold fewer X ops."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    n = 13
+    specs = w.random_layered_circuit(n, 14)
+    start = ref.random_state(n, 21)
+    out, nx = {}, {}
+    for cz in (0, 1):
+        gpu.engine.set_option("cz_rewrite", cz)
+        gpu.engine.set_option("absorb", 0)
+        try:
+            out[cz], steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+        finally:
+            gpu.engine.set_option("cz_rewrite", 1)
+            gpu.engine.set_option("absorb", 1)
+        ops = np.concatenate([s[3] for s in steps if s[0] == "pass"])
+        nx[cz] = int((ops["kind"] == wi.WK_X).sum())
+    assert nx[1] < 0.6 * nx[0], nx
+    assert float(np.max(np.abs(out[1] - out[0]))) <= 4e-16          # same products and sums; merged table phases differ by an ulp
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(out[1] - want))) <= AMP_TOL
 
 
 @pytest.mark.parametrize("n", [9, 12])
@@ -207,6 +239,7 @@ def test_late_table_placement_fewer_diagonal_ops_same_state(ref):
     start = ref.random_state(n, 8)
     want = vec(w.build_circuit(ref, n, specs).execute(start))
     counts = {}
+    gpu.engine.set_option("cz_rewrite", 0)          # counts below: RZ tables only, no controlled-Z members
     for late in (0, 1):
         gpu.engine.set_option("late_tables", late)
         try:
@@ -218,8 +251,13 @@ def test_late_table_placement_fewer_diagonal_ops_same_state(ref):
         counts[late] = (int(((ops["kind"] == wi.WK_TABLE) | (ops["kind"] == wi.WK_RZ)).sum()), len(steps))
     assert counts[1][1] == counts[0][1]                       # same passes
     assert counts[1][0] < 0.8 * counts[0][0], counts          # fewer diagonal ops
-    # the benchmark circuit: at most 3 diagonal ops in any pass (6 without), 123 instead of 197 in total
-    steps, _, _ = wi.parse(wi.lower(w.build_circuit(gpu, 30, w.random_layered_circuit(30, 40)), 30))
+    # the benchmark circuit on the warp-tile executor: at most 3 diagonal ops in any pass (6 without), 123 instead of 197 in total
+    gpu.engine.set_option("tile", 0)
+    try:
+        steps, _, _ = wi.parse(wi.lower(w.build_circuit(gpu, 30, w.random_layered_circuit(30, 40)), 30))
+    finally:
+        gpu.engine.set_option("tile", 1)
+        gpu.engine.set_option("cz_rewrite", 1)
     per = [int(((s[3]["kind"] == wi.WK_TABLE) | (s[3]["kind"] == wi.WK_RZ)).sum()) for s in steps if s[0] == "pass"]
     assert max(per) <= 3 and sum(per) <= 130, (max(per), sum(per))
 
@@ -250,3 +288,78 @@ def test_heisenberg_expectation_groups(ref):
     want = hr.expectation_value(psi)
     assert not left and ngroups <= 6
     assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+
+
+# ---- CTA-tile passes (k_tile): rounds of 4 register qubits out of 11 tile qubits ---------------------------------------
+@pytest.fixture
+def tile11():
+    """Force the CTA-tile executor for every state with >= 11 local qubits (default: >= 18)."""
+    import quant_iron_b200 as gpu
+    gpu.engine.set_option("tile_min_qubits", 11)
+    yield
+    gpu.engine.set_option("tile_min_qubits", 18)
+
+
+def _tile_steps(steps):
+    return [s for s in steps if s[0] == "tile"]
+
+
+@pytest.mark.parametrize("n,seed", [(11, 1), (12, 2), (12, 3), (13, 4), (14, 5), (13, 6), (11, 7), (12, 8)])
+def test_tile_fuzzed_gate_lists_match_oracle(ref, tile11, n, seed):
+    import quant_iron_b200 as gpu
+    cg, cr = _fuzz_builders([gpu, ref], n, seed, count=260, lazy_swaps=(seed % 2 == 0))
+    start = ref.random_state(n, 140 + seed)
+    got, steps = _run(cg, n, start.state_vector)
+    want = vec(cr.execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    assert _tile_steps(steps) and not any(s[0] == "pass" for s in steps)
+
+
+@pytest.mark.parametrize("n,depth,lean", [(12, 12, 0), (14, 10, 0), (15, 8, 0), (13, 10, 1), (15, 6, 1)])
+def test_tile_layered_circuit_matches_oracle(ref, tile11, n, depth, lean):
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    specs = w.random_layered_circuit(n, depth)
+    start = ref.random_state(n, 5)
+    gpu.engine.set_option("lean", lean)
+    try:
+        got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    finally:
+        gpu.engine.set_option("lean", 0)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    tiles = _tile_steps(steps)
+    assert tiles
+    # the point of the tile pass: many rounds share one HBM pass, and gates on qubits 0..4 are register gates like any other
+    assert max(len(t[2]) for t in tiles) >= 3
+    kinds = np.concatenate([ops["kind"] for t in tiles for (_, _, ops) in t[2] if len(ops)])
+    assert (kinds == wi.WK_TABLE).any()
+    if lean:
+        assert (kinds >= wi.WK_REALUP).any()
+
+
+@pytest.mark.parametrize("n", [11, 14, 16])
+def test_tile_qft_matches_closed_form_and_oracle(ref, tile11, n):
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    c = w.build_circuit(gpu, n, w.qft_specs(n))
+    plus = np.full(1 << n, 1.0 / np.sqrt(float(1 << n)), dtype=np.complex128)
+    got, steps = _run(c, n, plus)
+    assert abs(got[0] - 1.0) <= AMP_TOL and float(np.max(np.abs(got[1:]))) <= AMP_TOL
+    assert _tile_steps(steps)
+    start = ref.random_state(n, 19)
+    got, _ = _run(c, n, start.state_vector)
+    want = vec(w.build_circuit(ref, n, w.qft_specs(n)).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+
+
+def test_tile_pass_count_of_the_benchmark_circuit():
+    """30 qubits, depth 40: the tile executor needs well under half of the 126 HBM passes of the warp-tile executor."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    c = w.build_circuit(gpu, 30, w.random_layered_circuit(30, 40))
+    steps, _, _ = wi.parse(wi.lower(c, 30))
+    tiles = _tile_steps(steps)
+    assert len(tiles) == len(steps)
+    assert len(tiles) <= 90, len(tiles)
+    assert sum(len(ops) for t in tiles for (_, _, ops) in t[2]) >= 1400

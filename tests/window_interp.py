@@ -12,13 +12,13 @@ import struct
 
 import numpy as np
 
-WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE = range(1, 14)
+WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE, WK_NEG = range(1, 15)
 LAST_PAIR = WK_RXSU
 IK_H, IK_X, IK_Y, IK_U2, IK_DIAG, IK_RZ, IK_SWAP, IK_MATCH = 1, 2, 3, 4, 5, 6, 7, 8
 CLS_LANE, CLS_REG, CLS_TILE = 1, 2, 3
 
 DOP = np.dtype([("kind", "u1"), ("tpos", "u1"), ("hub_cls", "u1"), ("hub_bit", "u1"), ("nchunks", "u1"), ("has_reg", "u1"),
-                ("pad", "u1", 2), ("c_lane", "<u4"), ("c_reg", "<u4"), ("t_lane", "<u4"), ("t_reg", "<u4"),
+                ("c_lval", "u1"), ("pad", "u1"), ("c_lane", "<u4"), ("c_reg", "<u4"), ("t_lane", "<u4"), ("t_reg", "<u4"),
                 ("c_tile", "<u8"), ("c_tval", "<u8"), ("t_tile", "<u8"), ("m", "<f8", 8)])
 PHYS = np.dtype([("kind", "<i4"), ("t0", "<i4"), ("t1", "<i4"), ("pad", "<i4"), ("cmask", "<u8"), ("p", "<f8", 8)])
 assert DOP.itemsize == 112 and PHYS.itemsize == 88
@@ -55,9 +55,21 @@ def parse(blob):
 
     steps = []
     for _ in range(u64()):
-        if u64():
+        tag = u64()
+        if tag == 1:
             steps.append(("simple", np.frombuffer(blob, PHYS, 1, off)[0]))
             off += PHYS.itemsize
+        elif tag == 2:                # one k_tile launch: 11 tile qubits, rounds of (4 register qubits, 7 thread-bit qubits, ops)
+            tile_qubits = [u64() for _ in range(11)]
+            rounds = []
+            for _ in range(u64()):
+                regs = [u64() for _ in range(4)]
+                thr = [u64() for _ in range(7)]
+                nops = u64()
+                ops = np.frombuffer(blob, DOP, nops, off)
+                off += nops * DOP.itemsize
+                rounds.append((regs, thr, ops))
+            steps.append(("tile", tile_qubits, rounds))
         else:
             R = u64()
             regs = [u64() for _ in range(8)][:R]
@@ -99,17 +111,22 @@ def _pair(v, idx0, tb, kind, m):
     v[idx0 | tb] = n1
 
 
-def run_pass(v, nl, R, regs, ops, arena):
+def run_pass(v, nl, R, regs, ops, arena, lane_qubits=(0, 1, 2, 3, 4)):
+    """One op list under one layout: `regs` = physical qubits of the slot bits, `lane_qubits` = physical qubits of the
+    lane-index bits (k_window: qubits 0..4; a k_tile round: the 7 thread-index bits); every other qubit is a tile bit."""
     S = 1 << R
+    NT = 1 << len(lane_qubits)
     idx = np.arange(1 << nl, dtype=np.uint64)
-    lane = (idx & np.uint64(31)).astype(np.uint32)
+    lane = np.zeros(1 << nl, dtype=np.uint32)
+    for j, q in enumerate(lane_qubits):
+        lane |= (((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)).astype(np.uint32)
     slot = np.zeros(1 << nl, dtype=np.uint32)
     for j, q in enumerate(regs):
         slot |= (((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)).astype(np.uint32)
     tile = np.zeros(1 << nl, dtype=np.uint64)
     t = 0
-    for q in range(5, nl):
-        if q in regs:
+    for q in range(nl):
+        if q in regs or q in lane_qubits:
             continue
         tile |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(t)
         t += 1
@@ -117,12 +134,13 @@ def run_pass(v, nl, R, regs, ops, arena):
         kind = int(op["kind"])
         m = op["m"]
         tile_ok = (tile & np.uint64(op["c_tile"])) == np.uint64(op["c_tval"])
-        lane_ok = (lane & np.uint32(op["c_lane"])) == np.uint32(op["c_lane"])
+        lane_ok = (lane & np.uint32(op["c_lane"])) == np.uint32(op["c_lval"])
         c_reg = int(op["c_reg"])
         slot_ok = ((np.uint32(c_reg) >> slot) & np.uint32(1)).astype(bool)
         if kind <= LAST_PAIR:
             tpos = int(op["tpos"])
-            tbit = tpos if tpos < 5 else regs[tpos - 5]
+            tbit = lane_qubits[tpos] if tpos < 5 else regs[tpos - 5]
+            assert tpos >= 5 or NT == 32, "a k_tile round has no lane-pair ops"
             tb = np.uint64(1 << tbit)
             # the predicate is evaluated on the member with the target bit clear; controls never include the target
             sel = tile_ok & lane_ok & slot_ok & ((idx & tb) == 0)
@@ -133,6 +151,8 @@ def run_pass(v, nl, R, regs, ops, arena):
             v[active & slot_ok] *= float(m[0])
         elif kind == WK_DIAG:
             v[active & slot_ok] *= complex(m[0], m[1])
+        elif kind == WK_NEG:                    # a phase of exactly -1 (Z, CZ): sign flips
+            v[active & slot_ok] *= -1.0
         elif kind == WK_RZ:
             p0, p1 = complex(m[0], m[1]), complex(m[2], m[3])
             t_thread = ((tile & np.uint64(op["t_tile"])) != 0) | ((lane & np.uint32(op["t_lane"])) != 0)
@@ -151,9 +171,9 @@ def run_pass(v, nl, R, regs, ops, arena):
                 active = active & (((slot >> np.uint32(hub_bit)) & np.uint32(1)) == 1)
             f = arena[base + lane.astype(np.int64)]
             for k in range(int(op["nchunks"])):
-                f = f * arena[base + 32 + S + 256 * k + ((tile >> np.uint64(8 * k)) & np.uint64(255)).astype(np.int64)]
+                f = f * arena[base + NT + S + 256 * k + ((tile >> np.uint64(8 * k)) & np.uint64(255)).astype(np.int64)]
             if op["has_reg"]:
-                f = f * arena[base + 32 + slot.astype(np.int64)]
+                f = f * arena[base + NT + slot.astype(np.int64)]
             v[active] *= f[active]
         else:
             raise AssertionError(f"unknown device op kind {kind}")
@@ -207,6 +227,14 @@ def execute(blob, v, nl):
     for st in steps:
         if st[0] == "simple":
             run_simple(v, nl, st[1])
+        elif st[0] == "tile":
+            tile_qubits, rounds = st[1], st[2]
+            assert tile_qubits[:5] == [0, 1, 2, 3, 4] and sorted(tile_qubits) == tile_qubits and len(set(tile_qubits)) == 11
+            for k, (regs, thr, ops) in enumerate(rounds):
+                assert sorted(regs + thr) == tile_qubits, "a round's register + thread qubits are the tile qubits"
+                if k in (0, len(rounds) - 1):          # IO layouts: coalesced 512-byte rows
+                    assert thr[:5] == [0, 1, 2, 3, 4], "first / last round: lanes on qubits 0..4"
+                run_pass(v, nl, 4, regs, ops, arena, lane_qubits=tuple(thr))
         else:
             run_pass(v, nl, st[1], st[2], st[3], arena)
     return phys, steps
