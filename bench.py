@@ -91,54 +91,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_baseline(num_qubits: int, specs, budget_s: float = 20.0):
-    """The reference's CPU path, restated (oracle/qi_oracle.c), timed on this box's host cores on a
-    bounded sample: the leading gates of the same circuit.  `faithful` = the reference's rayon-branch
-    pass structure (clone + parallel (index,value) updates with a heap allocation per pair + serial
-    scatter, operator.rs:339-360); `inplace` = same arithmetic, in place (a stronger CPU baseline)."""
-    import numpy as np
-    from oracle import refapi as ref
-    kinds = {"h": ref.G_H, "rx": ref.G_RX, "rz": ref.G_RZ, "cnot": ref.G_CNOT, "cp": ref.G_P, "swap": ref.G_SWAP,
-             "x": ref.G_X, "p": ref.G_P}
-    cores = ref.num_threads()
-    try:
-        avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
-    except Exception:
-        avail = 32 << 30
-    # calibrate at 22 qubits, then pick the largest n (<= requested) whose gate fits time and memory
-    n_cal = min(22, num_qubits)
-    v = np.zeros(1 << n_cal, dtype=np.complex128)
-    v[0] = 1.0
-    dst = np.empty_like(v)
-    t0 = time.perf_counter()
-    ref.gate_faithful(v, dst, n_cal, ref.G_H, [n_cal // 2], [], [])
-    per_amp = (time.perf_counter() - t0) / float(1 << n_cal)
-    n = num_qubits
-    while n > n_cal and (per_amp * (1 << n) > budget_s / 3.0 or 100 * (1 << n) > avail * 0.7):
-        n -= 1
-    del v, dst
+def load_workloads():
+    """quant_iron_b200/workloads.py by PATH: the generator is pure Python, and the reference arm must not map the
+    product's library into its process (importing the package would)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_qi_workloads", os.path.join(ROOT, "quant_iron_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
-    def run(kind: str):
-        a = np.zeros(1 << n, dtype=np.complex128)
-        a[0] = 1.0
-        b = np.empty_like(a) if kind == "faithful" else None
-        done, t_start = 0, time.perf_counter()
-        for name, targets, controls, params in specs:
-            if any(q >= n for q in targets + controls):
-                continue
-            if kind == "faithful":
-                ref.gate_faithful(a, b, n, kinds[name], targets, controls, params)
-                a, b = b, a
-            else:
-                ref.gate_inplace(a, n, kinds[name], targets, controls, params)
-            done += 1
-            if time.perf_counter() - t_start > budget_s / 2.0 and done >= 2:
-                break
-        return done / (time.perf_counter() - t_start), done
 
-    f_rate, f_done = run("faithful")
-    i_rate, i_done = run("inplace")
-    scale = float(1 << (num_qubits - n))
+def host_info():
     cpu_model = None
     try:
         with open("/proc/cpuinfo") as f:
@@ -148,41 +112,131 @@ def cpu_baseline(num_qubits: int, specs, budget_s: float = 20.0):
                     break
     except OSError:
         pass
+    try:
+        avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
+    except Exception:
+        avail = 32 << 30
+    return cpu_model, avail
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and uses every host core, so the
+    variable is set explicitly BEFORE the oracle's OpenMP runtime is loaded."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+
+def cpu_baseline(num_qubits: int, depth: int, budget_s: float = 20.0):
+    """The reference's CPU path, restated (oracle/qi_oracle.c), timed on this box's host cores on a bounded sample of the
+    SAME workload: whole layers (every single-qubit gate of the layer plus its CNOT row; at least one full layer) of the
+    same generator at the largest qubit count whose layer fits the time budget and host memory.
+    `faithful` = the reference's rayon-branch pass structure (clone + parallel (index, value) updates with a heap
+    allocation per pair + serial scatter, operator.rs:339-360); `inplace` = the same arithmetic in place (a stronger CPU
+    baseline).  A gate's cost is proportional to the state size, so the rate at the bench size is the measured rate times
+    2^-(bench qubits - sample qubits); both numbers and the factor are reported."""
+    import numpy as np
+    from oracle import refapi as ref
+    w = load_workloads()
+    kinds = {"h": ref.G_H, "rx": ref.G_RX, "rz": ref.G_RZ, "cnot": ref.G_CNOT}
+    cores = ref.num_threads()
+    cpu_model, avail = host_info()
+    # calibrate both variants at 22 qubits (one H)
+    n_cal = min(22, num_qubits)
+    v = np.zeros(1 << n_cal, dtype=np.complex128)
+    v[0] = 1.0
+    dst = np.empty_like(v)
+    ref.gate_faithful(v, dst, n_cal, ref.G_H, [n_cal // 2], [], [])
+    t0 = time.perf_counter()
+    ref.gate_faithful(v, dst, n_cal, ref.G_H, [n_cal // 2], [], [])
+    per_amp_f = (time.perf_counter() - t0) / float(1 << n_cal)
+    t0 = time.perf_counter()
+    ref.gate_inplace(v, n_cal, ref.G_H, [n_cal // 2], [], [])
+    per_amp_i = (time.perf_counter() - t0) / float(1 << n_cal)
+    del v, dst
+
+    def pick(per_amp, share, bytes_per_amp):
+        n = min(num_qubits, 30)
+        while n > n_cal and (per_amp * (1 << n) * 1.5 * n > budget_s * share or bytes_per_amp * (1 << n) > avail * 0.6):
+            n -= 1
+        return n
+
+    def run(kind, n, share):
+        specs = w.random_layered_circuit(n, depth)
+        per_layer = n + (n - 1 + 1) // 2                  # upper bound; layers are delimited by counting single-qubit gates
+        a = np.zeros(1 << n, dtype=np.complex128)
+        a[0] = 1.0
+        b = np.empty_like(a) if kind == "faithful" else None
+        done = layers = in_layer_1q = 0
+        t_start = time.perf_counter()
+        t_layer_end = t_start
+        i = 0
+        while i < len(specs):
+            # one whole layer: n single-qubit gates, then the CNOT row
+            j = i
+            one_q = 0
+            while j < len(specs) and (one_q < n or specs[j][0] == "cnot"):
+                one_q += specs[j][0] != "cnot"
+                j += 1
+            for name, targets, controls, params in specs[i:j]:
+                if kind == "faithful":
+                    ref.gate_faithful(a, b, n, kinds[name], targets, controls, params)
+                    a, b = b, a
+                else:
+                    ref.gate_inplace(a, n, kinds[name], targets, controls, params)
+            done += j - i
+            layers += 1
+            i = j
+            t_layer_end = time.perf_counter()
+            if t_layer_end - t_start > budget_s * share:
+                break
+        del per_layer, in_layer_1q
+        dt = t_layer_end - t_start
+        return {"qubits": n, "layers": layers, "gates": done, "seconds": dt, "gates_per_sec_at_sample": done / dt}
+
+    f = run("faithful", pick(per_amp_f, 0.6, 100), 0.6)
+    g = run("inplace", pick(per_amp_i, 0.3, 20), 0.3)
+    sf, sg = float(1 << (num_qubits - f["qubits"])), float(1 << (num_qubits - g["qubits"]))
     return {
         "cpu_model": cpu_model, "nproc": os.cpu_count(),
-        # `value` is in the headline's terms (gates/s on the bench-size state): the rate measured on the
-        # sample divided by 2^(bench qubits - sample qubits) (a gate's cost is proportional to the state size)
-        "value": f_rate / scale, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"first {f_done} gates of the same circuit at {n} qubits, reference pass structure "
-                  f"(clone + per-pair updates + serial scatter, operator.rs:339-360), scaled by 2^-{num_qubits - n}; "
-                  f"in-place variant of the same arithmetic: first {i_done} gates",
-        "qubits": n, "measured_at_sample_qubits": f_rate, "inplace_measured_at_sample_qubits": i_rate,
-        "scaled_to_bench_qubits": f_rate / scale,
-        "inplace_scaled_to_bench_qubits": i_rate / scale,
+        "value": f["gates_per_sec_at_sample"] / sf, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{f['layers']} whole layer(s) = {f['gates']} gates (every single-qubit gate + the CNOT row) of the same generator at "
+                  f"{f['qubits']} qubits, reference pass structure (clone + per-pair updates + serial scatter, operator.rs:339-360), "
+                  f"{f['seconds']:.1f} s measured; rate scaled by 2^-{num_qubits - f['qubits']} to the bench size",
+        "faithful": f, "inplace": g, "scale_factor_faithful": sf, "scale_factor_inplace": sg,
+        "scaled_to_bench_qubits": f["gates_per_sec_at_sample"] / sf,
+        "inplace_scaled_to_bench_qubits": g["gates_per_sec_at_sample"] / sg,
     }
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's own CPU implementation of the path (its Rust crate cannot
-    be built here; the C restatement under oracle/ is what is timed), all host threads, rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path (its Rust crate cannot be built here; the C
+    restatement under oracle/ is what is timed), all host threads, rank 0 only.  A step = a bounded sample of the workload
+    (whole layers at the largest size that fits); `ms_per_step` is the MEASURED time of that sample, `value` the measured
+    rate scaled to the bench size by the stated factor."""
     if rank != 0:
         return
-    from quant_iron_b200 import workloads as w
+    use_all_host_threads()
     n = args.qubits + (world.bit_length() - 1)       # same total size as the GPU arm at this N
-    specs = w.random_layered_circuit(n, args.depth)
-    vals, base = [], None
+    vals, times, base = [], [], None
     budget = min(args.cpu_budget, 150.0 / (args.warmup + args.steps))   # whole run ends within a few minutes
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(n, specs, budget_s=budget)
+        t0 = time.perf_counter()
+        base = cpu_baseline(n, args.depth, budget_s=budget)
         if i >= args.warmup:
             vals.append(base["scaled_to_bench_qubits"] * world)     # unit of work: gate x 2^n_per_gpu shard (see config)
+            times.append(time.perf_counter() - t0)
     value = sum(vals) / len(vals)
+    f = base["faithful"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * len(specs) * world / value, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth}, {n} qubits "
-                               f"(CPU sample measured at {base['qubits']} qubits, scaled by 2^-{n - base['qubits']})"},
+        "config": {"workload": f"random layered circuit H/RX/RZ/CNOT depth {args.depth}, {n} qubits; each step times a bounded sample: "
+                               f"{f['layers']} whole layer(s) at {f['qubits']} qubits (reference pass structure) and "
+                               f"{base['inplace']['layers']} layer(s) at {base['inplace']['qubits']} qubits (in-place port); "
+                               f"value = measured rate x 2^-{n - f['qubits']} (x N: one unit of work = one gate on one 2^{args.qubits} shard)",
+                   "sample_qubits": f["qubits"], "scale_factor": base["scale_factor_faithful"],
+                   "ms_per_step_is": "measured wall time of one step's samples (both variants), not an extrapolation",
+                   "inplace_port_value": base["inplace_scaled_to_bench_qubits"] * world},
         "cpu_baseline": dict(base, value=value),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -230,6 +284,197 @@ def single_gate_table(qi, n, peak_gbs, passes=20):
             "f1_gates_min_frac_of_8TBs_nominal": min(full_f) / 8000.0, "f1_gates_min_frac_of_measured_peak": min(full_f) / peak_gbs}
 
 
+def _kernel_rooflines(prof, peak_gbs):
+    """achieved algorithmic GB/s per kernel family of a profiled run (qi_set_option("profile", 1) brackets every launch with
+    CUDA events on the engine stream; algorithmic bytes per launch are the library's own accounting)."""
+    out = {}
+    for k, v in prof.items():
+        if v["launches"] and v["total_ms"] > 0 and v["algorithmic_bytes"] > 0:
+            gbs = v["algorithmic_bytes"] / (v["total_ms"] * 1e-3) / 1e9
+            out[k] = {"launches": v["launches"], "avg_launch_ms": round(v["total_ms"] / v["launches"], 4), "achieved_gbs": round(gbs, 1),
+                      "frac_of_measured_hbm": round(gbs / peak_gbs, 3)}
+    return out
+
+
+def probe_indices(n, count=64, seed=20260007):
+    """`count` amplitude indices below 2^n from the splitmix64 stream (the same on every rank)."""
+    from quant_iron_b200 import workloads as w
+    rng = w.SplitMix64(seed)
+    return [rng.next_u64() & ((1 << n) - 1) for _ in range(count)]
+
+
+def extras_single_gpu(qi, w, peak_gbs):
+    """BASELINE configs 1, 3, 4 and the measurement path on one B200, each with a correctness field next to its time."""
+    import numpy as np
+    out = {}
+    # ---- config 1: 20-qubit QFT (Subroutine::qft, subroutine.rs:90-112) on new_plus(20) via CircuitBuilder; full parity vs the oracle
+    try:
+        n = 20
+        qft = qi.CircuitBuilder(n).add_subroutine(qi.Subroutine.qft(list(range(n)), n)).build()
+        st = qi.State.new_plus(n)
+        res = qft.execute(st)
+        qi.engine.synchronize()
+        qi.engine.timer_start()
+        for _ in range(20):
+            qft.execute(st)
+        ms_clone = qi.engine.timer_stop() / 20
+        work = qi.State.new_plus(n)
+        qi.engine.timer_start()
+        for _ in range(20):
+            qft.execute_(work)
+        ms_inplace = qi.engine.timer_stop() / 20
+        v = res.state_vector
+        rec = {"gates": len(qft.gates), "gpu_ms_execute": ms_clone, "gpu_ms_execute_in_place": ms_inplace,
+               "amp0_minus_1": abs(v[0] - 1.0), "max_other_amp": float(np.abs(v[1:]).max())}
+        from oracle import refapi as ref                       # checker + CPU time of the same call (cpu_baseline leg)
+        rq = ref.CircuitBuilder(n).add_subroutine(ref.Subroutine.qft(list(range(n)), n)).build()
+        t0 = time.perf_counter()
+        ro = rq.execute(ref.State.new_plus(n))
+        rec["cpu_oracle_inplace_ms"] = (time.perf_counter() - t0) * 1e3
+        rec["cpu_threads"] = ref.num_threads()
+        rec["max_abs_amp_err_vs_oracle"] = float(np.abs(v - ro.state_vector).max())
+        out["config1_qft20"] = rec
+        del st, res, work
+    except Exception as ex:  # noqa: BLE001
+        out["config1_qft20"] = {"error": repr(ex)[:300]}
+    # ---- config 3: heisenberg_1d(24), 50 first-order Trotter steps (time_evolution.rs:140-167) + <H> (pauli_string.rs:485-507)
+    try:
+        n = 24
+        h = qi.heisenberg_1d(n, 1.0, 2.0, 3.0, 0.5, 0.1)
+        st = qi.State.new_plus(n)
+        qi.trotter_evolve_state_(h, st, 0.01, 1, qi.TrotterOrder.First)
+        st = qi.State.new_plus(n)
+        qi.engine.synchronize()
+        qi.engine.timer_start()
+        qi.trotter_evolve_state_(h, st, 0.01, 50, qi.TrotterOrder.First)
+        ms = qi.engine.timer_stop()
+        h.expectation_value(st)
+        qi.engine.synchronize()
+        t0 = time.perf_counter()
+        e = h.expectation_value(st)
+        ms_e = (time.perf_counter() - t0) * 1e3
+        rec = {"terms": h.num_terms(), "exp_applications": 50 * h.num_terms(), "trotter_ms": ms, "expectation_ms": ms_e,
+               "expectation": [e.real, e.imag], "norm_sqr": st.norm_sqr()}
+        qi.engine.stats_reset()
+        qi.engine.set_option("profile", 1)
+        sp = qi.State.new_plus(n)
+        qi.trotter_evolve_state_(h, sp, 0.01, 50, qi.TrotterOrder.First)
+        h.expectation_value(sp)
+        qi.engine.synchronize()
+        qi.engine.set_option("profile", 0)
+        rec["kernels"] = _kernel_rooflines(qi.engine.stats(), peak_gbs)
+        del sp, st
+        # parity vs the oracle at 16 sites (the 24-site oracle takes minutes; tests/test_gpu_parity.py holds the 24-site case)
+        from oracle import refapi as ref
+        m = 16
+        hg, hr = qi.heisenberg_1d(m, 1.0, 2.0, 3.0, 0.5, 0.1), ref.heisenberg_1d(m, 1.0, 2.0, 3.0, 0.5, 0.1)
+        sg = qi.State.new_plus(m)
+        qi.trotter_evolve_state_(hg, sg, 0.01, 5, qi.TrotterOrder.First)
+        sr = ref.trotter_evolve_state(hr, ref.State.new_plus(m), 0.01, 5, ref.TrotterOrder.First)
+        eg, er = hg.expectation_value(sg), hr.expectation_value(sr)
+        rec["parity_16_sites_5_steps"] = {"expectation_rel_err": abs(eg - er) / abs(er),
+                                          "max_abs_amp_err": float(np.abs(sg.state_vector - sr.state_vector).max())}
+        out["config3_heisenberg24_trotter50"] = rec
+    except Exception as ex:  # noqa: BLE001
+        out["config3_heisenberg24_trotter50"] = {"error": repr(ex)[:300]}
+    # ---- measurement (state.rs:525-784) at 30 qubits: marginal probabilities, seeded sampling, collapse
+    try:
+        n = 30
+        st = qi.State.new_random(n)
+        qs = [0, 7, 13, 22, 29]
+        st.probabilities(qs)
+        qi.engine.stats_reset()
+        qi.engine.set_option("profile", 1)
+        p = st.probabilities(qs)
+        bins = st.sample_counts(qs, 4096, 20260003)
+        st.measure_(qi.MeasurementBasis.Computational, qs, seed=20260003)
+        qi.engine.synchronize()
+        qi.engine.set_option("profile", 0)
+        out["measurement_30q"] = {"qubits": qs, "prob_sum_minus_1": abs(float(p.sum()) - 1.0), "shots": int(bins.sum()),
+                                  "norm_after_collapse": st.norm_sqr(), "kernels": _kernel_rooflines(qi.engine.stats(), peak_gbs)}
+        del st
+    except Exception as ex:  # noqa: BLE001
+        out["measurement_30q"] = {"error": repr(ex)[:300]}
+    # ---- config 4: 33-qubit QFT on one B200 (128 GiB state, in place only): closed form QFT|+..+> = |0..0>
+    try:
+        n = 33
+        info = qi.engine.device_info()
+        if info["free_mem"] < 16 * (1 << n) + (2 << 30):
+            raise RuntimeError(f"needs 128 GiB of free HBM, {info['free_mem'] >> 30} GiB free")
+        qft = qi.CircuitBuilder(n).add_subroutine(qi.Subroutine.qft(list(range(n)), n)).build()
+        st = qi.State.new_plus(n)
+        qi.engine.stats_reset()
+        qi.engine.synchronize()
+        qi.engine.timer_start()
+        qft.execute_(st)
+        ms = qi.engine.timer_stop()
+        a0 = st.amplitude(0)
+        out["config4_qft33"] = {"gates": len(qft.gates), "gpu_ms": ms, "amp0_minus_1": abs(a0 - 1.0), "norm_sqr": st.norm_sqr(),
+                                "max_probe_amp": max(abs(st.amplitude(i)) for i in probe_indices(n, 16) if i),
+                                "kernels": {k: v["launches"] for k, v in qi.engine.stats().items()},
+                                "effective_gbs_one_pass_per_launch": sum(v["algorithmic_bytes"] for v in qi.engine.stats().values()) / (ms * 1e-3) / 1e9}
+        del st
+    except Exception as ex:  # noqa: BLE001
+        out["config4_qft33"] = {"error": repr(ex)[:300]}
+    return out
+
+
+def extras_multi_gpu(qi, w, dist, world, n_local_cfg5):
+    """BASELINE config 5 on N GPUs (QFT on 33 local qubits per GPU: 34/35/36 qubits on 2/4/8) and a sharded-vs-single-GPU
+    parity field: the same circuit on the N-GPU sharded state and on one GPU of this rank, 64 seeded probe amplitudes."""
+    import math
+    from quant_iron_b200 import sharded
+    out = {}
+    p = int(math.log2(world))
+
+    def timed(fn):
+        qi.engine.synchronize()
+        dist.barrier()
+        qi.engine.timer_start()
+        fn()
+        return qi.engine.timer_stop()
+
+    try:
+        n = n_local_cfg5 + p
+        st = sharded.new_plus(n, dist)
+        qft = qi.CircuitBuilder(n).add_subroutine(qi.Subroutine.qft(list(range(n)), n)).build()
+        qi.engine.stats_reset()
+        qi.engine.set_option("profile", 1)
+        ms = timed(lambda: qft.execute_(st))
+        prof = qi.engine.stats()
+        qi.engine.set_option("profile", 0)
+        a0, nrm = st.amplitude(0), st.norm_sqr()
+        probes = max(abs(st.amplitude(i)) for i in probe_indices(n, 8) if i)
+        cs = sharded.comm_stats(st)
+        ex_ms = prof.get("exchange", {}).get("total_ms", 0.0)
+        out[f"config5_qft{n}"] = {
+            "qubits": n, "local_qubits": n_local_cfg5, "gib_per_gpu": 16 * (1 << n_local_cfg5) / 2**30, "gates": len(qft.gates),
+            "wall_ms": ms, "exchanges": cs["exchanges"], "bytes_sent_per_rank": cs["bytes_sent"], "exchange_ms": ex_ms,
+            "nvlink_gbs_per_gpu_per_direction": cs["bytes_sent"] / max(1e-9, ex_ms * 1e-3) / 1e9 if ex_ms else None,
+            "amp0_minus_1": abs(a0 - 1.0), "norm_sqr": nrm, "max_probe_amp": probes,
+            "per_kernel_ms": {k: round(v["total_ms"], 2) for k, v in prof.items()}}
+        del st
+    except Exception as ex:  # noqa: BLE001
+        out["config5_qft"] = {"error": repr(ex)[:300]}
+    try:
+        n = 30                                                   # <= 33: one GPU holds the whole state next to a shard
+        specs = w.random_layered_circuit(n, 8) + w.qft_specs(n)
+        circ = w.build_circuit(qi, n, specs)
+        st = sharded.new_zero(n, dist)
+        circ.execute_(st)
+        one = qi.State.new_zero(n)
+        circ.execute_(one)
+        idx = probe_indices(n)
+        diff = max(abs(st.amplitude(i) - one.amplitude(i)) for i in idx)
+        out["sharded_vs_single_gpu"] = {"qubits": n, "gates": len(specs), "probes": len(idx), "max_abs_amp_diff": diff,
+                                        "norm_sharded": st.norm_sqr(), "norm_single": one.norm_sqr(),
+                                        "exchanges": sharded.comm_stats(st)["exchanges"]}
+        del st, one
+    except Exception as ex:  # noqa: BLE001
+        out["sharded_vs_single_gpu"] = {"error": repr(ex)[:300]}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -241,7 +486,6 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's "NCCL version ..." banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     qi.engine.init(local_rank)
     options = {}
@@ -321,10 +565,12 @@ def run_ours(args, rank, world, local_rank):
     comm = None
     if world > 1:
         from quant_iron_b200 import sharded
+        ones = torch.ones(1, dtype=torch.float64, device="cuda")
+        dist.all_reduce(ones)                                  # NCCL sees every rank: the sum of ones is the rank count
         cs = sharded.comm_stats(state)
         per_step_ex = cs["exchanges"] / (args.warmup + args.steps + 1)
         ex_ms = prof.get("exchange", {}).get("total_ms", 0.0)
-        comm = {"exchanges_per_step": per_step_ex, "bytes_sent_per_rank_per_step": cs["bytes_sent"] / (args.warmup + args.steps + 1),
+        comm = {"nranks": dist.get_world_size(), "nccl_allreduce_of_ones": float(ones.item()), "exchanges_per_step": per_step_ex, "bytes_sent_per_rank_per_step": cs["bytes_sent"] / (args.warmup + args.steps + 1),
                 "exchange_ms_per_step": ex_ms,
                 "nvlink_gbs_per_gpu_per_direction": (cs["bytes_sent"] / (args.warmup + args.steps + 1)) / max(1e-9, ex_ms * 1e-3) / 1e9}
 
@@ -419,12 +665,16 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     del state
 
+    extras = {}
+    if world > 1 and not args.skip_extras:
+        extras.update(extras_multi_gpu(qi, w, dist, world, args.config5_local_qubits))      # collective: every rank takes part
     if rank != 0:
         if dist is not None:
             dist.barrier()
         return
 
-    extras = {}
+    if world == 1 and not args.skip_extras:
+        extras.update(extras_single_gpu(qi, w, peak_gbs))
     if world == 1 and not args.skip_extras:
         try:
             extras["single_gate"] = single_gate_table(qi, n_local, peak_gbs)
@@ -450,7 +700,8 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.skip_cpu:
         try:
-            cpu = cpu_baseline(n, specs, budget_s=args.cpu_budget)
+            use_all_host_threads()
+            cpu = cpu_baseline(n, args.depth, budget_s=args.cpu_budget)
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"[:200]}
 
@@ -485,6 +736,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU")
     ap.add_argument("--depth", type=int, default=40)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--config5-local-qubits", type=int, default=33, help="N > 1: local qubits per GPU of the config-5 QFT (33 = 128 GiB per GPU)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")

@@ -37,7 +37,7 @@ int cuda_fail(cudaError_t e, const char* what);
 enum KernelFamily {
     KF_INIT = 0, KF_PAIR, KF_DIAG, KF_SWAP, KF_MATCH, KF_WINDOW, KF_PAULI, KF_PAULI_EXP, KF_EXPECT,
     KF_REDUCE, KF_ELEMENTWISE, KF_PROB, KF_SCAN, KF_SAMPLE, KF_COLLAPSE, KF_EXCHANGE, KF_BARRIER,
-    KF_PAULI_WINDOW, KF_COUNT
+    KF_PAULI_WINDOW, KF_TILE, KF_COUNT
 };
 extern const char* const kFamilyNames[KF_COUNT];
 
@@ -65,6 +65,7 @@ struct Context {
     int opt_prefetch = 0;             // lean instantiations only: L2 prefetch of the warp's next tile (unmeasured: off)
     int opt_cz_rewrite = 1;           // fused executor: a controlled X next to a Hadamard on its target becomes a controlled Z (bit-exact)
     int opt_tile = 1;                 // window passes on the CTA-tile kernel (k_tile: 11 qubits per pass, rounds regrouped through shared memory)
+    int opt_tile_slide = 1;           // tile passes leave the qubits the next tile wants at positions 0..4 (relabelling the qubit map)
     int opt_tile_min_qubits = 18;     // ... for states with at least this many local qubits (>= 11)
     int opt_lean = 0;                 // window passes: unit-form H / RX / real 2x2 with one deferred scale per pass (unmeasured: off)
     int64_t opt_pool_mb = 4096;       // device-buffer cache: at most this many MiB are kept for reuse (0 = off)
@@ -226,10 +227,10 @@ int validate_gate(const qi_state* s, const qi_gate* g);
 const qi_gate* normalise_gates(const qi_gate* gates, uint64_t count, std::vector<qi_gate>* own);   // gates.cu: aliased-control Matchgates -> P
 int launch_simple_gate(qi_state* s, const PhysGate& g);      // one pass with the per-gate kernels
 // window.cu
-int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates);
+int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates, bool allow_relabel = false);
 bool window_supported(const qi_state* s);
 int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<std::vector<int>>* summary);
-int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<uint8_t>* blob);
+int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates, int R, std::vector<uint8_t>* blob, std::vector<int>* relabel_out = nullptr);
 // shard.cu
 int shard_prepare_gate(qi_state* s, const qi_gate* g, PhysGate* out, bool* skip);
 int apply_circuit_sharded(qi_state* s, const qi_gate* gates, uint64_t count, bool use_window);   // staged around exchanges

@@ -11,7 +11,7 @@ namespace qi {
 const char* const kFamilyNames[KF_COUNT] = {
     "init", "gate_pair", "gate_diag", "gate_swap", "gate_matchgate", "gate_window", "pauli_apply",
     "pauli_exp", "pauli_expect", "reduce", "elementwise", "probabilities", "scan", "sample",
-    "collapse", "exchange", "barrier", "pauli_exp_window"};
+    "collapse", "exchange", "barrier", "pauli_exp_window", "gate_tile"};
 
 static thread_local uint64_t tl_payload[2] = {0, 0};
 static thread_local char tl_msg[256] = {0};
@@ -252,6 +252,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "absorb")) c.opt_absorb = (int)value;
     else if (!strcmp(name, "lean")) c.opt_lean = (int)value;
     else if (!strcmp(name, "tile")) c.opt_tile = (int)value;
+    else if (!strcmp(name, "tile_slide")) c.opt_tile_slide = (int)value;
     else if (!strcmp(name, "cz_rewrite")) c.opt_cz_rewrite = (int)value;
     else if (!strcmp(name, "tile_min_qubits")) c.opt_tile_min_qubits = (int)value;
     else if (!strcmp(name, "prefetch")) c.opt_prefetch = (int)value;

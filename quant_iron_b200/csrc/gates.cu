@@ -401,7 +401,7 @@ int qi_apply_circuit(qi_state* s, const qi_gate* gates, uint64_t count) {
     auto flush = [&]() -> int {
         if (run.empty()) return QI_OK;
         int st = QI_OK;
-        if (use_window) st = run_circuit_windowed(s, run);
+        if (use_window) st = run_circuit_windowed(s, run, true);
         else for (const PhysGate& g : run) { st = launch_simple_gate(s, g); if (st != QI_OK) break; }
         run.clear();
         return st;
@@ -490,7 +490,10 @@ int qi_debug_lower(uint32_t num_qubits, int rank, int world, const uint8_t* phys
     int R = window_regs ? window_regs : 4;
     while (R > 3 && (int)s.n_local < 5 + R) R--;
     std::vector<uint8_t> out;
-    QI_TRY(debug_lower(&s, run, R, &out));
+    std::vector<int> relabel;
+    QI_TRY(debug_lower(&s, run, R, &out, &relabel));
+    if (!relabel.empty())          // tile passes left the qubits at other positions
+        for (uint32_t q = 0; q < num_qubits; q++) s.phys[q] = (uint8_t)relabel[s.phys[q]];
     // the final logical -> physical map (lazy SWAPs), so the interpreter can undo it
     out.insert(out.end(), s.phys, s.phys + 64);
     if (used) *used = out.size();

@@ -48,6 +48,13 @@ enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK
 static const int kLastPairKind = WK_RXSU;
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 112 B + header < 16 KB)
+// CTA-tile kernel (k_tile, below)
+static const int kTileBits = 11;            // local bits of a CTA tile
+static const int kTileThreads = 128;        // 2^(kTileBits - 4)
+static const int kTileThrBits = 7;
+static const int kTileWindow = kTileBits - kLaneQubits;   // window qubits per pass (6)
+static const int kMaxRounds = 24;
+static const int kMaxTileOps = 232;         // parameter space: 232 * 112 B + rounds + header < 32 KiB
 
 struct DOp {                 // device op, 112 bytes
     uint8_t kind;            // WK_*
@@ -57,7 +64,7 @@ struct DOp {                 // device op, 112 bytes
     uint8_t nchunks;         // WK_TABLE: number of 8-bit tile chunks with a table
     uint8_t has_reg;         // WK_TABLE: register table is not all ones
     uint8_t c_lval;          // value the c_lane bits of the lane / thread index must have: (idx & c_lane) == c_lval
-    uint8_t pad;
+    uint8_t code;            // k_tile: index of the op's specialised straight-line routine (fast_code), 0 = generic interpreter
     uint32_t c_lane, c_reg;  // c_lane: control bits in lane space (k_window: lane bits 0..4; k_tile: the 7 thread-index bits).
                              // c_reg: SLOT MASK -- bit s is set iff slot s passes the register-bit controls (positive and
                              // negative), expanded on the host
@@ -144,9 +151,9 @@ __device__ __forceinline__ void upd_rxu(amp_t& a0, amp_t& a1, double t) {
             "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
             : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(t));
     else
-        asm("{\n\t.reg .f64 t0, t1, nt;\n\tneg.f64 nt, %4;\n\t"
-            "fma.rn.f64 t0, %4, %1, %2;\n\tfma.rn.f64 t1, nt, %0, %3;\n\tfma.rn.f64 %2, %4, %3, %0;\n\tfma.rn.f64 %3, nt, %2, %1;\n\t"
-            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\t}"
+        asm("{\n\t.reg .f64 t0, t1, t2, t3, nt;\n\tneg.f64 nt, %4;\n\t"
+            "fma.rn.f64 t0, %4, %1, %2;\n\tfma.rn.f64 t1, nt, %0, %3;\n\tfma.rn.f64 t2, %4, %3, %0;\n\tfma.rn.f64 t3, nt, %2, %1;\n\t"
+            "mov.f64 %0, t0;\n\tmov.f64 %1, t1;\n\tmov.f64 %2, t2;\n\tmov.f64 %3, t3;\n\t}"
             : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(t));
 }
 
@@ -343,80 +350,182 @@ __device__ __forceinline__ void lane_pair_op(amp_t (&v)[1 << R], uint32_t kind, 
 // ---- the op program on one register tile -------------------------------------------------------------
 // LANES = the program contains pair gates on lane qubits; programs without them run an instantiation that does not
 // carry the shuffle code at all (smaller, fewer live registers).
+// one device op on a register tile (the tile predicate has been checked by the caller)
 // NT = entries of a phase table's lane part: 32 (k_window: lanes) or 128 (k_tile: the thread index of the round's layout)
+template <int R, bool LANES, bool U2K, bool LEAN, int NT>
+__device__ __forceinline__ void exec_op(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const DOp& op, const amp_t* __restrict__ tables) {
+    constexpr int S = 1 << R;
+    const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lval;
+    const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
+
+    if (LANES && kind <= kLastPairKind && tpos < 5) {             // pair gate across lanes
+        lane_pair_op<R, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
+        return;
+    }
+    if (!thread_ok) return;                                     // lane-bit controls: skip at op granularity
+    if (kind == WK_DIAG) {
+        const amp_t ph = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((c_reg >> s) & 1u) upd_cmul(v[s], ph);
+    } else if (kind == WK_RZ) {
+        const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
+        const uint32_t t_reg = op.t_reg;
+        if (t_reg == 0 && c_reg == kAllSlots<R>) {                 // target outside the registers: one phase per thread
+            const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+            const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+            for (int s = 0; s < S; s++) upd_cmul(v[s], pt);
+        } else {
+            const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
+            const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((c_reg >> s) & 1u) {
+                    if (s & t_reg) upd_cmul(v[s], p1);
+                    else upd_cmul(v[s], pt);
+                }
+        }
+    } else if (kind == WK_TABLE) {
+        const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
+        const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
+        if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) return;
+        if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) return;
+        amp_t f = tab[lane];                                        // lane table (NT entries)
+        const uint32_t nch = op.nchunks;
+        for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
+            f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
+        const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
+        if (op.has_reg) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], cmul(f, __ldg(tab + NT + s)));
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], f);
+        }
+    } else if (kind == WK_NEG) {
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
+    } else if (LEAN && kind == WK_SCALE) {                          // the product of the pass's deferred gate scales
+        const double g = op.m[0];
+#pragma unroll
+        for (int s = 0; s < S; s++) upd_scale(v[s], g);
+    } else {
+        switch (tpos - 5) {
+            case 0: reg_pair_op<R, 0, U2K, LEAN>(v, kind, c_reg, op.m); break;
+            case 1: reg_pair_op<R, (R > 1 ? 1 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+            case 2: reg_pair_op<R, (R > 2 ? 2 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+            case 3: reg_pair_op<R, (R > 3 ? 3 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+            default: reg_pair_op<R, (R > 4 ? 4 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
+        }
+    }
+}
+
 template <int R, bool LANES, bool U2K, bool LEAN = false, int NT = 32>
 __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile, const int lane, const DOp* __restrict__ ops, const uint32_t nops,
                                         const amp_t* __restrict__ tables) {
-    constexpr int S = 1 << R;
 #pragma unroll 1
     for (uint32_t o = 0; o < nops; o++) {
         const DOp& op = ops[o];
         if ((tile & op.c_tile) != op.c_tval) continue;                // warp-uniform control (positive and negative bits)
-        const bool thread_ok = ((uint32_t)lane & op.c_lane) == op.c_lval;
-        const uint32_t kind = op.kind, c_reg = op.c_reg, tpos = op.tpos;
-        if (LANES && kind <= kLastPairKind && tpos < 5) {             // pair gate across lanes
-            lane_pair_op<R, U2K, LEAN>(v, kind, tpos, c_reg, thread_ok, op.m, lane);
-            continue;
-        }
-        if (!thread_ok) continue;                                     // lane-bit controls: skip at op granularity
-        if (kind == WK_DIAG) {
-            const amp_t ph = make_double2(op.m[0], op.m[1]);
+        exec_op<R, LANES, U2K, LEAN, NT>(v, tile, lane, op, tables);
+    }
+}
+
+// ---- k_tile: specialised straight-line routines ---------------------------------------------------------------
+// The generic interpreter above costs ~85 non-FP64 instructions per op (slot-mask predicates per pair, selects, branches;
+// ncu r02c) -- more than the 64 FP64 instructions of the gate itself.  On the CTA-tile kernel a pass is compute-bound,
+// so the common ops get one routine each, chosen by ONE indexed branch on a code the host computes:
+//   full:  pair kind K on register bit B, all 8 pairs                                  (4 per kind)
+//   half:  the same under ONE register-bit control C with value CV, 4 pairs             (24 per kind; C != B)
+// Controls on thread or tile bits are handled before the dispatch (skip), so "full" also covers gates controlled from
+// outside the registers.  Everything else (several register-bit controls, complex 2x2, diagonal ops) takes exec_op.
+static const int kFastPerKind = 28;
+__host__ __device__ constexpr int fast_kind_index(int kind) {
+    return kind == WK_REAL ? 0 : kind == WK_RX ? 1 : kind == WK_RXS ? 2 : kind == WK_X ? 3 : kind == WK_REALUP ? 4 : kind == WK_REALUM ? 5
+         : kind == WK_RXU ? 6 : kind == WK_RXSU ? 7 : -1;
+}
+// host: code of an op (0 = none).  pos / neg: register-bit controls that must be 1 / 0
+static inline int fast_code(int kind, int B, uint32_t pos, uint32_t neg) {
+    const int ki = fast_kind_index(kind);
+    if (ki < 0 || B < 0 || B > 3 || ((pos | neg) >> B) & 1u) return 0;
+    if ((pos | neg) == 0) return 1 + ki * kFastPerKind + B;
+    if (__builtin_popcount(pos | neg) != 1) return 0;
+    const int C = __builtin_ctz(pos | neg), CI = C < B ? C : C - 1, CV = pos ? 1 : 0;
+    return 1 + ki * kFastPerKind + 4 + (B * 3 + CI) * 2 + CV;
+}
+
+template <int KIND>
+__device__ __forceinline__ void fast_pair(amp_t& a0, amp_t& a1, double k0, double k1, double k2, double k3) {
+    if (KIND == WK_REAL) upd_real(a0, a1, k0, k1, k2, k3);
+    else if (KIND == WK_RX) upd_rx(a0, a1, k0, k1);
+    else if (KIND == WK_RXS) upd_rxs(a0, a1, k0, k1);
+    else if (KIND == WK_REALUP) upd_realu<false>(a0, a1, k0, k1);
+    else if (KIND == WK_REALUM) upd_realu<true>(a0, a1, k0, k1);
+    else if (KIND == WK_RXU) upd_rxu<false>(a0, a1, k0);
+    else if (KIND == WK_RXSU) upd_rxu<true>(a0, a1, k0);
+    else { const amp_t t = a0; a0 = a1; a1 = t; }
+}
+template <int KIND, int B>
+__device__ __forceinline__ void fast_full(amp_t (&v)[16], double k0, double k1, double k2, double k3) {
 #pragma unroll
-            for (int s = 0; s < S; s++)
-                if ((c_reg >> s) & 1u) upd_cmul(v[s], ph);
-        } else if (kind == WK_RZ) {
-            const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
-            const uint32_t t_reg = op.t_reg;
-            if (t_reg == 0 && c_reg == kAllSlots<R>) {                 // target outside the registers: one phase per thread
-                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
-                const amp_t pt = t_thread ? p1 : p0;
+    for (int p = 0; p < 8; p++) {
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        fast_pair<KIND>(v[s0], v[s0 | (1 << B)], k0, k1, k2, k3);
+    }
+}
+template <int KIND, int B, int CI, int CV>
+__device__ __forceinline__ void fast_half(amp_t (&v)[16], double k0, double k1, double k2, double k3) {
+    constexpr int C = CI < B ? CI : CI + 1;
 #pragma unroll
-                for (int s = 0; s < S; s++) upd_cmul(v[s], pt);
-            } else {
-                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)lane & op.t_lane) != 0);
-                const amp_t pt = t_thread ? p1 : p0;
-#pragma unroll
-                for (int s = 0; s < S; s++)
-                    if ((c_reg >> s) & 1u) {
-                        if (s & t_reg) upd_cmul(v[s], p1);
-                        else upd_cmul(v[s], pt);
+    for (int p = 0; p < 8; p++) {
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        if (((s0 >> C) & 1) == CV) fast_pair<KIND>(v[s0], v[s0 | (1 << B)], k0, k1, k2, k3);
+    }
+}
+
+#define QI_FAST_FULL(K) \
+    case 1 + fast_kind_index(K) * kFastPerKind + 0: fast_full<K, 0>(v, k0, k1, k2, k3); break; \
+    case 1 + fast_kind_index(K) * kFastPerKind + 1: fast_full<K, 1>(v, k0, k1, k2, k3); break; \
+    case 1 + fast_kind_index(K) * kFastPerKind + 2: fast_full<K, 2>(v, k0, k1, k2, k3); break; \
+    case 1 + fast_kind_index(K) * kFastPerKind + 3: fast_full<K, 3>(v, k0, k1, k2, k3); break;
+#define QI_FAST_HALF1(K, B, CI, CV) \
+    case 1 + fast_kind_index(K) * kFastPerKind + 4 + (B * 3 + CI) * 2 + CV: fast_half<K, B, CI, CV>(v, k0, k1, k2, k3); break;
+#define QI_FAST_HALF6(K, B) \
+    QI_FAST_HALF1(K, B, 0, 0) QI_FAST_HALF1(K, B, 0, 1) QI_FAST_HALF1(K, B, 1, 0) QI_FAST_HALF1(K, B, 1, 1) QI_FAST_HALF1(K, B, 2, 0) QI_FAST_HALF1(K, B, 2, 1)
+#define QI_FAST_HALF(K) QI_FAST_HALF6(K, 0) QI_FAST_HALF6(K, 1) QI_FAST_HALF6(K, 2) QI_FAST_HALF6(K, 3)
+
+// the op program of one round on the CTA-tile kernel
+template <bool U2K, bool LEAN>
+__device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp* __restrict__ ops, const uint32_t nops,
+                                             const amp_t* __restrict__ tables) {
+#pragma unroll 1
+    for (uint32_t o = 0; o < nops; o++) {
+        const DOp& op = ops[o];
+        if ((tile & op.c_tile) != op.c_tval) continue;                // tile-uniform control (positive and negative bits)
+        const uint32_t code = op.code;
+        if (code == 0) { exec_op<4, false, U2K, LEAN, kTileThreads>(v, tile, t, op, tables); continue; }
+        if (((uint32_t)t & op.c_lane) != op.c_lval) continue;         // thread-bit controls
+        const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
+        switch (code) {
+            QI_FAST_FULL(WK_REAL)
+            QI_FAST_FULL(WK_RX) QI_FAST_HALF(WK_RX)
+            QI_FAST_FULL(WK_RXS) QI_FAST_HALF(WK_RXS)
+            QI_FAST_FULL(WK_X) QI_FAST_HALF(WK_X)
+            default:
+                if (LEAN) {
+                    switch (code) {
+                        QI_FAST_FULL(WK_REALUP)
+                        QI_FAST_FULL(WK_REALUM)
+                        QI_FAST_FULL(WK_RXU) QI_FAST_HALF(WK_RXU)
+                        QI_FAST_FULL(WK_RXSU) QI_FAST_HALF(WK_RXSU)
+                        default: break;
                     }
-            }
-        } else if (kind == WK_TABLE) {
-            const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
-            const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
-            if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) continue;
-            if (hub_cls == CLS_LANE && !((lane >> hub_bit) & 1)) continue;
-            amp_t f = tab[lane];                                        // lane table (NT entries)
-            const uint32_t nch = op.nchunks;
-            for (uint32_t k = 0; k < nch; k++)                          // tile chunk tables (256 entries each)
-                f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
-            const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
-            if (op.has_reg) {
-#pragma unroll
-                for (int s = 0; s < S; s++)
-                    if ((s & hub_slot) == hub_slot) upd_cmul(v[s], cmul(f, __ldg(tab + NT + s)));
-            } else {
-#pragma unroll
-                for (int s = 0; s < S; s++)
-                    if ((s & hub_slot) == hub_slot) upd_cmul(v[s], f);
-            }
-        } else if (kind == WK_NEG) {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
-        } else if (LEAN && kind == WK_SCALE) {                          // the product of the pass's deferred gate scales
-            const double g = op.m[0];
-#pragma unroll
-            for (int s = 0; s < S; s++) upd_scale(v[s], g);
-        } else {
-            switch (tpos - 5) {
-                case 0: reg_pair_op<R, 0, U2K, LEAN>(v, kind, c_reg, op.m); break;
-                case 1: reg_pair_op<R, (R > 1 ? 1 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
-                case 2: reg_pair_op<R, (R > 2 ? 2 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
-                case 3: reg_pair_op<R, (R > 3 ? 3 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
-                default: reg_pair_op<R, (R > 4 ? 4 : 0), U2K, LEAN>(v, kind, c_reg, op.m); break;
-            }
+                }
+                break;
         }
     }
 }
@@ -537,12 +646,6 @@ __global__ void __launch_bounds__(128, QI_WINDOW_BLOCKS(R)) k_window_tma(amp_t* 
 // use the IO layout (register qubits = 4 of the window qubits), the only one whose global accesses coalesce.
 // Measured on the prototype (tools/micro/tile_proto.cu, profiles/r02_tile_proto_microbench.txt): a regroup costs ~0.3 ms
 // at 30 qubits against 5.5 ms for the HBM pass it replaces; a register gate costs 0.15-0.2 ms (the FP64 pipe).
-static const int kTileBits = 11;            // local bits of a CTA tile
-static const int kTileThreads = 128;        // 2^(kTileBits - 4)
-static const int kTileThrBits = 7;
-static const int kTileWindow = kTileBits - kLaneQubits;   // window qubits per pass (6)
-static const int kMaxRounds = 24;
-static const int kMaxTileOps = 232;         // parameter space: 232 * 112 B + rounds + header < 32 KiB
 
 struct TRound {                 // 64 bytes
     uint16_t sswz[16];          // swizzled tile-local offset of slot s (register bits of this round)
@@ -554,8 +657,10 @@ struct TRound {                 // 64 bytes
 static_assert(sizeof(TRound) == 64, "TRound layout");
 
 struct TProgram {
-    uint8_t tpos[kTileBits];    // physical qubit of tile-local bit j (ascending; tpos[0..4] = 0..4)
+    uint8_t tpos[kTileBits];    // physical position of tile-local bit j (ascending; tpos[0..4] = 0..4)
     uint8_t nrounds;
+    uint8_t tpos_out[kTileBits];   // position the content of local bit j is stored to (a permutation of tpos: the pass may leave
+    uint8_t pad0;                  // its 11 qubits in any order -- the five the next pass wants at positions 0..4)
     uint32_t flags;
     uint64_t goff_in[16];       // slot -> global index offset under the first round's layout (loads)
     uint64_t goff_out[16];      // ... under the last round's layout (stores)
@@ -586,7 +691,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
 #pragma unroll
     for (int k = 0; k < kTileThrBits; k++) {
         g_in |= (uint64_t)((t >> k) & 1u) << P.tpos[P.rounds[0].thr_pos[k]];
-        g_out |= (uint64_t)((t >> k) & 1u) << P.tpos[P.rounds[nr - 1].thr_pos[k]];
+        g_out |= (uint64_t)((t >> k) & 1u) << P.tpos_out[P.rounds[nr - 1].thr_pos[k]];
     }
     __syncthreads();
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -599,7 +704,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = QI_LD(g + P.goff_in[s]);
         }
-        run_ops<4, false, U2K, LEAN, kTileThreads>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
+        run_ops_tile<U2K, LEAN>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
 #pragma unroll 1
         for (int r = 1; r < nr; r++) {
             const TRound& prev = P.rounds[r - 1];
@@ -610,7 +715,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
             __syncthreads();
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = sm[rb ^ cur.sswz[s]];
-            run_ops<4, false, U2K, LEAN, kTileThreads>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
+            run_ops_tile<U2K, LEAN>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
         }
         {
             amp_t* __restrict__ g = a + tb + g_out;
@@ -1110,6 +1215,10 @@ static void lower_op(const Layout& L, const Pass& ps, const HOp& h, double* scal
         d.c_reg = slot_mask(L.R, pos_reg, neg_reg);
         d.c_tile = pos_tile | neg_tile;
         d.c_tval = pos_tile;
+        if (L.nt == kTileThreads && op.kind >= WK_X && op.kind <= kLastPairKind && L.cls[op.target] == CLS_REG) {
+            const bool has_half = op.kind == WK_RX || op.kind == WK_RXS || op.kind == WK_X || op.kind == WK_RXU || op.kind == WK_RXSU;
+            if ((pos_reg | neg_reg) == 0 || has_half) d.code = (uint8_t)fast_code((int)op.kind, L.idx[op.target], pos_reg, neg_reg);
+        }
     }
     if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
     memcpy(d.m, op.m, sizeof(d.m));
@@ -1142,13 +1251,18 @@ static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp
 }
 
 // ---- host: a tile pass = rounds ---------------------------------------------------------------------------
+struct TilePlan {                // a CTA-tile pass in the physical coordinates it runs under
+    int pin[kTileBits];          // ascending physical positions of the tile's local bits (pin[0..4] = 0..4)
+    int pout[kTileBits];         // position the content of local bit j is stored to: a permutation of pin (identity = no relabelling)
+};
 struct TileRoundHost {
     int regs[4];                 // tile-local bits held in registers (ascending)
     int thr[kTileThrBits];       // tile-local bit of thread-index bit k
     size_t first_op = 0, nops = 0;
 };
 struct TileLaunch {
-    int tile_qubits[kTileBits];  // physical qubit of tile-local bit j (ascending)
+    int tile_qubits[kTileBits];  // physical position of tile-local bit j (ascending)
+    int tile_out[kTileBits];     // physical position the content of local bit j is stored to
     std::vector<TileRoundHost> rounds;
     std::vector<DOp> dops;
     bool u2k = false, lean = false;
@@ -1195,22 +1309,34 @@ static void form_rounds(const Pass& ps, const std::vector<HOp>& ops, std::vector
     }
 }
 
-// thread-bit order of a round: bank-conflict-free regroups need the tile-local bits behind thread bits 0..2 in three
-// different classes of the swizzle (tile_swz folds bits 3-5, 6-8, 9-10 onto 0-2)
-static void order_thread_bits(const int regs[4], bool io, int thr[kTileThrBits]) {
+// Layout of a round.  `low` (5 tile-local bits, in order) makes it an IO layout: those bits become thread bits 0..4 -- the
+// lanes -- so that a warp's global access is one contiguous 512-byte row (loads: the local bits at positions 0..4; stores:
+// the local bits whose content goes to positions 0..4); the register bits then avoid them.  Without `low` the thread
+// bits are ordered for bank-conflict-free regroups: tile_swz folds local bits 3-5, 6-8, 9-10 onto 0-2, so the three
+// local bits behind thread bits 0..2 should fall into three different classes.
+static bool make_tile_round(const std::vector<int>& regs_local, const int* low, TileRoundHost* r) {
+    std::vector<int> loc(regs_local);
+    auto is_low = [&](int j) { if (!low) return false; for (int k = 0; k < kLaneQubits; k++) if (low[k] == j) return true; return false; };
+    for (int j : loc) if (is_low(j)) return false;
+    for (int j = kTileBits - 1; j >= 0 && (int)loc.size() < 4; j--)
+        if (!is_low(j) && std::find(loc.begin(), loc.end(), j) == loc.end()) loc.push_back(j);
+    std::sort(loc.begin(), loc.end());
+    for (int k = 0; k < 4; k++) r->regs[k] = loc[k];
     std::vector<int> free_bits;
     for (int j = 0; j < kTileBits; j++)
-        if (j != regs[0] && j != regs[1] && j != regs[2] && j != regs[3]) free_bits.push_back(j);
-    if (!io) {
+        if (std::find(loc.begin(), loc.end(), j) == loc.end() && !is_low(j)) free_bits.push_back(j);
+    std::vector<int> order;
+    if (low) {
+        for (int k = 0; k < kLaneQubits; k++) order.push_back(low[k]);
+        for (int j : free_bits) order.push_back(j);
+    } else {
         auto cls = [](int j) { return j < 9 ? j % 3 : j - 9; };
-        std::vector<int> first;
         bool have[3] = {false, false, false};
-        for (int j : free_bits) if (!have[cls(j)]) { have[cls(j)] = true; first.push_back(j); }
-        std::vector<int> out(first);
-        for (int j : free_bits) if (std::find(first.begin(), first.end(), j) == first.end()) out.push_back(j);
-        free_bits.swap(out);
+        for (int j : free_bits) if (!have[cls(j)]) { have[cls(j)] = true; order.push_back(j); }
+        for (int j : free_bits) if (std::find(order.begin(), order.end(), j) == order.end()) order.push_back(j);
     }
-    for (int k = 0; k < kTileThrBits; k++) thr[k] = free_bits[k];
+    for (int k = 0; k < kTileThrBits; k++) r->thr[k] = order[k];
+    return true;
 }
 
 static Layout round_layout(const qi_state* s, const int tile_qubits[kTileBits], const TileRoundHost& r) {
@@ -1236,42 +1362,17 @@ static Layout round_layout(const qi_state* s, const int tile_qubits[kTileBits], 
     return L;
 }
 
-// lower one pass to one or more k_tile launches
-static void lower_tile_pass(const qi_state* s, const Pass& ps, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
-    const int n = (int)s->n_local;
-    // tile qubits: 0..4 + the pass's window qubits, padded with the lowest free positions
-    std::vector<int> win(ps.regs);
-    std::sort(win.begin(), win.end());
-    for (int q = kLaneQubits; q < n && (int)win.size() < kTileWindow; q++)
-        if (std::find(win.begin(), win.end(), q) == win.end()) win.push_back(q);
-    std::sort(win.begin(), win.end());
-    int tile_qubits[kTileBits], local_of[64];
+// lower one pass to one or more k_tile launches; `plan` = the tile's positions and where its content is stored to
+static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& plan, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
+    int local_of[64];
     for (int q = 0; q < 64; q++) local_of[q] = -1;
-    for (int j = 0; j < kLaneQubits; j++) tile_qubits[j] = j;
-    for (int j = 0; j < kTileWindow; j++) tile_qubits[kLaneQubits + j] = win[j];
-    for (int j = 0; j < kTileBits; j++) local_of[tile_qubits[j]] = j;
+    for (int j = 0; j < kTileBits; j++) local_of[plan.pin[j]] = j;
 
     std::vector<HOp> ops(ps.ops);
     double scale = ctx().opt_lean ? lean_convert(ops) : 1.0;
     std::vector<std::vector<size_t>> round_ops;
     std::vector<std::vector<int>> round_regs;
     form_rounds(ps, ops, &round_ops, &round_regs);
-
-    auto make_round = [&](const std::vector<int>& Q, bool force_io) {
-        TileRoundHost r;
-        std::vector<int> loc;
-        bool io = true;
-        for (int q : Q) { loc.push_back(local_of[q]); io &= local_of[q] >= kLaneQubits; }
-        io |= force_io;
-        // pad to 4 register bits: IO rounds from the window bits (highest first), others from any free tile bit (highest first)
-        for (int j = kTileBits - 1; j >= (io ? kLaneQubits : 0) && (int)loc.size() < 4; j--)
-            if (std::find(loc.begin(), loc.end(), j) == loc.end()) loc.push_back(j);
-        std::sort(loc.begin(), loc.end());
-        for (int k = 0; k < 4; k++) r.regs[k] = loc[k];
-        order_thread_bits(r.regs, io, r.thr);
-        return std::make_pair(r, io);
-    };
-
     // a round never carries more ops than one launch holds
     {
         std::vector<std::vector<size_t>> ro;
@@ -1287,40 +1388,59 @@ static void lower_tile_pass(const qi_state* s, const Pass& ps, std::vector<TileL
         round_regs.swap(rq);
     }
     const size_t nrounds = round_ops.size();
+    const int low_id[kLaneQubits] = {0, 1, 2, 3, 4};
+    int low_out_last[kLaneQubits];
+    for (int k = 0; k < kLaneQubits; k++)
+        for (int j = 0; j < kTileBits; j++) if (plan.pout[j] == k) low_out_last[k] = j;
     size_t ri = 0;
     while (ri < nrounds) {
+        // rounds of this launch
+        size_t end = ri, nops = 0;
+        while (end < nrounds && (end == ri || (nops + round_ops[end].size() + 2 <= (size_t)kMaxTileOps && (end - ri) + 3 <= (size_t)kMaxRounds))) {
+            nops += round_ops[end].size();
+            end++;
+        }
+        const bool last_launch = end == nrounds;
+        const int* low_out = last_launch ? low_out_last : low_id;
+        const bool same_io = !memcmp(low_out, low_id, sizeof(low_id));
         TileLaunch tl;
-        memcpy(tl.tile_qubits, tile_qubits, sizeof(tile_qubits));
-        bool last_io = false;
-        while (ri < nrounds) {
-            const std::vector<size_t>& idx = round_ops[ri];
-            if (!tl.rounds.empty() && (tl.dops.size() + idx.size() + 1 > (size_t)kMaxTileOps || (int)tl.rounds.size() + 2 > kMaxRounds)) break;
-            auto rr = make_round(round_regs[ri], false);
-            if (tl.rounds.empty() && !rr.second) {          // a launch starts in an IO layout: empty IO round first
-                TileRoundHost io = make_round(std::vector<int>(), true).first;
+        for (int j = 0; j < kTileBits; j++) { tl.tile_qubits[j] = plan.pin[j]; tl.tile_out[j] = last_launch ? plan.pout[j] : plan.pin[j]; }
+        for (size_t r = ri; r < end; r++) {
+            std::vector<int> loc;
+            for (int q : round_regs[r]) loc.push_back(local_of[q]);
+            TileRoundHost rd;
+            bool is_in = false, is_out = false;
+            if (r == ri && r + 1 == end) {                    // only round: loads and stores
+                if (same_io && make_tile_round(loc, low_id, &rd)) is_in = is_out = true;
+                else if (make_tile_round(loc, low_id, &rd)) is_in = true;
+            } else if (r == ri) is_in = make_tile_round(loc, low_id, &rd);
+            else if (r + 1 == end) is_out = make_tile_round(loc, low_out, &rd);
+            if (!is_in && !is_out) make_tile_round(loc, nullptr, &rd);
+            if (r == ri && !is_in) {                          // a launch starts in the load layout: empty round first
+                TileRoundHost io;
+                make_tile_round(std::vector<int>(), low_id, &io);
                 io.first_op = tl.dops.size();
                 tl.rounds.push_back(io);
             }
-            TileRoundHost r = rr.first;
-            r.first_op = tl.dops.size();
-            const Layout L = round_layout(s, tile_qubits, r);
-            for (size_t i : idx) lower_op(L, ps, ops[i], &scale, tl.dops, arena);
-            if (ri + 1 == nrounds && scale != 1.0) { push_scale_op(L, scale, tl.dops); scale = 1.0; }
-            r.nops = tl.dops.size() - r.first_op;
-            tl.rounds.push_back(r);
-            last_io = rr.second;
-            ri++;
-        }
-        if (!last_io) {                                      // ... and ends in one
-            TileRoundHost io = make_round(std::vector<int>(), true).first;
-            io.first_op = tl.dops.size();
-            tl.rounds.push_back(io);
+            rd.first_op = tl.dops.size();
+            const Layout L = round_layout(s, tl.tile_qubits, rd);
+            for (size_t i : round_ops[r]) lower_op(L, ps, ops[i], &scale, tl.dops, arena);
+            if (r + 1 == nrounds && scale != 1.0) { push_scale_op(L, scale, tl.dops); scale = 1.0; }
+            rd.nops = tl.dops.size() - rd.first_op;
+            tl.rounds.push_back(rd);
+            if (r + 1 == end && !is_out) {                    // ... and ends in the store layout
+                TileRoundHost io;
+                make_tile_round(std::vector<int>(), low_out, &io);
+                io.first_op = tl.dops.size();
+                tl.rounds.push_back(io);
+            }
         }
         for (const DOp& d : tl.dops) {
             if (d.kind >= WK_X && d.kind <= kLastPairKind) { tl.u2k |= d.kind == WK_U2; tl.lean |= d.kind >= WK_REALUP; }
             tl.lean |= d.kind == WK_SCALE;
         }
         launches.push_back(std::move(tl));
+        ri = end;
     }
 }
 
@@ -1328,7 +1448,7 @@ static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables)
     Context& c = ctx();
     static TProgram P;            // 30 KB: not on the stack
     memset(&P, 0, sizeof(P));
-    for (int j = 0; j < kTileBits; j++) P.tpos[j] = (uint8_t)tl.tile_qubits[j];
+    for (int j = 0; j < kTileBits; j++) { P.tpos[j] = (uint8_t)tl.tile_qubits[j]; P.tpos_out[j] = (uint8_t)tl.tile_out[j]; }
     P.nrounds = (uint8_t)tl.rounds.size();
     P.tables = d_tables;
     for (size_t r = 0; r < tl.rounds.size(); r++) {
@@ -1348,14 +1468,14 @@ static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables)
     for (int sl = 0; sl < 16; sl++) {
         uint64_t oi = 0, oo = 0;
         for (int k = 0; k < 4; k++)
-            if ((sl >> k) & 1) { oi |= 1ull << tl.tile_qubits[in.regs[k]]; oo |= 1ull << tl.tile_qubits[out.regs[k]]; }
+            if ((sl >> k) & 1) { oi |= 1ull << tl.tile_qubits[in.regs[k]]; oo |= 1ull << tl.tile_out[out.regs[k]]; }
         P.goff_in[sl] = oi;
         P.goff_out[sl] = oo;
     }
     memcpy(P.ops, tl.dops.data(), tl.dops.size() * sizeof(DOp));
     const uint64_t ntiles = s->len >> kTileBits;
     uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
-    LaunchScope ls(KF_WINDOW, 32.0 * (double)s->len);
+    LaunchScope ls(KF_TILE, 32.0 * (double)s->len);
     if (tl.lean) {
         if (tl.u2k) k_tile<true, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
         else k_tile<false, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
@@ -1441,7 +1561,7 @@ static int ensure_tables(size_t count) {
     return QI_OK;
 }
 
-struct Step { bool simple; size_t gate; Pass pass; int R; };
+struct Step { bool simple; PhysGate sgate; Pass pass; int R; TilePlan plan; };
 
 // a fixed bit at position 0 makes the per-gate kernel touch every other amplitude: half of every 32-byte
 // sector is wasted and a full window pass is faster (measured: 6.6 ms vs 5.5 ms at 30 qubits)
@@ -1466,7 +1586,7 @@ static int schedule_passes(const qi_state* s, const std::vector<PhysGate>& gates
     while (first < G) {
         if (done[first]) { first++; continue; }
         if (!window_takes(gates[first])) {
-            steps.push_back(Step{true, first, Pass(), R});
+            steps.push_back(Step{true, gates[first], Pass(), R, TilePlan()});
             done[first++] = 1;
             continue;
         }
@@ -1503,12 +1623,234 @@ static int schedule_passes(const qi_state* s, const std::vector<PhysGate>& gates
         if (taken == 1 && touched_fraction(gates[last_taken]) <= 0.5 && !fixes_bit0(gates[last_taken])) {
             // a lone gate that can change at most half of the amplitudes: the per-gate kernel visits only
             // those (controls and the phase target are folded into its index expansion) and beats a full pass
-            steps.push_back(Step{true, last_taken, Pass(), R});
+            steps.push_back(Step{true, gates[last_taken], Pass(), R, TilePlan()});
             continue;
         }
         if (fuse && ctx().opt_late_tables) repack_unconditional_tables(ps);
-        steps.push_back(Step{false, 0, std::move(ps), R});   // (measured: the 8-amplitude kernel streams ~6% slower than R = 4)
+        steps.push_back(Step{false, PhysGate(), std::move(ps), R, TilePlan()});   // (measured: the 8-amplitude kernel streams ~6% slower than R = 4)
     }
+    return QI_OK;
+}
+
+// ---- pass construction for the CTA-tile kernel ------------------------------------------------------------------
+// A tile pass works on 11 qubits: whatever sits at physical positions 0..4 (coalescing) plus six more.  Two things make it
+// hold far more of a circuit than "first come" window allocation:
+//  * the tile is CHOSEN: for every seed qubit a candidate tile is grown breadth-first over the interaction graph of the
+//    gates still to run (qubits that share a gate are neighbours), the greedy gate selection is simulated for each
+//    candidate and the one that takes the most gates wins -- on a nearest-neighbour circuit the winners are windows of
+//    contiguous qubits, which a pass digs into as a trapezoid of layers;
+//  * the five LOW positions are a cache, not a fixed set of qubits (`permute`): a pass stores its tile with the 11 local
+//    bits in any order at no cost (the last regroup writes whatever layout it likes), so the five of its qubits that the
+//    NEXT tile wants are left at positions 0..4 and the tile slides over the register: tile k+1 only has to share five
+//    qubits with tile k.  The relabelling is folded into the state's logical -> physical map afterwards (like a lazy SWAP).
+// Gates are given in the physical coordinates at entry ("q"); pos[q] tracks where q lives now, and every pass / simple
+// step is translated to the positions current when it runs.
+struct TileSched {
+    int n = 0;
+    std::vector<int> pos, at;            // q -> physical position now; position -> q
+};
+
+static uint64_t remap_mask(const std::vector<int>& pos, uint64_t m) {
+    uint64_t o = 0;
+    for (int q = 0; m; q++, m >>= 1) if (m & 1) o |= 1ull << pos[q];
+    return o;
+}
+
+static void remap_gate(const std::vector<int>& pos, PhysGate* g) {
+    if (g->t0 >= 0) g->t0 = pos[g->t0];
+    if (g->t1 >= 0) g->t1 = pos[g->t1];
+    g->cmask = remap_mask(pos, g->cmask);
+}
+
+static void remap_pass(const std::vector<int>& pos, Pass* ps) {
+    for (HOp& h : ps->ops) {
+        if (h.kind == 0) continue;
+        if (h.target >= 0) h.target = pos[h.target];
+        h.cmask = remap_mask(pos, h.cmask);
+        h.nmask = remap_mask(pos, h.nmask);
+        h.tmask = remap_mask(pos, h.tmask);
+    }
+    for (DiagGroup& g : ps->groups) {
+        if (g.hub >= 0) g.hub = pos[g.hub];
+        if (g.hub_alt >= 0) g.hub_alt = pos[g.hub_alt];
+        for (int& q : g.bits) q = pos[q];
+        g.blocked_since = remap_mask(pos, g.blocked_since);
+    }
+    for (int& q : ps->regs) q = pos[q];
+}
+
+static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& gates, bool fuse, bool permute, std::vector<Step>& steps,
+                                std::vector<int>* final_pos) {
+    const size_t G = gates.size();
+    const int n = (int)s->n_local;
+    TileSched ts;
+    ts.n = n;
+    ts.pos.resize(64); ts.at.resize(64);
+    for (int q = 0; q < 64; q++) ts.pos[q] = ts.at[q] = q;
+    std::vector<char> done(G, 0);
+    std::vector<GateUse> use(G);
+    for (size_t i = 0; i < G; i++) use[i] = uses_of(gates[i]);
+    size_t first = 0;
+    const size_t kLookahead = 4096, kGraph = 512;
+    int prev_step = -1;                       // last tile step whose output layout is still open
+    std::vector<int> prev_tile;               // its qubits (q coordinates)
+
+    // light simulation of the greedy selection for a candidate tile: gates it would take (non-diagonal ones count 1, diagonal 1/4)
+    auto score_tile = [&](uint64_t tmask) {
+        uint64_t blocked_any = 0, blocked_n = 0;
+        size_t scanned = 0;
+        int score4 = 0;
+        for (size_t i = first; i < G && scanned < kLookahead; i++) {
+            if (done[i]) continue;
+            scanned++;
+            if (!window_takes(gates[i])) break;
+            const GateUse& u = use[i];
+            if ((u.n_use & blocked_any) == 0 && (u.d_use & blocked_n) == 0 && (u.n_use & ~tmask) == 0) score4 += u.n_use ? 4 : 1;
+            else { blocked_any |= u.n_use | u.d_use; blocked_n |= u.n_use; if ((blocked_n & tmask) == tmask) break; }
+        }
+        return score4;
+    };
+
+    while (first < G) {
+        if (done[first]) { first++; continue; }
+        if (!window_takes(gates[first])) {
+            prev_step = -1;                                   // the open layout stays as it is
+            PhysGate g = gates[first];
+            remap_gate(ts.pos, &g);
+            steps.push_back(Step{true, g, Pass(), kTileWindow, TilePlan()});
+            done[first++] = 1;
+            continue;
+        }
+        uint64_t resident = 0;                                // q's at positions 0..4
+        for (int p = 0; p < kLaneQubits; p++) resident |= 1ull << ts.at[p];
+        uint64_t prev_mask = 0;
+        for (int q : prev_tile) prev_mask |= 1ull << q;
+        const bool slide = permute && prev_step >= 0;         // this tile may pick its five low qubits among the previous tile's
+        // interaction graph of the gates ahead
+        std::vector<uint64_t> adj(n, 0);
+        {
+            size_t scanned = 0;
+            for (size_t i = first; i < G && scanned < kGraph; i++) {
+                if (done[i]) continue;
+                scanned++;
+                const uint64_t m = (use[i].n_use | use[i].d_use);
+                for (int q = 0; q < n; q++) if ((m >> q) & 1) adj[q] |= m;
+            }
+        }
+        const uint64_t need_first = use[first].n_use;         // progress: the oldest gate must fit
+        uint64_t best_tile = 0;
+        int best_score = -1;
+        for (int seed = 0; seed < n; seed++) {
+            // breadth-first order from the seed (the oldest gate's targets first)
+            std::vector<int> order;
+            uint64_t seen = 0;
+            for (int q = 0; q < n; q++) if ((need_first >> q) & 1) { order.push_back(q); seen |= 1ull << q; }
+            if (!((seen >> seed) & 1)) { order.push_back(seed); seen |= 1ull << seed; }
+            for (size_t k = 0; k < order.size() && (int)order.size() < n; k++) {
+                uint64_t nb = adj[order[k]] & ~seen;
+                for (int q = 0; q < n && nb; q++) if ((nb >> q) & 1) { order.push_back(q); seen |= 1ull << q; nb &= ~(1ull << q); }
+            }
+            for (int d = 1; (int)order.size() < n && d < n; d++) {        // isolated qubits: nearest positions first
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    const int q = seed + sgn * d;
+                    if (q >= 0 && q < n && !((seen >> q) & 1)) { order.push_back(q); seen |= 1ull << q; }
+                }
+            }
+            uint64_t tile = 0;
+            int cnt = 0;
+            if (!slide) {
+                tile = resident; cnt = kLaneQubits;
+                for (int q : order) { if (cnt >= kTileBits) break; if (!((tile >> q) & 1)) { tile |= 1ull << q; cnt++; } }
+            } else {
+                // eleven qubits in breadth-first order, at least five of them from the previous tile
+                int from_prev = 0;
+                std::vector<int> chosen;
+                for (int q : order) {
+                    if ((int)chosen.size() >= kTileBits) break;
+                    const bool in_prev = (prev_mask >> q) & 1;
+                    const int left = kTileBits - (int)chosen.size();
+                    if (!in_prev && left <= kLaneQubits - from_prev) continue;      // keep room for the previous tile's share
+                    chosen.push_back(q);
+                    from_prev += in_prev;
+                }
+                for (int q : chosen) tile |= 1ull << q;
+                cnt = (int)chosen.size();
+            }
+            if (cnt < kTileBits || (need_first & ~tile)) continue;
+            if (tile == best_tile) continue;
+            const int sc = fuse ? score_tile(tile) : 1;
+            if (sc > best_score) { best_score = sc; best_tile = tile; }
+            if (!fuse) break;
+        }
+        if (best_score < 0) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler found no tile");
+        // the five low qubits of this pass; a sliding tile takes them from the previous tile, whose output layout is fixed now
+        if (slide) {
+            std::vector<int> low;
+            for (int p = 0; p < kLaneQubits; p++) if ((best_tile >> ts.at[p]) & 1) low.push_back(ts.at[p]);      // already low: stay
+            for (int q : prev_tile) if ((int)low.size() < kLaneQubits && ((best_tile >> q) & 1) && ts.pos[q] >= kLaneQubits) low.push_back(q);
+            if ((int)low.size() < kLaneQubits) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler: fewer than five shared qubits");
+            uint64_t low_mask = 0;
+            for (int q : low) low_mask |= 1ull << q;
+            // evicted low qubits trade places with the newly low ones
+            std::vector<int> evicted, incoming;
+            for (int p = 0; p < kLaneQubits; p++) if (!((low_mask >> ts.at[p]) & 1)) evicted.push_back(ts.at[p]);
+            for (int q : low) if (ts.pos[q] >= kLaneQubits) incoming.push_back(q);
+            TilePlan& pl = steps[prev_step].plan;
+            for (size_t k = 0; k < evicted.size(); k++) {
+                const int qa = evicted[k], qb = incoming[k];
+                const int pa = ts.pos[qa], pb = ts.pos[qb];
+                for (int j = 0; j < kTileBits; j++) {           // both are in the previous tile: swap their destinations
+                    if (pl.pout[j] == pa) pl.pout[j] = pb;
+                    else if (pl.pout[j] == pb) pl.pout[j] = pa;
+                }
+                ts.pos[qa] = pb; ts.pos[qb] = pa;
+                ts.at[pa] = qb; ts.at[pb] = qa;
+            }
+        }
+        // the real selection
+        Pass ps;
+        uint64_t blocked_any = 0, blocked_n = 0;
+        size_t scanned = 0, taken = 0, last_taken = 0;
+        for (size_t i = first; i < G && scanned < kLookahead; i++) {
+            if (done[i]) continue;
+            scanned++;
+            const PhysGate& g = gates[i];
+            if (!window_takes(g)) break;
+            const GateUse& u = use[i];
+            const bool take = ((u.n_use & blocked_any) == 0) && ((u.d_use & blocked_n) == 0) && (u.n_use & ~best_tile) == 0;
+            if (take) {
+                lower_gate(ps, g, fuse);
+                done[i] = 1;
+                taken++;
+                last_taken = i;
+                if (!fuse) break;
+            } else {
+                blocked_any |= u.n_use | u.d_use;
+                blocked_n |= u.n_use;
+            }
+        }
+        if (taken == 0) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler made no progress");
+        if (taken == 1 && touched_fraction(gates[last_taken]) <= 0.5) {
+            PhysGate g = gates[last_taken];
+            remap_gate(ts.pos, &g);
+            if (!fixes_bit0(g)) {       // lone gate on at most half of the amplitudes: the per-gate kernel (see schedule_passes)
+                prev_step = -1;
+                steps.push_back(Step{true, g, Pass(), kTileWindow, TilePlan()});
+                continue;
+            }
+        }
+        if (fuse && ctx().opt_late_tables) repack_unconditional_tables(ps);
+        remap_pass(ts.pos, &ps);
+        Step st{false, PhysGate(), std::move(ps), kTileWindow, TilePlan()};
+        std::vector<int> ppos;
+        prev_tile.clear();
+        for (int q = 0; q < n; q++) if ((best_tile >> q) & 1) { ppos.push_back(ts.pos[q]); prev_tile.push_back(q); }
+        std::sort(ppos.begin(), ppos.end());
+        for (int j = 0; j < kTileBits; j++) st.plan.pin[j] = st.plan.pout[j] = ppos[j];
+        steps.push_back(std::move(st));
+        prev_step = (int)steps.size() - 1;
+    }
+    if (final_pos) { final_pos->assign(ts.pos.begin(), ts.pos.end()); }
     return QI_OK;
 }
 
@@ -1588,7 +1930,9 @@ static bool tile_mode(const qi_state* s) {
     return c.opt_tile && !c.opt_tma && (int)s->n_local >= std::max(kTileBits, c.opt_tile_min_qubits);
 }
 
-int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in) {
+// `allow_relabel`: tile passes may leave the qubits of the state at other physical positions (folded into s->phys, like a
+// lazy SWAP).  Callers that need the layout they came with (chunk views, shards, canonicalise) pass false.
+int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, bool allow_relabel) {
     Context& c = ctx();
     std::vector<PhysGate> rewritten;
     if (c.opt_cz_rewrite && c.opt_fuse) { rewritten = gates_in; rewrite_cx_next_to_h(rewritten); }
@@ -1596,7 +1940,10 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in) {
     const bool tile = tile_mode(s);
     const int R = tile ? kTileWindow : window_regs(s);
     std::vector<Step> steps;
-    QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
+    std::vector<int> final_pos;
+    const bool relabel = tile && allow_relabel && s->world == 1 && c.opt_tile_slide;
+    if (tile) QI_TRY(schedule_tile_passes(s, gates, c.opt_fuse != 0, relabel, steps, &final_pos));
+    else QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
     // lower every pass, upload all phase tables in one copy, then launch back to back
     std::vector<std::vector<DOp>> dops(steps.size());
     std::vector<Layout> layouts(steps.size());
@@ -1604,7 +1951,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in) {
     std::vector<amp_t> arena;
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) continue;
-        if (tile) lower_tile_pass(s, steps[i].pass, tiles[i], arena);
+        if (tile) lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena);
         else lower_pass(s, steps[i].pass, steps[i].R, dops[i], arena, &layouts[i]);
     }
     if (!arena.empty()) {
@@ -1615,12 +1962,14 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in) {
         QI_CUDA(cudaEventRecord(c.ops_event, c.stream));
     }
     for (size_t i = 0; i < steps.size(); i++) {
-        if (steps[i].simple) QI_TRY(launch_simple_gate(s, gates[steps[i].gate]));
+        if (steps[i].simple) QI_TRY(launch_simple_gate(s, steps[i].sgate));
         else if (tile) { for (const TileLaunch& tl : tiles[i]) QI_TRY(launch_tile(s, tl, (const amp_t*)c.d_ops)); }
         else if (steps[i].R == 3) QI_TRY(launch_program<3>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else if (steps[i].R == 4) QI_TRY(launch_program<4>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else QI_TRY(launch_program<5>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
     }
+    if (relabel)                  // where the tile passes left the qubits
+        for (uint32_t q = 0; q < s->num_qubits; q++) s->phys[q] = (uint8_t)final_pos[s->phys[q]];
     return QI_OK;
 }
 
@@ -1648,15 +1997,18 @@ int debug_schedule(const qi_state* s, const std::vector<PhysGate>& gates, int R,
 //   u64 nsteps, then per step: u64 simple;
 //     simple = 1: PhysGate (raw);   simple = 0: u64 R, u64 regs[8] (sorted window qubits), u64 nops, DOp[nops] (raw, 112 B each)
 //   then u64 arena_count and arena_count double2 phase-table entries (DOp::m[0] of a table op is an offset into it)
-//     simple = 2 (CTA-tile pass, one record per k_tile launch): u64 tile_qubits[11], u64 nrounds, then per round
+//     simple = 2 (CTA-tile pass, one record per k_tile launch): u64 tile_pos[11], u64 tile_out[11] (position the content of local bit j
+//                 is stored to), u64 nrounds, then per round
 //                 u64 regs[4] (physical qubits of slot bits 0..3), u64 thr[7] (physical qubit of thread-index bit k), u64 nops, DOp[nops]
-int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R, std::vector<uint8_t>* blob) {
+int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R, std::vector<uint8_t>* blob, std::vector<int>* relabel_out) {
     std::vector<PhysGate> gates(gates_in);
     if (ctx().opt_cz_rewrite && ctx().opt_fuse) rewrite_cx_next_to_h(gates);
     std::vector<Step> steps;
     const bool tile = tile_mode(s);
-    if (tile) R = kTileWindow;
-    QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
+    std::vector<int> final_pos;
+    const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide;
+    if (tile) QI_TRY(schedule_tile_passes(s, gates, ctx().opt_fuse != 0, relabel, steps, &final_pos));
+    else QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
     std::vector<amp_t> arena;
     auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };
     auto put64 = [&](uint64_t v) { put(&v, 8); };
@@ -1666,16 +2018,17 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
         std::vector<std::vector<TileLaunch>> tiles(steps.size());
         for (size_t i = 0; i < steps.size(); i++) {
             if (steps[i].simple) { nrec++; continue; }
-            lower_tile_pass(s, steps[i].pass, tiles[i], arena);
+            lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena);
             nrec += tiles[i].size();
         }
         blob->clear();
         put64(nrec);
         for (size_t i = 0; i < steps.size(); i++) {
-            if (steps[i].simple) { put64(1); put(&gates[steps[i].gate], sizeof(PhysGate)); continue; }
+            if (steps[i].simple) { put64(1); put(&steps[i].sgate, sizeof(PhysGate)); continue; }
             for (const TileLaunch& tl : tiles[i]) {
                 put64(2);
                 for (int j = 0; j < kTileBits; j++) put64((uint64_t)tl.tile_qubits[j]);
+                for (int j = 0; j < kTileBits; j++) put64((uint64_t)tl.tile_out[j]);
                 put64(tl.rounds.size());
                 for (const TileRoundHost& r : tl.rounds) {
                     for (int k = 0; k < 4; k++) put64((uint64_t)tl.tile_qubits[r.regs[k]]);
@@ -1687,11 +2040,12 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
         }
         put64(arena.size());
         put(arena.data(), arena.size() * sizeof(amp_t));
+        if (relabel_out && relabel) *relabel_out = final_pos;
         return QI_OK;
     }
     for (const Step& st : steps) {
         put64(st.simple ? 1 : 0);
-        if (st.simple) { put(&gates[st.gate], sizeof(PhysGate)); continue; }
+        if (st.simple) { put(&st.sgate, sizeof(PhysGate)); continue; }
         std::vector<DOp> dops;
         Layout L;
         lower_pass(s, st.pass, st.R, dops, arena, &L);

@@ -354,12 +354,13 @@ def test_tile_qft_matches_closed_form_and_oracle(ref, tile11, n):
 
 
 def test_tile_pass_count_of_the_benchmark_circuit():
-    """30 qubits, depth 40: the tile executor needs well under half of the 126 HBM passes of the warp-tile executor."""
+    """30 qubits, depth 40: chosen, sliding 11-qubit tiles need a fraction of the 126 HBM passes of the warp-tile executor."""
     import quant_iron_b200 as gpu
     from quant_iron_b200 import workloads as w
     c = w.build_circuit(gpu, 30, w.random_layered_circuit(30, 40))
     steps, _, _ = wi.parse(wi.lower(c, 30))
     tiles = _tile_steps(steps)
-    assert len(tiles) == len(steps)
-    assert len(tiles) <= 90, len(tiles)
-    assert sum(len(ops) for t in tiles for (_, _, ops) in t[2]) >= 1400
+    assert len(steps) - len(tiles) <= 2
+    assert len(tiles) <= 30, len(tiles)
+    assert sum(len(ops) for t in tiles for (_, _, ops) in t[2]) >= 1300
+    assert any(t[3] != t[1] for t in tiles)                # tiles slide: some pass stores its qubits in a new order

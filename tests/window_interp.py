@@ -61,6 +61,7 @@ def parse(blob):
             off += PHYS.itemsize
         elif tag == 2:                # one k_tile launch: 11 tile qubits, rounds of (4 register qubits, 7 thread-bit qubits, ops)
             tile_qubits = [u64() for _ in range(11)]
+            tile_out = [u64() for _ in range(11)]
             rounds = []
             for _ in range(u64()):
                 regs = [u64() for _ in range(4)]
@@ -69,7 +70,7 @@ def parse(blob):
                 ops = np.frombuffer(blob, DOP, nops, off)
                 off += nops * DOP.itemsize
                 rounds.append((regs, thr, ops))
-            steps.append(("tile", tile_qubits, rounds))
+            steps.append(("tile", tile_qubits, rounds, tile_out))
         else:
             R = u64()
             regs = [u64() for _ in range(8)][:R]
@@ -228,13 +229,26 @@ def execute(blob, v, nl):
         if st[0] == "simple":
             run_simple(v, nl, st[1])
         elif st[0] == "tile":
-            tile_qubits, rounds = st[1], st[2]
+            tile_qubits, rounds, tile_out = st[1], st[2], st[3]
             assert tile_qubits[:5] == [0, 1, 2, 3, 4] and sorted(tile_qubits) == tile_qubits and len(set(tile_qubits)) == 11
+            assert sorted(tile_out) == tile_qubits, "the store layout permutes the tile's own positions"
             for k, (regs, thr, ops) in enumerate(rounds):
                 assert sorted(regs + thr) == tile_qubits, "a round's register + thread qubits are the tile qubits"
-                if k in (0, len(rounds) - 1):          # IO layouts: coalesced 512-byte rows
-                    assert thr[:5] == [0, 1, 2, 3, 4], "first / last round: lanes on qubits 0..4"
+                if k == 0:                              # load layout: coalesced 512-byte rows
+                    assert thr[:5] == [0, 1, 2, 3, 4], "first round: lanes on positions 0..4"
+                if k == len(rounds) - 1:                # store layout: the lanes hold what goes to positions 0..4
+                    dest = dict(zip(tile_qubits, tile_out))
+                    assert [dest[q] for q in thr[:5]] == [0, 1, 2, 3, 4], "last round: lanes on the bits stored to positions 0..4"
                 run_pass(v, nl, 4, regs, ops, arena, lane_qubits=tuple(thr))
+            if tile_out != tile_qubits:                 # the pass stores its tile with the local bits in a new order
+                idx = np.arange(1 << nl, dtype=np.uint64)
+                tmask = np.uint64(sum(1 << p for p in tile_qubits))
+                new = idx & ~tmask
+                for pin, pout in zip(tile_qubits, tile_out):
+                    new |= ((idx >> np.uint64(pin)) & np.uint64(1)) << np.uint64(pout)
+                w = np.empty_like(v)
+                w[new] = v
+                v[:] = w
         else:
             run_pass(v, nl, st[1], st[2], st[3], arena)
     return phys, steps

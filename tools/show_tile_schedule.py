@@ -37,7 +37,8 @@ for i, s in enumerate(steps):
     tab = int((kinds == wi.WK_TABLE).sum())
     tot_rounds += len(rounds)
     tot_ops += sum(nops)
-    print(f"{i:3d} window={s[1][5:]} rounds={len(rounds):2d} ops={sum(nops):3d} (pair {pair}, x {x}, table {tab}, other {len(kinds) - pair - tab}) per-round={nops}")
+    moved = sum(1 for a_, b_ in zip(s[1], s[3]) if a_ != b_)
+    print(f"{i:3d} window={s[1][5:]} moved={moved} rounds={len(rounds):2d} ops={sum(nops):3d} (pair {pair}, x {x}, table {tab}, other {len(kinds) - pair - tab}) per-round={nops}")
     if a.v:
         for regs, thr, ops in rounds:
             print("      regs", regs, "thr", thr, "kinds", list(ops["kind"]))
