@@ -253,6 +253,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "lean")) c.opt_lean = (int)value;
     else if (!strcmp(name, "tile")) c.opt_tile = (int)value;
     else if (!strcmp(name, "tile_slide")) c.opt_tile_slide = (int)value;
+    else if (!strcmp(name, "tile_absorb")) c.opt_tile_absorb = (int)value;
     else if (!strcmp(name, "cz_rewrite")) c.opt_cz_rewrite = (int)value;
     else if (!strcmp(name, "tile_min_qubits")) c.opt_tile_min_qubits = (int)value;
     else if (!strcmp(name, "prefetch")) c.opt_prefetch = (int)value;

@@ -44,7 +44,9 @@ namespace qi {
 //   REALUP = [[1, p], [q, 1]]   REALUM = [[1, p], [q, -1]]   (m[0] = p, m[1] = q; H / g = REALUM with p = q = 1)
 //   RXU = [[1, -i t], [-i t, 1]]   RXSU = RXU with its inputs swapped   (m[0] = t = tan(theta / 2))
 enum { WK_X = 1, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE,
-       WK_NEG /* WK_DIAG with phase -1 (Z, CZ): sign flips, no FP64 work */ };
+       WK_NEG /* WK_DIAG with phase -1 (Z, CZ): sign flips, no FP64 work */,
+       // k_tile only: LIFTED forms of REAL / RX -- the same 2x2 as two in-place accumulations per amplitude (see fast routines)
+       WK_REALL /* m = (k00, k01, k10 / k00, det / k00) */, WK_RXL /* m = (c, s, 1 / c, s / c) */ };
 static const int kLastPairKind = WK_RXSU;
 
 static const int kMaxOps = 120;      // per launch (parameter space: 120 * 112 B + header < 16 KB)
@@ -56,7 +58,7 @@ static const int kTileWindow = kTileBits - kLaneQubits;   // window qubits per p
 static const int kMaxRounds = 24;
 static const int kMaxTileOps = 232;         // parameter space: 232 * 112 B + rounds + header < 32 KiB
 
-struct DOp {                 // device op, 112 bytes
+struct alignas(16) DOp {     // device op, 112 bytes; the first 32 bytes are everything the dispatch needs (two 16-byte loads)
     uint8_t kind;            // WK_*
     uint8_t tpos;            // pair ops: 0..4 lane bit, 5+j register bit j
     uint8_t hub_cls;         // WK_TABLE: class of the hub bit (CLS_*)
@@ -68,9 +70,9 @@ struct DOp {                 // device op, 112 bytes
     uint32_t c_lane, c_reg;  // c_lane: control bits in lane space (k_window: lane bits 0..4; k_tile: the 7 thread-index bits).
                              // c_reg: SLOT MASK -- bit s is set iff slot s passes the register-bit controls (positive and
                              // negative), expanded on the host
-    uint32_t t_lane, t_reg;  // WK_RZ: target bit in lane space / slot space (0 if elsewhere)
     uint64_t c_tile;         // control bits in compact tile-index space (positive and negative controls)
     uint64_t c_tval;         // value those bits must have: (tile & c_tile) == c_tval
+    uint32_t t_lane, t_reg;  // WK_RZ: target bit in lane space / slot space (0 if elsewhere)
     uint64_t t_tile;         // WK_RZ: target bit in tile space
     double m[8];             // matrix / phases; WK_TABLE: m[0] holds the table offset (as integer bits)
 };
@@ -436,96 +438,187 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 }
 
 // ---- k_tile: specialised straight-line routines ---------------------------------------------------------------
-// The generic interpreter above costs ~85 non-FP64 instructions per op (slot-mask predicates per pair, selects, branches;
-// ncu r02c) -- more than the 64 FP64 instructions of the gate itself.  On the CTA-tile kernel a pass is compute-bound,
-// so the common ops get one routine each, chosen by ONE indexed branch on a code the host computes:
-//   full:  pair kind K on register bit B, all 8 pairs                                  (4 per kind)
-//   half:  the same under ONE register-bit control C with value CV, 4 pairs             (24 per kind; C != B)
-// Controls on thread or tile bits are handled before the dispatch (skip), so "full" also covers gates controlled from
-// outside the registers.  Everything else (several register-bit controls, complex 2x2, diagonal ops) takes exec_op.
-static const int kFastPerKind = 28;
-__host__ __device__ constexpr int fast_kind_index(int kind) {
-    return kind == WK_REAL ? 0 : kind == WK_RX ? 1 : kind == WK_RXS ? 2 : kind == WK_X ? 3 : kind == WK_REALUP ? 4 : kind == WK_REALUM ? 5
-         : kind == WK_RXU ? 6 : kind == WK_RXSU ? 7 : -1;
-}
-// host: code of an op (0 = none).  pos / neg: register-bit controls that must be 1 / 0
+// On the CTA-tile kernel a pass is compute-bound, and the generic interpreter above spends more instructions around a gate
+// than on it (~85 non-FP64 instructions per op against 64 FP64 ones; ncu r02c): slot-mask predicates per pair, selects,
+// branches -- and ~64 register moves per op, because a 2x2 written as  n0 = k0 a0 + k1 a1, n1 = k2 a0 + k3 a1  produces its
+// results in fresh registers, which ptxas then copies back to the canonical ones at the loop's merge point.
+// The common ops therefore get one straight-line routine each, chosen by a code the host computes, in forms that are
+// IN PLACE instruction by instruction -- every instruction overwrites the one operand that dies there (LIFTING):
+//     a0 <- k0 a0;  a0 <- a0 + k1 a1          (a0 is final)
+//     a1 <- k3' a1; a1 <- a1 + k2' a0         with k2' = k2 / k0, k3' = det / k0   (a0 is already the new value)
+// Same FP64 instruction count (8 per amplitude pair), no moves (measured on SASS: 0 MOV against 130 for the plain form).
+// The divisions by k0 are done on the host; ops whose pivot |k0| is below 0.05 keep the generic form (RX: 3 % of
+// random angles), so the rounding error of a lifted op stays below ~20 ulp of the amplitudes it touches.
+//   codes: 1..4 REALL on register bit B; 5..8 RXL; 9..12 X (register swaps); 13..36 X under ONE register-bit control
+//          (C, CV); 0 = everything else (exec_op_tile).  Controls on thread or tile bits are checked before the dispatch.
+static const double kLiftMinPivot = 0.05;
 static inline int fast_code(int kind, int B, uint32_t pos, uint32_t neg) {
-    const int ki = fast_kind_index(kind);
-    if (ki < 0 || B < 0 || B > 3 || ((pos | neg) >> B) & 1u) return 0;
-    if ((pos | neg) == 0) return 1 + ki * kFastPerKind + B;
-    if (__builtin_popcount(pos | neg) != 1) return 0;
+    if (B < 0 || B > 3 || ((pos | neg) >> B) & 1u) return 0;
+    if ((pos | neg) == 0) return kind == WK_REALL ? 1 + B : kind == WK_RXL ? 5 + B : kind == WK_X ? 9 + B : 0;
+    if (kind != WK_X || __builtin_popcount(pos | neg) != 1) return 0;
     const int C = __builtin_ctz(pos | neg), CI = C < B ? C : C - 1, CV = pos ? 1 : 0;
-    return 1 + ki * kFastPerKind + 4 + (B * 3 + CI) * 2 + CV;
+    return 13 + (B * 3 + CI) * 2 + CV;
 }
 
-template <int KIND>
-__device__ __forceinline__ void fast_pair(amp_t& a0, amp_t& a1, double k0, double k1, double k2, double k3) {
-    if (KIND == WK_REAL) upd_real(a0, a1, k0, k1, k2, k3);
-    else if (KIND == WK_RX) upd_rx(a0, a1, k0, k1);
-    else if (KIND == WK_RXS) upd_rxs(a0, a1, k0, k1);
-    else if (KIND == WK_REALUP) upd_realu<false>(a0, a1, k0, k1);
-    else if (KIND == WK_REALUM) upd_realu<true>(a0, a1, k0, k1);
-    else if (KIND == WK_RXU) upd_rxu<false>(a0, a1, k0);
-    else if (KIND == WK_RXSU) upd_rxu<true>(a0, a1, k0);
-    else { const amp_t t = a0; a0 = a1; a1 = t; }
-}
-template <int KIND, int B>
-__device__ __forceinline__ void fast_full(amp_t (&v)[16], double k0, double k1, double k2, double k3) {
+template <int B>
+__device__ __forceinline__ void fast_reall(amp_t (&v)[16], const double k0, const double k1, const double k2, const double k3) {
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
-        fast_pair<KIND>(v[s0], v[s0 | (1 << B)], k0, k1, k2, k3);
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        v[s0].x *= k0; v[s0].x = fma(k1, v[s1].x, v[s0].x);
+        v[s0].y *= k0; v[s0].y = fma(k1, v[s1].y, v[s0].y);
+        v[s1].x *= k3; v[s1].x = fma(k2, v[s0].x, v[s1].x);
+        v[s1].y *= k3; v[s1].y = fma(k2, v[s0].y, v[s1].y);
     }
 }
-template <int KIND, int B, int CI, int CV>
-__device__ __forceinline__ void fast_half(amp_t (&v)[16], double k0, double k1, double k2, double k3) {
+// RX = [[c, -i s], [-i s, c]]:  a0' = c a0 - i s a1;  a1' = (1 / c) a1 - i (s / c) a0'      (k = c, s, 1 / c, s / c)
+template <int B>
+__device__ __forceinline__ void fast_rxl(amp_t (&v)[16], const double k0, const double k1, const double k2, const double k3) {
+    const double n1 = -k1, n3 = -k3;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        v[s0].x *= k0; v[s0].x = fma(k1, v[s1].y, v[s0].x);
+        v[s0].y *= k0; v[s0].y = fma(n1, v[s1].x, v[s0].y);
+        v[s1].x *= k2; v[s1].x = fma(k3, v[s0].y, v[s1].x);
+        v[s1].y *= k2; v[s1].y = fma(n3, v[s0].x, v[s1].y);
+    }
+}
+template <int B>
+__device__ __forceinline__ void fast_x(amp_t (&v)[16]) {
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        const amp_t t = v[s0]; v[s0] = v[s1]; v[s1] = t;
+    }
+}
+template <int B, int CI, int CV>
+__device__ __forceinline__ void fast_cx(amp_t (&v)[16]) {
     constexpr int C = CI < B ? CI : CI + 1;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
-        if (((s0 >> C) & 1) == CV) fast_pair<KIND>(v[s0], v[s0 | (1 << B)], k0, k1, k2, k3);
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        if (((s0 >> C) & 1) == CV) { const amp_t t = v[s0]; v[s0] = v[s1]; v[s1] = t; }
     }
 }
 
-#define QI_FAST_FULL(K) \
-    case 1 + fast_kind_index(K) * kFastPerKind + 0: fast_full<K, 0>(v, k0, k1, k2, k3); break; \
-    case 1 + fast_kind_index(K) * kFastPerKind + 1: fast_full<K, 1>(v, k0, k1, k2, k3); break; \
-    case 1 + fast_kind_index(K) * kFastPerKind + 2: fast_full<K, 2>(v, k0, k1, k2, k3); break; \
-    case 1 + fast_kind_index(K) * kFastPerKind + 3: fast_full<K, 3>(v, k0, k1, k2, k3); break;
-#define QI_FAST_HALF1(K, B, CI, CV) \
-    case 1 + fast_kind_index(K) * kFastPerKind + 4 + (B * 3 + CI) * 2 + CV: fast_half<K, B, CI, CV>(v, k0, k1, k2, k3); break;
-#define QI_FAST_HALF6(K, B) \
-    QI_FAST_HALF1(K, B, 0, 0) QI_FAST_HALF1(K, B, 0, 1) QI_FAST_HALF1(K, B, 1, 0) QI_FAST_HALF1(K, B, 1, 1) QI_FAST_HALF1(K, B, 2, 0) QI_FAST_HALF1(K, B, 2, 1)
-#define QI_FAST_HALF(K) QI_FAST_HALF6(K, 0) QI_FAST_HALF6(K, 1) QI_FAST_HALF6(K, 2) QI_FAST_HALF6(K, 3)
+// everything without a routine of its own: diagonal ops, and pair gates under register-bit controls / complex 2x2 (predicated)
+template <int B, bool U2K>
+__device__ __forceinline__ void tile_pair_cond(amp_t (&v)[16], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
+    switch (kind) {
+        case WK_X: reg_pair_kind<4, B, WK_X, true>(v, c_reg, m); break;
+        case WK_RX: reg_pair_kind<4, B, WK_RX, true>(v, c_reg, m); break;
+        case WK_RXS: reg_pair_kind<4, B, WK_RXS, true>(v, c_reg, m); break;
+        case WK_REAL: reg_pair_kind<4, B, WK_REAL, true>(v, c_reg, m); break;
+        default: if (U2K) reg_pair_kind<4, B, WK_U2, true>(v, c_reg, m); break;
+    }
+}
 
-// the op program of one round on the CTA-tile kernel
-template <bool U2K, bool LEAN>
+template <bool U2K>
+__device__ __forceinline__ void exec_op_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp& op, const amp_t* __restrict__ tables) {
+    constexpr int S = 16, NT = kTileThreads;
+    if (((uint32_t)t & op.c_lane) != op.c_lval) return;              // thread-bit controls
+    const uint32_t kind = op.kind, c_reg = op.c_reg;
+    if (kind == WK_TABLE) {
+        const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
+        const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
+        if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) return;
+        if (hub_cls == CLS_LANE && !((t >> hub_bit) & 1)) return;
+        amp_t f = tab[t];                                             // thread table (128 entries)
+        const uint32_t nch = op.nchunks;
+        for (uint32_t k = 0; k < nch; k++)                            // tile chunk tables (256 entries each)
+            f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
+        const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
+        if (op.has_reg) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], cmul(f, __ldg(tab + NT + s)));
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], f);
+        }
+    } else if (kind == WK_NEG) {
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
+    } else if (kind == WK_DIAG) {
+        const amp_t ph = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((c_reg >> s) & 1u) upd_cmul(v[s], ph);
+    } else if (kind == WK_RZ) {
+        const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
+        const uint32_t t_reg = op.t_reg;
+        const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)t & op.t_lane) != 0);
+        const amp_t pt = t_thread ? p1 : p0;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((c_reg >> s) & 1u) {
+                if (s & t_reg) upd_cmul(v[s], p1);
+                else upd_cmul(v[s], pt);
+            }
+    } else if (kind == WK_SCALE) {
+        const double g = op.m[0];
+#pragma unroll
+        for (int s = 0; s < S; s++) upd_scale(v[s], g);
+    } else {
+        switch (op.tpos - 5) {
+            case 0: tile_pair_cond<0, U2K>(v, kind, c_reg, op.m); break;
+            case 1: tile_pair_cond<1, U2K>(v, kind, c_reg, op.m); break;
+            case 2: tile_pair_cond<2, U2K>(v, kind, c_reg, op.m); break;
+            default: tile_pair_cond<3, U2K>(v, kind, c_reg, op.m); break;
+        }
+    }
+}
+
+#define QI_CX6(B) \
+    case 13 + (B * 3 + 0) * 2 + 0: fast_cx<B, 0, 0>(v); break; case 13 + (B * 3 + 0) * 2 + 1: fast_cx<B, 0, 1>(v); break; \
+    case 13 + (B * 3 + 1) * 2 + 0: fast_cx<B, 1, 0>(v); break; case 13 + (B * 3 + 1) * 2 + 1: fast_cx<B, 1, 1>(v); break; \
+    case 13 + (B * 3 + 2) * 2 + 0: fast_cx<B, 2, 0>(v); break; case 13 + (B * 3 + 2) * 2 + 1: fast_cx<B, 2, 1>(v); break;
+
+// the op program of one round on the CTA-tile kernel.  Everything the dispatch needs sits in the first 32 bytes of an op
+// and is loaded one op AHEAD (the loads are warp-uniform: they live in uniform registers), so that the constant-bank
+// latency of op o+1 hides behind the arithmetic of op o instead of heading a chain of dependent loads, compares and
+// branches per op (43 % of all stall samples before, ncu r02c).
+struct OpHead { uint4 a; ulonglong2 b; };
+__device__ __forceinline__ OpHead load_head(const DOp* __restrict__ op) {
+    OpHead h;
+    h.a = *reinterpret_cast<const uint4*>(op);
+    h.b = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const char*>(op) + 16);
+    return h;
+}
+
+template <bool U2K>
 __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp* __restrict__ ops, const uint32_t nops,
                                              const amp_t* __restrict__ tables) {
+    if (nops == 0) return;
+    OpHead nxt = load_head(ops);
 #pragma unroll 1
     for (uint32_t o = 0; o < nops; o++) {
+        const OpHead h = nxt;
         const DOp& op = ops[o];
-        if ((tile & op.c_tile) != op.c_tval) continue;                // tile-uniform control (positive and negative bits)
-        const uint32_t code = op.code;
-        if (code == 0) { exec_op<4, false, U2K, LEAN, kTileThreads>(v, tile, t, op, tables); continue; }
-        if (((uint32_t)t & op.c_lane) != op.c_lval) continue;         // thread-bit controls
+        if (o + 1 < nops) nxt = load_head(ops + o + 1);
+        if ((tile & h.b.x) != h.b.y) continue;                         // tile-uniform control (positive and negative bits)
+        const uint32_t code = h.a.y >> 24;
+        if (code == 0) { exec_op_tile<U2K>(v, tile, t, op, tables); continue; }
+        if (((uint32_t)t & h.a.z) != ((h.a.y >> 16) & 0xffu)) continue;   // thread-bit controls
         const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
         switch (code) {
-            QI_FAST_FULL(WK_REAL)
-            QI_FAST_FULL(WK_RX) QI_FAST_HALF(WK_RX)
-            QI_FAST_FULL(WK_RXS) QI_FAST_HALF(WK_RXS)
-            QI_FAST_FULL(WK_X) QI_FAST_HALF(WK_X)
-            default:
-                if (LEAN) {
-                    switch (code) {
-                        QI_FAST_FULL(WK_REALUP)
-                        QI_FAST_FULL(WK_REALUM)
-                        QI_FAST_FULL(WK_RXU) QI_FAST_HALF(WK_RXU)
-                        QI_FAST_FULL(WK_RXSU) QI_FAST_HALF(WK_RXSU)
-                        default: break;
-                    }
-                }
-                break;
+            case 1: fast_reall<0>(v, k0, k1, k2, k3); break;
+            case 2: fast_reall<1>(v, k0, k1, k2, k3); break;
+            case 3: fast_reall<2>(v, k0, k1, k2, k3); break;
+            case 4: fast_reall<3>(v, k0, k1, k2, k3); break;
+            case 5: fast_rxl<0>(v, k0, k1, k2, k3); break;
+            case 6: fast_rxl<1>(v, k0, k1, k2, k3); break;
+            case 7: fast_rxl<2>(v, k0, k1, k2, k3); break;
+            case 8: fast_rxl<3>(v, k0, k1, k2, k3); break;
+            case 9: fast_x<0>(v); break;
+            case 10: fast_x<1>(v); break;
+            case 11: fast_x<2>(v); break;
+            case 12: fast_x<3>(v); break;
+            QI_CX6(0) QI_CX6(1) QI_CX6(2) QI_CX6(3)
+            default: break;
         }
     }
 }
@@ -674,7 +767,7 @@ static_assert(sizeof(TProgram) <= 32000, "kernel parameter space");
 // the three tile-local bits behind thread bits 0..2 fall into three different classes mod 3 (the host orders them so)
 __host__ __device__ __forceinline__ uint32_t tile_swz(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 3u); }
 
-template <bool U2K, bool LEAN>
+template <bool U2K>
 __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ TProgram P) {
     __shared__ __align__(16) amp_t sm[1 << kTileBits];
     __shared__ uint16_t lbs[kMaxRounds][kTileThreads];       // swizzled tile-local base of thread t in round r
@@ -704,7 +797,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = QI_LD(g + P.goff_in[s]);
         }
-        run_ops_tile<U2K, LEAN>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
+        run_ops_tile<U2K>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
 #pragma unroll 1
         for (int r = 1; r < nr; r++) {
             const TRound& prev = P.rounds[r - 1];
@@ -715,7 +808,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
             __syncthreads();
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = sm[rb ^ cur.sswz[s]];
-            run_ops_tile<U2K, LEAN>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
+            run_ops_tile<U2K>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
         }
         {
             amp_t* __restrict__ g = a + tb + g_out;
@@ -772,6 +865,7 @@ struct Pass {
     std::vector<HOp> ops;
     std::vector<DiagGroup> groups;
     int next_pair = 0;
+    bool absorb = true;                  // fold CNOTs into neighbouring gates (k_window); tile passes keep them as register swaps
 };
 
 static void classify_u2(const double* p, HOp* op) {
@@ -896,7 +990,7 @@ static void push_pair(Pass& ps, uint32_t kind, int target, uint64_t cmask, const
     op.target = target;
     op.cmask = cmask;
     if (m8) memcpy(op.m, m8, 8 * sizeof(double));
-    if (ctx().opt_absorb) {
+    if (ctx().opt_absorb && ps.absorb) {
         HOp off;
         if (absorb_cnot_before(ps, &op)) { append_op(ps, op, 1ull << target); return; }     // op now carries nmask
         if (absorb_cnot_after(ps, op, &off)) { append_op(ps, off, 1ull << target); return; }
@@ -1216,13 +1310,25 @@ static void lower_op(const Layout& L, const Pass& ps, const HOp& h, double* scal
         d.c_tile = pos_tile | neg_tile;
         d.c_tval = pos_tile;
         if (L.nt == kTileThreads && op.kind >= WK_X && op.kind <= kLastPairKind && L.cls[op.target] == CLS_REG) {
-            const bool has_half = op.kind == WK_RX || op.kind == WK_RXS || op.kind == WK_X || op.kind == WK_RXU || op.kind == WK_RXSU;
-            if ((pos_reg | neg_reg) == 0 || has_half) d.code = (uint8_t)fast_code((int)op.kind, L.idx[op.target], pos_reg, neg_reg);
+            // k_tile: ops with a straight-line routine; REAL / RX without register-bit controls take their lifted forms
+            if ((pos_reg | neg_reg) == 0 && op.kind == WK_REAL && std::fabs(op.m[0]) >= kLiftMinPivot) {
+                const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
+                op.kind = WK_REALL;
+                op.m[2] = k2 / k0;
+                op.m[3] = (k0 * k3 - k1 * k2) / k0;
+            } else if ((pos_reg | neg_reg) == 0 && op.kind == WK_RX && std::fabs(op.m[0]) >= kLiftMinPivot) {
+                const double c = op.m[0], sn = op.m[1];
+                op.kind = WK_RXL;
+                op.m[2] = 1.0 / c;
+                op.m[3] = sn / c;
+            }
+            d.kind = (uint8_t)op.kind;
+            d.code = (uint8_t)fast_code((int)op.kind, L.idx[op.target], pos_reg, neg_reg);
         }
     }
     if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
     memcpy(d.m, op.m, sizeof(d.m));
-    if (op.kind != WK_DIAG && op.kind != WK_RZ && op.kind != WK_NEG) {
+    if (op.kind != WK_DIAG && op.kind != WK_RZ && op.kind != WK_NEG) {      // pair ops (WK_REALL / WK_RXL included)
         const int t = op.target;
         d.tpos = (uint8_t)(L.cls[t] == CLS_LANE ? L.idx[t] : kLaneQubits + L.idx[t]);
     }
@@ -1265,7 +1371,7 @@ struct TileLaunch {
     int tile_out[kTileBits];     // physical position the content of local bit j is stored to
     std::vector<TileRoundHost> rounds;
     std::vector<DOp> dops;
-    bool u2k = false, lean = false;
+    bool u2k = false;
 };
 
 static GateUse uses_of_hop(const Pass& ps, const HOp& h) {
@@ -1369,7 +1475,7 @@ static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& p
     for (int j = 0; j < kTileBits; j++) local_of[plan.pin[j]] = j;
 
     std::vector<HOp> ops(ps.ops);
-    double scale = ctx().opt_lean ? lean_convert(ops) : 1.0;
+    double scale = 1.0;      // (the lean unit forms of k_window are not used here: the lifted forms already avoid the moves)
     std::vector<std::vector<size_t>> round_ops;
     std::vector<std::vector<int>> round_regs;
     form_rounds(ps, ops, &round_ops, &round_regs);
@@ -1436,8 +1542,7 @@ static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& p
             }
         }
         for (const DOp& d : tl.dops) {
-            if (d.kind >= WK_X && d.kind <= kLastPairKind) { tl.u2k |= d.kind == WK_U2; tl.lean |= d.kind >= WK_REALUP; }
-            tl.lean |= d.kind == WK_SCALE;
+            tl.u2k |= d.kind == WK_U2;
         }
         launches.push_back(std::move(tl));
         ri = end;
@@ -1476,13 +1581,8 @@ static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables)
     const uint64_t ntiles = s->len >> kTileBits;
     uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
     LaunchScope ls(KF_TILE, 32.0 * (double)s->len);
-    if (tl.lean) {
-        if (tl.u2k) k_tile<true, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
-        else k_tile<false, true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
-    } else {
-        if (tl.u2k) k_tile<true, false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
-        else k_tile<false, false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
-    }
+    if (tl.u2k) k_tile<true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+    else k_tile<false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
     return check_launch("k_tile");
 }
 
@@ -1809,6 +1909,7 @@ static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& 
         }
         // the real selection
         Pass ps;
+        ps.absorb = ctx().opt_tile_absorb != 0;
         uint64_t blocked_any = 0, blocked_n = 0;
         size_t scanned = 0, taken = 0, last_taken = 0;
         for (size_t i = first; i < G && scanned < kLookahead; i++) {

@@ -12,14 +12,15 @@ import struct
 
 import numpy as np
 
-WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE, WK_NEG = range(1, 15)
+WK_X, WK_RX, WK_RXS, WK_REAL, WK_U2, WK_REALUP, WK_REALUM, WK_RXU, WK_RXSU, WK_DIAG, WK_RZ, WK_TABLE, WK_SCALE, WK_NEG, WK_REALL, WK_RXL = range(1, 17)
+PAIR_KINDS = set(range(WK_X, WK_RXSU + 1)) | {WK_REALL, WK_RXL}
 LAST_PAIR = WK_RXSU
 IK_H, IK_X, IK_Y, IK_U2, IK_DIAG, IK_RZ, IK_SWAP, IK_MATCH = 1, 2, 3, 4, 5, 6, 7, 8
 CLS_LANE, CLS_REG, CLS_TILE = 1, 2, 3
 
 DOP = np.dtype([("kind", "u1"), ("tpos", "u1"), ("hub_cls", "u1"), ("hub_bit", "u1"), ("nchunks", "u1"), ("has_reg", "u1"),
-                ("c_lval", "u1"), ("pad", "u1"), ("c_lane", "<u4"), ("c_reg", "<u4"), ("t_lane", "<u4"), ("t_reg", "<u4"),
-                ("c_tile", "<u8"), ("c_tval", "<u8"), ("t_tile", "<u8"), ("m", "<f8", 8)])
+                ("c_lval", "u1"), ("code", "u1"), ("c_lane", "<u4"), ("c_reg", "<u4"), ("c_tile", "<u8"), ("c_tval", "<u8"),
+                ("t_lane", "<u4"), ("t_reg", "<u4"), ("t_tile", "<u8"), ("m", "<f8", 8)])
 PHYS = np.dtype([("kind", "<i4"), ("t0", "<i4"), ("t1", "<i4"), ("pad", "<i4"), ("cmask", "<u8"), ("p", "<f8", 8)])
 assert DOP.itemsize == 112 and PHYS.itemsize == 88
 
@@ -106,6 +107,12 @@ def _pair(v, idx0, tb, kind, m):
         n0, n1 = a0 - 1j * m[0] * a1, a1 - 1j * m[0] * a0
     elif kind == WK_RXSU:                     # the same with its inputs swapped
         n0, n1 = a1 - 1j * m[0] * a0, a0 - 1j * m[0] * a1
+    elif kind == WK_REALL:                    # k_tile, lifted real 2x2: the second row acts on the NEW a0 (m = k00, k01, k10/k00, det/k00)
+        n0 = m[0] * a0 + m[1] * a1
+        n1 = m[3] * a1 + m[2] * n0
+    elif kind == WK_RXL:                      # k_tile, lifted RX (m = c, s, 1/c, s/c)
+        n0 = m[0] * a0 - 1j * m[1] * a1
+        n1 = m[2] * a1 - 1j * m[3] * n0
     else:
         raise AssertionError(f"unknown pair kind {kind}")
     v[idx0] = n0
@@ -138,7 +145,7 @@ def run_pass(v, nl, R, regs, ops, arena, lane_qubits=(0, 1, 2, 3, 4)):
         lane_ok = (lane & np.uint32(op["c_lane"])) == np.uint32(op["c_lval"])
         c_reg = int(op["c_reg"])
         slot_ok = ((np.uint32(c_reg) >> slot) & np.uint32(1)).astype(bool)
-        if kind <= LAST_PAIR:
+        if kind in PAIR_KINDS:
             tpos = int(op["tpos"])
             tbit = lane_qubits[tpos] if tpos < 5 else regs[tpos - 5]
             assert tpos >= 5 or NT == 32, "a k_tile round has no lane-pair ops"
