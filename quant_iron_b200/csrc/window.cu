@@ -437,22 +437,34 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
     }
 }
 
-// ---- k_tile: specialised straight-line routines ---------------------------------------------------------------
-// On the CTA-tile kernel a pass is compute-bound, and the generic interpreter above spends more instructions around a gate
-// than on it (~85 non-FP64 instructions per op against 64 FP64 ones; ncu r02c): slot-mask predicates per pair, selects,
-// branches -- and ~64 register moves per op, because a 2x2 written as  n0 = k0 a0 + k1 a1, n1 = k2 a0 + k3 a1  produces its
-// results in fresh registers, which ptxas then copies back to the canonical ones at the loop's merge point.
-// The common ops therefore get one straight-line routine each, chosen by a code the host computes, in forms that are
-// IN PLACE instruction by instruction -- every instruction overwrites the one operand that dies there (LIFTING):
-//     a0 <- k0 a0;  a0 <- a0 + k1 a1          (a0 is final)
-//     a1 <- k3' a1; a1 <- a1 + k2' a0         with k2' = k2 / k0, k3' = det / k0   (a0 is already the new value)
-// Same FP64 instruction count (8 per amplitude pair), no moves (measured on SASS: 0 MOV against 130 for the plain form).
-// The divisions by k0 are done on the host; ops whose pivot |k0| is below 0.05 keep the generic form (RX: 3 % of
-// random angles), so the rounding error of a lifted op stays below ~20 ulp of the amplitudes it touches.
-//   codes: 1..4 REALL on register bit B; 5..8 RXL; 9..12 X (register swaps); 13..36 X under ONE register-bit control
-//          (C, CV); 0 = everything else (exec_op_tile).  Controls on thread or tile bits are checked before the dispatch.
+// ---- k_tile: the op set of the CTA-tile kernel -------------------------------------------------------------------
+// On the CTA-tile kernel a pass is compute-bound, so the op loop is built around what ptxas does with 64 live amplitude
+// registers in a loop (measured on SASS and with ncu, profiles/r02_*):
+//  * a 2x2 written as  n0 = k0 a0 + k1 a1, n1 = k2 a0 + k3 a1  leaves its results in fresh registers, and every path through
+//    the loop body then ends with ~64 moves back to the canonical assignment -- and ONE such path (a register swap, a
+//    complex multiply) makes ptxas shuffle the whole file at every merge point of the loop: 4 x 64 moves per op.
+//  * so EVERY op of this kernel is in place instruction by instruction -- each instruction overwrites the one operand
+//    that dies there:
+//      real 2x2 (LIFTING):  a0 <- k0 a0;  a0 <- a0 + k1 a1;  a1 <- k3' a1;  a1 <- a1 + k2' a0     k2' = k2 / k0, k3' = det / k0
+//                           (the second row acts on the NEW a0; same 8 FP64 instructions per pair, no moves)
+//      RX:                  the same with the off-diagonal products crossing x and y
+//      phase e^{i phi}:     three shears  x <- x - t y;  y <- y + s x;  x <- x - t y   (t = tan(phi/2), s = sin phi; 3 FMA, not 4)
+//      X / CNOT:            xor swaps (PTX, so that they stay three xors and never become a register renaming)
+//  * the divisions are done on the host; a 2x2 whose pivot |k0| is below 0.05 is lowered as X followed by the 2x2 with its
+//    columns swapped (a unitary's other pivot is then ~1), RX likewise through RX(theta) = -i X RX(theta - pi); a complex
+//    2x2 is lowered to phase . real rotation . phase.  Rounding stays within ~20 ulp of the amplitudes an op touches.
+//  * pair gates never see a register-bit control: the round builder keeps the controls of a controlled gate out of the
+//    round's register qubits (they become thread or tile predicates); only X has variants under one register-bit control.
+//   codes: 1..4 REALL on register bit B; 5..8 RXL; 9..12 X; 13..36 X under one register-bit control (C, CV);
+//          40 TABLE, 41 NEG, 42 DIAG, 43 RZ, 44 SCALE.
 static const double kLiftMinPivot = 0.05;
+enum { FC_TABLE = 40, FC_NEG, FC_DIAG, FC_RZ, FC_SCALE };
 static inline int fast_code(int kind, int B, uint32_t pos, uint32_t neg) {
+    if (kind == WK_TABLE) return FC_TABLE;
+    if (kind == WK_NEG) return FC_NEG;
+    if (kind == WK_DIAG) return FC_DIAG;
+    if (kind == WK_RZ) return FC_RZ;
+    if (kind == WK_SCALE) return FC_SCALE;
     if (B < 0 || B > 3 || ((pos | neg) >> B) & 1u) return 0;
     if ((pos | neg) == 0) return kind == WK_REALL ? 1 + B : kind == WK_RXL ? 5 + B : kind == WK_X ? 9 + B : 0;
     if (kind != WK_X || __builtin_popcount(pos | neg) != 1) return 0;
@@ -484,12 +496,16 @@ __device__ __forceinline__ void fast_rxl(amp_t (&v)[16], const double k0, const 
         v[s1].y *= k2; v[s1].y = fma(n3, v[s0].x, v[s1].y);
     }
 }
+__device__ __forceinline__ void xor_swap(amp_t& a, amp_t& b) {
+    asm volatile("xor.b64 %0, %0, %1;\n\txor.b64 %1, %1, %0;\n\txor.b64 %0, %0, %1;" : "+d"(a.x), "+d"(b.x));
+    asm volatile("xor.b64 %0, %0, %1;\n\txor.b64 %1, %1, %0;\n\txor.b64 %0, %0, %1;" : "+d"(a.y), "+d"(b.y));
+}
 template <int B>
 __device__ __forceinline__ void fast_x(amp_t (&v)[16]) {
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
-        const amp_t t = v[s0]; v[s0] = v[s1]; v[s1] = t;
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        xor_swap(v[s0], v[s0 | (1 << B)]);
     }
 }
 template <int B, int CI, int CV>
@@ -497,79 +513,46 @@ __device__ __forceinline__ void fast_cx(amp_t (&v)[16]) {
     constexpr int C = CI < B ? CI : CI + 1;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)), s1 = s0 | (1 << B);
-        if (((s0 >> C) & 1) == CV) { const amp_t t = v[s0]; v[s0] = v[s1]; v[s1] = t; }
+        const int s0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        if (((s0 >> C) & 1) == CV) xor_swap(v[s0], v[s0 | (1 << B)]);
     }
 }
 
-// everything without a routine of its own: diagonal ops, and pair gates under register-bit controls / complex 2x2 (predicated)
-template <int B, bool U2K>
-__device__ __forceinline__ void tile_pair_cond(amp_t (&v)[16], uint32_t kind, uint32_t c_reg, const double* __restrict__ m) {
-    switch (kind) {
-        case WK_X: reg_pair_kind<4, B, WK_X, true>(v, c_reg, m); break;
-        case WK_RX: reg_pair_kind<4, B, WK_RX, true>(v, c_reg, m); break;
-        case WK_RXS: reg_pair_kind<4, B, WK_RXS, true>(v, c_reg, m); break;
-        case WK_REAL: reg_pair_kind<4, B, WK_REAL, true>(v, c_reg, m); break;
-        default: if (U2K) reg_pair_kind<4, B, WK_U2, true>(v, c_reg, m); break;
-    }
+// ---- in-place phase multiplication ----------------------------------------------------------------------------
+// a <- e^{i phi} a is a rotation of (x, y); as three shears it is in place instruction by instruction and costs 3 FMA instead
+// of 4 mul/FMA plus the register moves of the plain complex product:
+//     x <- x - t y;  y <- y + s x;  x <- x - t y        t = tan(phi / 2) = fy / (1 + fx),  s = sin phi = fy
+// For fx < 0 the amplitude is negated first (sign flips, in place) and the rotation uses -f, so 1 + fx >= 1 always.
+// Every diagonal factor of a unitary circuit has modulus one (phases of Z/S/T/P/RZ and their products).
+struct Rot { double nt, s; bool neg; };
+__host__ __device__ __forceinline__ Rot make_rot(double fx, double fy) {
+    Rot r;
+    r.neg = fx < 0.0;
+    if (r.neg) { fx = -fx; fy = -fy; }
+    r.nt = -fy / (1.0 + fx);
+    r.s = fy;
+    return r;
 }
-
-template <bool U2K>
-__device__ __forceinline__ void exec_op_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp& op, const amp_t* __restrict__ tables) {
-    constexpr int S = 16, NT = kTileThreads;
-    if (((uint32_t)t & op.c_lane) != op.c_lval) return;              // thread-bit controls
-    const uint32_t kind = op.kind, c_reg = op.c_reg;
-    if (kind == WK_TABLE) {
-        const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
-        const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
-        if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) return;
-        if (hub_cls == CLS_LANE && !((t >> hub_bit) & 1)) return;
-        amp_t f = tab[t];                                             // thread table (128 entries)
-        const uint32_t nch = op.nchunks;
-        for (uint32_t k = 0; k < nch; k++)                            // tile chunk tables (256 entries each)
-            f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
-        const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
-        if (op.has_reg) {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], cmul(f, __ldg(tab + NT + s)));
-        } else {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if ((s & hub_slot) == hub_slot) upd_cmul(v[s], f);
-        }
-    } else if (kind == WK_NEG) {
-#pragma unroll
-        for (int s = 0; s < S; s++)
-            if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
-    } else if (kind == WK_DIAG) {
-        const amp_t ph = make_double2(op.m[0], op.m[1]);
-#pragma unroll
-        for (int s = 0; s < S; s++)
-            if ((c_reg >> s) & 1u) upd_cmul(v[s], ph);
-    } else if (kind == WK_RZ) {
-        const amp_t p0 = make_double2(op.m[0], op.m[1]), p1 = make_double2(op.m[2], op.m[3]);
-        const uint32_t t_reg = op.t_reg;
-        const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)t & op.t_lane) != 0);
-        const amp_t pt = t_thread ? p1 : p0;
-#pragma unroll
-        for (int s = 0; s < S; s++)
-            if ((c_reg >> s) & 1u) {
-                if (s & t_reg) upd_cmul(v[s], p1);
-                else upd_cmul(v[s], pt);
-            }
-    } else if (kind == WK_SCALE) {
-        const double g = op.m[0];
-#pragma unroll
-        for (int s = 0; s < S; s++) upd_scale(v[s], g);
-    } else {
-        switch (op.tpos - 5) {
-            case 0: tile_pair_cond<0, U2K>(v, kind, c_reg, op.m); break;
-            case 1: tile_pair_cond<1, U2K>(v, kind, c_reg, op.m); break;
-            case 2: tile_pair_cond<2, U2K>(v, kind, c_reg, op.m); break;
-            default: tile_pair_cond<3, U2K>(v, kind, c_reg, op.m); break;
-        }
-    }
+__device__ __forceinline__ void rot_inplace(amp_t& a, const Rot& r) {
+    if (r.neg) { a.x = -a.x; a.y = -a.y; }
+    a.x = fma(r.nt, a.y, a.x);
+    a.y = fma(r.s, a.x, a.y);
+    a.x = fma(r.nt, a.y, a.x);
+}
+// host-side packing of a rotation into one amp_t: (nt with the negate flag in its lowest mantissa bit, s)
+static inline amp_t pack_rot(amp_t f) {
+    Rot r = make_rot(f.x, f.y);
+    uint64_t bits;
+    memcpy(&bits, &r.nt, 8);
+    bits = (bits & ~1ull) | (r.neg ? 1ull : 0ull);
+    memcpy(&r.nt, &bits, 8);
+    return make_double2(r.nt, r.s);
+}
+__device__ __forceinline__ Rot unpack_rot(double nt, double s) {
+    Rot r;
+    r.nt = nt; r.s = s;
+    r.neg = (__double2loint(nt) & 1) != 0;
+    return r;
 }
 
 #define QI_CX6(B) \
@@ -577,32 +560,17 @@ __device__ __forceinline__ void exec_op_tile(amp_t (&v)[16], const uint64_t tile
     case 13 + (B * 3 + 1) * 2 + 0: fast_cx<B, 1, 0>(v); break; case 13 + (B * 3 + 1) * 2 + 1: fast_cx<B, 1, 1>(v); break; \
     case 13 + (B * 3 + 2) * 2 + 0: fast_cx<B, 2, 0>(v); break; case 13 + (B * 3 + 2) * 2 + 1: fast_cx<B, 2, 1>(v); break;
 
-// the op program of one round on the CTA-tile kernel.  Everything the dispatch needs sits in the first 32 bytes of an op
-// and is loaded one op AHEAD (the loads are warp-uniform: they live in uniform registers), so that the constant-bank
-// latency of op o+1 hides behind the arithmetic of op o instead of heading a chain of dependent loads, compares and
-// branches per op (43 % of all stall samples before, ncu r02c).
-struct OpHead { uint4 a; ulonglong2 b; };
-__device__ __forceinline__ OpHead load_head(const DOp* __restrict__ op) {
-    OpHead h;
-    h.a = *reinterpret_cast<const uint4*>(op);
-    h.b = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const char*>(op) + 16);
-    return h;
-}
-
-template <bool U2K>
+// the op program of one round on the CTA-tile kernel
 __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp* __restrict__ ops, const uint32_t nops,
                                              const amp_t* __restrict__ tables) {
-    if (nops == 0) return;
-    OpHead nxt = load_head(ops);
+    constexpr int S = 16, NT = kTileThreads;
 #pragma unroll 1
     for (uint32_t o = 0; o < nops; o++) {
-        const OpHead h = nxt;
         const DOp& op = ops[o];
-        if (o + 1 < nops) nxt = load_head(ops + o + 1);
-        if ((tile & h.b.x) != h.b.y) continue;                         // tile-uniform control (positive and negative bits)
-        const uint32_t code = h.a.y >> 24;
-        if (code == 0) { exec_op_tile<U2K>(v, tile, t, op, tables); continue; }
-        if (((uint32_t)t & h.a.z) != ((h.a.y >> 16) & 0xffu)) continue;   // thread-bit controls
+        // tile-uniform controls and thread-bit controls: an op that does not apply becomes the empty case
+        const bool on = (tile & op.c_tile) == op.c_tval && ((uint32_t)t & op.c_lane) == op.c_lval;
+        const uint32_t code = on ? op.code : 0u;
+        const uint32_t c_reg = op.c_reg;
         const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
         switch (code) {
             case 1: fast_reall<0>(v, k0, k1, k2, k3); break;
@@ -618,6 +586,58 @@ __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile
             case 11: fast_x<2>(v); break;
             case 12: fast_x<3>(v); break;
             QI_CX6(0) QI_CX6(1) QI_CX6(2) QI_CX6(3)
+            case FC_TABLE: {
+                const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
+                const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
+                if (hub_cls == CLS_TILE && !((tile >> hub_bit) & 1)) break;
+                if (hub_cls == CLS_LANE && !((t >> hub_bit) & 1)) break;
+                amp_t f = tab[t];                                             // thread table (128 entries)
+                const uint32_t nch = op.nchunks;
+                for (uint32_t k = 0; k < nch; k++)                            // tile chunk tables (256 entries each)
+                    f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
+                const Rot rf = make_rot(f.x, f.y);                            // one division per thread and op
+                const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((s & hub_slot) == hub_slot) rot_inplace(v[s], rf);
+                if (op.has_reg) {                                             // slot factors: packed rotations behind the chunk tables
+                    const amp_t* __restrict__ sl = tab + NT + S + 256 * nch;
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        if ((s & hub_slot) == hub_slot) { const amp_t e = __ldg(sl + s); rot_inplace(v[s], unpack_rot(e.x, e.y)); }
+                }
+                break;
+            }
+            case FC_NEG:
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
+                break;
+            case FC_DIAG: {
+                const Rot r = unpack_rot(k2, k3);
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((c_reg >> s) & 1u) rot_inplace(v[s], r);
+                break;
+            }
+            case FC_RZ: {
+                const Rot r0 = unpack_rot(op.m[4], op.m[5]), r1 = unpack_rot(op.m[6], op.m[7]);
+                const uint32_t t_reg = op.t_reg;
+                const bool t_thread = ((tile & op.t_tile) != 0) || (((uint32_t)t & op.t_lane) != 0);
+                Rot rt;
+                rt.nt = t_thread ? r1.nt : r0.nt; rt.s = t_thread ? r1.s : r0.s; rt.neg = t_thread ? r1.neg : r0.neg;
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((c_reg >> s) & 1u) {
+                        if (s & t_reg) rot_inplace(v[s], r1);
+                        else rot_inplace(v[s], rt);
+                    }
+                break;
+            }
+            case FC_SCALE:
+#pragma unroll
+                for (int s = 0; s < S; s++) { v[s].x *= k0; v[s].y *= k0; }
+                break;
             default: break;
         }
     }
@@ -767,7 +787,6 @@ static_assert(sizeof(TProgram) <= 32000, "kernel parameter space");
 // the three tile-local bits behind thread bits 0..2 fall into three different classes mod 3 (the host orders them so)
 __host__ __device__ __forceinline__ uint32_t tile_swz(uint32_t j) { return j ^ ((j >> 3) & 7u) ^ ((j >> 6) & 7u) ^ ((j >> 9) & 3u); }
 
-template <bool U2K>
 __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ TProgram P) {
     __shared__ __align__(16) amp_t sm[1 << kTileBits];
     __shared__ uint16_t lbs[kMaxRounds][kTileThreads];       // swizzled tile-local base of thread t in round r
@@ -797,7 +816,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = QI_LD(g + P.goff_in[s]);
         }
-        run_ops_tile<U2K>(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
+        run_ops_tile(v, tile, t, P.ops + P.rounds[0].first_op, P.rounds[0].nops, P.tables);
 #pragma unroll 1
         for (int r = 1; r < nr; r++) {
             const TRound& prev = P.rounds[r - 1];
@@ -808,7 +827,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_tile(amp_t* __restrict__ a,
             __syncthreads();
 #pragma unroll
             for (int s = 0; s < 16; s++) v[s] = sm[rb ^ cur.sswz[s]];
-            run_ops_tile<U2K>(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
+            run_ops_tile(v, tile, t, P.ops + cur.first_op, cur.nops, P.tables);
         }
         {
             amp_t* __restrict__ g = a + tb + g_out;
@@ -1203,6 +1222,11 @@ static void build_tables(const Layout& L, const DiagGroup& g, std::vector<amp_t>
     }
     if (scale != 1.0)                      // lean lowering: the pass's deferred gate scale rides on an unconditional table
         for (int i = 0; i < NT; i++) lane_t[i] = make_double2(lane_t[i].x * scale, lane_t[i].y * scale);
+    if (NT == kTileThreads && has_reg) {   // k_tile applies the slot factors as packed in-place rotations (exec_op_tile)
+        std::vector<amp_t> packed(S);
+        for (int i = 0; i < S; i++) packed[i] = pack_rot(arena[off + NT + i]);
+        arena.insert(arena.end(), packed.begin(), packed.end());
+    }
     d->kind = WK_TABLE;
     d->nchunks = (uint8_t)used_chunks;
     d->has_reg = has_reg ? 1 : 0;
@@ -1309,26 +1333,10 @@ static void lower_op(const Layout& L, const Pass& ps, const HOp& h, double* scal
         d.c_reg = slot_mask(L.R, pos_reg, neg_reg);
         d.c_tile = pos_tile | neg_tile;
         d.c_tval = pos_tile;
-        if (L.nt == kTileThreads && op.kind >= WK_X && op.kind <= kLastPairKind && L.cls[op.target] == CLS_REG) {
-            // k_tile: ops with a straight-line routine; REAL / RX without register-bit controls take their lifted forms
-            if ((pos_reg | neg_reg) == 0 && op.kind == WK_REAL && std::fabs(op.m[0]) >= kLiftMinPivot) {
-                const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
-                op.kind = WK_REALL;
-                op.m[2] = k2 / k0;
-                op.m[3] = (k0 * k3 - k1 * k2) / k0;
-            } else if ((pos_reg | neg_reg) == 0 && op.kind == WK_RX && std::fabs(op.m[0]) >= kLiftMinPivot) {
-                const double c = op.m[0], sn = op.m[1];
-                op.kind = WK_RXL;
-                op.m[2] = 1.0 / c;
-                op.m[3] = sn / c;
-            }
-            d.kind = (uint8_t)op.kind;
-            d.code = (uint8_t)fast_code((int)op.kind, L.idx[op.target], pos_reg, neg_reg);
-        }
     }
     if (op.kind == WK_RZ) split_mask(L, op.tmask, &d.t_lane, &d.t_reg, &d.t_tile);
     memcpy(d.m, op.m, sizeof(d.m));
-    if (op.kind != WK_DIAG && op.kind != WK_RZ && op.kind != WK_NEG) {      // pair ops (WK_REALL / WK_RXL included)
+    if (op.kind != WK_DIAG && op.kind != WK_RZ && op.kind != WK_NEG) {
         const int t = op.target;
         d.tpos = (uint8_t)(L.cls[t] == CLS_LANE ? L.idx[t] : kLaneQubits + L.idx[t]);
     }
@@ -1342,6 +1350,134 @@ static void push_scale_op(const Layout& L, double scale, std::vector<DOp>& dops)
     d.c_reg = slot_mask(L.R, 0, 0);
     d.m[0] = scale;
     dops.push_back(d);
+}
+
+// ---- k_tile lowering: one host op -> one or more in-place device ops under the layout of its round ------------------
+// (the op set and why every op is in place: "k_tile: the op set" above)
+static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vector<DOp>& dops, std::vector<amp_t>& arena) {
+    DOp base;
+    memset(&base, 0, sizeof(base));
+    uint32_t pos_lane = 0, pos_reg = 0, neg_lane = 0, neg_reg = 0;
+    uint64_t pos_tile = 0, neg_tile = 0;
+    {
+        uint64_t cm = h.cmask, nm = h.nmask;
+        if (h.kind == WK_TABLE) { cm = 0; nm = 0; }            // a table's cmask only remembers its first gate (single-member fallback)
+        split_mask(L, cm, &pos_lane, &pos_reg, &pos_tile);
+        split_mask(L, nm, &neg_lane, &neg_reg, &neg_tile);
+    }
+    auto controls = [&](DOp* d, uint32_t preg, uint32_t nreg) {
+        d->c_lane = pos_lane | neg_lane;
+        d->c_lval = (uint8_t)pos_lane;
+        d->c_reg = slot_mask(L.R, preg, nreg);
+        d->c_tile = pos_tile | neg_tile;
+        d->c_tval = pos_tile;
+    };
+    auto emit = [&](DOp d, uint32_t preg, uint32_t nreg, int B) -> int {
+        d.code = (uint8_t)fast_code((int)d.kind, B, preg, nreg);
+        if (d.code == 0) return fail(QI_ERR_UNKNOWN, d.kind, 0, "internal: tile op without an in-place routine");
+        dops.push_back(d);
+        return QI_OK;
+    };
+    // diagonal op multiplying by `f0` where the target bit is 0 and by `f1` where it is 1 (same controls as the host op);
+    // tmask = 0: one phase f1 on everything the controls select (the target already sits in the control masks)
+    auto emit_phase = [&](amp_t f0, amp_t f1, uint64_t tmask) -> int {
+        DOp d = base;
+        if (tmask == 0) {
+            const bool neg = f1.x == -1.0 && f1.y == 0.0;
+            d.kind = neg ? WK_NEG : WK_DIAG;
+            controls(&d, pos_reg, neg_reg);
+            d.m[0] = f1.x; d.m[1] = f1.y;
+            const amp_t r = pack_rot(f1);
+            d.m[2] = r.x; d.m[3] = r.y;
+            return emit(d, pos_reg, neg_reg, -1);
+        }
+        d.kind = WK_RZ;
+        controls(&d, pos_reg, neg_reg);
+        split_mask(L, tmask, &d.t_lane, &d.t_reg, &d.t_tile);
+        d.m[0] = f0.x; d.m[1] = f0.y; d.m[2] = f1.x; d.m[3] = f1.y;
+        const amp_t r0 = pack_rot(f0), r1 = pack_rot(f1);
+        d.m[4] = r0.x; d.m[5] = r0.y; d.m[6] = r1.x; d.m[7] = r1.y;
+        return emit(d, pos_reg, neg_reg, -1);
+    };
+    auto emit_x = [&](int target) -> int {
+        DOp d = base;
+        d.kind = WK_X;
+        controls(&d, pos_reg, neg_reg);
+        d.tpos = (uint8_t)(kLaneQubits + L.idx[target]);
+        return emit(d, pos_reg, neg_reg, L.idx[target]);
+    };
+    // real 2x2 (k00, k01, k10, k11) in lifted form; a small pivot is moved away by an X in front (M = (M X) X)
+    auto emit_real = [&](int target, double k0, double k1, double k2, double k3) -> int {
+        if (pos_reg | neg_reg) return fail(QI_ERR_UNKNOWN, 0, 0, "internal: pair gate under a register-bit control in a tile round");
+        if (std::fabs(k0) < kLiftMinPivot) {
+            QI_TRY(emit_x(target));
+            std::swap(k0, k1);
+            std::swap(k2, k3);
+        }
+        DOp d = base;
+        d.kind = WK_REALL;
+        controls(&d, 0, 0);
+        d.tpos = (uint8_t)(kLaneQubits + L.idx[target]);
+        d.m[0] = k0; d.m[1] = k1; d.m[2] = k2 / k0; d.m[3] = (k0 * k3 - k1 * k2) / k0;
+        return emit(d, 0, 0, L.idx[target]);
+    };
+    // RX-form (c, s): [[c, -i s], [-i s, c]]; small |c|: RX = (-i X) . RX' with c' = s, s' = -c
+    auto emit_rx = [&](int target, double c, double sn) -> int {
+        if (pos_reg | neg_reg) return fail(QI_ERR_UNKNOWN, 0, 0, "internal: pair gate under a register-bit control in a tile round");
+        const bool pivot = std::fabs(c) < kLiftMinPivot;
+        if (pivot) { const double c2 = sn, s2 = -c; c = c2; sn = s2; }
+        DOp d = base;
+        d.kind = WK_RXL;
+        controls(&d, 0, 0);
+        d.tpos = (uint8_t)(kLaneQubits + L.idx[target]);
+        d.m[0] = c; d.m[1] = sn; d.m[2] = 1.0 / c; d.m[3] = sn / c;
+        QI_TRY(emit(d, 0, 0, L.idx[target]));
+        if (pivot) {
+            QI_TRY(emit_x(target));
+            QI_TRY(emit_phase(make_double2(0.0, -1.0), make_double2(0.0, -1.0), 0));
+        }
+        return QI_OK;
+    };
+
+    if (h.kind == WK_TABLE) {
+        const DiagGroup& g = ps.groups[h.group];
+        if (g.members >= 2) {
+            DOp d = base;
+            build_tables(L, g, arena, &d, 1.0);
+            d.c_tval = d.c_tile = 0;
+            d.c_reg = slot_mask(L.R, 0, 0);
+            return emit(d, 0, 0, -1);
+        }
+        // single member: the plain op (cmask / tmask / m remember the gate)
+        split_mask(L, h.cmask, &pos_lane, &pos_reg, &pos_tile);
+        neg_lane = neg_reg = 0; neg_tile = 0;
+        if (h.target == -2) return emit_phase(make_double2(h.m[0], h.m[1]), make_double2(h.m[2], h.m[3]), h.tmask);
+        return emit_phase(make_double2(1.0, 0.0), make_double2(h.m[0], h.m[1]), 0);
+    }
+    switch (h.kind) {
+        case WK_DIAG: return emit_phase(make_double2(1.0, 0.0), make_double2(h.m[0], h.m[1]), 0);
+        case WK_RZ: return emit_phase(make_double2(h.m[0], h.m[1]), make_double2(h.m[2], h.m[3]), h.tmask);
+        case WK_X: return emit_x(h.target);
+        case WK_REAL: return emit_real(h.target, h.m[0], h.m[1], h.m[2], h.m[3]);
+        case WK_RX: return emit_rx(h.target, h.m[0], h.m[1]);
+        case WK_RXS: QI_TRY(emit_x(h.target)); return emit_rx(h.target, h.m[0], h.m[1]);      // RX o X
+        case WK_U2: {
+            // U = diag(p0, p1) . [[c, -s], [s, c]] . diag(1, q),  c = |m00|, s = |m10|  (exact for a unitary U)
+            const amp_t m00 = make_double2(h.m[0], h.m[1]), m01 = make_double2(h.m[2], h.m[3]);
+            const amp_t m10 = make_double2(h.m[4], h.m[5]), m11 = make_double2(h.m[6], h.m[7]);
+            const double c = std::hypot(m00.x, m00.y), sn = std::hypot(m10.x, m10.y);
+            const amp_t p0 = c > 0.0 ? make_double2(m00.x / c, m00.y / c) : make_double2(1.0, 0.0);
+            const amp_t p1 = sn > 0.0 ? make_double2(m10.x / sn, m10.y / sn) : make_double2(1.0, 0.0);
+            amp_t q;
+            if (c >= sn) { const amp_t z = cmul(m11, cconj(p1)); q = make_double2(z.x / c, z.y / c); }
+            else { const amp_t z = cmul(m01, cconj(p0)); q = make_double2(-z.x / sn, -z.y / sn); }
+            const uint64_t tb = 1ull << h.target;
+            QI_TRY(emit_phase(make_double2(1.0, 0.0), q, tb));
+            QI_TRY(emit_real(h.target, c, -sn, sn, c));
+            return emit_phase(p0, p1, tb);
+        }
+        default: return fail(QI_ERR_UNKNOWN, h.kind, 0, "internal: unknown host op kind in a tile round");
+    }
 }
 
 static void lower_pass(const qi_state* s, const Pass& ps, int R, std::vector<DOp>& dops, std::vector<amp_t>& arena, Layout* Lout) {
@@ -1371,7 +1507,6 @@ struct TileLaunch {
     int tile_out[kTileBits];     // physical position the content of local bit j is stored to
     std::vector<TileRoundHost> rounds;
     std::vector<DOp> dops;
-    bool u2k = false;
 };
 
 static GateUse uses_of_hop(const Pass& ps, const HOp& h) {
@@ -1390,27 +1525,38 @@ static GateUse uses_of_hop(const Pass& ps, const HOp& h) {
 // Split the ops of a pass into rounds of <= 4 register qubits.  Same commutation rule as the pass scheduler: an op may
 // move ahead of the ops skipped before it when on every shared qubit both act diagonally; a pair op needs its target
 // among the round's register qubits.  Returns op indices per round and the register qubits (physical) of each round.
-static void form_rounds(const Pass& ps, const std::vector<HOp>& ops, std::vector<std::vector<size_t>>* round_ops,
-                        std::vector<std::vector<int>>* round_regs) {
+static void form_rounds(const Pass& ps, const std::vector<HOp>& ops, uint64_t tile_mask, std::vector<std::vector<size_t>>* round_ops,
+                        std::vector<std::vector<int>>* round_regs, std::vector<uint64_t>* round_keep_out) {
     std::vector<size_t> rest;
     for (size_t i = 0; i < ops.size(); i++) if (ops[i].kind != 0) rest.push_back(i);
     while (!rest.empty()) {
         std::vector<size_t> take, keep;
         std::vector<int> Q;
         uint64_t qmask = 0, blocked_any = 0, blocked_n = 0;
+        uint64_t keep_out = 0;             // controls of the pair gates taken so far: they must not become register qubits
         for (size_t i : rest) {
             const HOp& h = ops[i];
             const GateUse u = uses_of_hop(ps, h);
             bool ok = ((u.n_use & blocked_any) == 0) && ((u.d_use & blocked_n) == 0);
-            if (ok && u.n_use && !(u.n_use & qmask)) {
-                if ((int)Q.size() < 4) { Q.push_back(h.target); qmask |= u.n_use; }
-                else ok = false;
+            const uint64_t ctrl = u.n_use ? (h.cmask | h.nmask) : 0ull;
+            // the in-place pair routines take no register-bit controls; X has variants under exactly one
+            const int reg_ctrl_ok = (h.kind == WK_X && __builtin_popcountll(ctrl) == 1) ? 1 : 0;
+            if (ok && u.n_use) {
+                const uint64_t ko = reg_ctrl_ok ? keep_out : (keep_out | ctrl);
+                if (__builtin_popcountll(ctrl & qmask) > reg_ctrl_ok) ok = false;
+                else if (__builtin_popcountll(tile_mask & ~ko) < 4) ok = false;       // four register qubits must remain possible
+                else if (!(u.n_use & qmask)) {
+                    if ((int)Q.size() < 4 && !(u.n_use & ko)) { Q.push_back(h.target); qmask |= u.n_use; }
+                    else ok = false;
+                }
+                if (ok) keep_out = ko;
             }
             if (ok) take.push_back(i);
             else { keep.push_back(i); blocked_any |= u.n_use | u.d_use; blocked_n |= u.n_use; }
         }
         round_ops->push_back(take);
         round_regs->push_back(Q);
+        round_keep_out->push_back(keep_out);
         rest.swap(keep);
     }
 }
@@ -1420,12 +1566,14 @@ static void form_rounds(const Pass& ps, const std::vector<HOp>& ops, std::vector
 // the local bits whose content goes to positions 0..4); the register bits then avoid them.  Without `low` the thread
 // bits are ordered for bank-conflict-free regroups: tile_swz folds local bits 3-5, 6-8, 9-10 onto 0-2, so the three
 // local bits behind thread bits 0..2 should fall into three different classes.
-static bool make_tile_round(const std::vector<int>& regs_local, const int* low, TileRoundHost* r) {
+static bool make_tile_round(const std::vector<int>& regs_local, const int* low, uint32_t avoid_local, TileRoundHost* r) {
     std::vector<int> loc(regs_local);
     auto is_low = [&](int j) { if (!low) return false; for (int k = 0; k < kLaneQubits; k++) if (low[k] == j) return true; return false; };
     for (int j : loc) if (is_low(j)) return false;
+    // pad to four register bits; never with a bit that controls one of the round's pair gates (`avoid_local`)
     for (int j = kTileBits - 1; j >= 0 && (int)loc.size() < 4; j--)
-        if (!is_low(j) && std::find(loc.begin(), loc.end(), j) == loc.end()) loc.push_back(j);
+        if (!is_low(j) && !((avoid_local >> j) & 1u) && std::find(loc.begin(), loc.end(), j) == loc.end()) loc.push_back(j);
+    if ((int)loc.size() < 4) return false;
     std::sort(loc.begin(), loc.end());
     for (int k = 0; k < 4; k++) r->regs[k] = loc[k];
     std::vector<int> free_bits;
@@ -1468,30 +1616,46 @@ static Layout round_layout(const qi_state* s, const int tile_qubits[kTileBits], 
     return L;
 }
 
+// device ops lower_op_tile emits for a host op (launch packing)
+static size_t tile_op_count(const HOp& h) {
+    switch (h.kind) {
+        case WK_REAL: return std::fabs(h.m[0]) < kLiftMinPivot ? 2 : 1;
+        case WK_RX: return std::fabs(h.m[0]) < kLiftMinPivot ? 3 : 1;
+        case WK_RXS: return std::fabs(h.m[0]) < kLiftMinPivot ? 4 : 2;
+        case WK_U2: return 4;
+        default: return 1;
+    }
+}
+
 // lower one pass to one or more k_tile launches; `plan` = the tile's positions and where its content is stored to
-static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& plan, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
+static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& plan, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
     int local_of[64];
     for (int q = 0; q < 64; q++) local_of[q] = -1;
     for (int j = 0; j < kTileBits; j++) local_of[plan.pin[j]] = j;
 
-    std::vector<HOp> ops(ps.ops);
-    double scale = 1.0;      // (the lean unit forms of k_window are not used here: the lifted forms already avoid the moves)
+    const std::vector<HOp>& ops = ps.ops;      // (the lean unit forms of k_window are not used here)
     std::vector<std::vector<size_t>> round_ops;
     std::vector<std::vector<int>> round_regs;
-    form_rounds(ps, ops, &round_ops, &round_regs);
+    std::vector<uint64_t> round_keep;          // per round: qubits that control one of its pair gates (never register qubits)
+    uint64_t tile_mask = 0;
+    for (int j = 0; j < kTileBits; j++) tile_mask |= 1ull << plan.pin[j];
+    form_rounds(ps, ops, tile_mask, &round_ops, &round_regs, &round_keep);
     // a round never carries more ops than one launch holds
     {
         std::vector<std::vector<size_t>> ro;
         std::vector<std::vector<int>> rq;
-        const size_t kChunk = 192;
+        std::vector<uint64_t> rk;
+        const size_t kChunk = 48;                 // host ops per round chunk (an op lowers to at most 4 device ops)
         for (size_t r = 0; r < round_ops.size(); r++)
             for (size_t first = 0; first < std::max<size_t>(1, round_ops[r].size()); first += kChunk) {
                 ro.emplace_back(round_ops[r].begin() + first, round_ops[r].begin() + std::min(round_ops[r].size(), first + kChunk));
                 rq.push_back(round_regs[r]);
+                rk.push_back(round_keep[r]);
             }
-        if (ro.empty()) { ro.emplace_back(); rq.emplace_back(); }
+        if (ro.empty()) { ro.emplace_back(); rq.emplace_back(); rk.push_back(0); }
         round_ops.swap(ro);
         round_regs.swap(rq);
+        round_keep.swap(rk);
     }
     const size_t nrounds = round_ops.size();
     const int low_id[kLaneQubits] = {0, 1, 2, 3, 4};
@@ -1502,8 +1666,9 @@ static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& p
     while (ri < nrounds) {
         // rounds of this launch
         size_t end = ri, nops = 0;
-        while (end < nrounds && (end == ri || (nops + round_ops[end].size() + 2 <= (size_t)kMaxTileOps && (end - ri) + 3 <= (size_t)kMaxRounds))) {
-            nops += round_ops[end].size();
+        auto cost = [&](size_t r) { size_t c = 0; for (size_t i : round_ops[r]) c += tile_op_count(ops[i]); return c; };
+        while (end < nrounds && (end == ri || (nops + cost(end) <= (size_t)kMaxTileOps && (end - ri) + 3 <= (size_t)kMaxRounds))) {
+            nops += cost(end);
             end++;
         }
         const bool last_launch = end == nrounds;
@@ -1515,38 +1680,39 @@ static void lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& p
             std::vector<int> loc;
             for (int q : round_regs[r]) loc.push_back(local_of[q]);
             TileRoundHost rd;
+            uint32_t avoid = 0;
+            for (int j = 0; j < kTileBits; j++) if ((round_keep[r] >> plan.pin[j]) & 1) avoid |= 1u << j;
             bool is_in = false, is_out = false;
             if (r == ri && r + 1 == end) {                    // only round: loads and stores
-                if (same_io && make_tile_round(loc, low_id, &rd)) is_in = is_out = true;
-                else if (make_tile_round(loc, low_id, &rd)) is_in = true;
-            } else if (r == ri) is_in = make_tile_round(loc, low_id, &rd);
-            else if (r + 1 == end) is_out = make_tile_round(loc, low_out, &rd);
-            if (!is_in && !is_out) make_tile_round(loc, nullptr, &rd);
+                if (same_io && make_tile_round(loc, low_id, avoid, &rd)) is_in = is_out = true;
+                else if (make_tile_round(loc, low_id, avoid, &rd)) is_in = true;
+            } else if (r == ri) is_in = make_tile_round(loc, low_id, avoid, &rd);
+            else if (r + 1 == end) is_out = make_tile_round(loc, low_out, avoid, &rd);
+            if (!is_in && !is_out && !make_tile_round(loc, nullptr, avoid, &rd))
+                return fail(QI_ERR_UNKNOWN, 0, 0, "internal: no register layout for a tile round");
             if (r == ri && !is_in) {                          // a launch starts in the load layout: empty round first
                 TileRoundHost io;
-                make_tile_round(std::vector<int>(), low_id, &io);
+                make_tile_round(std::vector<int>(), low_id, 0, &io);
                 io.first_op = tl.dops.size();
                 tl.rounds.push_back(io);
             }
             rd.first_op = tl.dops.size();
             const Layout L = round_layout(s, tl.tile_qubits, rd);
-            for (size_t i : round_ops[r]) lower_op(L, ps, ops[i], &scale, tl.dops, arena);
-            if (r + 1 == nrounds && scale != 1.0) { push_scale_op(L, scale, tl.dops); scale = 1.0; }
+            for (size_t i : round_ops[r]) QI_TRY(lower_op_tile(L, ps, ops[i], tl.dops, arena));
+            if (tl.dops.size() > (size_t)kMaxTileOps) return fail(QI_ERR_UNKNOWN, tl.dops.size(), 0, "internal: tile launch holds too many ops");
             rd.nops = tl.dops.size() - rd.first_op;
             tl.rounds.push_back(rd);
             if (r + 1 == end && !is_out) {                    // ... and ends in the store layout
                 TileRoundHost io;
-                make_tile_round(std::vector<int>(), low_out, &io);
+                make_tile_round(std::vector<int>(), low_out, 0, &io);
                 io.first_op = tl.dops.size();
                 tl.rounds.push_back(io);
             }
         }
-        for (const DOp& d : tl.dops) {
-            tl.u2k |= d.kind == WK_U2;
-        }
         launches.push_back(std::move(tl));
         ri = end;
     }
+    return QI_OK;
 }
 
 static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables) {
@@ -1581,8 +1747,7 @@ static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables)
     const uint64_t ntiles = s->len >> kTileBits;
     uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
     LaunchScope ls(KF_TILE, 32.0 * (double)s->len);
-    if (tl.u2k) k_tile<true><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
-    else k_tile<false><<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
+    k_tile<<<(unsigned)blocks, kTileThreads, 0, c.stream>>>(s->d, ntiles, P);
     return check_launch("k_tile");
 }
 
@@ -2052,7 +2217,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
     std::vector<amp_t> arena;
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) continue;
-        if (tile) lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena);
+        if (tile) QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena));
         else lower_pass(s, steps[i].pass, steps[i].R, dops[i], arena, &layouts[i]);
     }
     if (!arena.empty()) {
@@ -2119,7 +2284,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
         std::vector<std::vector<TileLaunch>> tiles(steps.size());
         for (size_t i = 0; i < steps.size(); i++) {
             if (steps[i].simple) { nrec++; continue; }
-            lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena);
+            QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena));
             nrec += tiles[i].size();
         }
         blob->clear();

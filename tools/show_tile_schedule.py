@@ -32,7 +32,7 @@ for i, s in enumerate(steps):
     rounds = s[2]
     nops = [len(r[2]) for r in rounds]
     kinds = np.concatenate([r[2]["kind"] for r in rounds]) if sum(nops) else np.zeros(0, dtype=np.uint8)
-    pair = int((kinds <= wi.LAST_PAIR).sum())
+    pair = int(np.isin(kinds, list(wi.PAIR_KINDS)).sum())
     x = int((kinds == wi.WK_X).sum())
     tab = int((kinds == wi.WK_TABLE).sum())
     tot_rounds += len(rounds)
