@@ -533,8 +533,14 @@ __host__ __device__ __forceinline__ Rot make_rot(double fx, double fy) {
     r.s = fy;
     return r;
 }
+// x <- -x where `mask` is 0x80000000, x where it is 0: one xor on the high word (ALU pipe, in place; no FP64 issue slot)
+__device__ __forceinline__ void flip_sign(double& x, uint32_t mask) {
+    x = __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
 __device__ __forceinline__ void rot_inplace(amp_t& a, const Rot& r) {
-    if (r.neg) { a.x = -a.x; a.y = -a.y; }
+    const uint32_t m = r.neg ? 0x80000000u : 0u;
+    flip_sign(a.x, m);
+    flip_sign(a.y, m);
     a.x = fma(r.nt, a.y, a.x);
     a.y = fma(r.s, a.x, a.y);
     a.x = fma(r.nt, a.y, a.x);
@@ -564,14 +570,28 @@ __device__ __forceinline__ Rot unpack_rot(double nt, double s) {
 __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile, const int t, const DOp* __restrict__ ops, const uint32_t nops,
                                              const amp_t* __restrict__ tables) {
     constexpr int S = 16, NT = kTileThreads;
+    if (nops == 0) return;
+    // everything the dispatch and the common routines need is loaded one op AHEAD (warp-uniform loads: uniform registers), so
+    // the constant-bank latency of op o+1 hides behind the arithmetic of op o instead of heading a dependent chain per op
+    uint4 nh = *reinterpret_cast<const uint4*>(ops);                                   // kind..code | c_lane | c_reg
+    ulonglong2 nt2 = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const char*>(ops) + 16);   // c_tile | c_tval
+    double nk0 = ops[0].m[0], nk1 = ops[0].m[1], nk2 = ops[0].m[2], nk3 = ops[0].m[3];
 #pragma unroll 1
     for (uint32_t o = 0; o < nops; o++) {
         const DOp& op = ops[o];
+        const uint4 h = nh;
+        const ulonglong2 tl = nt2;
+        const double k0 = nk0, k1 = nk1, k2 = nk2, k3 = nk3;
+        if (o + 1 < nops) {
+            const DOp& nx = ops[o + 1];
+            nh = *reinterpret_cast<const uint4*>(&nx);
+            nt2 = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const char*>(&nx) + 16);
+            nk0 = nx.m[0]; nk1 = nx.m[1]; nk2 = nx.m[2]; nk3 = nx.m[3];
+        }
         // tile-uniform controls and thread-bit controls: an op that does not apply becomes the empty case
-        const bool on = (tile & op.c_tile) == op.c_tval && ((uint32_t)t & op.c_lane) == op.c_lval;
-        const uint32_t code = on ? op.code : 0u;
-        const uint32_t c_reg = op.c_reg;
-        const double k0 = op.m[0], k1 = op.m[1], k2 = op.m[2], k3 = op.m[3];
+        const bool on = (tile & tl.x) == tl.y && ((uint32_t)t & h.z) == ((h.y >> 16) & 0xffu);
+        const uint32_t code = on ? (h.y >> 24) : 0u;
+        const uint32_t c_reg = h.w;
         switch (code) {
             case 1: fast_reall<0>(v, k0, k1, k2, k3); break;
             case 2: fast_reall<1>(v, k0, k1, k2, k3); break;
@@ -610,8 +630,11 @@ __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile
             }
             case FC_NEG:
 #pragma unroll
-                for (int s = 0; s < S; s++)
-                    if ((c_reg >> s) & 1u) { v[s].x = -v[s].x; v[s].y = -v[s].y; }
+                for (int s = 0; s < S; s++) {
+                    const uint32_t m = (c_reg << (31 - s)) & 0x80000000u;      // slot s selected: flip, else keep
+                    flip_sign(v[s].x, m);
+                    flip_sign(v[s].y, m);
+                }
                 break;
             case FC_DIAG: {
                 const Rot r = unpack_rot(k2, k3);
@@ -849,7 +872,7 @@ static GateUse uses_of(const PhysGate& g) {
     GateUse u{0, g.cmask};
     switch (g.kind) {
         case IK_H: case IK_X: case IK_Y: case IK_U2: u.n_use = 1ull << g.t0; break;
-        case IK_SWAP: u.n_use = (1ull << g.t0) | (1ull << g.t1); break;
+        case IK_SWAP: case IK_MATCH: u.n_use = (1ull << g.t0) | (1ull << g.t1); break;
         case IK_DIAG: case IK_RZ: if (g.t0 >= 0) u.d_use |= 1ull << g.t0; break;
         default: break;
     }
@@ -2125,8 +2148,9 @@ static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& 
 // s*(a1 + a0) == s*(a0 + a1)), so  [C..X(t), H(t)] == [H(t), C..Z(t)]  and  [H(t), C..X(t)] == [C..Z(t), H(t)]  exactly.
 // The controlled Z is diagonal: it merges into the phase table the pass carries anyway, whereas the X costs a register
 // swap op of its own or (absorbed) turns the neighbouring gate into two predicated half-populated ops.  An X also slides
-// past gates that commute with it bit for bit: RX-form 2x2 gates on its target (RX X = X RX: both orders evaluate the
-// same products) and anything diagonal on its controls.  Random H/RX/RZ + CNOT layers: 5 of 9 CNOTs are rewritten.
+// past RX-form 2x2 gates on its target (RX X = X RX bit for bit: both orders evaluate the same products).  The neighbour
+// need not be adjacent in the list: the next (previous) gate that touches the target commutes with everything between
+// it and the X, so it is pulled next to the X first.  Random H/RX/RZ + CNOT layers: 5 of 9 CNOTs are rewritten.
 static bool is_rx_form(const PhysGate& g) {
     const double* p = g.p;
     return g.kind == IK_U2 && g.cmask == 0 && p[1] == 0.0 && p[2] == 0.0 && p[4] == 0.0 && p[7] == 0.0 && p[0] == p[6] && p[3] == p[5];
@@ -2142,11 +2166,12 @@ static void rewrite_cx_next_to_h(std::vector<PhysGate>& gates) {
     std::vector<int> next(G + 1), prev(G + 1);     // doubly linked list through the sentinel
     for (int i = 0; i <= G; i++) { next[i] = i == G ? 0 : i + 1; prev[i] = i == 0 ? G : i - 1; }
     auto unlink = [&](int i) { next[prev[i]] = next[i]; prev[next[i]] = prev[i]; };
+    auto link_after = [&](int at, int id) { next[id] = next[at]; prev[id] = at; prev[next[at]] = id; next[at] = id; };
     auto insert_after = [&](int at, const PhysGate& g) {
         const int id = (int)pool.size();
         pool.push_back(g);
-        next.push_back(next[at]); prev.push_back(at);
-        prev[next[at]] = id; next[at] = id;
+        next.push_back(0); prev.push_back(0);
+        link_after(at, id);
     };
     bool any = false;
     for (int i = 0; i < G; i++) {
@@ -2157,30 +2182,51 @@ static void rewrite_cx_next_to_h(std::vector<PhysGate>& gates) {
         memset(&cz, 0, sizeof(cz));
         cz.kind = IK_DIAG; cz.t0 = x.t0; cz.t1 = -1; cz.cmask = cm; cz.p[0] = -1.0; cz.p[1] = 0.0;
         bool done = false;
-        // forward: [X ... H] -> [... H, CZ]
+        // forward: the next gate that touches the target.  Nothing between the X and that gate touches the target, so the gate
+        // (a single-qubit gate on the target alone) commutes with everything in between and may be pulled back to the X:
+        //   H:        [X, .., H]  = [X, H, ..]  = [H, CZ, ..]
+        //   RX-form:  [X, .., RX] = [X, RX, ..] = [RX, X, ..]   and the scan goes on from the X's new place
         int j = next[i];
-        for (int k = 0; k < kWindow && j != G; k++, j = next[j]) {
+        for (int k = 0; k < kWindow && j != G; k++) {
             const PhysGate& g = pool[j];
             const GateUse u = uses_of(g);
-            if (u.n_use & cm) break;                                   // a control changes: the X cannot move past it
+            const int nj = next[j];
             if ((u.n_use | u.d_use) & tb) {
-                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) { insert_after(j, cz); unlink(i); done = any = true; }
-                else if (is_rx_form(g) && g.t0 == x.t0) continue;     // commutes bit for bit
+                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) {
+                    unlink(j); link_after(prev[i], j);          // H right before the X ...
+                    insert_after(j, cz); unlink(i);             // ... and the X becomes the CZ behind it
+                    done = any = true;
+                } else if (is_rx_form(g) && g.t0 == x.t0) {
+                    unlink(j); link_after(prev[i], j);          // RX hops over the X
+                    any = true;
+                    j = nj;
+                    continue;
+                }
                 break;
             }
+            j = nj;
         }
         if (done) continue;
-        // backward: [H ... X] -> [CZ, H ...]
+        // backward, mirrored: [H, .., X] = [.., H, X] = [.., CZ, H];  [RX, .., X] = [.., X, RX]
         j = prev[i];
-        for (int k = 0; k < kWindow && j != G; k++, j = prev[j]) {
+        for (int k = 0; k < kWindow && j != G; k++) {
             const PhysGate& g = pool[j];
             const GateUse u = uses_of(g);
-            if (u.n_use & cm) break;
+            const int pj = prev[j];
             if ((u.n_use | u.d_use) & tb) {
-                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) { insert_after(prev[j], cz); unlink(i); any = true; }
-                else if (is_rx_form(g) && g.t0 == x.t0) continue;
+                if (g.kind == IK_H && g.cmask == 0 && g.t0 == x.t0) {
+                    unlink(j); link_after(i, j);                // H right behind the X ...
+                    insert_after(prev[i], cz); unlink(i);       // ... and the X becomes the CZ in front of it
+                    any = true;
+                } else if (is_rx_form(g) && g.t0 == x.t0) {
+                    unlink(j); link_after(i, j);
+                    any = true;
+                    j = pj;
+                    continue;
+                }
                 break;
             }
+            j = pj;
         }
     }
     if (!any) return;
