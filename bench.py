@@ -608,7 +608,10 @@ def run_ours(args, rank, world, local_rank):
             else:
                 state.upload_(hin)                         # H2D of the initial state (pinned)
                 circuit.execute_(state)
-                state.to_host(hout)                        # D2H of the final state (this rank's shard when sharded)
+                if world > 1:
+                    sharded.shard_to_host(state, hout)     # D2H of this rank's shard (physical order)
+                else:
+                    state.to_host(hout)                    # D2H of the final state
 
         def e2e_time(mode):
             times = []

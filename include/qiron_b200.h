@@ -223,6 +223,9 @@ int qi_shard_new_basis_n(uint32_t total_qubits, uint64_t n, int rank, int world,
 int qi_shard_export(qi_state* s, uint8_t* handles);
 /* map every peer's buffers; `all_handles` = world * 2 * QI_IPC_HANDLE_BYTES, gathered by the host (torch.distributed) */
 int qi_shard_attach(qi_state* s, const uint8_t* all_handles);
+/* this rank's shard as stored: PHYSICAL bit order (qi_state_layout gives the logical -> physical map), len = 2^n_local
+ * amplitudes.  (qi_state_to_host refuses sharded states: a shard is not the reference's `state_vector`.) */
+int qi_shard_to_host(const qi_state* s, double* amps, uint64_t len);
 int qi_shard_rank(const qi_state* s);
 int qi_shard_world(const qi_state* s);
 /* bytes this rank moved over NVLink and the number of exchanges since creation */

@@ -63,6 +63,7 @@ for _n in ("zero", "plus", "minus", "ghz"):
 _sig("qi_state_new_basis_n", [C.c_uint32, C.c_uint64, C.POINTER(state_p)])
 _sig("qi_state_from_host", [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(state_p)])
 _sig("qi_state_to_host", [state_p, C.c_void_p, C.c_uint64])
+_sig("qi_shard_to_host", [state_p, C.c_void_p, C.c_uint64])
 _sig("qi_state_upload", [state_p, C.c_void_p, C.c_uint64])
 _sig("qi_state_clone", [state_p, C.POINTER(state_p)])
 _sig("qi_state_free", [state_p], None)

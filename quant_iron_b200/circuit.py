@@ -215,6 +215,7 @@ class Circuit:
         self.gates: List[Gate] = []
         self.num_qubits = num_qubits
         self._records = None
+        self._records_fp = None
 
     @staticmethod
     def new(num_qubits):
@@ -258,7 +259,10 @@ class Circuit:
     def _lower(self):
         """Split the gate list into runs: ('ops', qi_gate[count], count, keepalive) |
         ('evol', qi_pauli_term[count], count, keepalive, factors) | ('gate', Gate, index)."""
-        if self._records is not None:
+        # `gates` is a public, mutable list of mutable gates (circuit.rs: `pub gates`): the cached records are only
+        # reused while every gate, its qubits and its operator's parameters are what they were when the cache was built
+        fp = self._fingerprint()
+        if self._records is not None and self._records_fp == fp:
             return self._records
         has_parametric = any(g.kind == "Parametric" for g in self.gates)
         runs = []
@@ -310,8 +314,18 @@ class Circuit:
         close()
         close_evol()
         if not has_parametric:
-            self._records = runs
+            self._records, self._records_fp = runs, fp
         return runs
+
+    def _fingerprint(self):
+        out = [len(self.gates)]
+        for g in self.gates:
+            out.append(id(g))
+            if g.kind == "Operator":
+                out.append((id(g.op), tuple(g.targets), tuple(g.controls), tuple(g.op.params())))
+            elif g.kind == "PauliTimeEvolution":
+                out.append((id(g.pauli_string), g.time))
+        return hash(tuple(out))
 
     def execute_(self, state, seed: Optional[int] = None):
         """Run the circuit IN PLACE on `state` (what a 33-qubit state needs)."""

@@ -65,6 +65,7 @@ struct Context {
     int opt_prefetch = 0;             // lean instantiations only: L2 prefetch of the warp's next tile (unmeasured: off)
     int opt_cz_rewrite = 1;           // fused executor: a controlled X next to a Hadamard on its target becomes a controlled Z (bit-exact)
     int opt_tile = 1;                 // window passes on the CTA-tile kernel (k_tile: 11 qubits per pass, rounds regrouped through shared memory)
+    int opt_peer_timeout_s = 120;     // sharded states: a peer missing at a device barrier for this long traps the kernel (shard.cu)
     int opt_tile_absorb = 0;          // tile passes: CNOT absorption (two predicated half-ops per pair) -- off: register swaps are cheaper there
     int opt_tile_slide = 1;           // tile passes leave the qubits the next tile wants at positions 0..4 (relabelling the qubit map)
     int opt_tile_min_qubits = 18;     // ... for states with at least this many local qubits (>= 11)

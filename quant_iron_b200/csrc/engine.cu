@@ -44,6 +44,8 @@ Context& ctx() { return g_ctx; }
 static int init_locked(int device) {
     Context& c = g_ctx;
     if (c.ready && (device < 0 || device == c.device)) return QI_OK;
+    if (c.ready)       // the stream, events, scratch and pooled buffers live on the first device: re-binding would mix devices
+        return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)device, (uint64_t)c.device, "the engine is already bound to another device (one process per GPU)");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -254,6 +256,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "tile")) c.opt_tile = (int)value;
     else if (!strcmp(name, "tile_slide")) c.opt_tile_slide = (int)value;
     else if (!strcmp(name, "tile_absorb")) c.opt_tile_absorb = (int)value;
+    else if (!strcmp(name, "peer_timeout_s")) c.opt_peer_timeout_s = (int)value;
     else if (!strcmp(name, "cz_rewrite")) c.opt_cz_rewrite = (int)value;
     else if (!strcmp(name, "tile_min_qubits")) c.opt_tile_min_qubits = (int)value;
     else if (!strcmp(name, "prefetch")) c.opt_prefetch = (int)value;

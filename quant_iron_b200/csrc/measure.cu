@@ -380,7 +380,8 @@ static int collapse_impl(qi_state* s, const std::vector<uint32_t>& qubits, uint6
             QI_TRY(check_launch("collapse_normalise"));
         }
     }
-    // State::new(collapsed) re-checks the norm (state.rs:667); a collapsed state that fails it is a bug here
+    else       // State::new(collapsed) re-checks the norm (state.rs:667, 117-121): a bin of probability zero fails there
+        return fail(QI_ERR_STATE_VECTOR_NOT_NORMALISED, 0, 0, "collapsed state has zero norm (the selected outcome has probability 0)");
     return QI_OK;
 }
 

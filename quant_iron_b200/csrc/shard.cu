@@ -40,15 +40,23 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 struct PeerPtrs { unsigned long long* f[8]; };
 
 // thread j: tell peer j "rank `me` reached epoch e", then wait until peer j has told me the same
+// A peer that has not arrived within `timeout_cycles` (option "peer_timeout_s", default 120 s) is dead or wedged: the
+// kernel records the epoch and TRAPS -- the exchange behind the barrier must not run against a shard that is still in
+// flight, so the context is poisoned and every later call on this rank fails loudly (QI_ERR_CUDA) instead of computing on
+// half-exchanged data.
 __global__ void k_barrier(PeerPtrs peers, unsigned long long* mine, int me, int world, unsigned long long epoch,
-                          unsigned long long* timeout_flag) {
+                          unsigned long long* timeout_flag, long long timeout_cycles) {
     int j = threadIdx.x;
     if (j >= world) return;
     __threadfence_system();
     st_release_sys(peers.f[j] + me, epoch);
     long long t0 = clock64();
     while (ld_acquire_sys(mine + j) < epoch) {
-        if (clock64() - t0 > 40000000000ll) { *timeout_flag = epoch; break; }   // ~20 s: a peer died
+        if (clock64() - t0 > timeout_cycles) {
+            *timeout_flag = epoch;
+            __threadfence_system();
+            __trap();
+        }
     }
     __threadfence_system();
 }
@@ -84,7 +92,8 @@ static int barrier(qi_state* s) {
     for (int r = 0; r < 8; r++) pp.f[r] = s->peer_flags[r];
     s->epoch++;
     LaunchScope ls(KF_BARRIER, 0.0);
-    k_barrier<<<1, 32, 0, c.stream>>>(pp, s->flags, s->rank, s->world, s->epoch, s->flags + 32);
+    const long long cycles = (long long)std::max(1, c.opt_peer_timeout_s) * 2000000000ll;      // clock64 ticks at <= 2 GHz
+    k_barrier<<<1, 32, 0, c.stream>>>(pp, s->flags, s->rank, s->world, s->epoch, s->flags + 32, cycles);
     return check_launch("k_barrier");
 }
 

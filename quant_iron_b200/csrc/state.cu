@@ -298,11 +298,22 @@ int qi_state_from_host(const double* amps, uint64_t len, uint32_t num_qubits, in
     return QI_OK;
 }
 
-int qi_state_to_host(const qi_state* s, double* amps, uint64_t len) {
+int qi_shard_to_host(const qi_state* s, double* amps, uint64_t len) {
     if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
     if (len != s->len) return fail(QI_ERR_INVALID_ARGUMENT, len, s->len, "length mismatch");
     QI_TRY(ensure_ctx());
-    if (s->world == 1 && !s->identity_layout()) QI_TRY(canonicalise(const_cast<qi_state*>(s)));   // lazy SWAPs become real
+    if (len) QI_CUDA(cudaMemcpyAsync(amps, s->d, len * sizeof(amp_t), cudaMemcpyDeviceToHost, ctx().stream));
+    QI_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QI_OK;
+}
+
+int qi_state_to_host(const qi_state* s, double* amps, uint64_t len) {
+    if (!s) return fail(QI_ERR_INVALID_ARGUMENT, 0, 0, "state is NULL");
+    if (len != s->len) return fail(QI_ERR_INVALID_ARGUMENT, len, s->len, "length mismatch");
+    if (s->world > 1)      // a shard is stored in physical bit order and holds 1 / world of the vector: never hand it out as `state_vector`
+        return fail(QI_ERR_INVALID_ARGUMENT, (uint64_t)s->world, 0, "sharded state: read shards with qi_shard_to_host (physical order, see qi_state_layout)");
+    QI_TRY(ensure_ctx());
+    if (!s->identity_layout()) QI_TRY(canonicalise(const_cast<qi_state*>(s)));   // lazy SWAPs / tile relabelling become real
     if (len) {
         QI_CUDA(cudaMemcpyAsync(amps, s->d, len * sizeof(amp_t), cudaMemcpyDeviceToHost, ctx().stream));
     }

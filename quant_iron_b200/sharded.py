@@ -78,11 +78,18 @@ def unpermute(physical: np.ndarray, phys: List[int]) -> np.ndarray:
     return physical[pidx]
 
 
+def shard_to_host(state: State, out: np.ndarray = None) -> np.ndarray:
+    """This rank's shard as stored (PHYSICAL bit order; `layout` gives the logical -> physical qubit map)."""
+    if out is None:
+        out = np.empty(len(state), dtype=np.complex128)
+    _ffi.check(_lib.qi_shard_to_host(state._h, out.ctypes.data_as(C.c_void_p), out.shape[0]))
+    return out
+
+
 def gather_state_vector(state: State, dist) -> np.ndarray:
     """Every rank's shard, concatenated in rank order and put back into logical qubit order
     (test helper: only for states that fit host memory)."""
-    local = np.empty(len(state), dtype=np.complex128)
-    _ffi.check(_lib.qi_state_to_host(state._h, local.ctypes.data_as(C.c_void_p), local.shape[0]))
+    local = shard_to_host(state)
     parts = [None] * dist.get_world_size()
     dist.all_gather_object(parts, local)
     phys, _ = layout(state)
