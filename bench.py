@@ -512,8 +512,13 @@ def run_ours(args, rank, world, local_rank):
         state = qi.State.new_zero(n)
     circuit = w.build_circuit(qi, n, specs)
 
-    for _ in range(args.warmup):
+    t_jit0 = time.time()
+    jit_wait_s = 0.0
+    for i in range(args.warmup):
         circuit.execute_(state)
+        if i == 0:
+            qi.engine.jit_drain()          # the tile modules of this circuit are assembled during warm-up (background workers, csrc/tile_jit.cuh)
+            jit_wait_s = time.time() - t_jit0
     barrier()
     qi.engine.stats_reset()
     sampler = ClockSampler(local_rank)
@@ -525,6 +530,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     stats = qi.engine.stats()
+    jit_timed = qi.engine.jit_stats()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -561,6 +567,20 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "share_of_step": d["total_ms"] / max(1e-9, sum(v["total_ms"] for v in prof.values())),
                 "per_kernel_ms": {k: round(v["total_ms"], 3) for k, v in prof.items()}}
+    # the tile modules are bound by the FP64 pipe, not by HBM (one pass carries ~100 gates): instruction roofline next to the
+    # HBM one.  Numerator: FP64 warp instructions the modules launched in the timed steps (static count per pass, controlled
+    # ops weighted by the fraction of threads their controls select; qi_jit_stats).  Denominator: the DMUL+DFMA issue rate
+    # measured on this GPU type by tools/micro/fp64_peak.cu (profiles/r02_fp64_dmma_peak.txt: 1.936 warp-instr/clk/SM at the
+    # nominal 1965 MHz over 148 SMs).
+    if jit_timed["fp64_warp_instr"] > 0 and dname == "gate_tile_jit":
+        peak_rate = 1.936 * 148 * 1.965e9
+        rate = jit_timed["fp64_warp_instr"] / (ms_total * 1e-3)
+        roofline["fp64_pipe"] = {"achieved_warp_instr_per_s": rate, "peak_warp_instr_per_s": peak_rate, "frac": rate / peak_rate,
+                                 "fp64_warp_instr_per_step": jit_timed["fp64_warp_instr"] / args.steps,
+                                 "peak_source": "measured DMUL+DFMA issue rate, profiles/r02_fp64_dmma_peak.txt",
+                                 "note": "the dominant kernel is FP64-issue bound: `frac` above (HBM) is low BECAUSE ~100 gates share one HBM pass"}
+    jit_info = dict(qi.engine.jit_stats(), wait_in_warmup_s=round(jit_wait_s, 2))
+    jit_info.pop("fp64_warp_instr", None)
     norm = state.norm_sqr()
     comm = None
     if world > 1:
@@ -723,7 +743,7 @@ def run_ours(args, rank, world, local_rank):
                    "effective_gbs_per_gpu_vs_unfused_bytes": w.algorithmic_bytes(n, specs) / world / (ms_per_step * 1e-3) / 1e9},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "kernels": {k: v["launches"] for k, v in stats.items()}, "clocks": clocks,
-        "final_norm_sqr": norm, "comm": comm, "extras": extras,
+        "final_norm_sqr": norm, "comm": comm, "jit": jit_info, "extras": extras,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -68,8 +68,19 @@ int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_m
  *          "lean" = 0/1 window passes apply H / RX / real 2x2 gates in unit form with one deferred scale per pass
  *          (half the FP64 instructions per gate; results differ from the default by rounding only; off until measured);
  *          "prefetch" = 0/1 (with "lean" = 1 only) L2 prefetch of every warp's next tile (off until measured);
- *          "host_chunk_qubits", "host_min_qubits": see qi_execute_host */
+ *          "host_chunk_qubits", "host_min_qubits": see qi_execute_host;
+ *          "tile" = 1/0 fused passes on the CTA-tile executor (11 qubits per HBM pass) for states of >= "tile_min_qubits";
+ *          "jit" = tile passes as circuit-specialised straight-line sm_100a modules, assembled from generated PTX by the
+ *          driver (csrc/tile_jit.cuh): 0 never | 1 (default) in the background once a pass structure has been seen, for
+ *          states of >= "jit_min_qubits" local qubits (the interpreting kernel runs the pass meanwhile; results are
+ *          bit-identical) | 2 before the first launch; "jit_ctas" = 4|3 resident CTAs per SM the modules are built for */
 int qi_set_option(const char* name, int64_t value);
+/* wait until every queued tile module is assembled (benchmarks: call after the first execution of a circuit) */
+int qi_jit_drain(void);
+/* modules assembled / rejected by the driver / still queued, the host milliseconds spent assembling, and the FP64 warp
+ * instructions launched on modules since the last qi_stats_reset (static count per pass, instructions under a control
+ * weighted by the fraction of threads the control selects) -- the numerator of the FP64-pipe roofline in bench.py */
+int qi_jit_stats(uint64_t* modules, uint64_t* failed, uint64_t* pending, double* assemble_ms, double* fp64_warp_instr);
 
 /* kernel accounting for bench.py (gpu_launches, roofline.achieved) */
 typedef struct qi_kernel_stat {

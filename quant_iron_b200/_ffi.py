@@ -52,6 +52,8 @@ _sig("qi_last_error", [u64p, C.c_char_p, C.c_size_t], None)
 _sig("qi_version", [], C.c_char_p)
 _sig("qi_init", [C.c_int])
 _sig("qi_synchronize", [])
+_sig("qi_jit_drain", [])
+_sig("qi_jit_stats", [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)])
 _sig("qi_device_info", [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), u64p, u64p])
 _sig("qi_set_option", [C.c_char_p, C.c_int64])
 _sig("qi_stats_reset", [])

@@ -37,7 +37,7 @@ int cuda_fail(cudaError_t e, const char* what);
 enum KernelFamily {
     KF_INIT = 0, KF_PAIR, KF_DIAG, KF_SWAP, KF_MATCH, KF_WINDOW, KF_PAULI, KF_PAULI_EXP, KF_EXPECT,
     KF_REDUCE, KF_ELEMENTWISE, KF_PROB, KF_SCAN, KF_SAMPLE, KF_COLLAPSE, KF_EXCHANGE, KF_BARRIER,
-    KF_PAULI_WINDOW, KF_TILE, KF_COUNT
+    KF_PAULI_WINDOW, KF_TILE, KF_TILE_JIT, KF_COUNT
 };
 extern const char* const kFamilyNames[KF_COUNT];
 
@@ -69,6 +69,11 @@ struct Context {
     int opt_tile_absorb = 0;          // tile passes: CNOT absorption (two predicated half-ops per pair) -- off: register swaps are cheaper there
     int opt_tile_slide = 1;           // tile passes leave the qubits the next tile wants at positions 0..4 (relabelling the qubit map)
     int opt_tile_min_qubits = 18;     // ... for states with at least this many local qubits (>= 11)
+    int opt_jit = 1;                  // tile passes as circuit-specialised straight-line PTX (tile_jit.cuh): 0 never, 1 assembled in the background
+                                      // after a pass structure is first seen (k_tile runs it meanwhile), 2 assembled before the first launch
+    int opt_jit_min_qubits = 24;      // jit = 1 only for states with at least this many local qubits (a module costs ~1 s of one host core)
+    int opt_jit_ctas = 4;             // resident CTAs per SM the modules are assembled for (4 = 128 registers, 3 = 168)
+    int opt_debug_ptx = 0;            // qi_debug_lower returns the PTX of the tile passes instead of the op blob (CPU-side syntax checks)
     int opt_lean = 0;                 // window passes: unit-form H / RX / real 2x2 with one deferred scale per pass (unmeasured: off)
     int64_t opt_pool_mb = 4096;       // device-buffer cache: at most this many MiB are kept for reuse (0 = off)
     // stats

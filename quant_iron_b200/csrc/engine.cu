@@ -8,10 +8,13 @@
 
 namespace qi {
 
+void jit_drain();      // window.cu (tile_jit.cuh)
+void jit_stats(uint64_t*, uint64_t*, uint64_t*, double*, double*, int);
+
 const char* const kFamilyNames[KF_COUNT] = {
     "init", "gate_pair", "gate_diag", "gate_swap", "gate_matchgate", "gate_window", "pauli_apply",
     "pauli_exp", "pauli_expect", "reduce", "elementwise", "probabilities", "scan", "sample",
-    "collapse", "exchange", "barrier", "pauli_exp_window", "gate_tile"};
+    "collapse", "exchange", "barrier", "pauli_exp_window", "gate_tile", "gate_tile_jit"};
 
 static thread_local uint64_t tl_payload[2] = {0, 0};
 static thread_local char tl_msg[256] = {0};
@@ -224,6 +227,19 @@ int qi_init(int device) {
     return init_locked(device);
 }
 
+int qi_jit_drain(void) { qi::jit_drain(); return QI_OK; }
+int qi_jit_stats(uint64_t* modules, uint64_t* failed, uint64_t* pending, double* assemble_ms, double* fp64_warp_instr) {
+    uint64_t a = 0, b = 0, c = 0;
+    double d = 0.0, e = 0.0;
+    qi::jit_stats(&a, &b, &c, &d, &e, 0);
+    if (fp64_warp_instr) *fp64_warp_instr = e;
+    if (modules) *modules = a;
+    if (failed) *failed = b;
+    if (pending) *pending = c;
+    if (assemble_ms) *assemble_ms = d;
+    return QI_OK;
+}
+
 int qi_synchronize(void) {
     QI_TRY(ensure_ctx());
     QI_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -254,6 +270,10 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "absorb")) c.opt_absorb = (int)value;
     else if (!strcmp(name, "lean")) c.opt_lean = (int)value;
     else if (!strcmp(name, "tile")) c.opt_tile = (int)value;
+    else if (!strcmp(name, "jit")) c.opt_jit = (int)value;
+    else if (!strcmp(name, "jit_min_qubits")) c.opt_jit_min_qubits = (int)value;
+    else if (!strcmp(name, "jit_ctas")) c.opt_jit_ctas = (int)value;
+    else if (!strcmp(name, "debug_ptx")) c.opt_debug_ptx = (int)value;
     else if (!strcmp(name, "tile_slide")) c.opt_tile_slide = (int)value;
     else if (!strcmp(name, "tile_absorb")) c.opt_tile_absorb = (int)value;
     else if (!strcmp(name, "peer_timeout_s")) c.opt_peer_timeout_s = (int)value;
@@ -273,6 +293,9 @@ int qi_stats_reset(void) {
     Context& c = ctx();
     drain_profile();
     for (int i = 0; i < KF_COUNT; i++) { c.launches[i] = 0; c.alg_bytes[i] = 0; c.total_ms[i] = 0; }
+    uint64_t a, b, d;
+    double e, f;
+    qi::jit_stats(&a, &b, &d, &e, &f, 1);          // the FP64 instruction count of the JIT modules restarts with the launch counters
     return QI_OK;
 }
 

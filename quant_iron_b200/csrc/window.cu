@@ -30,7 +30,17 @@
 //   * the kernel is instantiated by pass content (k_window<R, LANES, U2K>): passes without lane
 //     gates / complex 2x2 gates run code that does not carry those paths;
 //   * k_window_tma is a TMA-prefetched persistent variant kept behind the "tma" option (slower).
+#include <cuda.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "window_layout.cuh"
@@ -1774,6 +1784,55 @@ static int launch_tile(qi_state* s, const TileLaunch& tl, const amp_t* d_tables)
     return check_launch("k_tile");
 }
 
+#include "tile_jit.cuh"
+
+// a tile pass prepared for the JIT path: its module (queued, ready or failed) and the coefficient block of THIS execution
+struct TileJit {
+    jit::Entry* e = nullptr;
+    std::vector<double> coef;
+    double fp64 = 0.0;           // FP64 instructions per thread and tile (weighted by control regions)
+};
+static bool jit_wanted(const qi_state* s) {
+    const Context& c = ctx();
+    return c.opt_jit >= 2 || (c.opt_jit == 1 && (int)s->n_local >= c.opt_jit_min_qubits);
+}
+static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const amp_t* arena, TileJit* out) {
+    Context& c = ctx();
+    if (!jit_wanted(s) || !jit::driver().ok) return QI_OK;
+    const int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
+    const uint64_t key = jit::structure_key(tl, arena, ctas);
+    jit::Entry* e = jit::find(key);
+    if (e) QI_TRY(jit::generate(tl, arena, ctas, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
+    else {
+        std::string text;
+        QI_TRY(jit::generate(tl, arena, ctas, &text, &out->coef, &out->fp64));
+        e = jit::enqueue(key, std::move(text), c.device);
+    }
+    if (out->coef.size() * 8 + 64 > 32000) return QI_OK;          // parameter space: leave this launch to k_tile
+    out->e = e;
+    return QI_OK;
+}
+// launches the pass's module when it is ready; *launched = false leaves the pass to k_tile
+static int launch_tile_jit(qi_state* s, const TileJit& tj, const amp_t* d_tables, bool* launched) {
+    *launched = false;
+    if (!tj.e || tj.e->state.load(std::memory_order_acquire) != 1) return QI_OK;
+    Context& c = ctx();
+    uint64_t ntiles = s->len >> kTileBits;
+    const uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
+    static const double zero = 0.0;
+    void* params[] = {(void*)&s->d, (void*)&ntiles, (void*)&d_tables, tj.coef.empty() ? (void*)&zero : (void*)tj.coef.data()};
+    LaunchScope ls(KF_TILE_JIT, 32.0 * (double)s->len);
+    const CUresult r = jit::driver().LaunchKernel(tj.e->fn, (unsigned)blocks, 1, 1, kTileThreads, 1, 1, 0, (CUstream)c.stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(QI_ERR_CUDA, (uint64_t)r, 0, "cuLaunchKernel failed for a JIT tile module");
+    *launched = true;
+    {
+        jit::Cache& jc = jit::cache();
+        std::lock_guard<std::mutex> lk(jc.mu);
+        jc.fp64_warp_instr += tj.fp64 * (kTileThreads / 32) * (double)ntiles;
+    }
+    return check_launch("qi_tile_jit");
+}
+
 template <int R>
 static int launch_program(qi_state* s, const Layout& L, const DOp* ops, size_t nops, const amp_t* d_tables) {
     Context& c = ctx();
@@ -2273,9 +2332,23 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
         QI_CUDA(cudaMemcpyAsync(c.d_ops, c.h_ops, arena.size() * sizeof(amp_t), cudaMemcpyHostToDevice, c.stream));
         QI_CUDA(cudaEventRecord(c.ops_event, c.stream));
     }
+    std::vector<std::vector<TileJit>> jits(steps.size());
+    if (tile && jit_wanted(s)) {
+        for (size_t i = 0; i < steps.size(); i++) {
+            jits[i].resize(tiles[i].size());
+            for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(prepare_tile_jit(s, tiles[i][k], arena.data(), &jits[i][k]));
+        }
+        if (c.opt_jit >= 2) jit::drain();            // every module of this circuit is assembled (in parallel) before the first launch
+    }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, steps[i].sgate));
-        else if (tile) { for (const TileLaunch& tl : tiles[i]) QI_TRY(launch_tile(s, tl, (const amp_t*)c.d_ops)); }
+        else if (tile) {
+            for (size_t k = 0; k < tiles[i].size(); k++) {
+                bool launched = false;
+                if (!jits[i].empty()) QI_TRY(launch_tile_jit(s, jits[i][k], (const amp_t*)c.d_ops, &launched));
+                if (!launched) QI_TRY(launch_tile(s, tiles[i][k], (const amp_t*)c.d_ops));
+            }
+        }
         else if (steps[i].R == 3) QI_TRY(launch_program<3>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else if (steps[i].R == 4) QI_TRY(launch_program<4>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
         else QI_TRY(launch_program<5>(s, layouts[i], dops[i].data(), dops[i].size(), (const amp_t*)c.d_ops));
@@ -2334,6 +2407,20 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
             nrec += tiles[i].size();
         }
         blob->clear();
+        if (ctx().opt_debug_ptx) {          // the PTX of every tile launch, separated by a marker line (assembled by the CPU tests with ptxas)
+            for (size_t i = 0; i < steps.size(); i++)
+                for (const TileLaunch& tl : tiles[i]) {
+                    std::string text;
+                    std::vector<double> coef;
+                    double fp64 = 0.0;
+                    QI_TRY(jit::generate(tl, arena.data(), ctx().opt_jit_ctas == 3 ? 3 : 4, &text, &coef, &fp64));
+                    char mark[64];
+                    snprintf(mark, sizeof(mark), "//---PASS fp64=%.1f coef=%zu---\n", fp64, coef.size());
+                    put(mark, strlen(mark));
+                    put(text.data(), text.size());
+                }
+            return QI_OK;
+        }
         put64(nrec);
         for (size_t i = 0; i < steps.size(); i++) {
             if (steps[i].simple) { put64(1); put(&steps[i].sgate, sizeof(PhysGate)); continue; }
@@ -2369,6 +2456,15 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
     put64(arena.size());
     put(arena.data(), arena.size() * sizeof(amp_t));
     return QI_OK;
+}
+
+void jit_drain() { jit::drain(); }
+void jit_stats(uint64_t* modules, uint64_t* failed, uint64_t* pending, double* assemble_ms, double* fp64_warp_instr, int reset) {
+    jit::Cache& c = jit::cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    *modules = c.assembled; *failed = c.failed; *pending = (uint64_t)c.pending; *assemble_ms = c.assemble_ms;
+    *fp64_warp_instr = c.fp64_warp_instr;
+    if (reset) c.fp64_warp_instr = 0.0;
 }
 
 }  // namespace qi

@@ -32,6 +32,17 @@ def set_option(name: str, value: int):
     _ffi.check(_lib.qi_set_option(name.encode(), int(value)))
 
 
+def jit_drain():
+    """Wait until every queued tile module is assembled (csrc/tile_jit.cuh)."""
+    _ffi.check(_lib.qi_jit_drain())
+
+
+def jit_stats() -> dict:
+    m, f, p, ms, wi = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double(), C.c_double()
+    _ffi.check(_lib.qi_jit_stats(C.byref(m), C.byref(f), C.byref(p), C.byref(ms), C.byref(wi)))
+    return {"modules": m.value, "failed": f.value, "pending": p.value, "assemble_ms": ms.value, "fp64_warp_instr": wi.value}
+
+
 def stats_reset():
     _ffi.check(_lib.qi_stats_reset())
 
