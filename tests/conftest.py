@@ -23,6 +23,7 @@ EXP_RTOL = 1e-10     # north star: relative error on expectation values
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+    config.addinivalue_line("markers", "large: GPU parity at BASELINE.json's full sizes (2^26-2^28 amplitudes; the oracle needs minutes of host time)")
     config.addinivalue_line("markers", "unproven: GPU test of a path that has not run on hardware yet; ordered last")
     # a fresh checkout has no built artefacts (they are git-ignored): build them once instead of failing at import
     if not os.path.exists(os.path.join(ROOT, "quant_iron_b200", "lib", "libqiron_b200.so")):
