@@ -31,6 +31,7 @@ struct Driver {
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
 };
 static Driver& driver() {
     static Driver d;
@@ -41,7 +42,8 @@ static Driver& driver() {
             return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
         };
         d.ok = get("cuModuleLoadDataEx", (void**)&d.ModuleLoadDataEx) && get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) &&
-               get("cuLaunchKernel", (void**)&d.LaunchKernel) && get("cuModuleUnload", (void**)&d.ModuleUnload);
+               get("cuLaunchKernel", (void**)&d.LaunchKernel) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
+               get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute);
         if (!d.ok) cudaGetLastError();
     });
     return d;
@@ -326,20 +328,27 @@ static uint32_t swz_of_regs(const TileRoundHost& h, int sl) {
 
 // the whole pass as PTX; `coef` receives the parameter block that goes with this text
 // (text == nullptr: only the coefficients, in the order the text of this structure reads them)
-static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
+// `groups`: tiles a CTA works on side by side (128 threads each).  The module is straight-line code far larger than the 32 KB
+// L1.5 instruction cache, so every group of warps that drifts apart is one more instruction stream the SM pulls from L2
+// (ncu: `no_instruction` was the top stall with four independent 128-thread CTAs per SM); groups of one CTA meet at every
+// regroup barrier and share one stream.
+static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
     Gen gn;
     gn.arena = arena;
     gn.dry = text == nullptr;
     const int nr = (int)tl.rounds.size();
     // ---- prologue: thread constants ----
-    gn.emit("mov.u32 %%t, %%tid.x;");
+    gn.emit("mov.u32 %%rx, %%tid.x;");
+    gn.emit("and.b32 %%t, %%rx, %d;", kTileThreads - 1);
+    gn.emit("shr.u32 %%grp, %%rx, %d;", kTileThrBits);
     gn.emit("ld.param.u64 %%pa, [p_a];");
     gn.emit("cvta.to.global.u64 %%pa, %%pa;");
     gn.emit("ld.param.u64 %%ptab, [p_tab];");
     gn.emit("cvta.to.global.u64 %%ptab, %%ptab;");
     gn.emit("ld.param.u64 %%ntiles, [p_ntiles];");
-    gn.emit("mov.u32 %%smb, sm;");
-    gn.emit("mov.u32 %%lbsa, lbs;");
+    gn.emit("mov.u32 %%smb, dsm;");
+    gn.emit("add.u32 %%lbsa, %%smb, %d;", groups * (int)(sizeof(amp_t) << kTileBits));     // W table behind the tile images (every group writes the same values)
+    gn.emit("mad.lo.u32 %%smb, %%grp, %d, %%smb;", (int)(sizeof(amp_t) << kTileBits));
     gn.emit("shl.b32 %%rx, %%t, 2;");
     gn.emit("add.u32 %%lbsa, %%lbsa, %%rx;");
     for (int r = 0; r < nr; r++) {           // W_r(t) = &sm[swz(b_r(t))]: the XOR swizzle only touches the three low index bits
@@ -372,8 +381,10 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, s
     thread_offset("%gin", tl.rounds.front(), tl.tile_qubits);
     thread_offset("%gout", tl.rounds.back(), tl.tile_out);
     gn.emit("mov.u32 %%rx, %%ctaid.x;");
+    gn.emit("mad.lo.u32 %%rx, %%rx, %d, %%grp;", groups);
     gn.emit("cvt.u64.u32 %%tile, %%rx;");
     gn.emit("mov.u32 %%rx, %%nctaid.x;");
+    gn.emit("mul.lo.u32 %%rx, %%rx, %d;", groups);
     gn.emit("cvt.u64.u32 %%tstep, %%rx;");
     gn.emit("setp.ge.u64 %%pq, %%tile, %%ntiles;");
     gn.emit("@%%pq bra.uni LEND;");
@@ -448,17 +459,16 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, s
     char head[1024];
     const size_t nb = std::max<size_t>(coef->size(), 1) * 8;
     snprintf(head, sizeof(head),
-             ".version 8.6\n.target sm_100a\n.address_size 64\n\n"
+             ".version 8.6\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 128 .b8 dsm[];\n\n"
              ".visible .entry qi_tile_jit(.param .u64 p_a, .param .u64 p_ntiles, .param .u64 p_tab, .param .align 16 .b8 p_c[%zu])\n"
              ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
              "  .reg .pred %%pq, %%pt;\n"
-             "  .reg .b32 %%t, %%smb, %%lbsa, %%wb, %%rb, %%rx, %%ry, %%rz, %%rm, %%rlo, %%rhi;\n"
+             "  .reg .b32 %%t, %%grp, %%smb, %%lbsa, %%wb, %%rb, %%rx, %%ry, %%rz, %%rm, %%rlo, %%rhi;\n"
              "  .reg .b64 %%pa, %%ptab, %%ntiles, %%tile, %%tstep, %%tb, %%gin, %%gout, %%rdx, %%rdy;\n"
              "  .reg .f64 %%fx, %%fy, %%gx, %%gy, %%h0, %%h1;\n"
              "  .reg .f64 %%a<%d>;\n  .reg .f64 %%c<%zu>;\n  .reg .f64 %%g<%d>;\n"
-             "  .shared .align 128 .b8 sm[%d];\n  .shared .align 16 .b8 lbs[%d];\n",
-             nb, kTileThreads, ctas_per_sm, gn.na, std::max<size_t>(coef->size(), 1), std::max(gn.ng, 1),
-             (int)(sizeof(amp_t) << kTileBits), 512 * std::max(nr, 1));
+             "",
+             nb, kTileThreads * groups, std::max(1, ctas_per_sm / groups), gn.na, std::max<size_t>(coef->size(), 1), std::max(gn.ng, 1));
     text->assign(head);
     text->append(gn.s);
     return QI_OK;
@@ -469,7 +479,10 @@ struct Entry {
     std::atomic<int> state{0};     // 0 = queued / assembling, 1 = ready, -1 = failed (k_tile runs the pass)
     CUfunction fn = nullptr;
     size_t text_len = 0;
+    int groups = 1;                // tiles per CTA (128 threads each)
+    unsigned smem = 0;             // dynamic shared memory: the groups' tile images + the W table
 };
+static unsigned smem_bytes(int groups, int nrounds) { return (unsigned)groups * (unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1); }
 struct Cache {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
@@ -489,9 +502,9 @@ struct Fnv {
 };
 // everything the text of a pass depends on: positions, rounds, the non-coefficient half of every op, table offsets and the
 // negate flags packed into the rotations (generate() reads nothing else but coefficients)
-static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm) {
+static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups) {
     Fnv f;
-    f.u64((uint64_t)ctas_per_sm);
+    f.u64((uint64_t)ctas_per_sm | ((uint64_t)groups << 8));
     f.bytes(tl.tile_qubits, sizeof(tl.tile_qubits));
     f.bytes(tl.tile_out, sizeof(tl.tile_out));
     f.u64(tl.rounds.size());
@@ -525,6 +538,7 @@ static void assemble(Entry* e, const std::string& text) {
     const auto t0 = std::chrono::steady_clock::now();
     CUresult r = d.ModuleLoadDataEx(&mod, text.c_str(), 2, opts, vals);
     if (r == CUDA_SUCCESS) r = d.ModuleGetFunction(&e->fn, mod, "qi_tile_jit");
+    if (r == CUDA_SUCCESS && e->smem > 48 * 1024) r = d.FuncSetAttribute(e->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)e->smem);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     Cache& c = cache();
     {
@@ -566,12 +580,14 @@ static Entry* find(uint64_t key) {
     return it == c.map.end() ? nullptr : it->second;
 }
 // a structure seen for the first time: its text is queued for assembly.  Returns the entry (state says whether it can be launched).
-static Entry* enqueue(uint64_t h, std::string&& text, int device) {
+static Entry* enqueue(uint64_t h, std::string&& text, int device, int groups, unsigned smem) {
     Cache& c = cache();
     std::unique_lock<std::mutex> lk(c.mu);
     auto it = c.map.find(h);
     if (it != c.map.end()) return it->second;
     Entry* e = new Entry;
+    e->groups = groups;
+    e->smem = smem;
     e->text_len = text.size();
     c.map.emplace(h, e);
     c.device = device;

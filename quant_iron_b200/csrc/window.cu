@@ -1800,13 +1800,17 @@ static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const amp_t
     Context& c = ctx();
     if (!jit_wanted(s) || !jit::driver().ok) return QI_OK;
     const int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
-    const uint64_t key = jit::structure_key(tl, arena, ctas);
+    const uint64_t ntiles = s->len >> kTileBits;
+    int groups = c.opt_jit_groups == 4 ? 4 : (c.opt_jit_groups == 2 ? 2 : 1);
+    while ((uint64_t)groups > ntiles) groups >>= 1;
+    if (ctas == 3) groups = 1;
+    const uint64_t key = jit::structure_key(tl, arena, ctas, groups);
     jit::Entry* e = jit::find(key);
-    if (e) QI_TRY(jit::generate(tl, arena, ctas, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
+    if (e) QI_TRY(jit::generate(tl, arena, ctas, groups, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
     else {
         std::string text;
-        QI_TRY(jit::generate(tl, arena, ctas, &text, &out->coef, &out->fp64));
-        e = jit::enqueue(key, std::move(text), c.device);
+        QI_TRY(jit::generate(tl, arena, ctas, groups, &text, &out->coef, &out->fp64));
+        e = jit::enqueue(key, std::move(text), c.device, groups, jit::smem_bytes(groups, (int)tl.rounds.size()));
     }
     if (out->coef.size() * 8 + 64 > 32000) return QI_OK;          // parameter space: leave this launch to k_tile
     out->e = e;
@@ -1818,11 +1822,12 @@ static int launch_tile_jit(qi_state* s, const TileJit& tj, const amp_t* d_tables
     if (!tj.e || tj.e->state.load(std::memory_order_acquire) != 1) return QI_OK;
     Context& c = ctx();
     uint64_t ntiles = s->len >> kTileBits;
-    const uint64_t blocks = std::min<uint64_t>(ntiles, (uint64_t)c.sm_count * 32);
+    const uint64_t G = (uint64_t)tj.e->groups;
+    const uint64_t blocks = std::min<uint64_t>(ntiles / G, (uint64_t)c.sm_count * 32 / G);
     static const double zero = 0.0;
     void* params[] = {(void*)&s->d, (void*)&ntiles, (void*)&d_tables, tj.coef.empty() ? (void*)&zero : (void*)tj.coef.data()};
     LaunchScope ls(KF_TILE_JIT, 32.0 * (double)s->len);
-    const CUresult r = jit::driver().LaunchKernel(tj.e->fn, (unsigned)blocks, 1, 1, kTileThreads, 1, 1, 0, (CUstream)c.stream, params, nullptr);
+    const CUresult r = jit::driver().LaunchKernel(tj.e->fn, (unsigned)blocks, 1, 1, (unsigned)(kTileThreads * G), 1, 1, tj.e->smem, (CUstream)c.stream, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(QI_ERR_CUDA, (uint64_t)r, 0, "cuLaunchKernel failed for a JIT tile module");
     *launched = true;
     {
@@ -2312,7 +2317,10 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
     const int R = tile ? kTileWindow : window_regs(s);
     std::vector<Step> steps;
     std::vector<int> final_pos;
-    const bool relabel = tile && allow_relabel && s->world == 1 && c.opt_tile_slide;
+    // Sliding tiles leave the state in another qubit order after every execution, so the next execution of the same circuit is
+    // scheduled from another layout and shares no pass structure with this one: modules would never be reused.  States
+    // that run on JIT modules therefore keep their layout (more, cheaper passes: the modules are FP64-bound, not HBM-bound).
+    const bool relabel = tile && allow_relabel && s->world == 1 && c.opt_tile_slide && !jit_wanted(s);
     if (tile) QI_TRY(schedule_tile_passes(s, gates, c.opt_fuse != 0, relabel, steps, &final_pos));
     else QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
     // lower every pass, upload all phase tables in one copy, then launch back to back
@@ -2391,7 +2399,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
     std::vector<Step> steps;
     const bool tile = tile_mode(s);
     std::vector<int> final_pos;
-    const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide;
+    const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide && !jit_wanted(s);
     if (tile) QI_TRY(schedule_tile_passes(s, gates, ctx().opt_fuse != 0, relabel, steps, &final_pos));
     else QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
     std::vector<amp_t> arena;
@@ -2413,7 +2421,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
                     std::string text;
                     std::vector<double> coef;
                     double fp64 = 0.0;
-                    QI_TRY(jit::generate(tl, arena.data(), ctx().opt_jit_ctas == 3 ? 3 : 4, &text, &coef, &fp64));
+                    QI_TRY(jit::generate(tl, arena.data(), ctx().opt_jit_ctas == 3 ? 3 : 4, ctx().opt_jit_ctas == 3 ? 1 : std::max(1, ctx().opt_jit_groups), &text, &coef, &fp64));
                     char mark[64];
                     snprintf(mark, sizeof(mark), "//---PASS fp64=%.1f coef=%zu---\n", fp64, coef.size());
                     put(mark, strlen(mark));
