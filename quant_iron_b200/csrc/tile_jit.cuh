@@ -153,6 +153,39 @@ struct Gen {
         }
         end_region(L);
     }
+    // unit forms (never under a control): results go to fresh registers, the slots are renamed
+    void op_realu(const DOp& d, bool minus) {
+        const int B = (int)d.tpos - kLaneQubits;
+        const int p = c(d.m[0]), q = c(d.m[1]);
+        for (int i = 0; i < 8; i++) {
+            const int s0 = ((i >> B) << (B + 1)) | (i & ((1 << B) - 1)), s1 = s0 | (1 << B);
+            const int nx0 = fresh(), ny0 = fresh(), nx1 = fresh(), ny1 = fresh();
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", nx0, p, ax[s1], ax[s0]);
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", ny0, p, ay[s1], ay[s0]);
+            if (minus) {
+                emit("neg.f64 %%a%d, %%a%d;", ax[s1], ax[s1]);
+                emit("neg.f64 %%a%d, %%a%d;", ay[s1], ay[s1]);
+            }
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", nx1, q, ax[s0], ax[s1]);
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", ny1, q, ay[s0], ay[s1]);
+            ax[s0] = nx0; ay[s0] = ny0; ax[s1] = nx1; ay[s1] = ny1;
+        }
+    }
+    void op_rxu(const DOp& d) {
+        const int B = (int)d.tpos - kLaneQubits;
+        const int t = c(d.m[0]);
+        const int nt = g();
+        emit("neg.f64 %%g%d, %%c%d;", nt, t);
+        for (int i = 0; i < 8; i++) {
+            const int s0 = ((i >> B) << (B + 1)) | (i & ((1 << B) - 1)), s1 = s0 | (1 << B);
+            const int nx0 = fresh(), ny0 = fresh(), nx1 = fresh(), ny1 = fresh();
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", nx0, t, ay[s1], ax[s0]);
+            emit("fma.rn.f64 %%a%d, %%g%d, %%a%d, %%a%d;", ny0, nt, ax[s1], ay[s0]);
+            emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%a%d;", nx1, t, ay[s0], ax[s1]);
+            emit("fma.rn.f64 %%a%d, %%g%d, %%a%d, %%a%d;", ny1, nt, ax[s0], ay[s1]);
+            ax[s0] = nx0; ay[s0] = ny0; ax[s1] = nx1; ay[s1] = ny1;
+        }
+    }
     void op_x(const DOp& d) {
         const int B = (int)d.tpos - kLaneQubits;
         const bool cond = d.c_tile || d.c_lane;
@@ -309,6 +342,11 @@ struct Gen {
         switch (d.kind) {
             case WK_REALL: op_reall(d); return QI_OK;
             case WK_RXL: op_rxl(d); return QI_OK;
+            case WK_REALUP: case WK_REALUM:
+            case WK_RXU:
+                if (d.c_tile || d.c_lane || (d.c_reg & 0xffffu) != 0xffffu) return fail(QI_ERR_UNKNOWN, d.kind, 0, "internal: unit-form tile op under a control");
+                if (d.kind == WK_RXU) op_rxu(d); else op_realu(d, d.kind == WK_REALUM);
+                return QI_OK;
             case WK_X: op_x(d); return QI_OK;
             case WK_NEG: op_neg(d); return QI_OK;
             case WK_DIAG: op_diag(d); return QI_OK;
@@ -347,7 +385,8 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
     gn.emit("cvta.to.global.u64 %%ptab, %%ptab;");
     gn.emit("ld.param.u64 %%ntiles, [p_ntiles];");
     gn.emit("mov.u32 %%smb, dsm;");
-    gn.emit("add.u32 %%lbsa, %%smb, %d;", groups * (int)(sizeof(amp_t) << kTileBits));     // W table behind the tile images (every group writes the same values)
+    gn.emit("add.u32 %%lbsa, %%smb, %d;", groups * (int)(sizeof(amp_t) << kTileBits));     // W tables (one per group: W holds the group's own image address) behind the tile images
+    gn.emit("mad.lo.u32 %%lbsa, %%grp, %d, %%lbsa;", 512 * std::max(nr, 1));
     gn.emit("mad.lo.u32 %%smb, %%grp, %d, %%smb;", (int)(sizeof(amp_t) << kTileBits));
     gn.emit("shl.b32 %%rx, %%t, 2;");
     gn.emit("add.u32 %%lbsa, %%lbsa, %%rx;");
@@ -482,7 +521,7 @@ struct Entry {
     int groups = 1;                // tiles per CTA (128 threads each)
     unsigned smem = 0;             // dynamic shared memory: the groups' tile images + the W table
 };
-static unsigned smem_bytes(int groups, int nrounds) { return (unsigned)groups * (unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1); }
+static unsigned smem_bytes(int groups, int nrounds) { return (unsigned)groups * ((unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1)); }
 struct Cache {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;

@@ -468,8 +468,10 @@ __device__ __forceinline__ void run_ops(amp_t (&v)[1 << R], const uint64_t tile,
 //   codes: 1..4 REALL on register bit B; 5..8 RXL; 9..12 X; 13..36 X under one register-bit control (C, CV);
 //          40 TABLE, 41 NEG, 42 DIAG, 43 RZ, 44 SCALE.
 static const double kLiftMinPivot = 0.05;
-enum { FC_TABLE = 40, FC_NEG, FC_DIAG, FC_RZ, FC_SCALE };
+enum { FC_TABLE = 40, FC_NEG, FC_DIAG, FC_RZ, FC_SCALE, FC_REALUP = 45 /* + B */, FC_REALUM = 49 /* + B */, FC_RXU = 53 /* + B */ };
 static inline int fast_code(int kind, int B, uint32_t pos, uint32_t neg) {
+    if ((kind == WK_REALUP || kind == WK_REALUM || kind == WK_RXU) && B >= 0 && B <= 3 && (pos | neg) == 0)
+        return (kind == WK_REALUP ? FC_REALUP : kind == WK_REALUM ? FC_REALUM : FC_RXU) + B;
     if (kind == WK_TABLE) return FC_TABLE;
     if (kind == WK_NEG) return FC_NEG;
     if (kind == WK_DIAG) return FC_DIAG;
@@ -504,6 +506,35 @@ __device__ __forceinline__ void fast_rxl(amp_t (&v)[16], const double k0, const 
         v[s0].y *= k0; v[s0].y = fma(n1, v[s1].x, v[s0].y);
         v[s1].x *= k2; v[s1].x = fma(k3, v[s0].y, v[s1].x);
         v[s1].y *= k2; v[s1].y = fma(n3, v[s0].x, v[s1].y);
+    }
+}
+// UNIT forms (uncontrolled gates only; the omitted factor g of every such gate of a launch is multiplied on the host and applied
+// by one WK_SCALE op at the end of the launch): half the FP64 instructions of the lifted forms.
+//   REALUP / REALUM = [[1, p], [q, +-1]]:  a0' = a0 + p a1,  a1' = q a0 +- a1        (H / g: p = q = 1, minus)
+template <int B, bool MINUS>
+__device__ __forceinline__ void fast_realu(amp_t (&v)[16], const double p, const double q) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int s0 = ((i >> B) << (B + 1)) | (i & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        const double tx = v[s0].x, ty = v[s0].y;
+        v[s0].x = fma(p, v[s1].x, tx);
+        v[s0].y = fma(p, v[s1].y, ty);
+        v[s1].x = fma(q, tx, MINUS ? -v[s1].x : v[s1].x);
+        v[s1].y = fma(q, ty, MINUS ? -v[s1].y : v[s1].y);
+    }
+}
+//   RXU = [[1, -i t], [-i t, 1]]:  a0' = a0 - i t a1,  a1' = a1 - i t a0
+template <int B>
+__device__ __forceinline__ void fast_rxu(amp_t (&v)[16], const double t) {
+    const double nt = -t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int s0 = ((i >> B) << (B + 1)) | (i & ((1 << B) - 1)), s1 = s0 | (1 << B);
+        const double tx = v[s0].x, ty = v[s0].y;
+        v[s0].x = fma(t, v[s1].y, tx);
+        v[s0].y = fma(nt, v[s1].x, ty);
+        v[s1].x = fma(t, ty, v[s1].x);
+        v[s1].y = fma(nt, tx, v[s1].y);
     }
 }
 __device__ __forceinline__ void xor_swap(amp_t& a, amp_t& b) {
@@ -616,6 +647,18 @@ __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile
             case 11: fast_x<2>(v); break;
             case 12: fast_x<3>(v); break;
             QI_CX6(0) QI_CX6(1) QI_CX6(2) QI_CX6(3)
+            case FC_REALUP + 0: fast_realu<0, false>(v, k0, k1); break;
+            case FC_REALUP + 1: fast_realu<1, false>(v, k0, k1); break;
+            case FC_REALUP + 2: fast_realu<2, false>(v, k0, k1); break;
+            case FC_REALUP + 3: fast_realu<3, false>(v, k0, k1); break;
+            case FC_REALUM + 0: fast_realu<0, true>(v, k0, k1); break;
+            case FC_REALUM + 1: fast_realu<1, true>(v, k0, k1); break;
+            case FC_REALUM + 2: fast_realu<2, true>(v, k0, k1); break;
+            case FC_REALUM + 3: fast_realu<3, true>(v, k0, k1); break;
+            case FC_RXU + 0: fast_rxu<0>(v, k0); break;
+            case FC_RXU + 1: fast_rxu<1>(v, k0); break;
+            case FC_RXU + 2: fast_rxu<2>(v, k0); break;
+            case FC_RXU + 3: fast_rxu<3>(v, k0); break;
             case FC_TABLE: {
                 const amp_t* __restrict__ tab = tables + (uint64_t)__double_as_longlong(op.m[0]);
                 const uint32_t hub_cls = op.hub_cls, hub_bit = op.hub_bit;
@@ -1387,7 +1430,8 @@ static void push_scale_op(const Layout& L, double scale, std::vector<DOp>& dops)
 
 // ---- k_tile lowering: one host op -> one or more in-place device ops under the layout of its round ------------------
 // (the op set and why every op is in place: "k_tile: the op set" above)
-static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vector<DOp>& dops, std::vector<amp_t>& arena) {
+// `scale`: product of the factors the launch's unit-form gates leave out (applied by one WK_SCALE op at the end of the launch)
+static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vector<DOp>& dops, std::vector<amp_t>& arena, double* scale) {
     DOp base;
     memset(&base, 0, sizeof(base));
     uint32_t pos_lane = 0, pos_reg = 0, neg_lane = 0, neg_reg = 0;
@@ -1448,9 +1492,16 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
             std::swap(k2, k3);
         }
         DOp d = base;
-        d.kind = WK_REALL;
         controls(&d, 0, 0);
         d.tpos = (uint8_t)(kLaneQubits + L.idx[target]);
+        const bool uncontrolled = !(pos_lane | neg_lane) && !(pos_tile | neg_tile);
+        if (uncontrolled && ctx().opt_tile_lean && (k3 == k0 || k3 == -k0)) {       // unit form: k0 . [[1, k1 / k0], [k2 / k0, +-1]]
+            d.kind = k3 == k0 ? WK_REALUP : WK_REALUM;
+            d.m[0] = k1 / k0; d.m[1] = k2 / k0;
+            *scale *= k0;
+            return emit(d, 0, 0, L.idx[target]);
+        }
+        d.kind = WK_REALL;
         d.m[0] = k0; d.m[1] = k1; d.m[2] = k2 / k0; d.m[3] = (k0 * k3 - k1 * k2) / k0;
         return emit(d, 0, 0, L.idx[target]);
     };
@@ -1460,10 +1511,17 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
         const bool pivot = std::fabs(c) < kLiftMinPivot;
         if (pivot) { const double c2 = sn, s2 = -c; c = c2; sn = s2; }
         DOp d = base;
-        d.kind = WK_RXL;
         controls(&d, 0, 0);
         d.tpos = (uint8_t)(kLaneQubits + L.idx[target]);
-        d.m[0] = c; d.m[1] = sn; d.m[2] = 1.0 / c; d.m[3] = sn / c;
+        const bool uncontrolled = !(pos_lane | neg_lane) && !(pos_tile | neg_tile);
+        if (uncontrolled && ctx().opt_tile_lean) {                                  // unit form: c . [[1, -i t], [-i t, 1]]
+            d.kind = WK_RXU;
+            d.m[0] = sn / c;
+            *scale *= c;
+        } else {
+            d.kind = WK_RXL;
+            d.m[0] = c; d.m[1] = sn; d.m[2] = 1.0 / c; d.m[3] = sn / c;
+        }
         QI_TRY(emit(d, 0, 0, L.idx[target]));
         if (pivot) {
             QI_TRY(emit_x(target));
@@ -1700,7 +1758,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
         // rounds of this launch
         size_t end = ri, nops = 0;
         auto cost = [&](size_t r) { size_t c = 0; for (size_t i : round_ops[r]) c += tile_op_count(ops[i]); return c; };
-        while (end < nrounds && (end == ri || (nops + cost(end) <= (size_t)kMaxTileOps && (end - ri) + 3 <= (size_t)kMaxRounds))) {
+        while (end < nrounds && (end == ri || (nops + cost(end) <= (size_t)kMaxTileOps - 1 && (end - ri) + 3 <= (size_t)kMaxRounds))) {
             nops += cost(end);
             end++;
         }
@@ -1708,6 +1766,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
         const int* low_out = last_launch ? low_out_last : low_id;
         const bool same_io = !memcmp(low_out, low_id, sizeof(low_id));
         TileLaunch tl;
+        double scale = 1.0;
         for (int j = 0; j < kTileBits; j++) { tl.tile_qubits[j] = plan.pin[j]; tl.tile_out[j] = last_launch ? plan.pout[j] : plan.pin[j]; }
         for (size_t r = ri; r < end; r++) {
             std::vector<int> loc;
@@ -1731,7 +1790,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
             }
             rd.first_op = tl.dops.size();
             const Layout L = round_layout(s, tl.tile_qubits, rd);
-            for (size_t i : round_ops[r]) QI_TRY(lower_op_tile(L, ps, ops[i], tl.dops, arena));
+            for (size_t i : round_ops[r]) QI_TRY(lower_op_tile(L, ps, ops[i], tl.dops, arena, &scale));
             if (tl.dops.size() > (size_t)kMaxTileOps) return fail(QI_ERR_UNKNOWN, tl.dops.size(), 0, "internal: tile launch holds too many ops");
             rd.nops = tl.dops.size() - rd.first_op;
             tl.rounds.push_back(rd);
@@ -1741,6 +1800,16 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
                 io.first_op = tl.dops.size();
                 tl.rounds.push_back(io);
             }
+        }
+        if (scale != 1.0) {                 // the factors the unit-form gates of this launch left out, on every amplitude, in the last round
+            DOp d;
+            memset(&d, 0, sizeof(d));
+            d.kind = WK_SCALE;
+            d.code = (uint8_t)FC_SCALE;
+            d.c_reg = 0xffffu;
+            d.m[0] = scale;
+            tl.dops.push_back(d);
+            tl.rounds.back().nops++;
         }
         launches.push_back(std::move(tl));
         ri = end;

@@ -227,3 +227,22 @@ def test_jit_background_policy_switches_to_modules(gpu, ref, tile11):
         assert gpu.engine.jit_stats()["modules"] == mods          # cached
     finally:
         gpu.engine.set_option("jit_min_qubits", 24)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups", [2, 4])
+def test_jit_tile_groups_per_cta_bit_identical(gpu, ref, tile11, groups):
+    """modules whose CTAs work on 2 or 4 tiles side by side (option jit_groups) compute exactly what the one-tile CTAs compute"""
+    from quant_iron_b200 import workloads as w
+    n = 17
+    specs = w.random_layered_circuit(n, 14, seed=4242) + w.qft_specs(n)
+    cg = w.build_circuit(gpu, n, specs)
+    r0 = ref.random_state(n, 11)
+    sv_1, _ = _run(gpu, cg, gpu.State(r0.state_vector, n), 2)
+    gpu.engine.set_option("jit_groups", groups)
+    try:
+        sv_g, st = _run(gpu, cg, gpu.State(r0.state_vector, n), 2)
+    finally:
+        gpu.engine.set_option("jit_groups", 1)
+    assert st.get("gate_tile_jit", {}).get("launches", 0) > 0
+    assert np.array_equal(sv_1, sv_g)

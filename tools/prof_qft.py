@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import quant_iron_b200 as qi  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 qi.engine.init(0)
 qft = qi.CircuitBuilder(n).add_subroutine(qi.Subroutine.qft(list(range(n)), n)).build()
 for name, tile, jit in (("tile_jit", 1, 2), ("tile_interpreter", 1, 0), ("window", 0, 0)):
@@ -16,6 +16,9 @@ for name, tile, jit in (("tile_jit", 1, 2), ("tile_interpreter", 1, 0), ("window
     qft.execute_(st)
     qi.engine.synchronize()
     a0 = st.amplitude(0)
+    for _ in range(3):            # the QFT's trailing swaps are a relabelling: the layout (and the modules) alternate with period 2
+        qft.execute_(st)
+    qi.engine.synchronize()
     del st
     st = qi.State.new_plus(n)
     qi.engine.stats_reset()
