@@ -370,7 +370,7 @@ static uint32_t swz_of_regs(const TileRoundHost& h, int sl) {
 // L1.5 instruction cache, so every group of warps that drifts apart is one more instruction stream the SM pulls from L2
 // (ncu: `no_instruction` was the top stall with four independent 128-thread CTAs per SM); groups of one CTA meet at every
 // regroup barrier and share one stream.
-static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
+static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
     Gen gn;
     gn.arena = arena;
     gn.dry = text == nullptr;
@@ -453,6 +453,37 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
             gn.emit("add.u64 %%rdx, %%rdy, %llu;", (unsigned long long)o);
             gn.emit("ld.global.cs.v2.f64 {%%a%d, %%a%d}, [%%rdx];", gn.ax[sl], gn.ay[sl]);
         }
+    }
+    if (prefetch) {
+        // the CTA's next tile into L2 while this one is computed (no registers held): one 128-byte line per 8 lanes and slot.
+        // A pass of ~40 gates is no longer far above its HBM time, and with 4 CTAs per SM the DRAM latency of the loads at
+        // the head of every tile is exposed (ncu: long_scoreboard is the top stall of the unit-form modules).
+        const int L = gn.nlab++;
+        gn.emit("add.u64 %%rdx, %%tile, %%tstep;");
+        gn.emit("setp.ge.u64 %%pq, %%rdx, %%ntiles;");
+        gn.emit("@%%pq bra.uni LS%d;", L);
+        gn.emit("and.b32 %%rx, %%t, 7;");
+        gn.emit("setp.ne.u32 %%pq, %%rx, 0;");
+        gn.emit("@%%pq bra LS%d;", L);
+        for (int j = 0; j < kTileBits; j++) {
+            const int p = tl.tile_qubits[j];
+            gn.emit("shr.u64 %%rdy, %%rdx, %d;", p);
+            gn.emit("shl.b64 %%rdy, %%rdy, %d;", p + 1);
+            gn.emit("and.b64 %%rdx, %%rdx, %llu;", (1ull << p) - 1ull);
+            gn.emit("or.b64 %%rdx, %%rdx, %%rdy;");
+        }
+        gn.emit("add.u64 %%rdx, %%rdx, %%gin;");
+        gn.emit("shl.b64 %%rdx, %%rdx, 4;");
+        gn.emit("add.u64 %%rdx, %%rdx, %%pa;");
+        for (int sl = 0; sl < 16; sl++) {
+            const uint64_t o = slot_offset(tl.rounds.front(), tl.tile_qubits, sl);
+            if (o < (1ull << 31)) gn.emit("prefetch.global.L2 [%%rdx+%llu];", (unsigned long long)o);
+            else {
+                gn.emit("add.u64 %%rdy, %%rdx, %llu;", (unsigned long long)o);
+                gn.emit("prefetch.global.L2 [%%rdy];");
+            }
+        }
+        gn.end_region(L);
     }
     for (int r = 0; r < nr; r++) {
         const TileRoundHost& cur = tl.rounds[r];
@@ -541,9 +572,9 @@ struct Fnv {
 };
 // everything the text of a pass depends on: positions, rounds, the non-coefficient half of every op, table offsets and the
 // negate flags packed into the rotations (generate() reads nothing else but coefficients)
-static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups) {
+static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch) {
     Fnv f;
-    f.u64((uint64_t)ctas_per_sm | ((uint64_t)groups << 8));
+    f.u64((uint64_t)ctas_per_sm | ((uint64_t)groups << 8) | ((uint64_t)(prefetch != 0) << 16));
     f.bytes(tl.tile_qubits, sizeof(tl.tile_qubits));
     f.bytes(tl.tile_out, sizeof(tl.tile_out));
     f.u64(tl.rounds.size());

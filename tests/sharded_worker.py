@@ -112,6 +112,24 @@ for n in (10, 13):
     check(f"measure n={n}", st, mr.get_new_state())
     del st
 
+# 6. the CTA-tile executor on shards, interpreted (k_tile) and as JIT modules: rank-bit controls are per-rank constants, so
+#    every rank assembles its own modules
+for jit in (0, 2):
+    qi.engine.set_option("tile_min_qubits", 11)
+    qi.engine.set_option("jit", jit)
+    n = 12 + int(math.log2(world))
+    specs = w.random_layered_circuit(n, 8, seed=777) + w.qft_specs(n) + w.random_layered_circuit(n, 3, seed=778)
+    st = sharded.new_zero(n, dist)
+    qi.engine.stats_reset()
+    w.build_circuit(qi, n, specs).execute_(st)
+    kernels = {k: v["launches"] for k, v in qi.engine.stats().items()}
+    rs = w.build_circuit(ref, n, specs).execute(ref.State.new_zero(n))
+    check(f"tile executor on shards jit={jit} n={n} kernels={kernels}", st, rs)
+    assert kernels.get("gate_tile_jit" if jit else "gate_tile", 0) > 0, kernels
+    del st
+qi.engine.set_option("tile_min_qubits", 18)
+qi.engine.set_option("jit", 1)
+
 if args.big:
     n = args.big + int(math.log2(world))
     st = sharded.new_plus(n, dist)

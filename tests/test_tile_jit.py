@@ -63,10 +63,14 @@ def _assemble(texts):
 
 @pytest.fixture
 def tile11():
+    """k_tile / the modules take every state they can hold; tiles do not slide, so that the interpreter (jit = 0) runs the very
+    schedule the modules are generated from (states that run on modules never slide: run_circuit_windowed)."""
     import quant_iron_b200 as gpu
     gpu.engine.set_option("tile_min_qubits", 11)
+    gpu.engine.set_option("tile_slide", 0)
     yield gpu
     gpu.engine.set_option("tile_min_qubits", 18)
+    gpu.engine.set_option("tile_slide", 1)
 
 
 def test_benchmark_circuit_modules_assemble():
