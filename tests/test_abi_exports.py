@@ -93,3 +93,21 @@ def test_rust_sys_bindings_match_the_header():
     assert len(names) >= 59
     for n in names:
         assert re.search(rf"pub fn {n}\(", lib_rs), n
+
+
+def test_struct_layouts_agree_between_c_rust_asserts_and_ctypes():
+    """The generated crate asserts size / alignment / field offsets of every C struct at compile time (gcc's layout of the header
+    on x86_64); the same numbers must hold for the ctypes mirror this repository's Python host layer uses."""
+    import ctypes as C
+    import re
+
+    from quant_iron_b200 import _ffi
+    src = open(os.path.join(ROOT, "bindings", "rust", "quant-iron-b200-sys", "src", "lib.rs")).read()
+    sizes = {m.group(1): int(m.group(2)) for m in re.finditer(r"size_of::<(\w+)>\(\) == (\d+)", src)}
+    offsets = {(m.group(1), m.group(2)): int(m.group(3)) for m in re.finditer(r"offset_of!\((\w+), (\w+)\) == (\d+)", src)}
+    assert {"qi_gate", "qi_pauli_term", "qi_kernel_stat"} <= set(sizes)
+    mirrors = {"qi_gate": _ffi.QiGate, "qi_pauli_term": _ffi.QiPauliTerm, "qi_kernel_stat": _ffi.QiKernelStat}
+    for name, cls in mirrors.items():
+        assert C.sizeof(cls) == sizes[name], name
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == offsets[(name, fname)], (name, fname)
