@@ -11,7 +11,9 @@ RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-add
 timeout 900 $RUN --master-port 29611 tests/sharded_worker.py --big 24 > "$OUT/sharded_parity.log" 2>&1
 echo "parity exit $?" >> "$OUT/sharded_parity.log"
 timeout 1500 $RUN --master-port 29612 bench.py --gpus $N --config5-local-qubits $Q5 > "$OUT/bench.json" 2> "$OUT/bench.err"
-timeout 600 $RUN --master-port 29613 bench.py --gpus $N --skip-e2e --skip-extras --skip-cpu --opt jit=0 > "$OUT/bench_nojit.json" 2> "$OUT/bench_nojit.err"
+if [ "$N" -le 2 ]; then
+  timeout 600 $RUN --master-port 29613 bench.py --gpus $N --skip-e2e --skip-extras --skip-cpu --opt jit=0 > "$OUT/bench_nojit.json" 2> "$OUT/bench_nojit.err"
+fi
 timeout 600 $RUN --master-port 29614 tools/nccl_halfshard_ab.py 30 > "$OUT/nccl_halfshard_ab.json" 2> "$OUT/nccl_halfshard_ab.err"
 nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
 ls -la "$OUT"
