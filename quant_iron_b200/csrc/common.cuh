@@ -73,6 +73,7 @@ struct Context {
                                       // after a pass structure is first seen (k_tile runs it meanwhile), 2 assembled before the first launch
     int opt_jit_min_qubits = 24;      // jit = 1 only for states with at least this many local qubits (a module costs ~1 s of one host core)
     int opt_jit_ctas = 4;             // resident CTAs per SM the modules are assembled for (4 = 128 registers, 3 = 168)
+    int opt_jit_stage = 0;            // modules bring the CTA's next tile into shared memory with bulk async copies (cp.async.bulk + mbarrier) while the current one is computed
     int opt_jit_prefetch = 0;         // modules prefetch the CTA's next tile into L2 while the current one is computed
     int opt_tile_lean = 1;            // tile passes: uncontrolled H / RY / RX in unit form (2 FP64 instructions per amplitude instead of 4), one scale op per launch
     int opt_jit_groups = 1;           // tiles a module's CTA works on side by side (1, 2 or 4 x 128 threads; measured: 1 = 2 > 4)

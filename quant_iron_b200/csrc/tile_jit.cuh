@@ -370,7 +370,12 @@ static uint32_t swz_of_regs(const TileRoundHost& h, int sl) {
 // L1.5 instruction cache, so every group of warps that drifts apart is one more instruction stream the SM pulls from L2
 // (ncu: `no_instruction` was the top stall with four independent 128-thread CTAs per SM); groups of one CTA meet at every
 // regroup barrier and share one stream.
-static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
+// `stage` (groups == 1): the CTA's NEXT tile is brought into a second 32 KiB shared-memory buffer by the async proxy while the
+// current one is computed -- 64 bulk copies of one 512-byte row each (cp.async.bulk ... mbarrier::complete_tx::bytes), issued
+// by threads 0..63 and counted by one mbarrier -- and the first round reads its registers from that buffer instead of from
+// global memory.  No registers are held across the copy (a register prefetch would need 64 more per thread), the loads
+// leave the critical path of the tile, and the row addresses need not coalesce per warp.  3 CTAs per SM (2 x 32 KiB each).
+static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch, int stage, std::string* text, std::vector<double>* coef, double* fp64_per_thread) {
     Gen gn;
     gn.arena = arena;
     gn.dry = text == nullptr;
@@ -385,7 +390,7 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
     gn.emit("cvta.to.global.u64 %%ptab, %%ptab;");
     gn.emit("ld.param.u64 %%ntiles, [p_ntiles];");
     gn.emit("mov.u32 %%smb, dsm;");
-    gn.emit("add.u32 %%lbsa, %%smb, %d;", groups * (int)(sizeof(amp_t) << kTileBits));     // W tables (one per group: W holds the group's own image address) behind the tile images
+    gn.emit("add.u32 %%lbsa, %%smb, %d;", (groups + (stage ? 1 : 0)) * (int)(sizeof(amp_t) << kTileBits));     // W tables (one per group: W holds the group's own image address) behind the tile images
     gn.emit("mad.lo.u32 %%lbsa, %%grp, %d, %%lbsa;", 512 * std::max(nr, 1));
     gn.emit("mad.lo.u32 %%smb, %%grp, %d, %%smb;", (int)(sizeof(amp_t) << kTileBits));
     gn.emit("shl.b32 %%rx, %%t, 2;");
@@ -419,6 +424,53 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
     };
     thread_offset("%gin", tl.rounds.front(), tl.tile_qubits);
     thread_offset("%gout", tl.rounds.back(), tl.tile_out);
+    const int kImage = (int)(sizeof(amp_t) << kTileBits);
+    auto insert_zeros = [&](const char* reg, const char* tmp) {          // reg <- reg with zero bits inserted at the tile's positions
+        for (int j = 0; j < kTileBits; j++) {
+            const int p = tl.tile_qubits[j];
+            gn.emit("shr.u64 %s, %s, %d;", tmp, reg, p);
+            gn.emit("shl.b64 %s, %s, %d;", tmp, tmp, p + 1);
+            gn.emit("and.b64 %s, %s, %llu;", reg, reg, (1ull << p) - 1ull);
+            gn.emit("or.b64 %s, %s, %s;", reg, reg, tmp);
+        }
+    };
+    // stage: bulk copies of the tile whose compact index is in %rdx (clobbers %rdx, %rdy)
+    auto issue_stage = [&]() {
+        insert_zeros("%rdx", "%rdy");
+        gn.emit("@%%pt0 mbarrier.arrive.expect_tx.shared::cta.b64 _, [%%mbar], %d;", kImage);
+        gn.emit("add.u64 %%rdx, %%rdx, %%rowoff;");
+        gn.emit("shl.b64 %%rdx, %%rdx, 4;");
+        gn.emit("add.u64 %%rdx, %%rdx, %%pa;");
+        gn.emit("@%%pld cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%%rowdst], [%%rdx], 512, [%%mbar];");
+    };
+    if (stage) {
+        const TileRoundHost& io = tl.rounds.front();
+        gn.emit("mov.u32 %%rawt, dsm;");
+        gn.emit("add.u32 %%mbar, %%rawt, %d;", 2 * kImage + 512 * std::max(nr, 1));
+        gn.emit("add.u32 %%rawt, %%rawt, %d;", kImage);
+        gn.emit("shl.b32 %%rx, %%t, 9;");
+        gn.emit("add.u32 %%rowdst, %%rawt, %%rx;");                     // row t of the raw tile (threads 0..63)
+        gn.emit("mov.u32 %%ry, 0;");                                    // this thread's tile-local base under the load layout
+        for (int k = 0; k < kTileThrBits; k++) {
+            gn.emit("bfe.u32 %%rx, %%t, %d, 1;", k);
+            gn.emit("shl.b32 %%rx, %%rx, %d;", io.thr[k] + 4);
+            gn.emit("or.b32 %%ry, %%ry, %%rx;");
+        }
+        gn.emit("add.u32 %%rawt, %%rawt, %%ry;");
+        gn.emit("mov.u64 %%rowoff, 0;");                                // global index offset of row t: window bit k of t -> position tile_qubits[5 + k]
+        for (int k = 0; k < kTileBits - kLaneQubits; k++) {
+            gn.emit("bfe.u32 %%rx, %%t, %d, 1;", k);
+            gn.emit("cvt.u64.u32 %%rdx, %%rx;");
+            gn.emit("shl.b64 %%rdx, %%rdx, %d;", tl.tile_qubits[kLaneQubits + k]);
+            gn.emit("or.b64 %%rowoff, %%rowoff, %%rdx;");
+        }
+        gn.emit("setp.lt.u32 %%pld, %%t, %d;", 1 << (kTileBits - kLaneQubits));
+        gn.emit("setp.eq.u32 %%pt0, %%t, 0;");
+        gn.emit("@%%pt0 mbarrier.init.shared::cta.b64 [%%mbar], 1;");
+        gn.emit("@%%pt0 fence.mbarrier_init.release.cluster;");
+        gn.emit("bar.sync 0;");
+        gn.emit("mov.u32 %%phase, 0;");
+    }
     gn.emit("mov.u32 %%rx, %%ctaid.x;");
     gn.emit("mad.lo.u32 %%rx, %%rx, %d, %%grp;", groups);
     gn.emit("cvt.u64.u32 %%tile, %%rx;");
@@ -427,6 +479,10 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
     gn.emit("cvt.u64.u32 %%tstep, %%rx;");
     gn.emit("setp.ge.u64 %%pq, %%tile, %%ntiles;");
     gn.emit("@%%pq bra.uni LEND;");
+    if (stage) {
+        gn.emit("mov.u64 %%rdx, %%tile;");
+        issue_stage();
+    }
     if (!gn.dry) gn.s.append("LTILE:\n");
     // ---- tile base: zero bits inserted at the tile's positions (ascending) ----
     gn.emit("mov.u64 %%tb, %%tile;");
@@ -446,6 +502,27 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
         for (int k = 0; k < 4; k++) if ((sl >> k) & 1) o |= 1ull << pos[h.regs[k]];
         return o * 16ull;
     };
+    if (stage) {
+        // wait for this tile's 32 KiB, read the registers under the load layout, then hand the buffer to the next tile's copies
+        const int LW = gn.nlab++, LN = gn.nlab++;
+        if (!gn.dry) { gn.s.append("LS"); gn.s.append(std::to_string(LW)); gn.s.append(":\n"); }
+        gn.emit("mbarrier.try_wait.parity.shared::cta.b64 %%pq, [%%mbar], %%phase;");
+        gn.emit("@!%%pq bra LS%d;", LW);
+        gn.emit("xor.b32 %%phase, %%phase, 1;");
+        const TileRoundHost& io = tl.rounds.front();
+        for (int sl = 0; sl < 16; sl++) {
+            uint32_t o = 0;
+            for (int k = 0; k < 4; k++) if ((sl >> k) & 1) o |= 1u << io.regs[k];
+            gn.emit("ld.shared.v2.f64 {%%a%d, %%a%d}, [%%rawt+%u];", gn.ax[sl], gn.ay[sl], o * 16u);
+        }
+        gn.emit("bar.sync 0;");
+        gn.emit("add.u64 %%rdx, %%tile, %%tstep;");
+        gn.emit("setp.ge.u64 %%pq, %%rdx, %%ntiles;");
+        gn.emit("@%%pq bra.uni LS%d;", LN);
+        gn.emit("fence.proxy.async.shared::cta;");
+        issue_stage();
+        if (!gn.dry) { gn.s.append("LS"); gn.s.append(std::to_string(LN)); gn.s.append(":\n"); }
+    } else
     for (int sl = 0; sl < 16; sl++) {
         const uint64_t o = slot_offset(tl.rounds.front(), tl.tile_qubits, sl);
         if (o < (1ull << 31)) gn.emit("ld.global.cs.v2.f64 {%%a%d, %%a%d}, [%%rdy+%llu];", gn.ax[sl], gn.ay[sl], (unsigned long long)o);
@@ -454,10 +531,12 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
             gn.emit("ld.global.cs.v2.f64 {%%a%d, %%a%d}, [%%rdx];", gn.ax[sl], gn.ay[sl]);
         }
     }
-    if (prefetch) {
+    auto emit_prefetch = [&]() {
         // the CTA's next tile into L2 while this one is computed (no registers held): one 128-byte line per 8 lanes and slot.
         // A pass of ~40 gates is no longer far above its HBM time, and with 4 CTAs per SM the DRAM latency of the loads at
         // the head of every tile is exposed (ncu: long_scoreboard is the top stall of the unit-form modules).
+        // prefetch = 1: issued before the LAST round (the whole GPU streams ~150 MB through the 126 MB L2 per tile period, so a
+        // line prefetched at the head of the tile is evicted before it is used); 2: at the head of the tile.
         const int L = gn.nlab++;
         gn.emit("add.u64 %%rdx, %%tile, %%tstep;");
         gn.emit("setp.ge.u64 %%pq, %%rdx, %%ntiles;");
@@ -484,7 +563,9 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
             }
         }
         gn.end_region(L);
-    }
+    };
+    if (stage) prefetch = 0;
+    if (prefetch == 2 || (prefetch == 1 && nr == 1)) emit_prefetch();
     for (int r = 0; r < nr; r++) {
         const TileRoundHost& cur = tl.rounds[r];
         if (r > 0) {              // regroup through the shared-memory image of the tile (one barrier: see k_tile)
@@ -504,6 +585,7 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
                 else gn.emit("ld.shared.v2.f64 {%%a%d, %%a%d}, [%%rb+%u];", gn.ax[sl], gn.ay[sl], hi);
             }
         }
+        if (prefetch == 1 && nr > 1 && r == nr - 1) emit_prefetch();
         for (size_t o = 0; o < cur.nops; o++) QI_TRY(gn.op(tl.dops[cur.first_op + o]));
     }
     gn.emit("add.u64 %%rdy, %%tb, %%gout;");
@@ -532,9 +614,9 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
              ".version 8.6\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 128 .b8 dsm[];\n\n"
              ".visible .entry qi_tile_jit(.param .u64 p_a, .param .u64 p_ntiles, .param .u64 p_tab, .param .align 16 .b8 p_c[%zu])\n"
              ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
-             "  .reg .pred %%pq, %%pt;\n"
-             "  .reg .b32 %%t, %%grp, %%smb, %%lbsa, %%wb, %%rb, %%rx, %%ry, %%rz, %%rm, %%rlo, %%rhi;\n"
-             "  .reg .b64 %%pa, %%ptab, %%ntiles, %%tile, %%tstep, %%tb, %%gin, %%gout, %%rdx, %%rdy;\n"
+             "  .reg .pred %%pq, %%pt, %%pt0, %%pld;\n"
+             "  .reg .b32 %%t, %%grp, %%smb, %%lbsa, %%wb, %%rb, %%rx, %%ry, %%rz, %%rm, %%rlo, %%rhi, %%rawt, %%rowdst, %%mbar, %%phase;\n"
+             "  .reg .b64 %%pa, %%ptab, %%ntiles, %%tile, %%tstep, %%tb, %%gin, %%gout, %%rdx, %%rdy, %%rowoff;\n"
              "  .reg .f64 %%fx, %%fy, %%gx, %%gy, %%h0, %%h1;\n"
              "  .reg .f64 %%a<%d>;\n  .reg .f64 %%c<%zu>;\n  .reg .f64 %%g<%d>;\n"
              "",
@@ -552,7 +634,10 @@ struct Entry {
     int groups = 1;                // tiles per CTA (128 threads each)
     unsigned smem = 0;             // dynamic shared memory: the groups' tile images + the W table
 };
-static unsigned smem_bytes(int groups, int nrounds) { return (unsigned)groups * ((unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1)); }
+static unsigned smem_bytes(int groups, int nrounds, int stage) {
+    if (stage) return 2u * (unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1) + 16u;      // image, raw tile, W table, mbarrier
+    return (unsigned)groups * ((unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1));
+}
 struct Cache {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
@@ -572,9 +657,9 @@ struct Fnv {
 };
 // everything the text of a pass depends on: positions, rounds, the non-coefficient half of every op, table offsets and the
 // negate flags packed into the rotations (generate() reads nothing else but coefficients)
-static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch) {
+static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, int groups, int prefetch, int stage) {
     Fnv f;
-    f.u64((uint64_t)ctas_per_sm | ((uint64_t)groups << 8) | ((uint64_t)(prefetch != 0) << 16));
+    f.u64((uint64_t)ctas_per_sm | ((uint64_t)groups << 8) | ((uint64_t)prefetch << 16) | ((uint64_t)(stage != 0) << 24));
     f.bytes(tl.tile_qubits, sizeof(tl.tile_qubits));
     f.bytes(tl.tile_out, sizeof(tl.tile_out));
     f.u64(tl.rounds.size());

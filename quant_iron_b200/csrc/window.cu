@@ -1868,19 +1868,21 @@ static bool jit_wanted(const qi_state* s) {
 static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const amp_t* arena, TileJit* out) {
     Context& c = ctx();
     if (!jit_wanted(s) || !jit::driver().ok) return QI_OK;
-    const int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
+    int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
     const uint64_t ntiles = s->len >> kTileBits;
     int groups = c.opt_jit_groups == 4 ? 4 : (c.opt_jit_groups == 2 ? 2 : 1);
     while ((uint64_t)groups > ntiles) groups >>= 1;
     if (ctas == 3) groups = 1;
     const int pf = c.opt_jit_prefetch;
-    const uint64_t key = jit::structure_key(tl, arena, ctas, groups, pf);
+    const int stage = c.opt_jit_stage ? 1 : 0;
+    if (stage) { groups = 1; ctas = 3; }
+    const uint64_t key = jit::structure_key(tl, arena, ctas, groups, pf, stage);
     jit::Entry* e = jit::find(key);
-    if (e) QI_TRY(jit::generate(tl, arena, ctas, groups, pf, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
+    if (e) QI_TRY(jit::generate(tl, arena, ctas, groups, pf, stage, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
     else {
         std::string text;
-        QI_TRY(jit::generate(tl, arena, ctas, groups, pf, &text, &out->coef, &out->fp64));
-        e = jit::enqueue(key, std::move(text), c.device, groups, jit::smem_bytes(groups, (int)tl.rounds.size()));
+        QI_TRY(jit::generate(tl, arena, ctas, groups, pf, stage, &text, &out->coef, &out->fp64));
+        e = jit::enqueue(key, std::move(text), c.device, groups, jit::smem_bytes(groups, (int)tl.rounds.size(), stage));
     }
     if (out->coef.size() * 8 + 64 > 32000) return QI_OK;          // parameter space: leave this launch to k_tile
     out->e = e;
@@ -2491,7 +2493,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
                     std::string text;
                     std::vector<double> coef;
                     double fp64 = 0.0;
-                    QI_TRY(jit::generate(tl, arena.data(), ctx().opt_jit_ctas == 3 ? 3 : 4, ctx().opt_jit_ctas == 3 ? 1 : std::max(1, ctx().opt_jit_groups), ctx().opt_jit_prefetch, &text, &coef, &fp64));
+                    QI_TRY(jit::generate(tl, arena.data(), (ctx().opt_jit_ctas == 3 || ctx().opt_jit_stage) ? 3 : 4, (ctx().opt_jit_ctas == 3 || ctx().opt_jit_stage) ? 1 : std::max(1, ctx().opt_jit_groups), ctx().opt_jit_prefetch, ctx().opt_jit_stage ? 1 : 0, &text, &coef, &fp64));
                     char mark[64];
                     snprintf(mark, sizeof(mark), "//---PASS fp64=%.1f coef=%zu---\n", fp64, coef.size());
                     put(mark, strlen(mark));

@@ -234,19 +234,31 @@ def test_jit_background_policy_switches_to_modules(gpu, ref, tile11):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("groups", [2, 4])
-def test_jit_tile_groups_per_cta_bit_identical(gpu, ref, tile11, groups):
-    """modules whose CTAs work on 2 or 4 tiles side by side (option jit_groups) compute exactly what the one-tile CTAs compute"""
+@pytest.mark.parametrize("option,value", [("jit_groups", 2), ("jit_groups", 4), ("jit_ctas", 3), ("jit_prefetch", 1), ("jit_prefetch", 2), ("jit_stage", 1)])
+def test_jit_module_variants_bit_identical(gpu, ref, tile11, option, value):
+    """The variants of the module skeleton -- CTAs that work on 2 or 4 tiles side by side, 3 CTAs per SM, L2 prefetch of the
+    next tile, and the next tile staged into shared memory by bulk async copies (cp.async.bulk + mbarrier) -- move the data
+    differently and compute exactly the same."""
     from quant_iron_b200 import workloads as w
     n = 17
     specs = w.random_layered_circuit(n, 14, seed=4242) + w.qft_specs(n)
     cg = w.build_circuit(gpu, n, specs)
     r0 = ref.random_state(n, 11)
     sv_1, _ = _run(gpu, cg, gpu.State(r0.state_vector, n), 2)
-    gpu.engine.set_option("jit_groups", groups)
+    gpu.engine.set_option(option, value)
     try:
         sv_g, st = _run(gpu, cg, gpu.State(r0.state_vector, n), 2)
+        # a second, longer run on the same modules: many tiles per CTA (the staged variant's mbarrier phase flips every tile)
+        n2 = 21
+        c2 = w.build_circuit(gpu, n2, w.random_layered_circuit(n2, 6, seed=99))
+        b_1 = None
+        gpu.engine.set_option(option, {"jit_groups": 1, "jit_ctas": 4}.get(option, 0))
+        b_1, _ = _run(gpu, c2, gpu.State.new_zero(n2), 2)
+        gpu.engine.set_option(option, value)
+        b_g, _ = _run(gpu, c2, gpu.State.new_zero(n2), 2)
     finally:
-        gpu.engine.set_option("jit_groups", 1)
+        gpu.engine.set_option(option, {"jit_groups": 1, "jit_ctas": 4}.get(option, 0))
     assert st.get("gate_tile_jit", {}).get("launches", 0) > 0
+    assert gpu.engine.jit_stats()["failed"] == 0
     assert np.array_equal(sv_1, sv_g)
+    assert np.array_equal(b_1, b_g)
