@@ -311,22 +311,16 @@ struct Gen {
             emit("mov.f64 %%fx, %%h0;");
             emit("mov.f64 %%fy, %%h1;");
         }
-        // make_rot: negate when fx < 0, nt = -fy / (1 + fx), s = fy; the sign flips of the amplitudes use the runtime mask
-        emit("setp.lt.f64 %%pt, %%fx, 0d0000000000000000;");
-        emit("neg.f64 %%h0, %%fx;");
-        emit("neg.f64 %%h1, %%fy;");
-        emit("selp.f64 %%fx, %%h0, %%fx, %%pt;");
-        emit("selp.f64 %%fy, %%h1, %%fy, %%pt;");
-        emit("selp.b32 %%rm, 0x80000000, 0, %%pt;");
-        emit("add.f64 %%h0, %%fx, 0d3FF0000000000000;");
-        emit("neg.f64 %%h1, %%fy;");
-        emit("div.rn.f64 %%h0, %%h1, %%h0;");
+        // the thread's factor as a plain complex product, instruction for instruction what run_ops_tile does
         const uint32_t hub_slot = d.hub_cls == CLS_REG ? (1u << d.hub_bit) : 0u;
         for (int sl = 0; sl < S; sl++) {
             if ((sl & hub_slot) != hub_slot) continue;
-            flip_runtime(ax[sl]);
-            flip_runtime(ay[sl]);
-            shear(sl, "%h0", "%fy");
+            const int t0 = g(), t1 = g();
+            emit("mul.f64 %%g%d, %%fy, %%a%d;", t0, ay[sl]);
+            emit("mul.f64 %%g%d, %%fy, %%a%d;", t1, ax[sl]);
+            emit("neg.f64 %%g%d, %%g%d;", t0, t0);
+            emit("fma.rn.f64 %%a%d, %%fx, %%a%d, %%g%d;", ax[sl], ax[sl], t0);
+            emit("fma.rn.f64 %%a%d, %%fx, %%a%d, %%g%d;", ay[sl], ay[sl], t1);
         }
         if (d.has_reg) {            // slot factors: packed rotations behind the chunk tables (host arena -> coefficients)
             const amp_t* sl_t = arena + off + NT + S + 256 * (long long)d.nchunks;

@@ -668,11 +668,17 @@ __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile
                 const uint32_t nch = op.nchunks;
                 for (uint32_t k = 0; k < nch; k++)                            // tile chunk tables (256 entries each)
                     f = cmul(f, __ldg(tab + NT + S + 256 * k + ((tile >> (8 * k)) & 255)));
-                const Rot rf = make_rot(f.x, f.y);                            // one division per thread and op
+                // the thread's factor as a plain complex product (2 DMUL + 2 DFMA per amplitude, written with explicit roundings
+                // so that the JIT modules, which emit the same four instructions, stay bit-identical): the three-shear form
+                // needs one division per thread and op (a subroutine call in straight-line code) and two sign flips per amplitude
                 const uint32_t hub_slot = hub_cls == CLS_REG ? (1u << hub_bit) : 0u;
 #pragma unroll
                 for (int s = 0; s < S; s++)
-                    if ((s & hub_slot) == hub_slot) rot_inplace(v[s], rf);
+                    if ((s & hub_slot) == hub_slot) {
+                        const double t0 = __dmul_rn(f.y, v[s].y), t1 = __dmul_rn(f.y, v[s].x);
+                        v[s].x = __fma_rn(f.x, v[s].x, -t0);
+                        v[s].y = __fma_rn(f.x, v[s].y, t1);
+                    }
                 if (op.has_reg) {                                             // slot factors: packed rotations behind the chunk tables
                     const amp_t* __restrict__ sl = tab + NT + S + 256 * nch;
 #pragma unroll
