@@ -68,11 +68,13 @@ struct Context {
     int opt_peer_timeout_s = 120;     // sharded states: a peer missing at a device barrier for this long traps the kernel (shard.cu)
     int opt_tile_absorb = 0;          // tile passes: CNOT absorption (two predicated half-ops per pair) -- off: register swaps are cheaper there
     int opt_tile_slide = 1;           // tile passes leave the qubits the next tile wants at positions 0..4 (relabelling the qubit map)
+    int opt_tile_min_gates = 3;       // ... and runs of at least this many gates (a lone gate is a pure HBM pass: k_window streams it best)
     int opt_tile_min_qubits = 18;     // ... for states with at least this many local qubits (>= 11)
     int opt_jit = 1;                  // tile passes as circuit-specialised straight-line PTX (tile_jit.cuh): 0 never, 1 assembled in the background
                                       // after a pass structure is first seen (k_tile runs it meanwhile), 2 assembled before the first launch
     int opt_jit_min_qubits = 24;      // jit = 1 only for states with at least this many local qubits (a module costs ~1 s of one host core)
     int opt_jit_ctas = 4;             // resident CTAs per SM the modules are assembled for (4 = 128 registers, 3 = 168)
+    int opt_jit_smem_kb = 0;          // modules request at least this much dynamic shared memory (56 = at most 4 CTAs per SM however few registers a small module needs)
     int opt_jit_stage = 0;            // modules bring the CTA's next tile into shared memory with bulk async copies (cp.async.bulk + mbarrier) while the current one is computed
     int opt_jit_prefetch = 0;         // modules prefetch the CTA's next tile into L2 while the current one is computed
     int opt_tile_lean = 1;            // tile passes: uncontrolled H / RY / RX in unit form (2 FP64 instructions per amplitude instead of 4), one scale op per launch

@@ -277,12 +277,14 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "tile_lean")) c.opt_tile_lean = (int)value;
     else if (!strcmp(name, "jit_prefetch")) c.opt_jit_prefetch = (int)value;
     else if (!strcmp(name, "jit_stage")) c.opt_jit_stage = (int)value;
+    else if (!strcmp(name, "jit_smem_kb")) c.opt_jit_smem_kb = (int)value;
     else if (!strcmp(name, "debug_ptx")) c.opt_debug_ptx = (int)value;
     else if (!strcmp(name, "tile_slide")) c.opt_tile_slide = (int)value;
     else if (!strcmp(name, "tile_absorb")) c.opt_tile_absorb = (int)value;
     else if (!strcmp(name, "peer_timeout_s")) c.opt_peer_timeout_s = (int)value;
     else if (!strcmp(name, "cz_rewrite")) c.opt_cz_rewrite = (int)value;
     else if (!strcmp(name, "tile_min_qubits")) c.opt_tile_min_qubits = (int)value;
+    else if (!strcmp(name, "tile_min_gates")) c.opt_tile_min_gates = (int)value;
     else if (!strcmp(name, "prefetch")) c.opt_prefetch = (int)value;
     else if (!strcmp(name, "late_tables")) c.opt_late_tables = (int)value;
     else if (!strcmp(name, "host_chunk_qubits")) c.opt_host_chunk_qubits = (int)(value < 0 ? 0 : (value > 4 ? 4 : value));

@@ -632,11 +632,19 @@ static unsigned smem_bytes(int groups, int nrounds, int stage) {
     if (stage) return 2u * (unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1) + 16u;      // image, raw tile, W table, mbarrier
     return (unsigned)groups * ((unsigned)(sizeof(amp_t) << kTileBits) + 512u * (unsigned)std::max(nrounds, 1));
 }
+// a structure seen for the first time: the worker writes the text (generate) AND assembles it, so the thread that executes the
+// circuit only pays for the key and for copies of the launch record and (once per circuit) the table arena
+struct Job {
+    Entry* e = nullptr;
+    std::shared_ptr<const TileLaunch> tl;
+    std::shared_ptr<const std::vector<amp_t>> arena;
+    int ctas = 4, groups = 1, prefetch = 0, stage = 0;
+};
 struct Cache {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
     std::unordered_map<uint64_t, Entry*> map;
-    std::deque<std::pair<Entry*, std::string>> queue;
+    std::deque<Job> queue;
     int workers = 0, pending = 0, device = 0;
     uint64_t assembled = 0, failed = 0;
     double assemble_ms = 0.0;
@@ -706,14 +714,24 @@ static void worker_main(int device) {
     cudaFree(0);                                   // binds the primary context to this thread
     Cache& c = cache();
     for (;;) {
-        std::pair<Entry*, std::string> job;
+        Job job;
         {
             std::unique_lock<std::mutex> lk(c.mu);
             c.cv_work.wait(lk, [&] { return !c.queue.empty(); });
             job = std::move(c.queue.front());
             c.queue.pop_front();
         }
-        assemble(job.first, job.second);
+        std::string text;
+        std::vector<double> coef;
+        double fp64 = 0.0;
+        if (generate(*job.tl, job.arena->data(), job.ctas, job.groups, job.prefetch, job.stage, &text, &coef, &fp64) == QI_OK) {
+            job.e->text_len = text.size();
+            assemble(job.e, text);
+        } else {
+            job.e->state.store(-1, std::memory_order_release);
+            std::lock_guard<std::mutex> lk(c.mu);
+            c.failed++;
+        }
         {
             std::lock_guard<std::mutex> lk(c.mu);
             c.pending--;
@@ -729,19 +747,19 @@ static Entry* find(uint64_t key) {
     return it == c.map.end() ? nullptr : it->second;
 }
 // a structure seen for the first time: its text is queued for assembly.  Returns the entry (state says whether it can be launched).
-static Entry* enqueue(uint64_t h, std::string&& text, int device, int groups, unsigned smem) {
+static Entry* enqueue(uint64_t h, Job&& job, int device, unsigned smem) {
     Cache& c = cache();
     std::unique_lock<std::mutex> lk(c.mu);
     auto it = c.map.find(h);
     if (it != c.map.end()) return it->second;
     Entry* e = new Entry;
-    e->groups = groups;
+    e->groups = job.groups;
     e->smem = smem;
-    e->text_len = text.size();
+    job.e = e;
     c.map.emplace(h, e);
     c.device = device;
     const int want = std::max(1, std::min(12, (int)std::thread::hardware_concurrency() - 2));
-    c.queue.emplace_back(e, std::move(text));
+    c.queue.push_back(std::move(job));
     c.pending++;
     if (c.workers < want && c.workers < (int)c.queue.size()) {
         c.workers++;

@@ -38,6 +38,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -1866,12 +1867,21 @@ struct TileJit {
     jit::Entry* e = nullptr;
     std::vector<double> coef;
     double fp64 = 0.0;           // FP64 instructions per thread and tile (weighted by control regions)
+    int ctas = 4, groups = 1, prefetch = 0, stage = 0;
+    bool ready = false;          // the module was assembled when this execution collected its coefficients: launch it
 };
+// upper bound of the coefficients a launch's module reads (4 per pair op, 4 per phase op, 2 + 32 per table)
+static size_t tile_coef_bound(const TileLaunch& tl) {
+    size_t n = 0;
+    for (const DOp& d : tl.dops) n += d.kind == WK_TABLE ? 34 : 4;
+    return n;
+}
 static bool jit_wanted(const qi_state* s) {
     const Context& c = ctx();
     return c.opt_jit >= 2 || (c.opt_jit == 1 && (int)s->n_local >= c.opt_jit_min_qubits);
 }
-static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const amp_t* arena, TileJit* out) {
+// `arena_copy`: filled (once per circuit execution) the first time a new structure needs the tables on a worker thread
+static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const std::vector<amp_t>& arena, std::shared_ptr<const std::vector<amp_t>>* arena_copy, TileJit* out) {
     Context& c = ctx();
     if (!jit_wanted(s) || !jit::driver().ok) return QI_OK;
     int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
@@ -1882,22 +1892,33 @@ static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const amp_t
     const int pf = c.opt_jit_prefetch;
     const int stage = c.opt_jit_stage ? 1 : 0;
     if (stage) { groups = 1; ctas = 3; }
-    const uint64_t key = jit::structure_key(tl, arena, ctas, groups, pf, stage);
+    const uint64_t key = jit::structure_key(tl, arena.data(), ctas, groups, pf, stage) ^ (0x9e3779b97f4a7c15ull * (uint64_t)std::max(0, c.opt_jit_smem_kb));
     jit::Entry* e = jit::find(key);
-    if (e) QI_TRY(jit::generate(tl, arena, ctas, groups, pf, stage, nullptr, &out->coef, &out->fp64));          // known structure: this execution's coefficients only
-    else {
-        std::string text;
-        QI_TRY(jit::generate(tl, arena, ctas, groups, pf, stage, &text, &out->coef, &out->fp64));
-        e = jit::enqueue(key, std::move(text), c.device, groups, jit::smem_bytes(groups, (int)tl.rounds.size(), stage));
+    if (!e) {
+        if (tile_coef_bound(tl) * 8 + 64 > 32000) return QI_OK;      // parameter space: leave this launch to k_tile
+        if (!*arena_copy) *arena_copy = std::make_shared<const std::vector<amp_t>>(arena);
+        jit::Job job;
+        job.tl = std::make_shared<const TileLaunch>(tl);
+        job.arena = *arena_copy;
+        job.ctas = ctas; job.groups = groups; job.prefetch = pf; job.stage = stage;
+        const unsigned smem = std::max<unsigned>(jit::smem_bytes(groups, (int)tl.rounds.size(), stage), (unsigned)std::max(0, c.opt_jit_smem_kb) * 1024u);
+        e = jit::enqueue(key, std::move(job), c.device, smem);
     }
-    if (out->coef.size() * 8 + 64 > 32000) return QI_OK;          // parameter space: leave this launch to k_tile
     out->e = e;
+    out->ctas = ctas; out->groups = groups; out->prefetch = pf; out->stage = stage;
+    return QI_OK;
+}
+// this execution's coefficient block, in the order the module's text reads it (dry run of the generator)
+static int collect_tile_coef(const TileLaunch& tl, const amp_t* arena, TileJit* tj) {
+    if (!tj->e || tj->ready || tj->e->state.load(std::memory_order_acquire) != 1) return QI_OK;
+    QI_TRY(jit::generate(tl, arena, tj->ctas, tj->groups, tj->prefetch, tj->stage, nullptr, &tj->coef, &tj->fp64));
+    tj->ready = true;
     return QI_OK;
 }
 // launches the pass's module when it is ready; *launched = false leaves the pass to k_tile
 static int launch_tile_jit(qi_state* s, const TileJit& tj, const amp_t* d_tables, bool* launched) {
     *launched = false;
-    if (!tj.e || tj.e->state.load(std::memory_order_acquire) != 1) return QI_OK;
+    if (!tj.e || !tj.ready) return QI_OK;       // (a module that finished assembling after the coefficients were collected waits for the next execution)
     Context& c = ctx();
     uint64_t ntiles = s->len >> kTileBits;
     const uint64_t G = (uint64_t)tj.e->groups;
@@ -2379,9 +2400,12 @@ static void rewrite_cx_next_to_h(std::vector<PhysGate>& gates) {
 }
 
 // passes run on the CTA-tile kernel (k_tile) when the state has enough local qubits; option "tile" = 0 keeps the warp-tile kernel
-static bool tile_mode(const qi_state* s) {
+// Runs of one or two gates stay on the warp-tile kernel: a lone gate is a pure HBM pass, and k_window streams it at 0.97-0.99 of
+// the measured copy bandwidth at every target qubit, the tile kernels at 0.77-1.0 depending on how many CTAs fit an SM
+// (profiles/r02_single_gate_executors.txt).
+static bool tile_mode(const qi_state* s, size_t ngates) {
     const Context& c = ctx();
-    return c.opt_tile && !c.opt_tma && (int)s->n_local >= std::max(kTileBits, c.opt_tile_min_qubits);
+    return c.opt_tile && !c.opt_tma && (int)s->n_local >= std::max(kTileBits, c.opt_tile_min_qubits) && ngates >= (size_t)std::max(1, c.opt_tile_min_gates);
 }
 
 // `allow_relabel`: tile passes may leave the qubits of the state at other physical positions (folded into s->phys, like a
@@ -2391,7 +2415,7 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
     std::vector<PhysGate> rewritten;
     if (c.opt_cz_rewrite && c.opt_fuse) { rewritten = gates_in; rewrite_cx_next_to_h(rewritten); }
     const std::vector<PhysGate>& gates = (c.opt_cz_rewrite && c.opt_fuse) ? rewritten : gates_in;
-    const bool tile = tile_mode(s);
+    const bool tile = tile_mode(s, gates.size());
     const int R = tile ? kTileWindow : window_regs(s);
     std::vector<Step> steps;
     std::vector<int> final_pos;
@@ -2419,12 +2443,15 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
         QI_CUDA(cudaEventRecord(c.ops_event, c.stream));
     }
     std::vector<std::vector<TileJit>> jits(steps.size());
+    std::shared_ptr<const std::vector<amp_t>> arena_copy;
     if (tile && jit_wanted(s)) {
         for (size_t i = 0; i < steps.size(); i++) {
             jits[i].resize(tiles[i].size());
-            for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(prepare_tile_jit(s, tiles[i][k], arena.data(), &jits[i][k]));
+            for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(prepare_tile_jit(s, tiles[i][k], arena, &arena_copy, &jits[i][k]));
         }
         if (c.opt_jit >= 2) jit::drain();            // every module of this circuit is assembled (in parallel) before the first launch
+        for (size_t i = 0; i < steps.size(); i++)
+            for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(collect_tile_coef(tiles[i][k], arena.data(), &jits[i][k]));
     }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, steps[i].sgate));
@@ -2475,7 +2502,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
     std::vector<PhysGate> gates(gates_in);
     if (ctx().opt_cz_rewrite && ctx().opt_fuse) rewrite_cx_next_to_h(gates);
     std::vector<Step> steps;
-    const bool tile = tile_mode(s);
+    const bool tile = tile_mode(s, gates.size());
     std::vector<int> final_pos;
     const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide && !jit_wanted(s);
     if (tile) QI_TRY(schedule_tile_passes(s, gates, ctx().opt_fuse != 0, relabel, steps, &final_pos));

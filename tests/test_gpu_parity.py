@@ -23,8 +23,10 @@ def _tile_threshold(request):
     cases exercise the kernel the benchmark sizes run on."""
     import quant_iron_b200
     quant_iron_b200.engine.set_option("tile_min_qubits", request.param)
+    quant_iron_b200.engine.set_option("tile_min_gates", 1 if request.param == 11 else 3)      # 11: lone gates take the tile kernel too
     yield
     quant_iron_b200.engine.set_option("tile_min_qubits", 18)
+    quant_iron_b200.engine.set_option("tile_min_gates", 3)
 
 
 def _pair(gpu, ref, n, seed=20260002):
