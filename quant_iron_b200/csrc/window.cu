@@ -2410,12 +2410,16 @@ static bool tile_mode(const qi_state* s, size_t ngates) {
 
 // `allow_relabel`: tile passes may leave the qubits of the state at other physical positions (folded into s->phys, like a
 // lazy SWAP).  Callers that need the layout they came with (chunk views, shards, canonicalise) pass false.
+static int run_circuit_windowed_impl(qi_state* s, const std::vector<PhysGate>& gates_in, bool allow_relabel, bool force_window);
 int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, bool allow_relabel) {
+    return run_circuit_windowed_impl(s, gates_in, allow_relabel, false);
+}
+static int run_circuit_windowed_impl(qi_state* s, const std::vector<PhysGate>& gates_in, bool allow_relabel, bool force_window) {
     Context& c = ctx();
     std::vector<PhysGate> rewritten;
     if (c.opt_cz_rewrite && c.opt_fuse) { rewritten = gates_in; rewrite_cx_next_to_h(rewritten); }
     const std::vector<PhysGate>& gates = (c.opt_cz_rewrite && c.opt_fuse) ? rewritten : gates_in;
-    const bool tile = tile_mode(s, gates.size());
+    const bool tile = !force_window && tile_mode(s, gates.size());
     const int R = tile ? kTileWindow : window_regs(s);
     std::vector<Step> steps;
     std::vector<int> final_pos;
@@ -2450,8 +2454,20 @@ int run_circuit_windowed(qi_state* s, const std::vector<PhysGate>& gates_in, boo
             for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(prepare_tile_jit(s, tiles[i][k], arena, &arena_copy, &jits[i][k]));
         }
         if (c.opt_jit >= 2) jit::drain();            // every module of this circuit is assembled (in parallel) before the first launch
+        bool any_ready = false;
         for (size_t i = 0; i < steps.size(); i++)
-            for (size_t k = 0; k < tiles[i].size(); k++) QI_TRY(collect_tile_coef(tiles[i][k], arena.data(), &jits[i][k]));
+            for (size_t k = 0; k < tiles[i].size(); k++) {
+                QI_TRY(collect_tile_coef(tiles[i][k], arena.data(), &jits[i][k]));
+                any_ready |= jits[i][k].ready;
+            }
+        // First sight of a circuit made mostly of diagonal gates (QFT: 92 % controlled phases): none of its modules exists yet
+        // (they are being assembled now), and for such circuits the warp-tile kernel with its merged phase tables beats the
+        // INTERPRETING tile kernel (33-qubit QFT: 450-517 ms vs 565-680 ms; the modules take 288 ms) -- this execution runs on it.
+        if (!any_ready && c.opt_jit == 1 && !gates.empty()) {
+            size_t diag = 0;
+            for (const PhysGate& g : gates) diag += (g.kind == IK_DIAG || g.kind == IK_RZ) ? 1 : 0;
+            if (10 * diag > 6 * gates.size()) return run_circuit_windowed_impl(s, gates_in, allow_relabel, true);
+        }
     }
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) QI_TRY(launch_simple_gate(s, steps[i].sgate));
