@@ -646,6 +646,7 @@ struct Cache {
     std::unordered_map<uint64_t, Entry*> map;
     std::deque<Job> queue;
     int workers = 0, pending = 0, device = 0;
+    bool stopping = false;             // process exit: queued jobs are dropped, running ones are waited for (shutdown())
     uint64_t assembled = 0, failed = 0;
     double assemble_ms = 0.0;
     double fp64_warp_instr = 0.0;      // launched on modules since the last stats reset (weighted static count x warps x tiles)
@@ -717,7 +718,7 @@ static void worker_main(int device) {
         Job job;
         {
             std::unique_lock<std::mutex> lk(c.mu);
-            c.cv_work.wait(lk, [&] { return !c.queue.empty(); });
+            c.cv_work.wait(lk, [&] { return !c.queue.empty() && !c.stopping; });
             job = std::move(c.queue.front());
             c.queue.pop_front();
         }
@@ -740,6 +741,7 @@ static void worker_main(int device) {
     }
 }
 
+static void shutdown();
 static Entry* find(uint64_t key) {
     Cache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
@@ -757,17 +759,30 @@ static Entry* enqueue(uint64_t h, Job&& job, int device, unsigned smem) {
     e->smem = smem;
     job.e = e;
     c.map.emplace(h, e);
+    if (c.stopping) { e->state.store(-1, std::memory_order_release); return e; }
     c.device = device;
     const int want = std::max(1, std::min(12, (int)std::thread::hardware_concurrency() - 2));
     c.queue.push_back(std::move(job));
     c.pending++;
     if (c.workers < want && c.workers < (int)c.queue.size()) {
+        if (c.workers == 0) std::atexit(shutdown);
         c.workers++;
         std::thread(worker_main, device).detach();
     }
     lk.unlock();
     c.cv_work.notify_one();
     return e;
+}
+// atexit: the CUDA runtime tears the primary context down in its own exit handler, which runs AFTER this one (ours is registered
+// later); a worker must not be inside cuModuleLoadDataEx at that point.  Queued jobs are dropped, running ones finish.
+static void shutdown() {
+    Cache& c = cache();
+    std::unique_lock<std::mutex> lk(c.mu);
+    c.stopping = true;
+    c.pending -= (int)c.queue.size();
+    for (Job& j : c.queue) if (j.e) j.e->state.store(-1, std::memory_order_release);
+    c.queue.clear();
+    c.cv_done.wait_for(lk, std::chrono::seconds(30), [&] { return c.pending <= 0; });
 }
 static void drain() {
     Cache& c = cache();

@@ -37,6 +37,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
+#include <cstdlib>
 #include <deque>
 #include <memory>
 #include <mutex>
