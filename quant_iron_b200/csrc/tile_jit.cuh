@@ -651,6 +651,7 @@ struct Cache {
     double assemble_ms = 0.0;
     double fp64_warp_instr = 0.0;      // launched on modules since the last stats reset (weighted static count x warps x tiles)
 };
+static const size_t kMaxModules = 4096;
 static Cache& cache() { static Cache* c = new Cache; return *c; }        // leaked on purpose: worker threads may outlive exit()
 
 struct Fnv {
@@ -759,7 +760,9 @@ static Entry* enqueue(uint64_t h, Job&& job, int device, unsigned smem) {
     e->smem = smem;
     job.e = e;
     c.map.emplace(h, e);
-    if (c.stopping) { e->state.store(-1, std::memory_order_release); return e; }
+    // modules are never unloaded: a process that keeps producing new pass structures stops assembling at kMaxModules
+    // (the interpreting kernel runs what has no module)
+    if (c.stopping || c.map.size() > kMaxModules) { e->state.store(-1, std::memory_order_release); return e; }
     c.device = device;
     const int want = std::max(1, std::min(12, (int)std::thread::hardware_concurrency() - 2));
     c.queue.push_back(std::move(job));

@@ -1809,7 +1809,17 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
                 tl.rounds.push_back(io);
             }
         }
-        if (scale != 1.0) {                 // the factors the unit-form gates of this launch left out, on every amplitude, in the last round
+        if (scale != 1.0) {                 // an unconditional phase table of the launch (it multiplies EVERY amplitude) carries the factor for free
+            for (DOp& t : tl.dops)
+                if (t.kind == WK_TABLE && t.hub_cls == CLS_NONE && !t.c_tile && !t.c_lane) {
+                    long long off;
+                    memcpy(&off, &t.m[0], 8);
+                    for (int i = 0; i < kTileThreads; i++) { arena[(size_t)off + i].x *= scale; arena[(size_t)off + i].y *= scale; }
+                    scale = 1.0;
+                    break;
+                }
+        }
+        if (scale != 1.0) {                 // else: the factors the unit-form gates of this launch left out, on every amplitude, in the last round
             DOp d;
             memset(&d, 0, sizeof(d));
             d.kind = WK_SCALE;
@@ -1885,11 +1895,11 @@ static bool jit_wanted(const qi_state* s) {
 static int prepare_tile_jit(const qi_state* s, const TileLaunch& tl, const std::vector<amp_t>& arena, std::shared_ptr<const std::vector<amp_t>>* arena_copy, TileJit* out) {
     Context& c = ctx();
     if (!jit_wanted(s) || !jit::driver().ok) return QI_OK;
-    int ctas = c.opt_jit_ctas == 3 ? 3 : 4;
+    int ctas = (c.opt_jit_ctas >= 3 && c.opt_jit_ctas <= 6) ? c.opt_jit_ctas : 4;
     const uint64_t ntiles = s->len >> kTileBits;
     int groups = c.opt_jit_groups == 4 ? 4 : (c.opt_jit_groups == 2 ? 2 : 1);
     while ((uint64_t)groups > ntiles) groups >>= 1;
-    if (ctas == 3) groups = 1;
+    if (ctas != 4) groups = 1;
     const int pf = c.opt_jit_prefetch;
     const int stage = c.opt_jit_stage ? 1 : 0;
     if (stage) { groups = 1; ctas = 3; }
@@ -2543,7 +2553,7 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
                     std::string text;
                     std::vector<double> coef;
                     double fp64 = 0.0;
-                    QI_TRY(jit::generate(tl, arena.data(), (ctx().opt_jit_ctas == 3 || ctx().opt_jit_stage) ? 3 : 4, (ctx().opt_jit_ctas == 3 || ctx().opt_jit_stage) ? 1 : std::max(1, ctx().opt_jit_groups), ctx().opt_jit_prefetch, ctx().opt_jit_stage ? 1 : 0, &text, &coef, &fp64));
+                    QI_TRY(jit::generate(tl, arena.data(), ctx().opt_jit_stage ? 3 : ((ctx().opt_jit_ctas >= 3 && ctx().opt_jit_ctas <= 6) ? ctx().opt_jit_ctas : 4), (ctx().opt_jit_ctas != 4 || ctx().opt_jit_stage) ? 1 : std::max(1, ctx().opt_jit_groups), ctx().opt_jit_prefetch, ctx().opt_jit_stage ? 1 : 0, &text, &coef, &fp64));
                     char mark[64];
                     snprintf(mark, sizeof(mark), "//---PASS fp64=%.1f coef=%zu---\n", fp64, coef.size());
                     put(mark, strlen(mark));
