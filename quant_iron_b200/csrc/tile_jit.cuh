@@ -267,7 +267,19 @@ struct Gen {
     void op_scale(const DOp& d) {
         const int L = begin_region(d);
         const int k0 = c(d.m[0]);
-        for (int sl = 0; sl < 16; sl++) { emit("mul.f64 %%a%d, %%a%d, %%c%d;", ax[sl], ax[sl], k0); emit("mul.f64 %%a%d, %%a%d, %%c%d;", ay[sl], ay[sl], k0); }
+        if (d.m[1] == 0.0) {
+            for (int sl = 0; sl < 16; sl++) { emit("mul.f64 %%a%d, %%a%d, %%c%d;", ax[sl], ax[sl], k0); emit("mul.f64 %%a%d, %%a%d, %%c%d;", ay[sl], ay[sl], k0); }
+        } else {                   // complex scalar: the same four instructions per amplitude as run_ops_tile
+            const int k1 = c(d.m[1]);
+            for (int sl = 0; sl < 16; sl++) {
+                const int t0 = g(), t1 = g();
+                emit("mul.f64 %%g%d, %%c%d, %%a%d;", t0, k1, ay[sl]);
+                emit("mul.f64 %%g%d, %%c%d, %%a%d;", t1, k1, ax[sl]);
+                emit("neg.f64 %%g%d, %%g%d;", t0, t0);
+                emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%g%d;", ax[sl], k0, ax[sl], t0);
+                emit("fma.rn.f64 %%a%d, %%c%d, %%a%d, %%g%d;", ay[sl], k0, ay[sl], t1);
+            }
+        }
         end_region(L);
     }
     // x <- -x where the runtime mask %rm is 0x80000000 (flip_sign of run_ops_tile)
@@ -671,6 +683,7 @@ static uint64_t structure_key(const TileLaunch& tl, const amp_t* arena, int ctas
     for (const DOp& d : tl.dops) {
         f.bytes(&d, offsetof(DOp, m));
         if (d.kind == WK_DIAG) f.u64(Gen::rot_neg(d.m[2]));
+        else if (d.kind == WK_SCALE) f.u64(d.m[1] != 0.0);
         else if (d.kind == WK_RZ) f.u64((uint64_t)Gen::rot_neg(d.m[4]) | ((uint64_t)Gen::rot_neg(d.m[6]) << 1));
         else if (d.kind == WK_TABLE) {
             long long off;

@@ -719,8 +719,17 @@ __device__ __forceinline__ void run_ops_tile(amp_t (&v)[16], const uint64_t tile
                 break;
             }
             case FC_SCALE:
+                if (k1 == 0.0) {
 #pragma unroll
-                for (int s = 0; s < S; s++) { v[s].x *= k0; v[s].y *= k0; }
+                    for (int s = 0; s < S; s++) { v[s].x *= k0; v[s].y *= k0; }
+                } else {               // complex scalar (k0, k1): the global phases the P-form diagonal ops left out
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        const double t0 = __dmul_rn(k1, v[s].y), t1 = __dmul_rn(k1, v[s].x);
+                        v[s].x = __fma_rn(k0, v[s].x, -t0);
+                        v[s].y = __fma_rn(k0, v[s].y, t1);
+                    }
+                }
                 break;
             default: break;
         }
@@ -1439,7 +1448,7 @@ static void push_scale_op(const Layout& L, double scale, std::vector<DOp>& dops)
 // ---- k_tile lowering: one host op -> one or more in-place device ops under the layout of its round ------------------
 // (the op set and why every op is in place: "k_tile: the op set" above)
 // `scale`: product of the factors the launch's unit-form gates leave out (applied by one WK_SCALE op at the end of the launch)
-static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vector<DOp>& dops, std::vector<amp_t>& arena, double* scale) {
+static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vector<DOp>& dops, std::vector<amp_t>& arena, amp_t* scale) {
     DOp base;
     memset(&base, 0, sizeof(base));
     uint32_t pos_lane = 0, pos_reg = 0, neg_lane = 0, neg_reg = 0;
@@ -1506,7 +1515,7 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
         if (uncontrolled && ctx().opt_tile_lean && (k3 == k0 || k3 == -k0)) {       // unit form: k0 . [[1, k1 / k0], [k2 / k0, +-1]]
             d.kind = k3 == k0 ? WK_REALUP : WK_REALUM;
             d.m[0] = k1 / k0; d.m[1] = k2 / k0;
-            *scale *= k0;
+            scale->x *= k0; scale->y *= k0;
             return emit(d, 0, 0, L.idx[target]);
         }
         d.kind = WK_REALL;
@@ -1525,7 +1534,7 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
         if (uncontrolled && ctx().opt_tile_lean) {                                  // unit form: c . [[1, -i t], [-i t, 1]]
             d.kind = WK_RXU;
             d.m[0] = sn / c;
-            *scale *= c;
+            scale->x *= c; scale->y *= c;
         } else {
             d.kind = WK_RXL;
             d.m[0] = c; d.m[1] = sn; d.m[2] = 1.0 / c; d.m[3] = sn / c;
@@ -1540,6 +1549,49 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
 
     if (h.kind == WK_TABLE) {
         const DiagGroup& g = ps.groups[h.group];
+        // A small UNCONDITIONAL group is a product of single-qubit diagonals diag(f0, f1) (the RZ gates of a layer that met in one
+        // table).  Each is applied in P FORM: f0 goes into the launch's scalar, diag(1, f1 / f0) is a phase on the HALF of the
+        // amplitudes whose bit is set -- 8 of a thread's 16 slots when the qubit is a register qubit (24 FMA), a predicate that
+        // skips whole threads / tiles otherwise -- instead of a table op (thread-table and chunk-table loads, 64 FP64
+        // instructions on all 16 slots, 48 more when register qubits take part).  Large groups (QFT ladders) stay tables.
+        if (ctx().opt_tile_pform && g.members >= 2 && g.hub < 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)ctx().opt_tile_pform) {
+            for (size_t k = 0; k < g.bits.size(); k++) {
+                const amp_t f0 = g.f0[k], f1 = g.f1[k];
+                const double n0 = f0.x * f0.x + f0.y * f0.y;
+                if (n0 == 0.0) return fail(QI_ERR_UNKNOWN, 0, 0, "internal: zero diagonal factor");
+                const amp_t ratio = make_double2((f1.x * f0.x + f1.y * f0.y) / n0, (f1.y * f0.x - f1.x * f0.y) / n0);      // f1 / f0
+                *scale = cmul(*scale, f0);
+                pos_lane = pos_reg = neg_lane = neg_reg = 0; pos_tile = neg_tile = 0;
+                split_mask(L, 1ull << g.bits[k], &pos_lane, &pos_reg, &pos_tile);
+                if (!(ratio.x == 1.0 && ratio.y == 0.0)) QI_TRY(emit_phase(make_double2(1.0, 0.0), ratio, 0));
+            }
+            return QI_OK;
+        }
+        // The same for a small group UNDER A HUB (controlled phases that share a qubit, e.g. the CZs a brick-work layer leaves
+        // on one qubit): with the hub set, member k multiplies by diag(f0, f1).  prod f0 is ONE phase on the hub half; each
+        // f1 / f0 is a phase on the quarter (hub, bit k) -- and a plain sign flip (free in the modules) when the member is a CZ.
+        if (ctx().opt_tile_pform && g.members >= 2 && g.hub >= 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)ctx().opt_tile_pform) {
+            amp_t F0 = make_double2(1.0, 0.0);
+            std::vector<amp_t> ratio(g.bits.size());
+            for (size_t k = 0; k < g.bits.size(); k++) {
+                const amp_t f0 = g.f0[k], f1 = g.f1[k];
+                const double n0 = f0.x * f0.x + f0.y * f0.y;
+                if (n0 == 0.0) return fail(QI_ERR_UNKNOWN, 0, 0, "internal: zero diagonal factor");
+                ratio[k] = (f0.x == 1.0 && f0.y == 0.0) ? f1 : make_double2((f1.x * f0.x + f1.y * f0.y) / n0, (f1.y * f0.x - f1.x * f0.y) / n0);
+                F0 = cmul(F0, f0);
+            }
+            auto under = [&](uint64_t mask) {
+                pos_lane = pos_reg = neg_lane = neg_reg = 0; pos_tile = neg_tile = 0;
+                split_mask(L, mask, &pos_lane, &pos_reg, &pos_tile);
+            };
+            if (!(F0.x == 1.0 && F0.y == 0.0)) { under(1ull << g.hub); QI_TRY(emit_phase(make_double2(1.0, 0.0), F0, 0)); }
+            for (size_t k = 0; k < g.bits.size(); k++) {
+                if (ratio[k].x == 1.0 && ratio[k].y == 0.0) continue;
+                under((1ull << g.hub) | (1ull << g.bits[k]));
+                QI_TRY(emit_phase(make_double2(1.0, 0.0), ratio[k], 0));
+            }
+            return QI_OK;
+        }
         if (g.members >= 2) {
             DOp d = base;
             build_tables(L, g, arena, &d, 1.0);
@@ -1722,6 +1774,7 @@ static size_t tile_op_count(const HOp& h) {
         case WK_RX: return std::fabs(h.m[0]) < kLiftMinPivot ? 3 : 1;
         case WK_RXS: return std::fabs(h.m[0]) < kLiftMinPivot ? 4 : 2;
         case WK_U2: return 4;
+        case WK_TABLE: return 9;          // a small group lowers to one P-form op per member qubit (+ one for the hub half)
         default: return 1;
     }
 }
@@ -1774,7 +1827,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
         const int* low_out = last_launch ? low_out_last : low_id;
         const bool same_io = !memcmp(low_out, low_id, sizeof(low_id));
         TileLaunch tl;
-        double scale = 1.0;
+        amp_t scale = make_double2(1.0, 0.0);
         for (int j = 0; j < kTileBits; j++) { tl.tile_qubits[j] = plan.pin[j]; tl.tile_out[j] = last_launch ? plan.pout[j] : plan.pin[j]; }
         for (size_t r = ri; r < end; r++) {
             std::vector<int> loc;
@@ -1809,23 +1862,25 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
                 tl.rounds.push_back(io);
             }
         }
-        if (scale != 1.0) {                 // an unconditional phase table of the launch (it multiplies EVERY amplitude) carries the factor for free
+        const auto unit = [](amp_t z) { return z.x == 1.0 && z.y == 0.0; };
+        if (!unit(scale)) {                 // an unconditional phase table of the launch (it multiplies EVERY amplitude) carries the factor for free
             for (DOp& t : tl.dops)
                 if (t.kind == WK_TABLE && t.hub_cls == CLS_NONE && !t.c_tile && !t.c_lane) {
                     long long off;
                     memcpy(&off, &t.m[0], 8);
-                    for (int i = 0; i < kTileThreads; i++) { arena[(size_t)off + i].x *= scale; arena[(size_t)off + i].y *= scale; }
-                    scale = 1.0;
+                    for (int i = 0; i < kTileThreads; i++) arena[(size_t)off + i] = cmul(arena[(size_t)off + i], scale);
+                    scale = make_double2(1.0, 0.0);
                     break;
                 }
         }
-        if (scale != 1.0) {                 // else: the factors the unit-form gates of this launch left out, on every amplitude, in the last round
+        if (!unit(scale)) {                 // else: one op on every amplitude in the last round (real: 2 DMUL per amplitude; complex: a product)
             DOp d;
             memset(&d, 0, sizeof(d));
             d.kind = WK_SCALE;
             d.code = (uint8_t)FC_SCALE;
             d.c_reg = 0xffffu;
-            d.m[0] = scale;
+            d.m[0] = scale.x;
+            d.m[1] = scale.y;
             tl.dops.push_back(d);
             tl.rounds.back().nops++;
         }

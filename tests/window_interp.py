@@ -155,8 +155,8 @@ def run_pass(v, nl, R, regs, ops, arena, lane_qubits=(0, 1, 2, 3, 4)):
             _pair(v, idx[sel], tb, kind, m)
             continue
         active = tile_ok & lane_ok
-        if kind == WK_SCALE:                  # product of the deferred scales of the pass's lean gates (real)
-            v[active & slot_ok] *= float(m[0])
+        if kind == WK_SCALE:                  # product of the deferred scalars of the launch: unit-form gates (real) and P-form diagonals (complex)
+            v[active & slot_ok] *= complex(m[0], m[1])
         elif kind == WK_DIAG:
             v[active & slot_ok] *= complex(m[0], m[1])
         elif kind == WK_NEG:                    # a phase of exactly -1 (Z, CZ): sign flips
