@@ -1554,7 +1554,7 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
         // amplitudes whose bit is set -- 8 of a thread's 16 slots when the qubit is a register qubit (24 FMA), a predicate that
         // skips whole threads / tiles otherwise -- instead of a table op (thread-table and chunk-table loads, 64 FP64
         // instructions on all 16 slots, 48 more when register qubits take part).  Large groups (QFT ladders) stay tables.
-        if (ctx().opt_tile_pform && g.members >= 2 && g.hub < 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)ctx().opt_tile_pform) {
+        if (ctx().opt_tile_pform && g.members >= 2 && g.hub < 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)std::min(4, ctx().opt_tile_pform)) {
             for (size_t k = 0; k < g.bits.size(); k++) {
                 const amp_t f0 = g.f0[k], f1 = g.f1[k];
                 const double n0 = f0.x * f0.x + f0.y * f0.y;
@@ -1570,7 +1570,7 @@ static int lower_op_tile(const Layout& L, const Pass& ps, const HOp& h, std::vec
         // The same for a small group UNDER A HUB (controlled phases that share a qubit, e.g. the CZs a brick-work layer leaves
         // on one qubit): with the hub set, member k multiplies by diag(f0, f1).  prod f0 is ONE phase on the hub half; each
         // f1 / f0 is a phase on the quarter (hub, bit k) -- and a plain sign flip (free in the modules) when the member is a CZ.
-        if (ctx().opt_tile_pform && g.members >= 2 && g.hub >= 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)ctx().opt_tile_pform) {
+        if (ctx().opt_tile_pform && g.members >= 2 && g.hub >= 0 && g.hub_alt < 0 && g.bits.size() <= (size_t)std::min(4, ctx().opt_tile_pform)) {
             amp_t F0 = make_double2(1.0, 0.0);
             std::vector<amp_t> ratio(g.bits.size());
             for (size_t k = 0; k < g.bits.size(); k++) {
@@ -1768,13 +1768,18 @@ static Layout round_layout(const qi_state* s, const int tile_qubits[kTileBits], 
 }
 
 // device ops lower_op_tile emits for a host op (launch packing)
-static size_t tile_op_count(const HOp& h) {
+static size_t tile_op_count(const Pass& ps, const HOp& h) {
     switch (h.kind) {
         case WK_REAL: return std::fabs(h.m[0]) < kLiftMinPivot ? 2 : 1;
         case WK_RX: return std::fabs(h.m[0]) < kLiftMinPivot ? 3 : 1;
         case WK_RXS: return std::fabs(h.m[0]) < kLiftMinPivot ? 4 : 2;
         case WK_U2: return 4;
-        case WK_TABLE: return 9;          // a small group lowers to one P-form op per member qubit (+ one for the hub half)
+        case WK_TABLE: {                  // a small group lowers to one P-form op per member qubit (+ one for the hub half)
+            const DiagGroup& g = ps.groups[h.group];
+            const size_t pf = (size_t)std::min(4, std::max(0, ctx().opt_tile_pform));
+            if (g.members >= 2 && g.hub_alt < 0 && g.bits.size() <= pf) return g.bits.size() + (g.hub >= 0 ? 1 : 0);
+            return 1;
+        }
         default: return 1;
     }
 }
@@ -1797,7 +1802,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
         std::vector<std::vector<size_t>> ro;
         std::vector<std::vector<int>> rq;
         std::vector<uint64_t> rk;
-        const size_t kChunk = 48;                 // host ops per round chunk (an op lowers to at most 4 device ops)
+        const size_t kChunk = 40;                 // host ops per round chunk (an op lowers to at most 5 device ops)
         for (size_t r = 0; r < round_ops.size(); r++)
             for (size_t first = 0; first < std::max<size_t>(1, round_ops[r].size()); first += kChunk) {
                 ro.emplace_back(round_ops[r].begin() + first, round_ops[r].begin() + std::min(round_ops[r].size(), first + kChunk));
@@ -1818,7 +1823,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
     while (ri < nrounds) {
         // rounds of this launch
         size_t end = ri, nops = 0;
-        auto cost = [&](size_t r) { size_t c = 0; for (size_t i : round_ops[r]) c += tile_op_count(ops[i]); return c; };
+        auto cost = [&](size_t r) { size_t c = 0; for (size_t i : round_ops[r]) c += tile_op_count(ps, ops[i]); return c; };
         while (end < nrounds && (end == ri || (nops + cost(end) <= (size_t)kMaxTileOps - 1 && (end - ri) + 3 <= (size_t)kMaxRounds))) {
             nops += cost(end);
             end++;
