@@ -485,16 +485,6 @@ static int generate(const TileLaunch& tl, const amp_t* arena, int ctas_per_sm, i
     gn.emit("cvt.u64.u32 %%tstep, %%rx;");
     gn.emit("setp.ge.u64 %%pq, %%tile, %%ntiles;");
     gn.emit("@%%pq bra.uni LEND;");
-    if (prefetch >= 1000) {
-        // experiment (option jit_prefetch >= 1000 = stagger in ns): the CTAs of one SM start together and stay in phase (all load,
-        // all compute, all store); CTA slot k of an SM starts k * ns late so that memory phases meet compute phases
-        gn.emit("mov.u32 %%rx, %%ctaid.x;");
-        gn.emit("div.u32 %%rx, %%rx, 148;");
-        gn.emit("and.b32 %%rx, %%rx, 3;");
-        gn.emit("mul.lo.u32 %%rx, %%rx, %d;", prefetch);
-        gn.emit("nanosleep.u32 %%rx;");
-        prefetch = 0;
-    }
     if (stage) {
         gn.emit("mov.u64 %%rdx, %%tile;");
         issue_stage();

@@ -1785,7 +1785,11 @@ static size_t tile_op_count(const Pass& ps, const HOp& h) {
 }
 
 // lower one pass to one or more k_tile launches; `plan` = the tile's positions and where its content is stored to
-static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& plan, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena) {
+// `carry`: the scalar earlier launches of this run left out (unit-form gates, P-form diagonals); a scalar commutes with everything,
+// so it travels from launch to launch and is applied once, by the LAST launch of the run (`last_of_run`) -- or earlier when its
+// magnitude leaves [2^-200, 2^200] (the stored amplitudes grow by its inverse)
+static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& plan, std::vector<TileLaunch>& launches, std::vector<amp_t>& arena,
+                           amp_t* carry, bool last_of_run) {
     int local_of[64];
     for (int q = 0; q < 64; q++) local_of[q] = -1;
     for (int j = 0; j < kTileBits; j++) local_of[plan.pin[j]] = j;
@@ -1832,7 +1836,7 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
         const int* low_out = last_launch ? low_out_last : low_id;
         const bool same_io = !memcmp(low_out, low_id, sizeof(low_id));
         TileLaunch tl;
-        amp_t scale = make_double2(1.0, 0.0);
+        amp_t scale = *carry;
         for (int j = 0; j < kTileBits; j++) { tl.tile_qubits[j] = plan.pin[j]; tl.tile_out[j] = last_launch ? plan.pout[j] : plan.pin[j]; }
         for (size_t r = ri; r < end; r++) {
             std::vector<int> loc;
@@ -1868,6 +1872,12 @@ static int lower_tile_pass(const qi_state* s, const Pass& ps, const TilePlan& pl
             }
         }
         const auto unit = [](amp_t z) { return z.x == 1.0 && z.y == 0.0; };
+        {
+            const double mag2 = scale.x * scale.x + scale.y * scale.y;
+            const bool in_range = mag2 > 3.0e-121 && mag2 < 3.0e120;          // |scale| within [2^-200, 2^200]
+            if (!(last_launch && last_of_run) && in_range) { *carry = scale; scale = make_double2(1.0, 0.0); }
+            else *carry = make_double2(1.0, 0.0);
+        }
         if (!unit(scale)) {                 // an unconditional phase table of the launch (it multiplies EVERY amplitude) carries the factor for free
             for (DOp& t : tl.dops)
                 if (t.kind == WK_TABLE && t.hub_cls == CLS_NONE && !t.c_tile && !t.c_lane) {
@@ -2505,9 +2515,14 @@ static int run_circuit_windowed_impl(qi_state* s, const std::vector<PhysGate>& g
     std::vector<Layout> layouts(steps.size());
     std::vector<std::vector<TileLaunch>> tiles(steps.size());
     std::vector<amp_t> arena;
+    amp_t carry = make_double2(1.0, 0.0);
     for (size_t i = 0; i < steps.size(); i++) {
         if (steps[i].simple) continue;
-        if (tile) QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena));
+        if (tile) {
+            bool last = true;
+            for (size_t k = i + 1; k < steps.size(); k++) last &= steps[k].simple;
+            QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena, &carry, last || !c.opt_tile_carry));
+        }
         else lower_pass(s, steps[i].pass, steps[i].R, dops[i], arena, &layouts[i]);
     }
     if (!arena.empty()) {
@@ -2600,10 +2615,13 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
     put64(steps.size());
     if (tile) {
         uint64_t nrec = 0;
+        amp_t carry = make_double2(1.0, 0.0);
         std::vector<std::vector<TileLaunch>> tiles(steps.size());
         for (size_t i = 0; i < steps.size(); i++) {
             if (steps[i].simple) { nrec++; continue; }
-            QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena));
+            bool last = true;
+            for (size_t k = i + 1; k < steps.size(); k++) last &= steps[k].simple;
+            QI_TRY(lower_tile_pass(s, steps[i].pass, steps[i].plan, tiles[i], arena, &carry, last || !ctx().opt_tile_carry));
             nrec += tiles[i].size();
         }
         blob->clear();
