@@ -2212,7 +2212,7 @@ static void remap_pass(const std::vector<int>& pos, Pass* ps) {
 }
 
 static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& gates, bool fuse, bool permute, std::vector<Step>& steps,
-                                std::vector<int>* final_pos) {
+                                std::vector<int>* final_pos, bool restore = false) {
     const size_t G = gates.size();
     const int n = (int)s->n_local;
     TileSched ts;
@@ -2383,6 +2383,66 @@ static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& 
         steps.push_back(std::move(st));
         prev_step = (int)steps.size() - 1;
     }
+    // ---- restore the layout the run started with (option tile_restore; states that run on modules) -------------------------
+    // Sliding tiles leave the qubits permuted.  A later execution of the same circuit would then be scheduled from another
+    // layout and share no pass structure -- no module -- with this one.  The permutation is undone here: first inside the
+    // last tile, whose output order is still open, then by relabel-only passes (no ops: one HBM pass each) over positions
+    // 0..4 plus six chosen positions; every such pass sends home each qubit whose home position is in its tile.
+    if (permute && restore) {
+        auto displaced = [&]() { int d = 0; for (int q = 0; q < n; q++) d += ts.pos[q] != q; return d; };
+        // place the qubits of a tile (given by its 11 positions): home if the home is in the tile, the free positions otherwise
+        auto settle = [&](TilePlan& pl) {
+            // pl.pin = positions of the tile before the pass; the pass may send the content of pin[j] to any pout[j] (a permutation of pin).
+            // Work on the CURRENT placement: position -> qubit (ts.at), restricted to the tile's positions.
+            std::vector<int> tile_pos(pl.pout, pl.pout + kTileBits);          // current positions of the tile's content (after earlier swaps)
+            uint64_t tmask = 0;
+            for (int p : tile_pos) tmask |= 1ull << p;
+            std::vector<int> qubits;
+            for (int p : tile_pos) qubits.push_back(ts.at[p]);
+            std::vector<int> new_pos(qubits.size(), -1);
+            uint64_t used = 0;
+            for (size_t k = 0; k < qubits.size(); k++)
+                if ((tmask >> qubits[k]) & 1) { new_pos[k] = qubits[k]; used |= 1ull << qubits[k]; }      // home is in the tile
+            for (size_t k = 0; k < qubits.size(); k++) {
+                if (new_pos[k] >= 0) continue;
+                if (!((used >> tile_pos[k]) & 1)) { new_pos[k] = tile_pos[k]; used |= 1ull << tile_pos[k]; }   // stay if the place is free
+            }
+            for (size_t k = 0; k < qubits.size(); k++) {
+                if (new_pos[k] >= 0) continue;
+                for (int p : tile_pos) if (!((used >> p) & 1)) { new_pos[k] = p; used |= 1ull << p; break; }
+            }
+            for (int j = 0; j < kTileBits; j++)
+                for (size_t k = 0; k < tile_pos.size(); k++)
+                    if (pl.pout[j] == tile_pos[k]) { pl.pout[j] = new_pos[k]; break; }
+            for (size_t k = 0; k < qubits.size(); k++) { ts.pos[qubits[k]] = new_pos[k]; ts.at[new_pos[k]] = qubits[k]; }
+        };
+        if (prev_step >= 0 && displaced()) settle(steps[prev_step].plan);
+        int guard = 0;
+        while (displaced() && guard++ < 64) {
+            // six high positions: follow the homes of displaced qubits, starting with those that sit at positions 0..4
+            std::vector<int> chosen;
+            uint64_t cm = 0;
+            auto add = [&](int p) { if (p >= kLaneQubits && p < n && !((cm >> p) & 1) && (int)chosen.size() < kTileBits - kLaneQubits) { chosen.push_back(p); cm |= 1ull << p; return true; } return false; };
+            for (int p = 0; p < kLaneQubits; p++) if (ts.at[p] != p) add(ts.at[p]);                  // homes of the low sitters
+            for (size_t k = 0; k < chosen.size(); k++) { const int q = ts.at[chosen[k]]; if (q != chosen[k]) add(q); }   // ... and of whoever sits there
+            for (int p = kLaneQubits; p < n && (int)chosen.size() < kTileBits - kLaneQubits; p++)
+                if (ts.at[p] != p && add(p))
+                    for (size_t k = chosen.size() - 1; k < chosen.size(); k++) { const int q = ts.at[chosen[k]]; if (q != chosen[k]) add(q); }
+            for (int p = kLaneQubits; p < n && (int)chosen.size() < kTileBits - kLaneQubits; p++) add(p);     // fill up
+            if ((int)chosen.size() < kTileBits - kLaneQubits) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler: cannot form a relabel pass");
+            Step st{false, PhysGate(), Pass(), kTileWindow, TilePlan()};
+            std::vector<int> ppos;
+            for (int p = 0; p < kLaneQubits; p++) ppos.push_back(p);
+            for (int p : chosen) ppos.push_back(p);
+            std::sort(ppos.begin(), ppos.end());
+            for (int j = 0; j < kTileBits; j++) st.plan.pin[j] = st.plan.pout[j] = ppos[j];
+            const int before = displaced();
+            settle(st.plan);
+            if (displaced() >= before) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler: relabel pass made no progress");
+            steps.push_back(std::move(st));
+        }
+        if (displaced()) return fail(QI_ERR_UNKNOWN, 0, 0, "tile scheduler: layout not restored");
+    }
     if (final_pos) { final_pos->assign(ts.pos.begin(), ts.pos.end()); }
     return QI_OK;
 }
@@ -2507,8 +2567,9 @@ static int run_circuit_windowed_impl(qi_state* s, const std::vector<PhysGate>& g
     // Sliding tiles leave the state in another qubit order after every execution, so the next execution of the same circuit is
     // scheduled from another layout and shares no pass structure with this one: modules would never be reused.  States
     // that run on JIT modules therefore keep their layout (more, cheaper passes: the modules are FP64-bound, not HBM-bound).
-    const bool relabel = tile && allow_relabel && s->world == 1 && c.opt_tile_slide && !jit_wanted(s);
-    if (tile) QI_TRY(schedule_tile_passes(s, gates, c.opt_fuse != 0, relabel, steps, &final_pos));
+    const bool restore = jit_wanted(s) && c.opt_tile_restore;       // sliding tiles whose permutation is undone at the end of the run
+    const bool relabel = tile && allow_relabel && s->world == 1 && c.opt_tile_slide && (!jit_wanted(s) || restore);
+    if (tile) QI_TRY(schedule_tile_passes(s, gates, c.opt_fuse != 0, relabel, steps, &final_pos, restore));
     else QI_TRY(schedule_passes(s, gates, c.opt_fuse != 0, R, steps));
     // lower every pass, upload all phase tables in one copy, then launch back to back
     std::vector<std::vector<DOp>> dops(steps.size());
@@ -2606,8 +2667,9 @@ int debug_lower(const qi_state* s, const std::vector<PhysGate>& gates_in, int R,
     std::vector<Step> steps;
     const bool tile = tile_mode(s, gates.size());
     std::vector<int> final_pos;
-    const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide && !jit_wanted(s);
-    if (tile) QI_TRY(schedule_tile_passes(s, gates, ctx().opt_fuse != 0, relabel, steps, &final_pos));
+    const bool restore = jit_wanted(s) && ctx().opt_tile_restore;
+    const bool relabel = tile && s->world == 1 && ctx().opt_tile_slide && (!jit_wanted(s) || restore);
+    if (tile) QI_TRY(schedule_tile_passes(s, gates, ctx().opt_fuse != 0, relabel, steps, &final_pos, restore));
     else QI_TRY(schedule_passes(s, gates, ctx().opt_fuse != 0, R, steps));
     std::vector<amp_t> arena;
     auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; blob->insert(blob->end(), b, b + n); };

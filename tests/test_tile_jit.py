@@ -262,3 +262,46 @@ def test_jit_module_variants_bit_identical(gpu, ref, tile11, option, value):
     assert gpu.engine.jit_stats()["failed"] == 0
     assert np.array_equal(sv_1, sv_g)
     assert np.array_equal(b_1, b_g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,depth", [(14, 16), (16, 24), (21, 12)])
+def test_jit_sliding_tiles_with_restored_layout(gpu, ref, n, depth):
+    """option tile_restore: the modules run the SLIDING schedule (fewer passes) and relabel-only passes put every qubit back, so
+    that the state keeps its layout and a second execution reuses every module."""
+    from quant_iron_b200 import sharded, workloads as w
+    specs = w.random_layered_circuit(n, depth, seed=77 + n)
+    cg = w.build_circuit(gpu, n, specs)
+    r0 = ref.random_state(n, 3)
+    gpu.engine.set_option("tile_min_qubits", 11)
+    gpu.engine.set_option("tile_restore", 1)
+    gpu.engine.set_option("jit", 2)
+    try:
+        st = gpu.State(r0.state_vector, n)
+        cg.execute_(st)
+        phys, _ = sharded.layout(st)
+        assert list(phys[:n]) == list(range(n)), phys[:n]
+        mods = gpu.engine.jit_stats()["modules"]
+        gpu.engine.stats_reset()
+        cg.execute_(st)                                       # same layout -> same structures -> no new module
+        assert gpu.engine.jit_stats()["modules"] == mods
+        assert gpu.engine.stats().get("gate_tile_jit", {}).get("launches", 0) > 0
+        st2 = gpu.State(r0.state_vector, n)
+        cg.execute_(st2)
+        sv = np.array(st2.state_vector)
+    finally:
+        gpu.engine.set_option("jit", 1)
+        gpu.engine.set_option("tile_restore", 0)
+        gpu.engine.set_option("tile_min_qubits", 18)
+    assert gpu.engine.jit_stats()["failed"] == 0
+    if n <= 16:
+        out_r = w.build_circuit(ref, n, specs).execute(r0)
+        assert np.max(np.abs(sv - vec(out_r))) <= 1e-12
+    else:
+        gpu.engine.set_option("jit", 0)
+        try:
+            st3 = gpu.State(r0.state_vector, n)
+            cg.execute_(st3)
+            assert np.max(np.abs(sv - np.array(st3.state_vector))) <= 1e-14
+        finally:
+            gpu.engine.set_option("jit", 1)
