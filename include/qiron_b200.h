@@ -73,7 +73,15 @@ int qi_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_m
  *          "jit" = tile passes as circuit-specialised straight-line sm_100a modules, assembled from generated PTX by the
  *          driver (csrc/tile_jit.cuh): 0 never | 1 (default) in the background once a pass structure has been seen, for
  *          states of >= "jit_min_qubits" local qubits (the interpreting kernel runs the pass meanwhile; results are
- *          bit-identical) | 2 before the first launch; "jit_ctas" = 4|3 resident CTAs per SM the modules are built for */
+ *          bit-identical) | 2 before the first launch; module skeleton variants kept for A/B (all measured slower or equal,
+ *          DESIGN 3.0): "jit_ctas" = 4|3|5|6 CTAs per SM, "jit_groups" = 1|2|4 tiles per CTA, "jit_prefetch" = 0|1|2 L2
+ *          prefetch of the next tile, "jit_stage" = 0|1 next tile staged in shared memory by bulk async copies,
+ *          "jit_smem_kb" = minimum dynamic shared memory of a module (caps occupancy);
+ *          tile lowering: "tile_lean" = 1/0 uncontrolled H / RY / RX in unit form, "tile_pform" = 0..4 diagonal groups of at
+ *          most that many qubits as P-form phase ops instead of tables, "tile_carry" = 1/0 one scale op per run,
+ *          "tile_slide" = 1/0 sliding tiles (interpreting kernel only), "tile_restore" = 0/1 sliding tiles + layout-restoring
+ *          relabel passes for states that run on modules, "tile_min_gates" = 3 shorter runs stay on the window kernel;
+ *          "peer_timeout_s" = seconds a sharded state waits for a peer at a device barrier before the kernel traps */
 int qi_set_option(const char* name, int64_t value);
 /* wait until every queued tile module is assembled (benchmarks: call after the first execution of a circuit) */
 int qi_jit_drain(void);
