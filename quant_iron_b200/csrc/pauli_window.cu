@@ -81,15 +81,27 @@ __device__ __forceinline__ void px_apply(amp_t (&v)[1 << R], const uint32_t xl, 
         return;
     }
     constexpr int HB = (M & 16) ? 16 : (M & 8) ? 8 : (M & 4) ? 4 : (M & 2) ? 2 : 1;
+    // the lane-flip test is hoisted out of the slot loop: inside it, it cost one branch per slot pair plus the register moves
+    // that set up the "no shuffle" defaults (SASS, round 2)
+    if (xl) {
 #pragma unroll
-    for (int s0 = 0; s0 < S; s0++) {
-        if (s0 & HB) continue;
-        const int s1 = s0 ^ M;
-        const amp_t a = v[s0], b = v[s1];
-        amp_t oa = a, ob = b;
-        if (xl) { oa = px_shfl(a, xl); ob = px_shfl(b, xl); }
-        v[s0] = px_mix<SW>(a, ob, c, s_re, s_im, QI_PX_SIGN(s0));     // (P psi)[s0] comes from slot s1
-        v[s1] = px_mix<SW>(b, oa, c, s_re, s_im, QI_PX_SIGN(s1));
+        for (int s0 = 0; s0 < S; s0++) {
+            if (s0 & HB) continue;
+            const int s1 = s0 ^ M;
+            const amp_t a = v[s0], b = v[s1];
+            const amp_t oa = px_shfl(a, xl), ob = px_shfl(b, xl);
+            v[s0] = px_mix<SW>(a, ob, c, s_re, s_im, QI_PX_SIGN(s0));     // (P psi)[s0] comes from slot s1
+            v[s1] = px_mix<SW>(b, oa, c, s_re, s_im, QI_PX_SIGN(s1));
+        }
+    } else {
+#pragma unroll
+        for (int s0 = 0; s0 < S; s0++) {
+            if (s0 & HB) continue;
+            const int s1 = s0 ^ M;
+            const amp_t a = v[s0], b = v[s1];
+            v[s0] = px_mix<SW>(a, b, c, s_re, s_im, QI_PX_SIGN(s0));
+            v[s1] = px_mix<SW>(b, a, c, s_re, s_im, QI_PX_SIGN(s1));
+        }
     }
 #undef QI_PX_SIGN
 }
@@ -302,16 +314,20 @@ __device__ __forceinline__ void px_expect(const amp_t (&v)[1 << R], const uint32
     constexpr int S = 1 << R;
     const uint32_t pm = px_parity_mask(zr);
     const uint32_t mre = nre ? 0x80000000u : 0u, mim = nim ? 0x80000000u : 0u;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        amp_t o = v[s ^ M];
-        if (xl) o = px_shfl(o, xl);
+    auto term = [&](int s, amp_t o) {
         const uint32_t par = (pm << (31 - s)) & 0x80000000u;
         double pre = SW ? o.y : o.x, pim = SW ? o.x : o.y;       // i^k o: component swap for odd k, then signs
         pre = px_sign(pre, mre ^ par);
         pim = px_sign(pim, mim ^ par);
         tr += v[s].x * pre + v[s].y * pim;                       // conj(v) * (pre + i pim)
         ti += v[s].x * pim - v[s].y * pre;
+    };
+    if (xl) {
+#pragma unroll
+        for (int s = 0; s < S; s++) term(s, px_shfl(v[s ^ M], xl));
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; s++) term(s, v[s ^ M]);
     }
 }
 
