@@ -37,7 +37,8 @@ struct PXProgram {
     BitInsert ins;
     uint64_t off[1 << R];
     uint32_t nops;
-    uint32_t pad;
+    uint32_t unit;           // the pass runs in unit form (every |c| >= 0.05): ops hold (1, s / c), `scale` = product of the c
+    double scale;
     PXOp ops[kMaxPX];
 };
 
@@ -56,15 +57,21 @@ __device__ __forceinline__ uint32_t px_parity_mask(uint32_t zr) {
     return ((zr & 1u) ? 0xAAAAAAAAu : 0u) ^ ((zr & 2u) ? 0xCCCCCCCCu : 0u) ^ ((zr & 4u) ? 0xF0F0F0F0u : 0u) ^ ((zr & 8u) ? 0xFF00FF00u : 0u) ^
            ((zr & 16u) ? 0xFFFF0000u : 0u);
 }
-template <bool SW>
+// UNIT: the pass runs in unit form -- every op is (1 / c) of itself (mine + (s / c) i^k other: one FMA per component instead of
+// a product and an FMA) and the product of the c is applied once, at the end of the pass (PXProgram::scale)
+template <bool SW, bool UNIT>
 __device__ __forceinline__ amp_t px_mix(amp_t mine, amp_t other, double c, double s_re, double s_im, uint32_t m) {
     const double kr = px_sign(s_re, m), ki = px_sign(s_im, m);
+    if (UNIT) {
+        const double src_re = SW ? other.y : other.x, src_im = SW ? other.x : other.y;
+        return make_double2(fma(kr, src_re, mine.x), fma(ki, src_im, mine.y));
+    }
     const double src_re = SW ? other.y : other.x, src_im = SW ? other.x : other.y;
     return make_double2(c * mine.x + kr * src_re, c * mine.y + ki * src_im);
 }
 
 // one term on the register tile; M = slot xor mask (compile time so every v[] index is a literal)
-template <int R, int M, bool SW>
+template <int R, int M, bool SW, bool UNIT>
 __device__ __forceinline__ void px_apply(amp_t (&v)[1 << R], const uint32_t xl, const uint32_t zr, const double c, const double s_re,
                                          const double s_im) {
     constexpr int S = 1 << R;
@@ -73,10 +80,10 @@ __device__ __forceinline__ void px_apply(amp_t (&v)[1 << R], const uint32_t xl, 
     if (M == 0) {
         if (xl) {
 #pragma unroll
-            for (int s = 0; s < S; s++) v[s] = px_mix<SW>(v[s], px_shfl(v[s], xl), c, s_re, s_im, QI_PX_SIGN(s));
+            for (int s = 0; s < S; s++) v[s] = px_mix<SW, UNIT>(v[s], px_shfl(v[s], xl), c, s_re, s_im, QI_PX_SIGN(s));
         } else {
 #pragma unroll
-            for (int s = 0; s < S; s++) v[s] = px_mix<SW>(v[s], v[s], c, s_re, s_im, QI_PX_SIGN(s));
+            for (int s = 0; s < S; s++) v[s] = px_mix<SW, UNIT>(v[s], v[s], c, s_re, s_im, QI_PX_SIGN(s));
         }
         return;
     }
@@ -90,8 +97,8 @@ __device__ __forceinline__ void px_apply(amp_t (&v)[1 << R], const uint32_t xl, 
             const int s1 = s0 ^ M;
             const amp_t a = v[s0], b = v[s1];
             const amp_t oa = px_shfl(a, xl), ob = px_shfl(b, xl);
-            v[s0] = px_mix<SW>(a, ob, c, s_re, s_im, QI_PX_SIGN(s0));     // (P psi)[s0] comes from slot s1
-            v[s1] = px_mix<SW>(b, oa, c, s_re, s_im, QI_PX_SIGN(s1));
+            v[s0] = px_mix<SW, UNIT>(a, ob, c, s_re, s_im, QI_PX_SIGN(s0));     // (P psi)[s0] comes from slot s1
+            v[s1] = px_mix<SW, UNIT>(b, oa, c, s_re, s_im, QI_PX_SIGN(s1));
         }
     } else {
 #pragma unroll
@@ -99,18 +106,18 @@ __device__ __forceinline__ void px_apply(amp_t (&v)[1 << R], const uint32_t xl, 
             if (s0 & HB) continue;
             const int s1 = s0 ^ M;
             const amp_t a = v[s0], b = v[s1];
-            v[s0] = px_mix<SW>(a, b, c, s_re, s_im, QI_PX_SIGN(s0));
-            v[s1] = px_mix<SW>(b, a, c, s_re, s_im, QI_PX_SIGN(s1));
+            v[s0] = px_mix<SW, UNIT>(a, b, c, s_re, s_im, QI_PX_SIGN(s0));
+            v[s1] = px_mix<SW, UNIT>(b, a, c, s_re, s_im, QI_PX_SIGN(s1));
         }
     }
 #undef QI_PX_SIGN
 }
 
-template <int R, bool SW>
+template <int R, bool SW, bool UNIT>
 __device__ __forceinline__ void px_dispatch(amp_t (&v)[1 << R], const uint32_t xr, const uint32_t xl, const uint32_t zr, const double c,
                                             const double s_re, const double s_im) {
     constexpr int S = 1 << R;
-#define QI_PX_CASE(m) case m: px_apply<R, ((m) < S ? (m) : 0), SW>(v, xl, zr, c, s_re, s_im); break;
+#define QI_PX_CASE(m) case m: px_apply<R, ((m) < S ? (m) : 0), SW, UNIT>(v, xl, zr, c, s_re, s_im); break;
     switch (xr) {
         QI_PX_CASE(0) QI_PX_CASE(1) QI_PX_CASE(2) QI_PX_CASE(3) QI_PX_CASE(4) QI_PX_CASE(5) QI_PX_CASE(6) QI_PX_CASE(7)
         QI_PX_CASE(8) QI_PX_CASE(9) QI_PX_CASE(10) QI_PX_CASE(11) QI_PX_CASE(12) QI_PX_CASE(13) QI_PX_CASE(14) QI_PX_CASE(15)
@@ -119,7 +126,7 @@ __device__ __forceinline__ void px_dispatch(amp_t (&v)[1 << R], const uint32_t x
 #undef QI_PX_CASE
 }
 
-template <int R>
+template <int R, bool UNIT>
 __global__ void __launch_bounds__(128, (R <= 3 ? 8 : 4)) k_pauli_window(amp_t* __restrict__ a, uint64_t ntiles, const __grid_constant__ PXProgram<R> P) {
     constexpr int S = 1 << R;
     const int lane = threadIdx.x & 31;
@@ -140,8 +147,13 @@ __global__ void __launch_bounds__(128, (R <= 3 ? 8 : 4)) k_pauli_window(amp_t* _
             const bool nre = (((k0 & 3) == 1) || ((k0 & 3) == 2)) != flip;      // i^1 = (-y, x), i^2 = (-x, -y), i^3 = (y, -x)
             const bool nim = ((k0 & 3) >= 2) != flip;
             const double s_re = nre ? -op.s : op.s, s_im = nim ? -op.s : op.s;
-            if (k0 & 1) px_dispatch<R, true>(v, op.xr, op.xl, op.zr, op.c, s_re, s_im);
-            else px_dispatch<R, false>(v, op.xr, op.xl, op.zr, op.c, s_re, s_im);
+            if (k0 & 1) px_dispatch<R, true, UNIT>(v, op.xr, op.xl, op.zr, op.c, s_re, s_im);
+            else px_dispatch<R, false, UNIT>(v, op.xr, op.xl, op.zr, op.c, s_re, s_im);
+        }
+        if (UNIT) {
+            const double g = P.scale;
+#pragma unroll
+            for (int s = 0; s < S; s++) { v[s].x *= g; v[s].y *= g; }
         }
 #pragma unroll
         for (int s = 0; s < S; s++) st_amp(a + base + P.off[s], v[s]);
@@ -219,7 +231,7 @@ static int schedule_pauli(const std::vector<PauliExp>& seq, Emit emit) {
 }
 
 // device program of one pass (host only)
-static int build_px_program(const qi_state* s, const std::vector<PauliExp>& seq, const PxPass& ps, PXProgram<kPauliR>* Pout, Layout* Lout) {
+static int build_px_program(const qi_state* s, const std::vector<PauliExp>& seq, const PxPass& ps, PXProgram<kPauliR>* Pout, Layout* Lout, bool allow_unit = false) {
     constexpr int R = kPauliR;
     Layout L = make_layout(s, ps.regs, R);
     PXProgram<R>& P = *Pout;
@@ -239,6 +251,15 @@ static int build_px_program(const qi_state* s, const std::vector<PauliExp>& seq,
         d.c = t.ch.x;
         d.s = imag ? t.sh.y : t.sh.x;
     }
+    P.scale = 1.0;
+    if (allow_unit && P.nops >= 2) {
+        bool ok = true;
+        for (uint32_t k = 0; k < P.nops; k++) ok &= std::fabs(P.ops[k].c) >= 0.05;
+        if (ok) {
+            P.unit = 1;
+            for (uint32_t k = 0; k < P.nops; k++) { P.scale *= P.ops[k].c; P.ops[k].s /= P.ops[k].c; P.ops[k].c = 1.0; }
+        }
+    }
     if (Lout) *Lout = L;
     return QI_OK;
 }
@@ -247,14 +268,15 @@ static int launch_pauli_pass(qi_state* s, const std::vector<PauliExp>& seq, cons
     Context& c = ctx();
     constexpr int R = kPauliR;
     PXProgram<R> P;
-    QI_TRY(build_px_program(s, seq, ps, &P, nullptr));
+    QI_TRY(build_px_program(s, seq, ps, &P, nullptr, c.opt_pauli_unit != 0));
     const uint64_t ntiles = s->len >> (kLaneQubits + R);
     const int warps_per_block = 4;
     uint64_t blocks = (ntiles + warps_per_block - 1) / warps_per_block;
     const uint64_t cap = (uint64_t)c.sm_count * 5 * 8;
     if (blocks > cap) blocks = cap;
     LaunchScope ls(KF_PAULI_WINDOW, 32.0 * (double)s->len);
-    k_pauli_window<R><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+    if (P.unit) k_pauli_window<R, true><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
+    else k_pauli_window<R, false><<<(unsigned)blocks, warps_per_block * 32, 0, c.stream>>>(s->d, ntiles, P);
     return check_launch("k_pauli_window");
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 set -u
-OUT=gpurun_out/r02za
+OUT=gpurun_out/r02zb
 mkdir -p "$OUT"
 timeout 900 python -m pytest tests -q -m "gpu and not large" -k "pauli or trotter or heisenberg or sumop or expect or golden or models" > "$OUT/pytest_pauli.log" 2>&1
 echo "exit $?" >> "$OUT/pytest_pauli.log"
