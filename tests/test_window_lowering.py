@@ -374,3 +374,56 @@ def test_tile_pass_count_of_the_benchmark_circuit():
     tiles = _tile_steps(steps)
     assert len(tiles) <= 40, len(tiles)
     assert all(t[3] == t[1] for t in tiles)
+
+
+@pytest.mark.parametrize("options", [{"tile_pform": 0}, {"tile_pform": 2}, {"tile_carry": 0}, {"tile_lean": 0}, {"tile_lean": 0, "tile_pform": 0, "tile_carry": 0}],
+                         ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_tile_lowering_options_match_oracle(ref, tile11, options):
+    """Round-2 lowering options of the tile passes -- unit-form pair ops, P-form phase ops instead of small tables, the scalar
+    carried across launches -- each against the oracle, with the remaining options at their defaults."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    n = 14
+    specs = w.random_layered_circuit(n, 14, seed=31) + w.qft_specs(n) + w.random_layered_circuit(n, 4, seed=32)
+    start = ref.random_state(n, 8)
+    defaults = {"tile_pform": 4, "tile_carry": 1, "tile_lean": 1}
+    for k, v in options.items():
+        gpu.engine.set_option(k, v)
+    try:
+        got, steps = _run(w.build_circuit(gpu, n, specs), n, start.state_vector)
+    finally:
+        for k, v in defaults.items():
+            gpu.engine.set_option(k, v)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
+    kinds = np.concatenate([ops["kind"] for t in _tile_steps(steps) for (_, _, ops) in t[2] if len(ops)])
+    if options.get("tile_lean", 1) == 0:
+        assert not np.isin(kinds, [wi.WK_REALUP, wi.WK_REALUM, wi.WK_RXU]).any()
+    if options.get("tile_carry", 1) == 1 and options.get("tile_lean", 1) == 1:
+        assert (kinds == wi.WK_SCALE).sum() <= 2              # one scalar per run (QFT swaps split the run in two at most)
+
+
+@pytest.mark.parametrize("n,depth", [(17, 10), (19, 8)])
+def test_tile_restore_relabel_passes_match_oracle(ref, n, depth):
+    """option tile_restore (states that run on modules): sliding tiles, then relabel-only passes that put every qubit back --
+    the final layout is the initial one and the amplitudes match the oracle."""
+    import quant_iron_b200 as gpu
+    from quant_iron_b200 import workloads as w
+    specs = w.random_layered_circuit(n, depth, seed=5 + n)
+    start = ref.random_state(n, 2)
+    for k, v in {"tile_min_qubits": 11, "jit_min_qubits": 11, "tile_restore": 1}.items():
+        gpu.engine.set_option(k, v)
+    try:
+        blob = wi.lower(w.build_circuit(gpu, n, specs), n)
+    finally:
+        for k, v in {"tile_min_qubits": 18, "jit_min_qubits": 24, "tile_restore": 0}.items():
+            gpu.engine.set_option(k, v)
+    steps, _, final_phys = wi.parse(blob)
+    tiles = _tile_steps(steps)
+    assert any(t[3] != t[1] for t in tiles)                                  # tiles slide ...
+    assert list(final_phys[:n]) == list(range(n))                            # ... and the layout comes back
+    v = np.array(start.state_vector)
+    out_phys, _ = wi.execute(blob, v, n)
+    got = wi.to_logical(v, n, out_phys)
+    want = vec(w.build_circuit(ref, n, specs).execute(start))
+    assert float(np.max(np.abs(got - want))) <= AMP_TOL
