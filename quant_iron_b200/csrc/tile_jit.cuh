@@ -57,6 +57,7 @@ struct Gen {
     int na = 32, ng = 0, nlab = 0;
     const amp_t* arena = nullptr;
     bool dry = false;              // collect the coefficients only (the module of this structure exists): no text
+    bool in_region = false;        // between begin_region and end_region: the code runs under a branch
     double weight = 1.0;           // fraction of the threads inside the current control region
     double fp64 = 0.0;             // FP64 instructions per thread and tile, weighted by the control regions they sit in
 
@@ -86,6 +87,7 @@ struct Gen {
     int begin_region(const DOp& d) {
         if (!d.c_tile && !d.c_lane) return -1;
         const int L = nlab++;
+        in_region = true;
         weight = std::ldexp(1.0, -(__builtin_popcountll(d.c_tile) + __builtin_popcount(d.c_lane)));
         if (d.c_tile) {
             emit("and.b64 %%rdx, %%tile, %llu;", (unsigned long long)d.c_tile);
@@ -99,7 +101,7 @@ struct Gen {
         }
         return L;
     }
-    void end_region(int L) { weight = 1.0; if (L >= 0 && !dry) { s.append("LS"); s.append(std::to_string(L)); s.append(":\n"); } }
+    void end_region(int L) { weight = 1.0; in_region = false; if (L >= 0 && !dry) { s.append("LS"); s.append(std::to_string(L)); s.append(":\n"); } }
     // %pq = the op applies (no branch)
     void on_pred(const DOp& d) {
         if (d.c_tile) {
@@ -202,7 +204,19 @@ struct Gen {
             ax[s0] = nx0; ax[s1] = nx1; ay[s0] = ny0; ay[s1] = ny1;
         }
     }
-    void neg_slot(int sl) { emit("neg.f64 %%a%d, %%a%d;", ax[sl], ax[sl]); emit("neg.f64 %%a%d, %%a%d;", ay[sl], ay[sl]); }
+    // x <- -x by an xor on the high word (ALU pipe).  Used wherever ptxas cannot fold a neg.f64 into an operand modifier -- under
+    // a branch or a predicate it becomes a DADD on the FP64 pipe, the pipe these modules are bound by (12 % of the FP64
+    // instructions of the heaviest benchmark pass were such DADDs)
+    void flip_const(int reg) {
+        emit("mov.b64 {%%rlo, %%rhi}, %%a%d;", reg);
+        emit("xor.b32 %%rhi, %%rhi, 0x80000000;");
+        emit("mov.b64 %%a%d, {%%rlo, %%rhi};", reg);
+    }
+    void neg_slot(int sl) {
+        if (in_region) { flip_const(ax[sl]); flip_const(ay[sl]); return; }
+        emit("neg.f64 %%a%d, %%a%d;", ax[sl], ax[sl]);
+        emit("neg.f64 %%a%d, %%a%d;", ay[sl], ay[sl]);
+    }
     // a <- e^{i phi} a as three shears with (nt, s) in registers named by `nt`, `sn` (printf patterns "%%c12" / "%%g3")
     void shear(int sl, const char* nt, const char* sn) {
         emit("fma.rn.f64 %%a%d, %s, %%a%d, %%a%d;", ax[sl], nt, ay[sl], ax[sl]);
@@ -219,9 +233,13 @@ struct Gen {
         shear(sl, a, b);
     }
     void op_neg(const DOp& d) {
-        const int L = begin_region(d);
+        if (d.c_tile || d.c_lane) {        // controlled sign flip (CZ with a thread- or tile-bit control): no branch, a runtime sign mask
+            on_pred(d);
+            emit("selp.b32 %%rm, 0x80000000, 0, %%pq;");
+            for (int sl = 0; sl < 16; sl++) if ((d.c_reg >> sl) & 1u) { flip_runtime(ax[sl]); flip_runtime(ay[sl]); }
+            return;
+        }
         for (int sl = 0; sl < 16; sl++) if ((d.c_reg >> sl) & 1u) neg_slot(sl);
-        end_region(L);
     }
     void op_diag(const DOp& d) {
         const int L = begin_region(d);
@@ -257,8 +275,11 @@ struct Gen {
                 if (!((d.c_reg >> sl) & 1u)) continue;
                 if (sl & d.t_reg) { rot_static(sl, d.m[6], d.m[7], k1n, k1s); continue; }
                 if (n0 && n1) neg_slot(sl);
-                else if (n1) { emit("@%%pt neg.f64 %%a%d, %%a%d;", ax[sl], ax[sl]); emit("@%%pt neg.f64 %%a%d, %%a%d;", ay[sl], ay[sl]); }
-                else if (n0) { emit("@!%%pt neg.f64 %%a%d, %%a%d;", ax[sl], ax[sl]); emit("@!%%pt neg.f64 %%a%d, %%a%d;", ay[sl], ay[sl]); }
+                else if (n1 || n0) {
+                    emit(n1 ? "selp.b32 %%rm, 0x80000000, 0, %%pt;" : "selp.b32 %%rm, 0, 0x80000000, %%pt;");
+                    flip_runtime(ax[sl]);
+                    flip_runtime(ay[sl]);
+                }
                 shear(sl, a, b);
             }
         }
