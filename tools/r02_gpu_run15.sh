@@ -2,7 +2,7 @@
 # round-2 record run on one B200: full GPU test tier, full bench (extras, e2e, cpu baseline), reference arm, sanitizers on the
 # JIT / tile paths, ncu launch list of the bench command and one full capture of a module
 set -u
-OUT=gpurun_out/r02final
+OUT=gpurun_out/r02final2
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > "$OUT/gpu.csv" 2>&1
 timeout 1500 python -m pytest tests -q -m gpu > "$OUT/pytest_gpu.log" 2>&1
