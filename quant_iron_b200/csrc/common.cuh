@@ -77,6 +77,7 @@ struct Context {
     int opt_jit_smem_kb = 0;          // modules request at least this much dynamic shared memory (56 = at most 4 CTAs per SM however few registers a small module needs)
     int opt_jit_stage = 0;            // modules bring the CTA's next tile into shared memory with bulk async copies (cp.async.bulk + mbarrier) while the current one is computed
     int opt_jit_prefetch = 0;         // modules prefetch the CTA's next tile into L2 while the current one is computed
+    int opt_tile_bfs_by_use = 1;      // tile scheduler: candidate tiles grow through neighbours in program order of their first non-diagonal use
     int opt_pauli_unit = 1;           // fused Pauli-exp passes in unit form (one FMA per component and op, one scale per pass)
     int opt_tile_restore = 0;         // states that run on modules: sliding tiles + relabel-only passes that restore the layout at the end of a run
     int opt_tile_carry = 1;           // the scalar the unit-form / P-form ops leave out travels across the launches of a run and is applied once

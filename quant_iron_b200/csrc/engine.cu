@@ -279,6 +279,7 @@ int qi_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "tile_carry")) c.opt_tile_carry = (int)value;
     else if (!strcmp(name, "tile_restore")) c.opt_tile_restore = (int)value;
     else if (!strcmp(name, "pauli_unit")) c.opt_pauli_unit = (int)value;
+    else if (!strcmp(name, "tile_bfs_by_use")) c.opt_tile_bfs_by_use = (int)value;
     else if (!strcmp(name, "jit_prefetch")) c.opt_jit_prefetch = (int)value;
     else if (!strcmp(name, "jit_stage")) c.opt_jit_stage = (int)value;
     else if (!strcmp(name, "jit_smem_kb")) c.opt_jit_smem_kb = (int)value;

@@ -2269,6 +2269,22 @@ static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& 
                 for (int q = 0; q < n; q++) if ((m >> q) & 1) adj[q] |= m;
             }
         }
+        // neighbours are visited in the order in which the gates ahead first act NON-diagonally on them (program order), not by
+        // qubit index: for a QFT in the bit-reversed layout its own swaps leave behind, index order fills the tile with the
+        // qubits whose Hadamards come LAST (12 passes instead of 5)
+        std::vector<int> by_use(n);
+        {
+            std::vector<size_t> first_use(n, (size_t)-1);
+            size_t scanned = 0;
+            for (size_t i = first; i < G && scanned < kGraph; i++) {
+                if (done[i]) continue;
+                scanned++;
+                for (int q = 0; q < n; q++) if (((use[i].n_use >> q) & 1) && first_use[q] == (size_t)-1) first_use[q] = i;
+            }
+            for (int q = 0; q < n; q++) by_use[q] = q;
+            if (ctx().opt_tile_bfs_by_use)
+                std::stable_sort(by_use.begin(), by_use.end(), [&](int a, int b) { return first_use[a] < first_use[b]; });
+        }
         const uint64_t need_first = use[first].n_use;         // progress: the oldest gate must fit
         uint64_t best_tile = 0;
         int best_score = -1;
@@ -2280,7 +2296,7 @@ static int schedule_tile_passes(const qi_state* s, const std::vector<PhysGate>& 
             if (!((seen >> seed) & 1)) { order.push_back(seed); seen |= 1ull << seed; }
             for (size_t k = 0; k < order.size() && (int)order.size() < n; k++) {
                 uint64_t nb = adj[order[k]] & ~seen;
-                for (int q = 0; q < n && nb; q++) if ((nb >> q) & 1) { order.push_back(q); seen |= 1ull << q; nb &= ~(1ull << q); }
+                for (int qi = 0; qi < n && nb; qi++) { const int q = by_use[qi]; if ((nb >> q) & 1) { order.push_back(q); seen |= 1ull << q; nb &= ~(1ull << q); } }
             }
             for (int d = 1; (int)order.size() < n && d < n; d++) {        // isolated qubits: nearest positions first
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
