@@ -19,13 +19,14 @@ from .parametric import (Parameter, ParametricGate, ParametricMatchgate, Paramet
                          ParametricRyPhase, ParametricRyPhaseDag, ParametricRz)
 from .pauli import PauliString, SumOp
 from .state import State
+from .chain import ChainableState, chain
 from . import workloads
 from . import engine
 from . import macros
 from .macros import circuit as circuit_macro
 
 __all__ = [
-    "State", "Operator", "Hadamard", "Pauli", "CNOT", "SWAP", "Toffoli", "Identity", "PhaseS", "PhaseT",
+    "State", "ChainableState", "chain", "Operator", "Hadamard", "Pauli", "CNOT", "SWAP", "Toffoli", "Identity", "PhaseS", "PhaseT",
     "PhaseSdag", "PhaseTdag", "PhaseShift", "RotateX", "RotateY", "RotateZ", "Unitary2", "Matchgate",
     "Gate", "Circuit", "CircuitBuilder", "Subroutine", "PauliString", "SumOp", "MeasurementBasis",
     "MeasurementResult", "TrotterOrder", "first_order_trotter_step", "second_order_trotter_step",

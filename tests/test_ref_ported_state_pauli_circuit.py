@@ -468,3 +468,26 @@ def test_circuit_builder_argument_order(qi):
     assert c.execute(S.new_zero(3)) == S.new_basis_n(3, 7)
     c = qi.CircuitBuilder(2).h_gates([0, 1]).cp_gates([1], [0], PI).build()
     assert_amps(c.execute(S.new_zero(2)), [0.5, 0.5, 0.5, -0.5])
+
+
+# ---- ChainableState (state.rs:2375-2684): gate methods on Result<State, Error> ---------------------------------------------
+def test_chainable_state_forwards_while_ok_and_short_circuits_on_the_first_error(qi):
+    """`impl ChainableState for Result<State, Error>` is `self.and_then(|state| state.method(..))` for every gate method
+    (state.rs:2611-2620): the chain evaluates to the state while every link succeeds and to the FIRST error otherwise."""
+    from quant_iron_b200.chain import chain
+    ok = chain(qi.State.new_zero(2)).h(0).cnot(0, 1)
+    assert ok.is_ok() and not ok.is_err()
+    bell = ok.unwrap()
+    v = np.asarray(bell.state_vector)
+    assert np.allclose(v, [1 / math.sqrt(2), 0, 0, 1 / math.sqrt(2)], atol=1e-15)
+    direct = qi.State.new_zero(2).h(0).cnot(0, 1)
+    assert np.array_equal(np.asarray(direct.state_vector), v)
+    bad = chain(qi.State.new_zero(2)).h(0).x(5).cnot(0, 1).h(7)          # x(5): InvalidQubitIndex(5, 2); the later links never run
+    assert bad.is_err() and bad.ok() is None
+    assert bad.unwrap_err().variant == "InvalidQubitIndex" and tuple(bad.unwrap_err().payload)[:2] == (5, 2)
+    with pytest.raises(Exception) as e:
+        bad.unwrap()
+    assert e.value.variant == "InvalidQubitIndex"
+    # and_then with a user function, operate through the chain
+    rot = chain(qi.State.new_zero(1)).operate(qi.Hadamard(), [0], []).and_then(lambda s: s.rz(0, 0.25))
+    assert rot.is_ok() and abs(abs(rot.unwrap().amplitude(0)) - 1 / math.sqrt(2)) < 1e-15
