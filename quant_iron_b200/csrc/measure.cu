@@ -55,6 +55,55 @@ __global__ void __launch_bounds__(256) k_prob_chunks(const amp_t* __restrict__ a
     acc = block_sum1(acc);
     if (threadIdx.x == 0) partials[bin * chunks + chunk] = acc;
 }
+// (A') the same when some measured qubits sit at positions 0..2: a bin then owns one half / quarter / eighth of every 32-, 64-
+//      or 128-byte piece of the state, and a block that reads ONE bin moves the whole sector for half of it (the marginal over
+//      qubits {0, 7, 13, 22, 29} of a 30-qubit state ran at 0.53 of the copy bandwidth).  Here a thread reads all 2^L
+//      amplitudes that differ in the L low measured bits -- neighbours in memory, the sector is used completely -- and keeps
+//      2^L accumulators; a block covers one combination of the HIGH measured bits.  Same fixed-shape reductions.
+struct LowBins {
+    int L;                    // measured positions below 3
+    uint8_t jlow[3];          // bin bit index of the k-th low measured position
+    uint8_t plow[3];          // its physical position
+    int nhigh;
+    uint8_t jhigh[64];        // bin bit index of the k-th high measured position
+};
+template <int L>
+__global__ void __launch_bounds__(256) k_prob_chunks_low(const amp_t* __restrict__ a, uint64_t rest_total, uint64_t chunk_len,
+                                                         BitInsert ins, BinMap bm, LowBins lb, double* partials, int chunks) {
+    const uint64_t hb = blockIdx.y;
+    const int chunk = blockIdx.x;
+    uint64_t bin_h = 0;
+    for (int k = 0; k < lb.nhigh; k++) bin_h |= ((hb >> k) & 1ull) << lb.jhigh[k];
+    const uint64_t fixed = bin_to_mask(bin_h, bm);
+    uint64_t lowmask[1 << L];
+    uint64_t bin_of[1 << L];
+#pragma unroll
+    for (int c = 0; c < (1 << L); c++) {
+        uint64_t m = 0, b = bin_h;
+#pragma unroll
+        for (int k = 0; k < L; k++) if ((c >> k) & 1) { m |= 1ull << lb.plow[k]; b |= 1ull << lb.jlow[k]; }
+        lowmask[c] = m;
+        bin_of[c] = b;
+    }
+    uint64_t lo = (uint64_t)chunk * chunk_len, hi = lo + chunk_len;
+    if (hi > rest_total) hi = rest_total;
+    double acc[1 << L];
+#pragma unroll
+    for (int c = 0; c < (1 << L); c++) acc[c] = 0.0;
+    for (uint64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+        const uint64_t base = expand_index(r, ins) | fixed;
+#pragma unroll
+        for (int c = 0; c < (1 << L); c++) {
+            const amp_t v = a[base | lowmask[c]];
+            acc[c] += v.x * v.x + v.y * v.y;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < (1 << L); c++) {
+        const double t = block_sum1(acc[c]);
+        if (threadIdx.x == 0) partials[bin_of[c] * chunks + chunk] = t;
+    }
+}
 __global__ void k_prob_finish(const double* partials, int chunks, uint64_t nbins, double* probs) {
     uint64_t bin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (bin >= nbins) return;
@@ -164,9 +213,14 @@ __global__ void k_sample(const double* __restrict__ cdf, uint64_t n, uint64_t se
 __global__ void __launch_bounds__(256) k_collapse_zero(amp_t* __restrict__ a, uint64_t len, uint64_t sel_mask, uint64_t sel_val, uint64_t high, double* partials) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     double acc = 0.0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        if (((i | high) & sel_mask) == sel_val) { amp_t v = a[i]; acc += v.x * v.x + v.y * v.y; }
-        else a[i] = make_double2(0.0, 0.0);
+    // a thread owns both amplitudes of a 32-byte sector, so that the zeros of a sector are written by ONE thread (two adjacent
+    // 16-byte stores) instead of by two threads of different iterations when qubit 0 is among the measured ones
+    const amp_t zero = make_double2(0.0, 0.0);
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * p < len; p += stride) {
+        const uint64_t i0 = 2 * p, i1 = i0 + 1;
+        const bool k0 = ((i0 | high) & sel_mask) == sel_val, k1 = i1 < len && ((i1 | high) & sel_mask) == sel_val;
+        if (k0) { const amp_t v = a[i0]; acc += v.x * v.x + v.y * v.y; } else a[i0] = zero;
+        if (i1 < len) { if (k1) { const amp_t v = a[i1]; acc += v.x * v.x + v.y * v.y; } else a[i1] = zero; }
     }
     acc = block_sum1(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
@@ -218,15 +272,25 @@ static int local_table(const qi_state* s, const std::vector<int>& pos, double** 
     const uint64_t rest_total = s->len >> m;
     BitInsert ins = make_insert(sorted, {});
     int st = QI_OK;
+    LowBins lb;
+    memset(&lb, 0, sizeof(lb));
+    for (int j = 0; j < m; j++) {
+        if (pos[j] < 3) { lb.jlow[lb.L] = (uint8_t)j; lb.plow[lb.L] = (uint8_t)pos[j]; lb.L++; }
+        else lb.jhigh[lb.nhigh++] = (uint8_t)j;
+    }
     if (rest_total >= 1024 && nbins <= 32768) {
-        int chunks = (int)std::min<uint64_t>(std::max<uint64_t>(1, rest_total / 4096), std::max<uint64_t>(1, (uint64_t)(c.sm_count * 8) / nbins));
+        const uint64_t nblocks_y = nbins >> lb.L;             // one block row per combination of the high measured bits
+        int chunks = (int)std::min<uint64_t>(std::max<uint64_t>(1, rest_total / 4096), std::max<uint64_t>(1, (uint64_t)(c.sm_count * 8) / nblocks_y));
         if (chunks < 1) chunks = 1;
         uint64_t chunk_len = (rest_total + chunks - 1) / chunks;
         st = ensure_partials((size_t)nbins * chunks);
         if (st == QI_OK) {
             LaunchScope ls(KF_PROB, 16.0 * (double)s->len);
-            dim3 grid(chunks, (unsigned)nbins);
-            k_prob_chunks<<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, c.d_partials, chunks);
+            dim3 grid(chunks, (unsigned)nblocks_y);
+            if (lb.L == 0) k_prob_chunks<<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, c.d_partials, chunks);
+            else if (lb.L == 1) k_prob_chunks_low<1><<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, lb, c.d_partials, chunks);
+            else if (lb.L == 2) k_prob_chunks_low<2><<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, lb, c.d_partials, chunks);
+            else k_prob_chunks_low<3><<<grid, kBlock, 0, c.stream>>>(s->d, rest_total, chunk_len, ins, bm, lb, c.d_partials, chunks);
             k_prob_finish<<<(unsigned)((nbins + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(c.d_partials, chunks, nbins, d_probs);
         }
     } else {
