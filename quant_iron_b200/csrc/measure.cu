@@ -47,11 +47,24 @@ __global__ void __launch_bounds__(256) k_prob_chunks(const amp_t* __restrict__ a
     uint64_t fixed = bin_to_mask(bin, bm);
     uint64_t lo = (uint64_t)chunk * chunk_len, hi = lo + chunk_len;
     if (hi > rest_total) hi = rest_total;
-    double acc = 0.0;
-    for (uint64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
-        amp_t v = a[expand_index(r, ins) | fixed];
-        acc += v.x * v.x + v.y * v.y;
+    // four independent loads per thread and iteration (one load in flight per thread left the pass latency-bound at 0.66 of the
+    // copy bandwidth); the four partial sums are added in a fixed order
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const uint64_t step = blockDim.x;
+    uint64_t r = lo + threadIdx.x;
+    for (; r + 3 * step < hi; r += 4 * step) {
+        const amp_t v0 = a[expand_index(r, ins) | fixed], v1 = a[expand_index(r + step, ins) | fixed];
+        const amp_t v2 = a[expand_index(r + 2 * step, ins) | fixed], v3 = a[expand_index(r + 3 * step, ins) | fixed];
+        acc0 += v0.x * v0.x + v0.y * v0.y;
+        acc1 += v1.x * v1.x + v1.y * v1.y;
+        acc2 += v2.x * v2.x + v2.y * v2.y;
+        acc3 += v3.x * v3.x + v3.y * v3.y;
     }
+    for (; r < hi; r += step) {
+        const amp_t v = a[expand_index(r, ins) | fixed];
+        acc0 += v.x * v.x + v.y * v.y;
+    }
+    double acc = (acc0 + acc1) + (acc2 + acc3);
     acc = block_sum1(acc);
     if (threadIdx.x == 0) partials[bin * chunks + chunk] = acc;
 }
@@ -90,7 +103,23 @@ __global__ void __launch_bounds__(256) k_prob_chunks_low(const amp_t* __restrict
     double acc[1 << L];
 #pragma unroll
     for (int c = 0; c < (1 << L); c++) acc[c] = 0.0;
-    for (uint64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+    constexpr int U = L == 1 ? 2 : 1;                 // L = 1: two rest indices per iteration (four loads in flight)
+    const uint64_t step = blockDim.x;
+    uint64_t r = lo + threadIdx.x;
+    for (; r + (U - 1) * step < hi; r += U * step) {
+        amp_t v[U << L];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t base = expand_index(r + u * step, ins) | fixed;
+#pragma unroll
+            for (int c = 0; c < (1 << L); c++) v[(u << L) | c] = a[base | lowmask[c]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int c = 0; c < (1 << L); c++) acc[c] += v[(u << L) | c].x * v[(u << L) | c].x + v[(u << L) | c].y * v[(u << L) | c].y;
+    }
+    for (; r < hi; r += step) {
         const uint64_t base = expand_index(r, ins) | fixed;
 #pragma unroll
         for (int c = 0; c < (1 << L); c++) {
